@@ -1,0 +1,433 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native libtsd filtering hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload ola|fft|fir|resample] [--impl reference]
+
+Metric (BASELINE.json): Gsamples/s of cf32 input samples filtered.  Default workload = BASELINE
+config 4, the FFT-domain filter `filtre_fft` (K = 4095 taps, Ne = 61441, N = 65536) on 256 channels x
+16 Mi cf32 samples per GPU; the other workloads are BASELINE configs 2, 3 and 5.  A "step" is one
+step() over the whole per-GPU batch.  Multi-GPU: channels are independent, every rank owns its own
+256 channels (weak scaling, no data-path collective); the timed region is bracketed by a barrier and a
+device synchronize, and the reported time is the max over ranks.
+
+The JSON line carries, besides the driver contract: `roofline` (HBM-bound: algorithmic bytes of the
+dominant kernel / its CUDA-event duration / measured HBM copy bandwidth), `cpu_baseline` (the reference's
+own CPU code, oracle/_ref, on all host cores over a bounded sample), `e2e` (same metric through the C ABI
+with pinned HOST buffers, copies inside the timed region) and `clocks` (nvidia-smi during the run).
+
+`--impl reference` times the reference's CPU implementation (oracle/_ref, else the C port) on the same
+workload definition with all host threads; under torchrun only rank 0 runs it.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (BASELINE config text, algorithmic HBM bytes per input sample)
+    "ola": ("overlap-save filtre_fft: 256 ch x 16Mi cf32 per GPU, 4095-tap filter, Ne=61441, N=65536", 16.0),
+    "fft": ("batched fft/ifft: 4096 ch x 65536-pt cf32, forward+inverse round trip", 32.0),
+    "fir": ("direct FIR: 1024 ch x 1Mi cf32, 127-tap low-pass, filtre_rif step() in 64Ki blocks", 16.0),
+    "resample": ("polyphase/LUT resampler 147/160 on 512 ch x 8Mi cf32, sinc LUT 64 taps x 257 phases", 8.0 + 8.0 * 147 / 160),
+}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for ln in self.lines:
+            f = [v.strip() for v in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------- CPU arm
+def cpu_workload_setup(workload):
+    """Builds the per-thread job of the CPU reference arm; returns (make_job, samples_per_job, kind, sample_text)."""
+    import oracle
+    have_ref = oracle.have_ref()
+    O = oracle.ref() if have_ref else oracle.port()
+    kind = "reference" if have_ref else "port"
+    rng = np.random.default_rng(0xC0FFEE)
+
+    def cn(n):
+        return (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+
+    if workload == "ola":
+        h = O.design_rif_fen(4095, "lp", 0.1)
+        H = O.ola_make_H(h, 65536)
+        n = 32 * 61441
+        x = cn(n)
+
+        def make_job():
+            f = O.ola(61441, 4095, H)
+            return lambda: f.step(x)
+        return make_job, n, kind, f"1 channel x {n} cf32 samples (32 Ne-blocks) per host thread, filtre_fft K=4095 Ne=61441"
+    if workload == "fft":
+        x = cn(65536)
+        reps = 64
+
+        def make_job():
+            p = O.fft(65536)
+
+            def job():
+                for _ in range(reps):
+                    p.step(p.step(x, True), False)
+            return job
+        return make_job, reps * 65536, kind, f"{reps} x 65536-pt fwd+inv round trips per host thread"
+    if workload == "fir":
+        h = O.design_rif_fen(127, "lp", 0.1)
+        blocks = 16
+        x = cn(65536)
+
+        def make_job():
+            f = O.fir(1, h)
+
+            def job():
+                for _ in range(blocks):
+                    f.step(x)
+            return job
+        return make_job, blocks * 65536, kind, f"1 channel x {blocks} step() of 65536 cf32 per host thread, 127 taps"
+    if workload == "resample":
+        n = 1 << 20
+        x = cn(n)
+        if have_ref:
+            def make_job():
+                f = O.itrp(147.0 / 160.0, 64, 256, 0.4)
+                return lambda: f.step(x)
+        else:
+            lut = O.itrp_sinc_lut(64, 256, 0.4)
+
+            def make_job():
+                f = O.itrp(147.0 / 160.0, lut, 256)
+                return lambda: f.step(x)
+        return make_job, n, kind, f"1 channel x {n} cf32 samples per host thread, filtre_itrp 147/160, sinc 64x257"
+    raise SystemExit(f"unknown workload {workload}")
+
+
+def cpu_run(workload, steps, warmup, threads=None):
+    """Each step: every host thread runs one job on its own filter object (objects are per-channel and
+    not thread-safe in the reference).  Returns (Gsamples/s, ms_per_step, threads, kind, sample_text)."""
+    threads = threads or (os.cpu_count() or 1)
+    make_job, n_job, kind, text = cpu_workload_setup(workload)
+    jobs = [None] * threads
+
+    def build(i):
+        jobs[i] = make_job()   # constructed inside its worker thread (avoids false sharing)
+
+    def run_all(fn):
+        ts = [threading.Thread(target=fn, args=(i,)) for i in range(threads)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+
+    run_all(build)
+    for _ in range(warmup):
+        run_all(lambda i: jobs[i]())
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        run_all(lambda i: jobs[i]())
+    dt = time.perf_counter() - t0
+    total = float(n_job) * threads * steps
+    return total / dt / 1e9, dt / steps * 1e3, threads, kind, text
+
+
+# --------------------------------------------------------------------------------------- GPU arm
+class GpuWorkload:
+    """Builds the device-resident synthetic batch and the filter objects of one workload."""
+
+    def __init__(self, name, scale=1.0):
+        import torch
+        import oracle
+        from libtsd_b200 import filtrage as F, fourier as Fo
+        self.name = name
+        self.torch = torch
+        O = oracle.ref() if oracle.have_ref() else oracle.port()   # set-up data (taps, H, LUT) only
+        g = torch.Generator(device="cuda")
+        g.manual_seed({"ola": 0x7D5D0004, "fft": 0x7D5D0002, "fir": 0x7D5D0003, "resample": 0x7D5D0005}[name])
+
+        def randc(nchan, n):
+            x = torch.empty((nchan, n), dtype=torch.complex64, device="cuda")
+            torch.view_as_real(x).normal_(generator=g)
+            return x
+
+        if name == "ola":
+            self.nchan, self.n = max(1, int(256 * scale)), 1 << 24
+            h = O.design_rif_fen(4095, "lp", 0.1)
+            self.H = O.ola_make_H(h, 65536)
+            self.flt, N = Fo.filtre_fft(Fo.FiltreFFTConfig(61441, 4095, H=self.H, fir_len=4095), self.nchan)
+            assert N == 65536
+            self.x = randc(self.nchan, self.n)
+            self.y = torch.empty((self.nchan, self.flt.Ne * ((self.n + self.flt.Ne - 1) // self.flt.Ne)), dtype=torch.complex64, device="cuda")
+            self.samples_per_step = self.nchan * self.n
+            self.step = lambda: self.flt.step(self.x, out=self.y)
+        elif name == "fft":
+            self.nchan, self.n = max(1, int(4096 * scale)), 65536
+            self.plan = Fo.tfrplan_creation(65536, batch=self.nchan)
+            self.x = randc(self.nchan, self.n)
+            self.X = torch.empty_like(self.x)
+            self.y = torch.empty_like(self.x)
+            self.samples_per_step = self.nchan * self.n
+
+            def step():
+                self.plan.step(self.x, True, out=self.X)
+                self.plan.step(self.X, False, out=self.y)
+            self.step = step
+        elif name == "fir":
+            self.nchan, self.n, self.blk = max(1, int(1024 * scale)), 1 << 20, 65536
+            h = O.design_rif_fen(127, "lp", 0.1)
+            self.flt = F.filtre_rif(h, np.complex64, self.nchan)
+            self.x = randc(self.nchan, self.n)
+            self.y = torch.empty_like(self.x)
+            self.samples_per_step = self.nchan * self.n
+
+            def step():
+                for b in range(self.n // self.blk):
+                    s = slice(b * self.blk, (b + 1) * self.blk)
+                    self.flt.step(self.x[:, s], out=self.y[:, s])
+            self.step = step
+        elif name == "resample":
+            self.nchan, self.n = max(1, int(512 * scale)), 1 << 23
+            lut = O.itrp_sinc_lut(64, 256, 0.4)
+            self.flt = F.filtre_itrp(147.0 / 160.0, F.InterpolateurLUT(lut), self.nchan)
+            self.x = randc(self.nchan, self.n)
+            self.samples_per_step = self.nchan * self.n
+            self.step = lambda: self.flt.step(self.x)
+        else:
+            raise SystemExit(f"unknown workload {name}")
+
+
+def e2e_measure(name, steps, warmup):
+    """Same metric through the C ABI with pinned HOST buffers (H2D + D2H inside the timed region)."""
+    import torch
+    import oracle
+    from libtsd_b200 import filtrage as F, fourier as Fo
+    O = oracle.ref() if oracle.have_ref() else oracle.port()
+    rng = np.random.default_rng(1)
+
+    def pinned(nchan, n):
+        t = torch.empty((nchan, n), dtype=torch.complex64).pin_memory()
+        a = t.numpy()
+        a.real[...] = rng.standard_normal((1, n), dtype=np.float32)
+        a.imag[...] = rng.standard_normal((1, n), dtype=np.float32)
+        return t, a
+
+    if name == "ola":
+        nchan, n = 8, 1 << 24
+        H = O.ola_make_H(O.design_rif_fen(4095, "lp", 0.1), 65536)
+        flt, _ = Fo.filtre_fft(Fo.FiltreFFTConfig(61441, 4095, H=H, fir_len=4095), nchan)
+        tx, x = pinned(nchan, n)
+        ty, y = pinned(nchan, 61441 * (n // 61441 + 1))
+        step = lambda: flt.step(x, out=y)   # noqa: E731
+        out_per_step = 61441 * (n // 61441)
+    elif name == "fft":
+        nchan, n = 256, 65536
+        plan = Fo.tfrplan_creation(65536, batch=nchan)
+        tx, x = pinned(nchan, n)
+        ty, y = pinned(nchan, n)
+
+        def step():
+            plan.step(x, True, out=y)
+            plan.step(y, False, out=y)
+        out_per_step = 2 * n
+        n = 2 * n   # two host round trips per step
+    elif name == "fir":
+        nchan, n = 64, 1 << 20
+        flt = F.filtre_rif(O.design_rif_fen(127, "lp", 0.1), np.complex64, nchan)
+        tx, x = pinned(nchan, n)
+        ty, y = pinned(nchan, n)
+        step = lambda: flt.step(x, out=y)   # noqa: E731
+        out_per_step = n
+    else:
+        nchan, n = 32, 1 << 22
+        flt = F.filtre_itrp(147.0 / 160.0, F.InterpolateurLUT(O.itrp_sinc_lut(64, 256, 0.4)), nchan)
+        tx, x = pinned(nchan, n)
+        step = lambda: flt.step(x)   # noqa: E731
+        out_per_step = int(n * 147 / 160)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()   # host-memory calls return when y is valid on the host
+    dt = (time.perf_counter() - t0) / steps
+    samples = nchan * (n if name != "fft" else n // 2)
+    return {"value": samples / dt / 1e9, "unit": "Gsamples/s", "h2d_bytes_per_step": int(nchan * n * 8),
+            "d2h_bytes_per_step": int(nchan * out_per_step * 8),
+            "sample": f"{nchan} channels x {n if name != 'fft' else n // 2} cf32 in pinned host memory per step"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="ola", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scale", type=float, default=1.0, help="channel-count multiplier (debug only; 1.0 = BASELINE size)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    text, bytes_per_sample = WORKLOADS[args.workload]
+
+    # ------------------------------------------------------------------ reference (CPU) arm
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        val, ms, threads, kind, sample = cpu_run(args.workload, max(1, args.steps), max(0, args.warmup))
+        line = {"impl": "reference", "metric": "Gsamples/s filtered (cf32)", "value": val, "unit": "Gsamples/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": text, "sample": sample},
+                "cpu_baseline": {"value": val, "unit": "Gsamples/s", "cores": threads, "kind": kind, "sample": sample},
+                "e2e": {"value": val, "unit": "Gsamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ B200 arm
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    import libtsd_b200
+    libtsd_b200.init(local_rank)
+    libtsd_b200.use_torch_stream()
+
+    wl = GpuWorkload(args.workload, args.scale)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        wl.step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    libtsd_b200.launch_count(reset=True)
+    libtsd_b200._lib.timing_enable(True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        wl.step()
+    ev1.record()
+    barrier()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    kern_ms, kern_launches = libtsd_b200._lib.timing_read()
+    libtsd_b200._lib.timing_enable(False)
+    launches = libtsd_b200.launch_count()
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([elapsed_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    total_samples = float(wl.samples_per_step) * world * args.steps
+    value = total_samples / (elapsed_ms * 1e-3) / 1e9
+
+    if rank == 0:
+        peaks, peak_kind = load_peaks()
+        peak = float(peaks["hbm_gbs"])
+        # dominant kernel: algorithmic bytes of one rank's launches / summed CUDA-event duration
+        achieved = bytes_per_sample * wl.samples_per_step * args.steps / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else None
+        kernel_name = {"ola": "ola64k_kernel", "fft": "fft64k_kernel", "fir": "fir_direct_kernel", "resample": "resamp_lut_kernel"}[args.workload]
+        roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_kind,
+                    "algorithmic_bytes_per_sample": bytes_per_sample, "kernel_ms_per_step": kern_ms / args.steps,
+                    "kernel_launches": kern_launches}
+        traffic_file = os.path.join(ROOT, "profiles", f"traffic_{args.workload}.json")
+        if os.path.exists(traffic_file):
+            with open(traffic_file) as f:
+                roofline["traffic"] = json.load(f).get("dram_bytes_per_launch")
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            v, ms, threads, kind, sample = cpu_run(args.workload, 2, 1)
+            cpu = {"value": v, "unit": "Gsamples/s", "cores": threads, "kind": kind, "sample": sample}
+        e2e = None
+        if not args.no_e2e:
+            del wl
+            torch.cuda.empty_cache()
+            e2e = e2e_measure(args.workload, 3, 1)
+        line = {"metric": "Gsamples/s filtered (cf32)", "value": value, "unit": "Gsamples/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": text, "per_gpu_batch": "fixed (weak scaling)", "l2": "inputs larger than L2 (no flush needed)",
+                           "parallelism": f"channel-sharded x{world}, no collective"},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

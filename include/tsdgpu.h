@@ -1,0 +1,130 @@
+/* tsdgpu.h — C ABI of the B200-native filtering hot path (libtsdgpu.so).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.  Each group of
+ * entry points replaces one reference interface of libtsd (paths relative to the reference's
+ * core/ directory); INTEGRATION.md shows the C++ adapters that subclass the reference's own
+ * FiltreGen<T> / FFTPlan and forward to these calls.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; the message is available from
+ *     tsdgpu_last_error() (thread-local).  The reference reports errors by exceptions only
+ *     (commun.hpp:152-163); the adapters turn a non-zero status into the same `échec`.
+ *   - cf32 samples are interleaved (re, im) floats, exactly std::complex<float> / Veccf storage.
+ *   - batches are channel-major: sample i of channel c is at base + c*stride + i (in samples).
+ *     One channel == one reference filter object (the reference has no batching).
+ *   - mem = TSDGPU_HOST: pointers are host memory, the call copies in and out and returns when
+ *     y is valid.  mem = TSDGPU_DEVICE: pointers are device memory on the current device, work
+ *     is enqueued on the library stream (tsdgpu_set_stream) and the call returns immediately.
+ *   - there is no CPU fallback: every entry fails if no CUDA device is usable.
+ */
+#ifndef TSDGPU_H
+#define TSDGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TSDGPU_HOST   0
+#define TSDGPU_DEVICE 1
+
+/* sample / tap kinds of filtre_rif<Tc,T> (filtre-rt.cc:816-818) */
+#define TSDGPU_FIR_F32_F32   0   /* float data,  float taps  : filtre_rif<float,float>   */
+#define TSDGPU_FIR_CF32_F32  1   /* cfloat data, float taps  : filtre_rif<float,cfloat>  */
+#define TSDGPU_FIR_CF32_CF32 2   /* cfloat data, cfloat taps : filtre_rif<cfloat,cfloat> */
+
+typedef struct tsdgpu_fir_s    *tsdgpu_fir_t;
+typedef struct tsdgpu_fft_s    *tsdgpu_fft_t;
+typedef struct tsdgpu_ola_s    *tsdgpu_ola_t;
+typedef struct tsdgpu_resamp_s *tsdgpu_resamp_t;
+
+/* ---- runtime ------------------------------------------------------------------------------ */
+/* Selects the CUDA device for the calling thread and creates the library stream. */
+int tsdgpu_init(int device);
+/* Use an existing cudaStream_t (e.g. torch's current stream) for all subsequent launches;
+ * NULL restores the library's own stream. */
+int tsdgpu_set_stream(void *cuda_stream);
+/* Blocks until everything enqueued by the library on its stream has completed. */
+int tsdgpu_synchronize(void);
+const char *tsdgpu_last_error(void);
+/* Number of kernels launched by this library since the last call with reset != 0. */
+long long tsdgpu_launch_count(int reset);
+/* Device-side timing of the dominant kernel of each path (fir_direct, fft64k, ola64k, resamp_lut):
+ * when enabled, every such launch is bracketed by a CUDA event pair on the launch stream;
+ * tsdgpu_timing_read synchronises, returns the summed duration and the number of launches, and
+ * clears the list.  Used by bench.py for the roofline figure. */
+int tsdgpu_timing_enable(int on);
+int tsdgpu_timing_read(double *total_ms, long long *launches);
+/* Bookkeeping shared with the reference, computed on the host with the same expressions:
+ * prochaine_puissance_de_2 (tsd.cc:287-291). */
+int tsdgpu_p2(int i);
+
+/* ---- direct-form FIR: replaces filtre_rif<Tc,T>(h) and FiltreRIF::step ---------------------- */
+/* (filtrage.hpp:1367-1368, filtre-rt.cc:53-109,171-175).  State per channel = the last K-1
+ * inputs, kept on the device across step() calls; `index` = (samples so far) mod K. */
+int tsdgpu_fir_create(int kind, const float *taps, int K, int nchan, tsdgpu_fir_t *out);
+/* y[c][i] = sum_k h[k] x[c][i-k] for i in [0,n); len(y) == len(x) (filtre-rt.cc:67-108).
+ * x == y (same pointer and stride) is allowed, like the reference (filtre-rt.cc:76-80). */
+int tsdgpu_fir_step(tsdgpu_fir_t f, const void *x, long long x_stride, int n,
+                    void *y, long long y_stride, int mem);
+/* Reference-layout state (filtre-rt.cc:56-58): fen[nchan][K] ring and the common ring index. */
+int tsdgpu_fir_get_state(tsdgpu_fir_t f, void *fen_host, int *index);
+int tsdgpu_fir_set_state(tsdgpu_fir_t f, const void *fen_host, int index);
+int tsdgpu_fir_destroy(tsdgpu_fir_t f);
+
+/* ---- FFT plan: replaces FFTPlan / tfrplan_création / fft() / ifft() ------------------------- */
+/* (fourier.hpp:19-32,69,163-205; fourier.cc:360-481).  Always unitary: the reference ignores
+ * `normalize` (fourier.cc:119-120,362).  n must be a power of two >= 1 in this version. */
+int tsdgpu_fft_plan(int n, int batch, tsdgpu_fft_t *out);
+/* y[b] = unitary DFT (forward != 0) or inverse DFT of x[b], b in [0,batch). x == y allowed. */
+int tsdgpu_fft_exec(tsdgpu_fft_t p, const void *x, long long x_stride,
+                    void *y, long long y_stride, int forward, int mem);
+int tsdgpu_fft_destroy(tsdgpu_fft_t p);
+
+/* ---- FFT-domain filter: replaces filtre_fft(FiltreFFTConfig) / OLA<cfloat> ------------------ */
+/* (fourier.hpp:305-320,370; fourier.cc:737-882,935-940), plain mode, with the spectral
+ * callback given as data: traitement_freq = "X *= H" (fourier.cc:956-959).
+ *   Ne = dim_blocs_temporel (<= 0 -> 512), N = p2(Ne + nb_zeros_min), N_zeros = N - Ne.
+ *   H        : N cfloat gains, or NULL for the identity callback.
+ *   fir_len  : 0 -> arbitrary H, true overlap-add (the partial sums `svg` are carried).
+ *              K > 0 -> caller guarantees H = fft(h2)*sqrt(N) with h2 = [0^(N-K), h] (the
+ *              FiltreFFTRIF convention, fourier.cc:962-965) and K <= N_zeros + 1; the same
+ *              samples are then produced in overlap-save form (single pass, plain stores).
+ * Fails with the reference's own precondition when N_zeros > Ne (fourier.cc:870). */
+int tsdgpu_ola_create(int dim_blocs_temporel, int nb_zeros_min, const float *H, int fir_len,
+                      int nchan, tsdgpu_ola_t *out);
+int tsdgpu_ola_dims(tsdgpu_ola_t f, int *Ne, int *N, int *N_zeros, int *residual);
+/* Number of samples the next step(n) will emit: Ne * ((residual + n) / Ne)
+ * (TamponNv2 re-blocking, tsd.cc:332-370; fourier.cc:813-833). */
+long long tsdgpu_ola_out_count(tsdgpu_ola_t f, int n);
+/* Feeds n samples per channel; writes *n_out = tsdgpu_ola_out_count(f, n) samples per channel. */
+int tsdgpu_ola_step(tsdgpu_ola_t f, const void *x, long long x_stride, int n,
+                    void *y, long long y_stride, long long *n_out, int mem);
+int tsdgpu_ola_destroy(tsdgpu_ola_t f);
+
+/* ---- arbitrary-ratio resampler: replaces filtre_itrp<cfloat>(ratio, itrp) ------------------- */
+/* (filtrage.hpp:2039; ra.cc:13-79; InterpolateurRIF::step filtrage.hpp:1873-1881; LUT of
+ * InterpolateurSinc itrp.cc:16-54).  lut[p*K + i], p in [0,nphases], is the interpolator's
+ * coefficient table handed over as data.  The float32 phase recurrence (ra.cc:64-73) is run
+ * on the host, once for all channels. */
+int tsdgpu_resamp_create(float ratio, const float *lut, int K, int nphases, int nchan,
+                         tsdgpu_resamp_t *out);
+/* Output count of the next step(n) (identical for every channel) and the current phase. */
+long long tsdgpu_resamp_out_count(tsdgpu_resamp_t f, int n);
+float tsdgpu_resamp_phase(tsdgpu_resamp_t f);
+int tsdgpu_resamp_step(tsdgpu_resamp_t f, const void *x, long long x_stride, int n,
+                       void *y, long long y_stride, long long y_capacity, long long *n_out, int mem);
+int tsdgpu_resamp_destroy(tsdgpu_resamp_t f);
+/* The host-side schedule on its own (no device needed): runs the reference's float32 phase
+ * recurrence (ra.cc:58-73) over n inputs starting from *phase, writes for every output j the index
+ * of the newest input of its window (in_idx[j]) and its LUT column (lut_idx[j] = (int)(phase*nphases)),
+ * updates *phase.  in_idx / lut_idx may be NULL to count only. */
+int tsdgpu_resamp_schedule(float *phase, float ratio, int nphases, int n, int32_t *in_idx,
+                           int32_t *lut_idx, long long capacity, long long *n_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TSDGPU_H */

@@ -1,0 +1,111 @@
+"""ctypes binding of libtsdgpu.so (the C ABI declared in include/tsdgpu.h).
+
+The product path is the CUDA library; there is no CPU fallback.  If the shared object is
+missing or no B200 is usable, every call fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(HERE, "libtsdgpu.so")
+HOST, DEVICE = 0, 1
+
+_vp, _i, _ll, _f = C.c_void_p, C.c_int, C.c_longlong, C.c_float
+
+
+class TsdGpuError(RuntimeError):
+    """Raised for any non-zero status of the C ABI (the reference raises `échec`, commun.hpp:152-163)."""
+
+
+def build(verbose: bool = False) -> str:
+    """Compile the CUDA sources for sm_100a (nvcc cross-compiles without a GPU)."""
+    out = None if verbose else subprocess.DEVNULL
+    subprocess.check_call(["make", "-C", os.path.join(HERE, "csrc"), "-j8"], stdout=out)
+    return SO_PATH
+
+
+_SIGS = {
+    "tsdgpu_init": (_i, [_i]),
+    "tsdgpu_set_stream": (_i, [_vp]),
+    "tsdgpu_synchronize": (_i, []),
+    "tsdgpu_last_error": (C.c_char_p, []),
+    "tsdgpu_launch_count": (_ll, [_i]),
+    "tsdgpu_p2": (_i, [_i]),
+    "tsdgpu_timing_enable": (_i, [_i]),
+    "tsdgpu_timing_read": (_i, [C.POINTER(C.c_double), C.POINTER(_ll)]),
+    "tsdgpu_fir_create": (_i, [_i, _vp, _i, _i, C.POINTER(_vp)]),
+    "tsdgpu_fir_step": (_i, [_vp, _vp, _ll, _i, _vp, _ll, _i]),
+    "tsdgpu_fir_get_state": (_i, [_vp, _vp, C.POINTER(_i)]),
+    "tsdgpu_fir_set_state": (_i, [_vp, _vp, _i]),
+    "tsdgpu_fir_destroy": (_i, [_vp]),
+    "tsdgpu_fft_plan": (_i, [_i, _i, C.POINTER(_vp)]),
+    "tsdgpu_fft_exec": (_i, [_vp, _vp, _ll, _vp, _ll, _i, _i]),
+    "tsdgpu_fft_destroy": (_i, [_vp]),
+    "tsdgpu_ola_create": (_i, [_i, _i, _vp, _i, _i, C.POINTER(_vp)]),
+    "tsdgpu_ola_dims": (_i, [_vp, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
+    "tsdgpu_ola_out_count": (_ll, [_vp, _i]),
+    "tsdgpu_ola_step": (_i, [_vp, _vp, _ll, _i, _vp, _ll, C.POINTER(_ll), _i]),
+    "tsdgpu_ola_destroy": (_i, [_vp]),
+    "tsdgpu_resamp_create": (_i, [_f, _vp, _i, _i, _i, C.POINTER(_vp)]),
+    "tsdgpu_resamp_out_count": (_ll, [_vp, _i]),
+    "tsdgpu_resamp_phase": (_f, [_vp]),
+    "tsdgpu_resamp_step": (_i, [_vp, _vp, _ll, _i, _vp, _ll, _ll, C.POINTER(_ll), _i]),
+    "tsdgpu_resamp_destroy": (_i, [_vp]),
+    "tsdgpu_resamp_schedule": (_i, [C.POINTER(_f), _f, _i, _i, _vp, _vp, _ll, C.POINTER(_ll)]),
+}
+
+EXPORTS = tuple(_SIGS)
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise TsdGpuError(
+                f"{SO_PATH} is missing: build it with libtsd_b200._lib.build() / __graft_entry__.build(). "
+                "There is no CPU fallback.")
+        L = C.CDLL(SO_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise TsdGpuError((lib().tsdgpu_last_error() or b"?").decode("utf-8", "replace"))
+
+
+def init(device: int = 0) -> None:
+    check(lib().tsdgpu_init(device))
+
+
+def use_torch_stream() -> None:
+    """Enqueue the library's launches on torch's current CUDA stream."""
+    import torch
+    check(lib().tsdgpu_set_stream(_vp(torch.cuda.current_stream().cuda_stream)))
+
+
+def synchronize() -> None:
+    check(lib().tsdgpu_synchronize())
+
+
+def launch_count(reset: bool = False) -> int:
+    return int(lib().tsdgpu_launch_count(1 if reset else 0))
+
+
+def timing_enable(on: bool = True) -> None:
+    check(lib().tsdgpu_timing_enable(1 if on else 0))
+
+
+def timing_read():
+    """(total milliseconds, launches) of the dominant kernels since the last read."""
+    ms, n = C.c_double(), _ll()
+    check(lib().tsdgpu_timing_read(C.byref(ms), C.byref(n)))
+    return ms.value, int(n.value)

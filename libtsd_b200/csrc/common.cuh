@@ -1,0 +1,140 @@
+// Shared host/device helpers of libtsdgpu (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <utility>
+#include <vector>
+
+namespace tsdgpu {
+
+// ---------------------------------------------------------------- host runtime state
+struct Runtime
+{
+  int device = -1;
+  int num_sms = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;     // stream every launch goes to
+  cudaStream_t copy_in = nullptr, copy_out = nullptr;
+  long long launches = 0;
+  // optional device-side timing of the dominant kernels (tsdgpu_timing_*)
+  bool timing = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;
+};
+// RAII bracket: records an event pair around a main-kernel launch when timing is enabled
+struct KernelTimer
+{
+  cudaEvent_t a = nullptr, b = nullptr;
+  KernelTimer();
+  ~KernelTimer();
+};
+Runtime &rt();
+int ensure_init();
+void set_error(const std::string &s);
+int fail(const std::string &s);
+
+#define TSD_CUDA(expr)                                                                  \
+  do {                                                                                  \
+    cudaError_t e__ = (expr);                                                           \
+    if(e__ != cudaSuccess)                                                              \
+      return ::tsdgpu::fail(std::string(#expr) + ": " + cudaGetErrorString(e__));       \
+  } while(0)
+
+#define TSD_LAUNCH_CHECK()                                                              \
+  do {                                                                                  \
+    ::tsdgpu::rt().launches++;                                                          \
+    cudaError_t e__ = cudaGetLastError();                                               \
+    if(e__ != cudaSuccess)                                                              \
+      return ::tsdgpu::fail(std::string("kernel launch: ") + cudaGetErrorString(e__));  \
+  } while(0)
+
+// ---------------------------------------------------------------- device helpers
+__device__ __forceinline__ float2 cmul(float2 a, float2 b)
+{
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+// a * conj(b)
+__device__ __forceinline__ float2 cmulc(float2 a, float2 b)
+{
+  return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+}
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+
+// exp(-+ 2*pi*i * num/den), den a power of two <= 2^24, 0 <= num: exact angle in revolutions.
+template<bool INV> __device__ __forceinline__ float2 twiddle(unsigned num, float two_over_den)
+{
+  float s, c;
+  sincospif((float) num * two_over_den, &s, &c);
+  return make_float2(c, INV ? s : -s);
+}
+
+// ---- mbarrier + 1-D bulk async copy (TMA unit, SASS UBLKCP) -----------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
+{
+  asm volatile(
+    "{\n\t.reg .pred p;\n\t"
+    "WAIT_%=:\n\t"
+    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+    "@p bra DONE_%=;\n\t"
+    "bra WAIT_%=;\n\t"
+    "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared, completion counted on the mbarrier (bytes multiple of 16, both 16-B aligned)
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, uint64_t *bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                 smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// shared -> global
+__device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, unsigned bytes)
+{
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- inter-CTA flags (release/acquire at gpu scope) -------------------------------------------
+__device__ __forceinline__ unsigned ld_acquire(const unsigned *p)
+{
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_add(unsigned *p, unsigned v)
+{
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// streaming global accesses (touched once: do not keep in L1)
+__device__ __forceinline__ float2 ldg_stream(const float2 *p)
+{
+  float2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void stg_stream(float2 *p, float2 v)
+{
+  asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
+}
+
+} // namespace tsdgpu

@@ -1,0 +1,176 @@
+// Register/shared-memory building blocks of the sm_100a FFT kernels.
+//
+// A "tile" is 16 independent 256-point transforms handled by one 256-thread CTA (4096 points,
+// 32 KB of shared memory).  Each thread runs two radix-16 butterflies in registers per
+// 256-point transform, with ONE shared-memory exchange in between.  Two access patterns:
+//   COLS  the 16 transforms are the 16 lanes `lo = tid & 15` (strided in memory: element n of
+//         lane lo is at n*pitch + lo), used for the column passes of the four-step FFT;
+//   ROWS  the 16 transforms are 16 contiguous rows, used for the row passes.
+// Both patterns keep global accesses in full 128-byte segments and shared accesses
+// conflict-free (skewed layout for ROWS).
+//
+// Arithmetic: the reference computes a unitary radix-2 DFT in float32 with double-generated
+// twiddles (fourier.cc:32-46,61-121).  Here the same DFT is evaluated with radix-16 butterflies;
+// twiddles come from sincospif on exact dyadic angles and short power trees (depth <= 4), so the
+// result differs from the reference by float rounding only (tests: <= 1e-5 of signal RMS).
+#pragma once
+#include "common.cuh"
+
+namespace tsdgpu {
+
+#define TSD_C1 0.92387953251128674f   // cos(pi/8)
+#define TSD_S1 0.38268343236508977f   // sin(pi/8)
+#define TSD_R2 0.70710678118654752f   // sqrt(1/2)
+
+// multiply by -i (forward) / +i (inverse)
+template<bool INV> __device__ __forceinline__ float2 mul_mi(float2 a)
+{
+  return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
+}
+
+// 4-point DFT, natural order in and out
+template<bool INV> __device__ __forceinline__ void fft4(float2 &a0, float2 &a1, float2 &a2, float2 &a3)
+{
+  float2 s0 = cadd(a0, a2), s1 = csub(a0, a2), s2 = cadd(a1, a3), s3 = mul_mi<INV>(csub(a1, a3));
+  a0 = cadd(s0, s2);
+  a2 = csub(s0, s2);
+  a1 = cadd(s1, s3);
+  a3 = csub(s1, s3);
+}
+
+// v *= W16^m (forward) or conj (inverse), m a compile-time constant in {1,2,3,6,9}
+template<bool INV, int M> __device__ __forceinline__ float2 mul_w16(float2 v)
+{
+  if(M == 2)
+  {
+    // (1 - i)/sqrt2 forward, (1 + i)/sqrt2 inverse
+    return INV ? make_float2((v.x - v.y) * TSD_R2, (v.x + v.y) * TSD_R2) : make_float2((v.x + v.y) * TSD_R2, (v.y - v.x) * TSD_R2);
+  }
+  if(M == 6)
+  {
+    // (-1 - i)/sqrt2 forward, (-1 + i)/sqrt2 inverse
+    return INV ? make_float2(-(v.x + v.y) * TSD_R2, (v.x - v.y) * TSD_R2) : make_float2((v.y - v.x) * TSD_R2, -(v.x + v.y) * TSD_R2);
+  }
+  float wr, wi;   // forward value of W16^M = exp(-2 pi i M / 16)
+  if(M == 1) { wr = TSD_C1; wi = -TSD_S1; }
+  else if(M == 3) { wr = TSD_S1; wi = -TSD_C1; }
+  else { wr = -TSD_C1; wi = TSD_S1; }   // M == 9
+  if(INV) wi = -wi;
+  return make_float2(v.x * wr - v.y * wi, v.x * wi + v.y * wr);
+}
+
+// 16-point DFT of v[0..15], natural order in and out, all indices static
+template<bool INV> __device__ __forceinline__ void fft16(float2 (&v)[16])
+{
+  // radix-4 over a (n = 4a + b): Y[b][k0] lands in v[4*k0 + b]
+#pragma unroll
+  for(int b = 0; b < 4; b++)
+  {
+    float2 a0 = v[b], a1 = v[4 + b], a2 = v[8 + b], a3 = v[12 + b];
+    fft4<INV>(a0, a1, a2, a3);
+    v[b] = a0;
+    v[4 + b] = a1;
+    v[8 + b] = a2;
+    v[12 + b] = a3;
+  }
+  // twiddles W16^(b*k0) on v[4*k0 + b]
+  v[5] = mul_w16<INV, 1>(v[5]);
+  v[6] = mul_w16<INV, 2>(v[6]);
+  v[7] = mul_w16<INV, 3>(v[7]);
+  v[9] = mul_w16<INV, 2>(v[9]);
+  v[10] = mul_mi<INV>(v[10]);
+  v[11] = mul_w16<INV, 6>(v[11]);
+  v[13] = mul_w16<INV, 3>(v[13]);
+  v[14] = mul_w16<INV, 6>(v[14]);
+  v[15] = mul_w16<INV, 9>(v[15]);
+  // radix-4 over b: X[k0 + 4*k1] lands in v[4*k0 + k1]
+#pragma unroll
+  for(int k0 = 0; k0 < 4; k0++) fft4<INV>(v[4 * k0], v[4 * k0 + 1], v[4 * k0 + 2], v[4 * k0 + 3]);
+  // digit reversal back to natural order (register renaming only)
+  float2 t;
+#define TSD_SWAP(i, j) t = v[i]; v[i] = v[j]; v[j] = t;
+  TSD_SWAP(1, 4) TSD_SWAP(2, 8) TSD_SWAP(3, 12) TSD_SWAP(6, 9) TSD_SWAP(7, 13) TSD_SWAP(11, 14)
+#undef TSD_SWAP
+}
+
+// v[k] *= base * step^k for k = 0..15 (power tree, depth <= 4)
+__device__ __forceinline__ void mul_geometric(float2 (&v)[16], float2 base, float2 step)
+{
+  float2 s2 = cmul(step, step), s4 = cmul(s2, s2), s8 = cmul(s4, s4);
+  float2 t[16];
+  t[0] = base;
+  t[1] = cmul(t[0], step);
+  t[2] = cmul(t[0], s2);
+  t[3] = cmul(t[1], s2);
+#pragma unroll
+  for(int k = 0; k < 4; k++) t[4 + k] = cmul(t[k], s4);
+#pragma unroll
+  for(int k = 0; k < 8; k++) t[8 + k] = cmul(t[k], s8);
+#pragma unroll
+  for(int k = 0; k < 16; k++) v[k] = cmul(v[k], t[k]);
+}
+// v[k] *= step^k for k = 0..15
+__device__ __forceinline__ void mul_powers(float2 (&v)[16], float2 step)
+{
+  float2 s2 = cmul(step, step), s4 = cmul(s2, s2), s8 = cmul(s4, s4);
+  float2 t[16];
+  t[1] = step;
+  t[2] = s2;
+  t[3] = cmul(step, s2);
+  t[4] = s4;
+#pragma unroll
+  for(int k = 1; k < 4; k++) t[4 + k] = cmul(t[k], s4);
+  t[8] = s8;
+#pragma unroll
+  for(int k = 1; k < 8; k++) t[8 + k] = cmul(t[k], s8);
+#pragma unroll
+  for(int k = 1; k < 16; k++) v[k] = cmul(v[k], t[k]);
+}
+
+// ---- 256-point transform, COLS pattern -------------------------------------------------------
+// in : thread (hi = tid>>4, lo = tid&15) holds v[j] = x_lo[16*j + hi]
+// out: thread (hi, lo) holds v[k2] = X_lo[hi + 16*k2]
+// w256_hi = exp(-2 pi i hi / 256) (forward value; conjugated here when INV)
+template<bool INV> __device__ __forceinline__ void fft256_cols(float2 (&v)[16], float2 *sm, int hi, int lo, float2 w256_hi)
+{
+  fft16<INV>(v);
+  mul_powers(v, INV ? make_float2(w256_hi.x, -w256_hi.y) : w256_hi);   // W256^(hi*k1)
+#pragma unroll
+  for(int k1 = 0; k1 < 16; k1++) sm[(hi * 16 + k1) * 16 + lo] = v[k1];
+  __syncthreads();
+#pragma unroll
+  for(int a = 0; a < 16; a++) v[a] = sm[(a * 16 + hi) * 16 + lo];
+  fft16<INV>(v);
+}
+
+// ---- 256-point transform, ROWS pattern -------------------------------------------------------
+// in : thread (hi = row r, lo = b) holds v[j] = x_r[16*j + b]
+// out: thread (hi = k1, lo = row r) holds v[k2] = X_r[k1 + 16*k2]
+// w256_lo = exp(-2 pi i lo / 256)
+template<bool INV> __device__ __forceinline__ void fft256_rows_a(float2 (&v)[16], float2 *sm, int hi, int lo, float2 w256_lo)
+{
+  fft16<INV>(v);
+  mul_powers(v, INV ? make_float2(w256_lo.x, -w256_lo.y) : w256_lo);   // W256^(b*k1)
+#pragma unroll
+  for(int k1 = 0; k1 < 16; k1++) sm[k1 * 256 + lo * 16 + ((hi + lo) & 15)] = v[k1];
+  __syncthreads();
+#pragma unroll
+  for(int b = 0; b < 16; b++) v[b] = sm[hi * 256 + b * 16 + ((lo + b) & 15)];
+  fft16<INV>(v);
+}
+// in : thread (hi = k1, lo = row r) holds v[k2] = X_r[k1 + 16*k2]
+// out: thread (hi = row r, lo = q) holds v[p] = x_r[16*p + q]
+// w256_hi = exp(-2 pi i hi / 256)
+template<bool INV> __device__ __forceinline__ void fft256_rows_b(float2 (&v)[16], float2 *sm, int hi, int lo, float2 w256_hi)
+{
+  fft16<INV>(v);                                                       // over k2 -> q
+  mul_powers(v, INV ? make_float2(w256_hi.x, -w256_hi.y) : w256_hi);   // W256^(k1*q)
+#pragma unroll
+  for(int q = 0; q < 16; q++) sm[hi * 256 + q * 16 + ((lo + q) & 15)] = v[q];
+  __syncthreads();
+#pragma unroll
+  for(int k1 = 0; k1 < 16; k1++) v[k1] = sm[k1 * 256 + lo * 16 + ((hi + lo) & 15)];
+  fft16<INV>(v);                                                       // over k1 -> p
+}
+
+} // namespace tsdgpu

@@ -1,0 +1,559 @@
+// FFT-domain block filter on sm_100a.  Replaces OLA<cfloat> / filtre_fft (reference
+// fourier.cc:737-882,935-940) in plain mode with the spectral callback "X *= H"
+// (fourier.cc:956-959) given as data.
+//
+// Bookkeeping is the reference's, computed on the host with the same expressions:
+// Ne, N = p2(Ne + nb_zeros_min), N_zeros = N - Ne (fourier.cc:764-776), re-blocking of arbitrary
+// input chunks into Ne-blocks with a residual (TamponNv2, tsd.cc:332-370), Ne samples out per
+// completed block (fourier.cc:813-833).
+//
+// N = 65536 runs as ONE persistent kernel per step(): every Ne-block goes through three tile
+// stages (fft_tiles.cuh) that hand over through an L2-resident scratch ring,
+//   A  gather the N-point window, 256 column DFTs, W_N twiddles
+//   B  256 row DFTs, multiply by H, 256 inverse row DFTs, conj(W_N) twiddles   (in place)
+//   C  256 inverse column DFTs, emit the Ne output samples
+// so a sample crosses HBM once on the way in and once on the way out.  Two output forms:
+//   overlap-save  (fir_len = K > 0): window = the N inputs ending K-1 samples after the block
+//                 start, plain stores — same samples as the reference's overlap-add for an H
+//                 that is the transform of K taps placed at the tail (fourier.cc:962-965);
+//   overlap-add   (fir_len = 0, any H): zero-padded block like the reference (fourier.cc:850),
+//                 tail of block b and head of block b+1 meet through two-addend red.add on a
+//                 zeroed region; the last block's tail is carried in `svg` (fourier.cc:870-872).
+// Other N use an unfused path built on the generic FFT plan (gather, FFT, *H, IFFT, overlap-add).
+#include "fft_tiles.cuh"
+#include "fft_plan.h"
+#include "tsdgpu.h"
+
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+namespace tsdgpu {
+
+struct OlaParams
+{
+  const float2 *x;        // this call's input, [nchan][x_stride]
+  float2 *y;              // this call's output, [nchan][y_stride]
+  const float2 *carry;    // [nchan][carry_len] samples preceding x[0]
+  float2 *svg;            // [nchan][Ne] overlap-add carry (OLA form)
+  const float2 *H;        // [65536], pre-scaled by 1/N
+  float2 *scratch;        // [ring][65536]
+  unsigned *done_a, *done_b, *done_c, *ticket;
+  long long x_stride, y_stride;
+  int carry_len;
+  int nblocks;            // Ne-blocks per channel in this call
+  int Q;                  // nchan * nblocks
+  int Ne, Nz;
+  int base_off;           // window position of element 0 relative to (block start - residual)
+  int zero_below;         // window elements n < zero_below are zero (OLA padding)
+  int residual;           // samples already buffered before x[0]
+  int out_shift;          // OLS: output i = j - out_shift
+  int ola_form;           // 0 overlap-save, 1 overlap-add
+  int ring, lag;
+};
+
+constexpr int OLA_NT = 256;
+
+__device__ __forceinline__ void red_add_f2(float2 *p, float2 v)
+{
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(&p->x), "f"(v.x) : "memory");
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(&p->y), "f"(v.y) : "memory");
+}
+
+__global__ void __launch_bounds__(OLA_NT, 2) ola64k_kernel(OlaParams p)
+{
+  __shared__ float2 sm[4096];
+  __shared__ unsigned s_ticket;
+  const int tid = threadIdx.x, hi = tid >> 4, lo = tid & 15;
+  const float2 w256_hi = twiddle<false>((unsigned) hi, 2.0f / 256.0f);
+  const float2 w256_lo = twiddle<false>((unsigned) lo, 2.0f / 256.0f);
+  const unsigned total = (unsigned) (p.Q + 2 * p.lag) * 48u;
+
+  for(;;)
+  {
+    __syncthreads();
+    if(tid == 0) s_ticket = atomicAdd(p.ticket, 1u);
+    __syncthreads();
+    const unsigned ticket = s_ticket;
+    if(ticket >= total) break;
+    const int s = (int) (ticket / 48u), sub = (int) (ticket - (unsigned) s * 48u);
+    const int g = sub & 15, stage = sub >> 4;
+    const int q = s - stage * p.lag;
+    if(q < 0 || q >= p.Q) continue;
+    const int chan = q / p.nblocks, blk = q - chan * p.nblocks;
+    float2 *sc = p.scratch + (long long) (q % p.ring) * 65536;
+    float2 v[16];
+
+    if(stage == 0)
+    {
+      if(q >= p.ring)
+      {
+        if(tid == 0)
+          while(ld_acquire(p.done_c + (q - p.ring)) < 16u) __nanosleep(64);
+        __syncthreads();
+      }
+      // window element n sits at position pos0 + n relative to x[0]
+      const long long pos0 = (long long) blk * p.Ne - p.residual + p.base_off;
+      const float2 *x = p.x + (long long) chan * p.x_stride;
+      const float2 *cr = p.carry + (long long) chan * p.carry_len + p.carry_len;
+#pragma unroll
+      for(int j = 0; j < 16; j++)
+      {
+        const int n = (16 * j + hi) * 256 + 16 * g + lo;
+        const long long pos = pos0 + n;
+        float2 val = make_float2(0.f, 0.f);
+        if(n >= p.zero_below) val = (pos >= 0) ? ldg_stream(x + pos) : __ldg(cr + pos);
+        v[j] = val;
+      }
+      fft256_cols<false>(v, sm, hi, lo, w256_hi);
+      const unsigned n2 = (unsigned) (16 * g + lo);
+      mul_geometric(v, twiddle<false>(n2 * (unsigned) hi, 2.0f / 65536.0f), twiddle<false>(16u * n2, 2.0f / 65536.0f));
+#pragma unroll
+      for(int p2 = 0; p2 < 16; p2++) sc[(hi + 16 * p2) * 256 + 16 * g + lo] = v[p2];
+      __syncthreads();
+      if(tid == 0)
+      {
+        __threadfence();
+        red_release_add(p.done_a + q, 1u);
+      }
+    }
+    else if(stage == 1)
+    {
+      if(tid == 0)
+        while(ld_acquire(p.done_a + q) < 16u) __nanosleep(64);
+      __syncthreads();
+      float2 *row = sc + (16 * g + hi) * 256 + lo;
+#pragma unroll
+      for(int j = 0; j < 16; j++) v[j] = __ldcg(row + 16 * j);
+      fft256_rows_a<false>(v, sm, hi, lo, w256_lo);
+      // thread (hi = k', lo = r): v[k2] = X[k], k = (16g + r) + 256*(k' + 16*k2)
+      const float2 *H = p.H + 16 * g + lo;
+#pragma unroll
+      for(int k2 = 0; k2 < 16; k2++) v[k2] = cmul(v[k2], __ldg(H + (hi + 16 * k2) * 256));
+      __syncthreads();   // exchange buffer is reused
+      fft256_rows_b<true>(v, sm, hi, lo, w256_hi);
+      // thread (hi = r, lo = q'): v[pp] = b[k1 = 16g + r][n2 = 16*pp + q']; conj four-step twiddle
+      const unsigned k1 = (unsigned) (16 * g + hi);
+      mul_geometric(v, twiddle<true>(k1 * (unsigned) lo, 2.0f / 65536.0f), twiddle<true>(16u * k1, 2.0f / 65536.0f));
+#pragma unroll
+      for(int pp = 0; pp < 16; pp++) row[16 * pp] = v[pp];
+      __syncthreads();
+      if(tid == 0)
+      {
+        __threadfence();
+        red_release_add(p.done_b + q, 1u);
+      }
+    }
+    else
+    {
+      if(tid == 0)
+        while(ld_acquire(p.done_b + q) < 16u) __nanosleep(64);
+      __syncthreads();
+      const float2 *col = sc + 16 * g + lo;
+#pragma unroll
+      for(int j = 0; j < 16; j++) v[j] = __ldcg(col + (16 * j + hi) * 256);
+      fft256_cols<true>(v, sm, hi, lo, w256_hi);
+      // thread (hi = p1, lo): v[p2] = x2[256*(p1 + 16*p2) + 16g + lo]
+      float2 *y = p.y + (long long) chan * p.y_stride;
+      if(!p.ola_form)
+      {
+        float2 *yb = y + (long long) blk * p.Ne;
+#pragma unroll
+        for(int p2 = 0; p2 < 16; p2++)
+        {
+          const int i = (hi + 16 * p2) * 256 + 16 * g + lo - p.out_shift;
+          if(i >= 0 && i < p.Ne) stg_stream(yb + i, v[p2]);
+        }
+      }
+      else
+      {
+        const bool last = (blk + 1 == p.nblocks);
+        float2 *svg = p.svg + (long long) chan * p.Ne;
+#pragma unroll
+        for(int p2 = 0; p2 < 16; p2++)
+        {
+          const int j = (hi + 16 * p2) * 256 + 16 * g + lo;
+          if(j < p.Nz)
+            red_add_f2(y + (long long) blk * p.Ne + (p.Ne - p.Nz) + j, v[p2]);   // tail of block blk
+          else if(last)
+            svg[j - p.Nz] = v[p2];                                                 // carried (fourier.cc:872)
+          else if(j < p.Ne)
+            stg_stream(y + (long long) (blk + 1) * p.Ne + (j - p.Nz), v[p2]);
+          else
+            red_add_f2(y + (long long) (blk + 1) * p.Ne + (j - p.Nz), v[p2]);     // meets head of block blk+1
+        }
+      }
+      __syncthreads();
+      if(tid == 0)
+      {
+        __threadfence();
+        red_release_add(p.done_c + q, 1u);
+      }
+    }
+  }
+}
+
+// OLA form: y[0..Ne) of every channel starts as the carried svg; the other two-addend regions
+// [b*Ne + Ne - Nz, (b+1)*Ne), b >= 1, start at zero.
+__global__ void ola_prepare_kernel(float2 *y, long long y_stride, const float2 *svg, int Ne, int Nz, int nblocks)
+{
+  const int chan = blockIdx.y;
+  float2 *yc = y + (long long) chan * y_stride;
+  const float2 *sv = svg + (long long) chan * Ne;
+  const long long total = (long long) Ne + (long long) (nblocks - 1) * Nz;
+  for(long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long) gridDim.x * blockDim.x)
+  {
+    if(i < Ne) yc[i] = sv[i];
+    else
+    {
+      const long long r = i - Ne;
+      const int b = (int) (r / Nz) + 1, j = (int) (r % Nz);
+      yc[(long long) b * Ne + (Ne - Nz) + j] = make_float2(0.f, 0.f);
+    }
+  }
+}
+
+// new_carry = last L samples of (old_carry ++ x[0..n))
+__global__ void carry_update_kernel(const float2 *x, long long x_stride, int n, const float2 *o, float2 *d, int L)
+{
+  const int chan = blockIdx.y;
+  for(int j = blockIdx.x * blockDim.x + threadIdx.x; j < L; j += gridDim.x * blockDim.x)
+  {
+    const long long pos = (long long) n - L + j;
+    d[(long long) chan * L + j] = (pos >= 0) ? x[(long long) chan * x_stride + pos] : o[(long long) chan * L + L + pos];
+  }
+}
+
+// ---- unfused path (N != 65536) ----------------------------------------------------------------
+// padded[q][n] = n < Nz ? 0 : stream[(b0+blk)*Ne - residual + n - Nz]     (fourier.cc:850)
+__global__ void ola_gather_kernel(const float2 *x, long long x_stride, const float2 *carry, int carry_len, float2 *work,
+                                  int N, int Ne, int Nz, int nb, int b0, int residual)
+{
+  const int q = blockIdx.y, chan = q / nb, blk = q - chan * nb;
+  const float2 *xc = x + (long long) chan * x_stride;
+  const float2 *cr = carry + (long long) chan * carry_len + carry_len;
+  for(int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x)
+  {
+    float2 v = make_float2(0.f, 0.f);
+    if(n >= Nz)
+    {
+      const long long pos = (long long) (b0 + blk) * Ne - residual + n - Nz;
+      v = (pos >= 0) ? xc[pos] : cr[pos];
+    }
+    work[(long long) q * N + n] = v;
+  }
+}
+__global__ void ola_mulH_kernel(float2 *work, const float2 *H, int N, long long total)
+{
+  for(long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long) gridDim.x * blockDim.x)
+    work[i] = cmul(work[i], H[i % N]);
+}
+// y_b[i] = prev[Nz + i] + (i >= Ne-Nz ? x2_b[i-(Ne-Nz)] : 0), prev = x2_{b-1} or svg   (fourier.cc:870-872)
+__global__ void ola_scatter_kernel(const float2 *work, float2 *svg, float2 *y, long long y_stride, int N, int Ne, int Nz,
+                                   int nb, int b0)
+{
+  const int q = blockIdx.y, chan = q / nb, blk = q - chan * nb;
+  const float2 *cur = work + (long long) q * N;
+  float2 *yb = y + (long long) chan * y_stride + (long long) (b0 + blk) * Ne;
+  for(int i = blockIdx.x * blockDim.x + threadIdx.x; i < Ne; i += gridDim.x * blockDim.x)
+  {
+    float2 a = (blk == 0) ? svg[(long long) chan * Ne + i] : cur[i + Nz - N];   // previous block, offset Nz
+    if(i >= Ne - Nz) a = cadd(a, cur[i - (Ne - Nz)]);
+    yb[i] = a;
+  }
+}
+__global__ void ola_svg_kernel(const float2 *work, float2 *svg, int N, int Ne, int Nz, int nb)
+{
+  const int chan = blockIdx.y;
+  const float2 *lastb = work + ((long long) chan * nb + (nb - 1)) * N;
+  for(int i = blockIdx.x * blockDim.x + threadIdx.x; i < Ne; i += gridDim.x * blockDim.x)
+    svg[(long long) chan * Ne + i] = lastb[Nz + i];
+}
+
+} // namespace tsdgpu
+
+using namespace tsdgpu;
+
+struct tsdgpu_ola_s
+{
+  int Ne = 0, N = 0, Nz = 0, K = 0, nchan = 0;
+  int residual = 0;            // TamponNv2 windex (tsd.cc:310)
+  long long blocks_done = 0;
+  bool fused = false;
+  float2 *d_H = nullptr;       // fused: H/N ; unfused: raw H (nullptr = identity)
+  float2 *d_carry[2] = {nullptr, nullptr};
+  int cur = 0, carry_len = 0;
+  float2 *d_svg = nullptr;
+  // fused
+  float2 *scratch = nullptr;
+  unsigned *flags = nullptr;
+  size_t flags_cap = 0;
+  int ring = 64, lag = 16, ctas = 0;
+  // unfused
+  tsdgpu_fft_s *plan = nullptr;
+  float2 *work = nullptr;
+  int plan_batch = 0;
+};
+
+static int ola_run_fused(tsdgpu_ola_s *f, const float2 *x, long long xs, float2 *y, long long ys, int B)
+{
+  Runtime &r = rt();
+  const long long Q = (long long) f->nchan * B;
+  if(Q > (1LL << 25)) return fail("tsdgpu_ola_step: too many blocks in one call (split the call)");
+  const size_t need = (size_t) 3 * Q + 1;
+  if(need > f->flags_cap)
+  {
+    if(f->flags) cudaFree(f->flags);
+    f->flags = nullptr;
+    f->flags_cap = 0;
+    TSD_CUDA(cudaMalloc(&f->flags, need * sizeof(unsigned)));
+    f->flags_cap = need;
+  }
+  TSD_CUDA(cudaMemsetAsync(f->flags, 0, need * sizeof(unsigned), r.stream));
+  OlaParams p;
+  p.x = x;
+  p.y = y;
+  p.carry = f->d_carry[f->cur];
+  p.svg = f->d_svg;
+  p.H = f->d_H;
+  p.scratch = f->scratch;
+  p.done_a = f->flags;
+  p.done_b = f->flags + Q;
+  p.done_c = f->flags + 2 * Q;
+  p.ticket = f->flags + 3 * Q;
+  p.x_stride = xs;
+  p.y_stride = ys;
+  p.carry_len = f->carry_len;
+  p.nblocks = B;
+  p.Q = (int) Q;
+  p.Ne = f->Ne;
+  p.Nz = f->Nz;
+  p.residual = f->residual;
+  p.ring = f->ring;
+  p.lag = f->lag;
+  if(f->K > 0)
+  {
+    p.ola_form = 0;
+    p.base_off = f->K - f->N;     // window = N inputs ending K-1 samples after the block start
+    p.zero_below = 0;
+    p.out_shift = f->Nz - f->K;
+  }
+  else
+  {
+    p.ola_form = 1;
+    p.base_off = -f->Nz;          // padded.tail(Ne) = x (fourier.cc:850)
+    p.zero_below = f->Nz;
+    p.out_shift = 0;
+    dim3 grid(std::min(1024LL, ((long long) f->Ne + (long long) (B - 1) * f->Nz + 255) / 256), f->nchan);
+    ola_prepare_kernel<<<grid, 256, 0, r.stream>>>(y, ys, f->d_svg, f->Ne, f->Nz, B);
+    TSD_LAUNCH_CHECK();
+  }
+  const long long tickets = (Q + 2LL * f->lag) * 48;
+  const int grid = (int) std::min<long long>(f->ctas, tickets);
+  {
+    KernelTimer timer;
+    ola64k_kernel<<<grid, OLA_NT, 0, r.stream>>>(p);
+    TSD_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+static int ola_run_unfused(tsdgpu_ola_s *f, const float2 *x, long long xs, float2 *y, long long ys, int B)
+{
+  Runtime &r = rt();
+  const int N = f->N, Ne = f->Ne, Nz = f->Nz;
+  // blocks per chunk: bounded work buffer (<= 256 MiB)
+  long long per_block = (long long) f->nchan * N * (long long) sizeof(float2);
+  int nb_max = (int) std::max(1LL, (256LL << 20) / per_block);
+  for(int b0 = 0; b0 < B; b0 += nb_max)
+  {
+    const int nb = std::min(nb_max, B - b0);
+    const int batch = f->nchan * nb;
+    if(batch > 65535) return fail("tsdgpu_ola_step: nchan * blocks per chunk > 65535 on the unfused path");
+    if(!f->plan || f->plan_batch != batch)
+    {
+      if(f->plan) fft_plan_destroy(f->plan);
+      f->plan = nullptr;
+      if(f->work) cudaFree(f->work);
+      f->work = nullptr;
+      if(fft_plan_create(N, batch, &f->plan)) return 1;
+      f->plan_batch = batch;
+      TSD_CUDA(cudaMalloc(&f->work, (size_t) batch * N * sizeof(float2)));
+    }
+    dim3 gg((N + 255) / 256, batch);
+    ola_gather_kernel<<<gg, 256, 0, r.stream>>>(x, xs, f->d_carry[f->cur], f->carry_len, f->work, N, Ne, Nz, nb, b0,
+                                               f->residual);
+    TSD_LAUNCH_CHECK();
+    if(fft_exec_device(f->plan, f->work, N, f->work, N, true)) return 1;
+    if(f->d_H)
+    {
+      const long long total = (long long) batch * N;
+      ola_mulH_kernel<<<(int) std::min<long long>((total + 255) / 256, rt().num_sms * 16), 256, 0, r.stream>>>(f->work, f->d_H,
+                                                                                                             N, total);
+      TSD_LAUNCH_CHECK();
+    }
+    if(fft_exec_device(f->plan, f->work, N, f->work, N, false)) return 1;
+    dim3 gs((Ne + 255) / 256, batch);
+    ola_scatter_kernel<<<gs, 256, 0, r.stream>>>(f->work, f->d_svg, y, ys, N, Ne, Nz, nb, b0);
+    TSD_LAUNCH_CHECK();
+    dim3 gv((Ne + 255) / 256, f->nchan);
+    ola_svg_kernel<<<gv, 256, 0, r.stream>>>(f->work, f->d_svg, N, Ne, Nz, nb);
+    TSD_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+static int ola_run_device(tsdgpu_ola_s *f, const float2 *x, long long xs, int n, float2 *y, long long ys, long long *n_out)
+{
+  Runtime &r = rt();
+  const long long tot = (long long) f->residual + n;
+  const int B = (int) (tot / f->Ne);
+  *n_out = (long long) B * f->Ne;
+  if(n <= 0) return 0;
+  if(B > 0)
+  {
+    if(ys < *n_out) return fail("tsdgpu_ola_step: output stride smaller than the emitted count");
+    int rc = f->fused ? ola_run_fused(f, x, xs, y, ys, B) : ola_run_unfused(f, x, xs, y, ys, B);
+    if(rc) return rc;
+  }
+  dim3 grid((f->carry_len + 255) / 256, f->nchan);
+  carry_update_kernel<<<grid, 256, 0, r.stream>>>(x, xs, n, f->d_carry[f->cur], f->d_carry[f->cur ^ 1], f->carry_len);
+  TSD_LAUNCH_CHECK();
+  f->cur ^= 1;
+  f->residual = (int) (tot % f->Ne);
+  f->blocks_done += B;
+  return 0;
+}
+
+extern "C" {
+
+int tsdgpu_ola_create(int dim_blocs_temporel, int nb_zeros_min, const float *H, int fir_len, int nchan, tsdgpu_ola_t *out)
+{
+  if(ensure_init()) return 1;
+  if(!out) return fail("tsdgpu_ola_create: null argument");
+  if(nchan <= 0) return fail("tsdgpu_ola_create: nchan must be > 0");
+  if(nb_zeros_min < 0) return fail("tsdgpu_ola_create: nb_zeros_min < 0");
+  int Ne = dim_blocs_temporel;
+  if(Ne <= 0) Ne = 512;                                   // fourier.cc:769-770
+  if((long long) Ne + nb_zeros_min > (1 << 24)) return fail("tsdgpu_ola_create: block too large");
+  const int N = tsdgpu_p2(Ne + nb_zeros_min);             // fourier.cc:775
+  const int Nz = N - Ne;
+  if(Nz > Ne)
+    return fail("tsdgpu_ola_create: N_zeros > Ne — the reference indexes before its svg buffer here "
+                "(svg.tail(N_zeros), fourier.cc:870); choose a larger dim_blocs_temporel");
+  // K taps at the tail of the N-vector convolve without wrap-around only if K <= N_zeros
+  if(fir_len < 0 || fir_len > Nz)
+    return fail("tsdgpu_ola_create: fir_len must be in [1, N_zeros] (or 0 for an arbitrary H)");
+  if(fir_len > 0 && !H) return fail("tsdgpu_ola_create: fir_len > 0 needs H");
+  auto *f = new tsdgpu_ola_s;
+  f->Ne = Ne;
+  f->N = N;
+  f->Nz = Nz;
+  f->nchan = nchan;
+  f->fused = (N == 65536);
+  f->K = f->fused ? fir_len : 0;   // the unfused path always runs the overlap-add form
+  f->carry_len = N + Ne;
+  cudaError_t e = cudaSuccess;
+  for(int i = 0; i < 2 && e == cudaSuccess; i++)
+  {
+    e = cudaMalloc(&f->d_carry[i], (size_t) nchan * f->carry_len * sizeof(float2));
+    if(e == cudaSuccess) e = cudaMemsetAsync(f->d_carry[i], 0, (size_t) nchan * f->carry_len * sizeof(float2), rt().stream);
+  }
+  if(e == cudaSuccess) e = cudaMalloc(&f->d_svg, (size_t) nchan * Ne * sizeof(float2));
+  if(e == cudaSuccess) e = cudaMemsetAsync(f->d_svg, 0, (size_t) nchan * Ne * sizeof(float2), rt().stream);   // svg.setZero(Ne), fourier.cc:785
+  if(e == cudaSuccess && (H || f->fused))
+  {
+    std::vector<float2> h((size_t) N);
+    const float sc = f->fused ? 1.0f / (float) N : 1.0f;   // both unitary scalings folded into H (exact: N = 2^16)
+    for(int i = 0; i < N; i++)
+      h[i] = H ? make_float2(H[2 * i] * sc, H[2 * i + 1] * sc) : make_float2(sc, 0.f);
+    e = cudaMalloc(&f->d_H, (size_t) N * sizeof(float2));
+    if(e == cudaSuccess) e = cudaMemcpy(f->d_H, h.data(), (size_t) N * sizeof(float2), cudaMemcpyHostToDevice);
+  }
+  if(e == cudaSuccess && f->fused)
+  {
+    e = cudaMalloc(&f->scratch, (size_t) f->ring * 65536 * sizeof(float2));
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ola64k_kernel, OLA_NT, 0);
+    f->ctas = rt().num_sms * std::max(1, occ);
+  }
+  if(e == cudaSuccess) e = cudaStreamSynchronize(rt().stream);
+  if(e != cudaSuccess)
+  {
+    tsdgpu_ola_destroy(f);
+    return fail(std::string("tsdgpu_ola_create: ") + cudaGetErrorString(e));
+  }
+  *out = f;
+  return 0;
+}
+
+int tsdgpu_ola_dims(tsdgpu_ola_t f, int *Ne, int *N, int *Nz, int *residual)
+{
+  if(!f) return fail("tsdgpu_ola_dims: null handle");
+  if(Ne) *Ne = f->Ne;
+  if(N) *N = f->N;
+  if(Nz) *Nz = f->Nz;
+  if(residual) *residual = f->residual;
+  return 0;
+}
+
+long long tsdgpu_ola_out_count(tsdgpu_ola_t f, int n)
+{
+  if(!f || n < 0) return 0;
+  return (((long long) f->residual + n) / f->Ne) * f->Ne;
+}
+
+int tsdgpu_ola_step(tsdgpu_ola_t f, const void *x, long long xs, int n, void *y, long long ys, long long *n_out, int mem)
+{
+  if(ensure_init()) return 1;
+  if(!f || !n_out) return fail("tsdgpu_ola_step: null argument");
+  *n_out = 0;
+  if(n < 0) return fail("tsdgpu_ola_step: n < 0");
+  if(n == 0) return 0;
+  if(!x) return fail("tsdgpu_ola_step: null input");
+  if(xs < n) return fail("tsdgpu_ola_step: channel stride smaller than n");
+  const long long cnt = tsdgpu_ola_out_count(f, n);
+  if(cnt > 0 && !y) return fail("tsdgpu_ola_step: null output");
+  if(mem == TSDGPU_DEVICE)
+  {
+    if(x == y) return fail("tsdgpu_ola_step: in-place operation is not supported (neither does the reference, fourier.cc:871)");
+    return ola_run_device(f, (const float2 *) x, xs, n, (float2 *) y, ys, n_out);
+  }
+  float2 *dx = nullptr, *dy = nullptr;
+  TSD_CUDA(cudaMalloc(&dx, (size_t) f->nchan * n * sizeof(float2)));
+  if(cudaMalloc(&dy, std::max<size_t>(1, (size_t) f->nchan * cnt) * sizeof(float2)) != cudaSuccess)
+  {
+    cudaFree(dx);
+    return fail("tsdgpu_ola_step: out of device memory");
+  }
+  int rc = 0;
+  cudaError_t e = cudaMemcpy2DAsync(dx, (size_t) n * 8, x, (size_t) xs * 8, (size_t) n * 8, f->nchan, cudaMemcpyHostToDevice,
+                                    rt().stream);
+  if(e == cudaSuccess) rc = ola_run_device(f, dx, n, n, dy, std::max(1LL, cnt), n_out);
+  if(e == cudaSuccess && !rc && cnt > 0)
+    e = cudaMemcpy2DAsync(y, (size_t) ys * 8, dy, (size_t) cnt * 8, (size_t) cnt * 8, f->nchan, cudaMemcpyDeviceToHost,
+                          rt().stream);
+  if(e == cudaSuccess) e = cudaStreamSynchronize(rt().stream);
+  cudaFree(dx);
+  cudaFree(dy);
+  if(e != cudaSuccess) return fail(std::string("tsdgpu_ola_step: ") + cudaGetErrorString(e));
+  return rc;
+}
+
+int tsdgpu_ola_destroy(tsdgpu_ola_t f)
+{
+  if(!f) return 0;
+  cudaStreamSynchronize(rt().stream);
+  cudaFree(f->d_H);
+  cudaFree(f->d_carry[0]);
+  cudaFree(f->d_carry[1]);
+  cudaFree(f->d_svg);
+  if(f->scratch) cudaFree(f->scratch);
+  if(f->flags) cudaFree(f->flags);
+  if(f->plan) fft_plan_destroy(f->plan);
+  if(f->work) cudaFree(f->work);
+  delete f;
+  return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,139 @@
+// Runtime of libtsdgpu: device selection, the library stream, error reporting, launch counter.
+#include "common.cuh"
+#include "tsdgpu.h"
+
+#include <cmath>
+
+namespace tsdgpu {
+
+static thread_local std::string g_error;
+
+Runtime &rt()
+{
+  static Runtime r;
+  return r;
+}
+void set_error(const std::string &s) { g_error = s; }
+int fail(const std::string &s)
+{
+  g_error = s;
+  return 1;
+}
+
+static int init_device(int device)
+{
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if(e != cudaSuccess || count == 0)
+    return fail(std::string("libtsdgpu: no CUDA device (") + cudaGetErrorString(e) + "); there is no CPU fallback");
+  if(device < 0 || device >= count) return fail("libtsdgpu: device index out of range");
+  TSD_CUDA(cudaSetDevice(device));
+  Runtime &r = rt();
+  if(r.device == device && r.own_stream) return 0;
+  cudaDeviceProp prop;
+  TSD_CUDA(cudaGetDeviceProperties(&prop, device));
+  if(prop.major < 10)
+    return fail("libtsdgpu: built for sm_100a (Blackwell B200) only; found compute capability " +
+                std::to_string(prop.major) + "." + std::to_string(prop.minor));
+  r.device = device;
+  r.num_sms = prop.multiProcessorCount;
+  TSD_CUDA(cudaStreamCreateWithFlags(&r.own_stream, cudaStreamNonBlocking));
+  TSD_CUDA(cudaStreamCreateWithFlags(&r.copy_in, cudaStreamNonBlocking));
+  TSD_CUDA(cudaStreamCreateWithFlags(&r.copy_out, cudaStreamNonBlocking));
+  r.stream = r.own_stream;
+  return 0;
+}
+
+int ensure_init()
+{
+  if(rt().device >= 0)
+  {
+    // CUDA's current device is per host thread
+    cudaSetDevice(rt().device);
+    return 0;
+  }
+  return init_device(0);
+}
+
+KernelTimer::KernelTimer()
+{
+  Runtime &r = rt();
+  if(!r.timing) return;
+  if(cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) { a = b = nullptr; return; }
+  cudaEventRecord(a, r.stream);
+}
+KernelTimer::~KernelTimer()
+{
+  if(!a) return;
+  Runtime &r = rt();
+  cudaEventRecord(b, r.stream);
+  r.timed.emplace_back(a, b);
+}
+
+} // namespace tsdgpu
+
+using namespace tsdgpu;
+
+extern "C" {
+
+int tsdgpu_init(int device) { return init_device(device); }
+
+int tsdgpu_set_stream(void *s)
+{
+  if(ensure_init()) return 1;
+  rt().stream = s ? (cudaStream_t) s : rt().own_stream;
+  return 0;
+}
+
+int tsdgpu_synchronize(void)
+{
+  if(ensure_init()) return 1;
+  TSD_CUDA(cudaStreamSynchronize(rt().stream));
+  return 0;
+}
+
+const char *tsdgpu_last_error(void) { return g_error.c_str(); }
+
+long long tsdgpu_launch_count(int reset)
+{
+  long long v = rt().launches;
+  if(reset) rt().launches = 0;
+  return v;
+}
+
+int tsdgpu_timing_enable(int on)
+{
+  if(ensure_init()) return 1;
+  rt().timing = on != 0;
+  return 0;
+}
+
+int tsdgpu_timing_read(double *total_ms, long long *launches)
+{
+  if(ensure_init()) return 1;
+  Runtime &r = rt();
+  TSD_CUDA(cudaStreamSynchronize(r.stream));
+  double tot = 0;
+  for(auto &pr : r.timed)
+  {
+    float ms = 0;
+    cudaEventSynchronize(pr.second);
+    cudaEventElapsedTime(&ms, pr.first, pr.second);
+    tot += ms;
+    cudaEventDestroy(pr.first);
+    cudaEventDestroy(pr.second);
+  }
+  if(total_ms) *total_ms = tot;
+  if(launches) *launches = (long long) r.timed.size();
+  r.timed.clear();
+  return 0;
+}
+
+// tsd.cc:287-291 — same float expression as the reference, evaluated on the host
+int tsdgpu_p2(int i)
+{
+  int lg2 = (int) ceilf(logf((float) i) / logf(2.0f));
+  return (int) (1l << lg2);
+}
+
+} // extern "C"

@@ -1,0 +1,324 @@
+"""Host-side mirror of tsd::filtrage for the GPU hot path (names and argument meaning follow the
+reference: core/include/tsd/filtrage.hpp; English aliases follow core/include/dsp/filter.hpp).
+
+Every object keeps the reference's per-object semantics (one object == one stream, state carried
+across step() calls); the only new surface is ``nchan``: a batch of independent channels that share
+the same configuration, laid out [nchan, n].  Arrays may be numpy (host memory: copied in and out)
+or torch CUDA tensors (device memory: no copies, asynchronous on the library stream).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from ._buf import Batch, empty_like_batch, restore_shape
+from ._lib import TsdGpuError, check, lib
+
+_vp = C.c_void_p
+
+
+class FiltreGen:
+    """tsd::FiltreGen<Te,Ts> (tsd.hpp:626-657): ``step(x) -> y``; the callee sizes ``y``."""
+
+    nchan = 1
+
+    def step(self, x):  # pragma: no cover - abstract
+        raise NotImplementedError
+
+    # English skin (dsp::FilterGen)
+    def __call__(self, x):
+        return self.step(x)
+
+
+# ----------------------------------------------------------------------------- design helpers
+def _sinc(T, f):
+    """tsd::sinc(T, f) (divers.cc:6-12), float32."""
+    T = np.float32(T)
+    f = np.asarray(f, np.float32)
+    a = np.float32(np.pi) * T * f
+    with np.errstate(divide="ignore", invalid="ignore"):
+        r = np.sin(a, dtype=np.float32) / (np.float32(np.pi) * f)
+    return np.where(np.abs(a) < np.float32(1e-7), T, r).astype(np.float32)
+
+
+def _linspace(a, b, n):
+    """tsd::linspace (tsd.hpp:916-931): double step, float32 storage."""
+    a = np.float32(a)
+    b = np.float32(b)
+    x = np.empty(n, np.float32)
+    if n > 0:
+        x[0] = a
+    if n > 1:
+        step = (float(b) - float(a)) / (n - 1)
+        x[1:] = (float(a) + step * np.arange(1, n)).astype(np.float32)
+    return x
+
+
+def fenetre(type_: str, n: int, symetrique: bool = True) -> np.ndarray:
+    """tsd::filtrage::fenêtre for "re"/"hn"/"hm" (fenetres.cc:17-59,125-128,204-232)."""
+    if type_ in ("", "re", "aucune", "none"):
+        return np.ones(n, np.float32)
+    if type_ in ("hn", "hann"):
+        a = np.float32(0.5)
+    elif type_ in ("hm", "hamming"):
+        a = np.float32(0.54)
+    else:
+        raise TsdGpuError(f"fenêtre: type '{type_}' non supporté")
+    tmin = -(n // 2)
+    if n % 2 == 0:
+        tmax = n // 2 if symetrique else (n - 1) // 2
+    else:
+        tmax = n // 2 if symetrique else np.float32(n // 2) - (np.float32(n) - 1) / np.float32(n)
+    t = _linspace(np.float32(tmin) / np.float32(n), np.float32(tmax) / np.float32(n), n)
+    return (a + (np.float32(1) - a) * np.cos(np.float32(2 * np.pi) * t, dtype=np.float32)).astype(np.float32)
+
+
+def design_rif_fen(n: int, type_: str, fc: float, fen: str = "hn") -> np.ndarray:
+    """tsd::filtrage::design_rif_fen (rif-fen.cc:30-107), low-pass only ("lp"/"pb")."""
+    if type_ not in ("lp", "pb"):
+        raise TsdGpuError("design_rif_fen: seul le type 'lp' est disponible dans cette version")
+    c = n // 2 if n % 2 else (n - 1) // 2
+    h = _sinc(np.float32(2) * np.float32(fc), (np.arange(n) - c).astype(np.float32)) * fenetre(fen, n, True)
+    h = h.astype(np.float32)
+    if type_ == "lp":
+        h = (h / np.float32(np.sum(h, dtype=np.float64))).astype(np.float32)
+    return h
+
+
+design_fir_wnd = design_rif_fen
+
+
+# ----------------------------------------------------------------------------- FIR
+class FiltreRIF(FiltreGen):
+    """GPU counterpart of FiltreRIF<T,Tc> (filtre-rt.cc:53-109), created by :func:`filtre_rif`."""
+
+    def __init__(self, coefs, T=np.complex64, nchan: int = 1):
+        coefs = np.asarray(coefs)
+        taps_complex = np.iscomplexobj(coefs)
+        T = np.dtype(T).type
+        if T not in (np.float32, np.complex64):
+            raise TsdGpuError("filtre_rif: T doit être float32 ou complex64")
+        if taps_complex and T is np.float32:
+            raise TsdGpuError("filtre_rif: coefficients complexes avec des données réelles")
+        self.kind = 0 if T is np.float32 else (2 if taps_complex else 1)
+        self.dtype = T
+        self.coefs = np.ascontiguousarray(coefs, np.complex64 if taps_complex else np.float32)
+        self.K = int(self.coefs.shape[0])
+        self.nchan = int(nchan)
+        h = _vp()
+        check(lib().tsdgpu_fir_create(self.kind, self.coefs.ctypes.data_as(_vp), self.K, self.nchan, C.byref(h)))
+        self._h = h
+
+    def step(self, x, out=None):
+        b = Batch(x, self.dtype, self.nchan)
+        if out is None:
+            y = empty_like_batch(b, self.dtype, b.n)
+            yb = Batch(y, self.dtype, self.nchan, "y")
+        else:
+            yb = Batch(out, self.dtype, self.nchan, "y")
+            y = yb.arr
+            if yb.n < b.n or yb.mem != b.mem:
+                raise TsdGpuError("filtre_rif.step: tampon de sortie incompatible")
+        check(lib().tsdgpu_fir_step(self._h, b.ptr, b.stride, b.n, yb.ptr, yb.stride, b.mem))
+        return restore_shape(y[:, : b.n], b.ndim)
+
+    @property
+    def index(self) -> int:
+        """Ring index of the reference object: (samples so far) mod K (filtre-rt.cc:89)."""
+        i = C.c_int()
+        check(lib().tsdgpu_fir_get_state(self._h, None, C.byref(i)))
+        return i.value
+
+    def get_state(self):
+        fen = np.zeros((self.nchan, self.K), self.dtype)
+        i = C.c_int()
+        check(lib().tsdgpu_fir_get_state(self._h, fen.ctypes.data_as(_vp), C.byref(i)))
+        return fen, i.value
+
+    def set_state(self, fen, index: int):
+        fen = np.ascontiguousarray(fen, self.dtype).reshape(self.nchan, self.K)
+        check(lib().tsdgpu_fir_set_state(self._h, fen.ctypes.data_as(_vp), int(index)))
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                lib().tsdgpu_fir_destroy(h)
+            except Exception:
+                pass
+
+
+def filtre_rif(coefs, T=np.complex64, nchan: int = 1) -> FiltreRIF:
+    """sptr<FiltreGen<T>> filtre_rif<Tc,T>(coefs) (filtrage.hpp:1367-1368, filtre-rt.cc:171-175)."""
+    return FiltreRIF(coefs, T, nchan)
+
+
+filter_fir = filtre_rif
+
+
+def filtrer(h, x):
+    """tsd::filtrage::filtrer(Design, x) for FIR designs (filtrage.hpp:1684-1711): one-shot filter."""
+    x_is_t = hasattr(x, "is_cuda")
+    cplx = (x.is_complex() if x_is_t else np.iscomplexobj(x))
+    nchan = 1 if x.ndim == 1 else x.shape[0]
+    return filtre_rif(h, np.complex64 if cplx else np.float32, nchan).step(x)
+
+
+filter = filtrer  # noqa: A001  (dsp::filter, dsp/filter.hpp:1662-1666)
+
+
+# ----------------------------------------------------------------------------- interpolators
+@dataclass
+class InterpolateurSincConfig:
+    """filtrage.hpp:1914-1927"""
+    ncoefs: int = 31
+    nphases: int = 256
+    fcut: float = 0.5
+    fenetre: str = "hn"
+
+
+class InterpolateurSinc:
+    """Windowed-sinc interpolator LUT (itrp.cc:10-55).  ``lut[p]`` = coefficients for delay p/nphases."""
+
+    def __init__(self, config: InterpolateurSincConfig):
+        if not (0 <= config.fcut <= 0.5):
+            raise TsdGpuError("interpolateur sinc : fréquence normalisée attendue (entre 0 et 0.5)")
+        self.config = config
+        K, P = config.ncoefs, config.nphases
+        self.K = K
+        self.delais = 0.5 * K
+        self.nom = f"sinc - ncoefs={K}, nphases={P}, fcut={config.fcut}, fen={config.fenetre}"
+        lin = _linspace(-(K // 2), (K - 1) // 2, K)
+        scale = np.float32(2 * np.pi / K)
+        i = np.arange(K)
+        lut = np.empty((P + 1, K), np.float32)
+        for p in range(P + 1):
+            tau = np.float32((1.0 * p) / P)
+            h = _sinc(np.float32(2) * np.float32(config.fcut), (i - K // 2).astype(np.float32) - tau)
+            if config.fenetre == "hn":
+                t = ((lin - tau) * scale).astype(np.float32)
+                h = h * (np.float32(0.5) + np.float32(0.5) * np.cos(t, dtype=np.float32))
+            lut[p] = h
+        self.lut = lut
+
+    def coefs(self, tau: float) -> np.ndarray:
+        idx = int(np.float32(tau) * np.float32(self.config.nphases))
+        return self.lut[idx]
+
+
+def itrp_sinc(config: InterpolateurSincConfig = InterpolateurSincConfig()) -> InterpolateurSinc:
+    return InterpolateurSinc(config)
+
+
+class InterpolateurLUT:
+    """Any InterpolateurRIF given directly by its coefficient table [nphases+1, K]."""
+
+    def __init__(self, lut):
+        self.lut = np.ascontiguousarray(lut, np.float32)
+        self.K = int(self.lut.shape[1])
+
+
+class AdaptationRythmeSimple(FiltreGen):
+    """GPU counterpart of AdaptationRythmeSimple (ra.cc:13-79), created by :func:`filtre_itrp`."""
+
+    def __init__(self, ratio: float, itrp, nchan: int = 1):
+        self.ratio = float(np.float32(ratio))
+        self.itrp = itrp
+        self.nchan = int(nchan)
+        lut = np.ascontiguousarray(itrp.lut, np.float32)
+        self.nphases = lut.shape[0] - 1
+        self.K = lut.shape[1]
+        h = _vp()
+        check(lib().tsdgpu_resamp_create(C.c_float(self.ratio), lut.ctypes.data_as(_vp), self.K, self.nphases,
+                                         self.nchan, C.byref(h)))
+        self._h = h
+
+    @property
+    def phase(self) -> float:
+        return float(lib().tsdgpu_resamp_phase(self._h))
+
+    def out_count(self, n: int) -> int:
+        return int(lib().tsdgpu_resamp_out_count(self._h, int(n)))
+
+    def step(self, x):
+        b = Batch(x, np.complex64, self.nchan)
+        cnt = self.out_count(b.n)
+        y = empty_like_batch(b, np.complex64, cnt)
+        if b.n == 0:
+            return restore_shape(y, b.ndim)
+        yb = Batch(y, np.complex64, self.nchan, "y")
+        no = C.c_longlong()
+        check(lib().tsdgpu_resamp_step(self._h, b.ptr, b.stride, b.n, yb.ptr, max(yb.stride, 1), cnt, C.byref(no), b.mem))
+        assert no.value == cnt
+        return restore_shape(y, b.ndim)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                lib().tsdgpu_resamp_destroy(h)
+            except Exception:
+                pass
+
+
+def filtre_itrp(ratio: float, itrp, nchan: int = 1) -> AdaptationRythmeSimple:
+    """sptr<FiltreGen<T>> filtre_itrp<T>(ratio, itrp) for T = cfloat (filtrage.hpp:2039, ra.cc:185-188)."""
+    return AdaptationRythmeSimple(ratio, itrp, nchan)
+
+
+filter_itrp = filtre_itrp
+
+
+class AdaptationRythmeArbitraire(FiltreGen):
+    """filtre_reechan<cfloat>(ratio) (ra.cc:84-183): stage planner + arbitrary-ratio interpolator.
+
+    Ratios whose post-interpolation factor needs half-band / x2 stages (ratio outside [0.5, 2))
+    are not built yet and raise.
+    """
+
+    def __init__(self, ratio: float, nchan: int = 1):
+        r = np.float32(ratio)
+        if r <= 0 or np.isinf(r) or r >= 1e9:   # ra.cc:108-112: logged, ratio forced to 1
+            r = np.float32(1)
+        self.ratio = float(r)
+        self.nchan = int(nchan)
+        f = r
+        self.nb_decimateurs = 0
+        self.nb_surechantillonneurs = 0
+        while f < 0.5:
+            self.nb_decimateurs += 1
+            f = np.float32(f * 2)
+        while f >= 2:
+            self.nb_surechantillonneurs += 1
+            f = np.float32(f / 2)
+        self.facteur_post_interpolation = float(f)
+        if self.nb_decimateurs or self.nb_surechantillonneurs:
+            raise TsdGpuError("filtre_reechan: ratio hors de [0.5, 2[ — étages demi-bande / x2 pas encore disponibles")
+        fcut = min(np.float32(0.4), np.float32(f / 2))
+        self.interpolateur = filtre_itrp(float(f), itrp_sinc(InterpolateurSincConfig(15, 256, float(fcut), "hn")), nchan)
+
+    def step(self, x):
+        if self.ratio == 1:                        # ra.cc:162-163
+            return x.clone() if hasattr(x, "clone") else np.array(x, np.complex64)
+        if abs(np.float32(self.facteur_post_interpolation) - 1) < 1e-6:   # ra.cc:173-174
+            return x.clone() if hasattr(x, "clone") else np.array(x, np.complex64)
+        return self.interpolateur.step(x)
+
+
+def filtre_reechan(ratio: float, nchan: int = 1) -> AdaptationRythmeArbitraire:
+    return AdaptationRythmeArbitraire(ratio, nchan)
+
+
+filter_resample = filtre_reechan
+
+
+def reechan(x, r: float):
+    """tsd::rééchan(x, r) (tsd.hpp:700-705) / dsp::resample (dsp/dsp.hpp:499-503)."""
+    nchan = 1 if x.ndim == 1 else x.shape[0]
+    return filtre_reechan(r, nchan).step(x)
+
+
+resample = reechan

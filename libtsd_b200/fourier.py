@@ -1,0 +1,220 @@
+"""Host-side mirror of tsd::fourier for the GPU hot path (reference: core/include/tsd/fourier.hpp;
+English aliases: core/include/dsp/fourier.hpp)."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+from ._buf import Batch, empty_like_batch, restore_shape
+from ._lib import TsdGpuError, check, lib
+from .filtrage import FiltreGen
+
+_vp = C.c_void_p
+
+
+def prochaine_puissance_de_2(i: int) -> int:
+    """tsd.cc:287-291 (float log, evaluated by the library with the reference's expression)."""
+    return int(lib().tsdgpu_p2(int(i)))
+
+
+class FFTPlan:
+    """tsd::fourier::FFTPlan (fourier.hpp:19-32) backed by the GPU plan.
+
+    Like TFRPlanDefaut the plan is always unitary (``normalize`` is accepted and ignored,
+    fourier.cc:119-120,362) and re-plans itself when the input length changes (fourier.cc:416-417).
+    ``batch`` transforms are laid out [batch, n].
+    """
+
+    def __init__(self, n: int = -1, avant: bool = True, normalize: bool = True, batch: int = 1):
+        self.n = -1
+        self.avant = avant
+        self.batch = int(batch)
+        self._h = None
+        if n >= 0:
+            self.configure(n, avant, normalize)
+
+    def configure(self, n: int, avant: bool = True, normalize: bool = True):
+        self._free()
+        self.n = int(n)
+        self.avant = avant
+        h = _vp()
+        check(lib().tsdgpu_fft_plan(self.n, self.batch, C.byref(h)))
+        self._h = h
+
+    def step(self, x, avant: Optional[bool] = None, out=None):
+        if avant is None:
+            avant = self.avant
+        nb = 1 if x.ndim == 1 else x.shape[0]
+        n = x.shape[-1]
+        if n <= 0:
+            raise TsdGpuError("Echec assertion : x.rows() > 0.")   # fourier.cc:414
+        if n != self.n or nb != self.batch:
+            self.batch = nb
+            self.configure(n, self.avant)
+        b = Batch(x, np.complex64, self.batch)
+        if out is None:
+            y = empty_like_batch(b, np.complex64, n)
+        else:
+            y = out if out.ndim == 2 else out[None]
+        yb = Batch(y, np.complex64, self.batch, "y")
+        check(lib().tsdgpu_fft_exec(self._h, b.ptr, b.stride, yb.ptr, yb.stride, 1 if avant else 0, b.mem))
+        return restore_shape(yb.arr, x.ndim)
+
+    def _free(self):
+        if self._h:
+            try:
+                lib().tsdgpu_fft_destroy(self._h)
+            except Exception:
+                pass
+            self._h = None
+
+    def __del__(self):
+        self._free()
+
+
+def tfrplan_creation(n: int = -1, avant: bool = True, normaliser: bool = True, batch: int = 1) -> FFTPlan:
+    """sptr<FFTPlan> tfrplan_création(n, avant, normaliser) (fourier.hpp:69, fourier.cc:475-481)."""
+    return FFTPlan(n, avant, normaliser, batch)
+
+
+fftplan_new = tfrplan_creation
+
+
+def fft(x):
+    """tsd::fourier::fft for complex input (fourier.hpp:163-170): unitary DFT."""
+    return FFTPlan().step(x, True)
+
+
+def ifft(X):
+    """tsd::fourier::ifft (fourier.hpp:199-205): unitary inverse DFT."""
+    return FFTPlan().step(X, False)
+
+
+@dataclass
+class FiltreFFTConfig:
+    """fourier.hpp:305-320.  The reference's ``traitement_freq`` callback is a host std::function; the
+    GPU path takes the callback of FiltreFFTRIF, "X *= H" (fourier.cc:956-959), as data:
+
+    H        : N complex gains (None = identity callback)
+    fir_len  : K > 0 declares H = fft([0^(N-K), h]) * sqrt(N) (fourier.cc:962-965) and lets the
+               library use its overlap-save form; 0 keeps the generic overlap-add.
+    """
+    dim_blocs_temporel: int = 0
+    nb_zeros_min: int = 0
+    avec_fenetrage: bool = False
+    H: Optional[np.ndarray] = None
+    fir_len: int = 0
+
+
+FFTFilterConfig = FiltreFFTConfig
+
+
+class OLA(FiltreGen):
+    """GPU counterpart of OLA<cfloat> (fourier.cc:737-932, plain mode)."""
+
+    def __init__(self, config: FiltreFFTConfig, nchan: int = 1):
+        if config.avec_fenetrage:
+            raise TsdGpuError("filtre_fft: mode fenêtré (Hann 50 %) pas encore disponible sur GPU")
+        self.config = config
+        self.nchan = int(nchan)
+        Ne = config.dim_blocs_temporel if config.dim_blocs_temporel > 0 else 512
+        N = prochaine_puissance_de_2(Ne + config.nb_zeros_min)
+        Hp = None
+        if config.H is not None:
+            H = np.ascontiguousarray(config.H, np.complex64)
+            if H.shape != (N,):
+                raise TsdGpuError(f"filtre_fft: H doit comporter N = {N} points")
+            Hp = H.ctypes.data_as(_vp)
+            self._H = H
+        h = _vp()
+        check(lib().tsdgpu_ola_create(int(config.dim_blocs_temporel), int(config.nb_zeros_min), Hp, int(config.fir_len),
+                                      self.nchan, C.byref(h)))
+        self._h = h
+        a, b, c, d = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        check(lib().tsdgpu_ola_dims(h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        self.Ne, self.N, self.N_zeros = a.value, b.value, c.value
+
+    @property
+    def residual(self) -> int:
+        d = C.c_int()
+        check(lib().tsdgpu_ola_dims(self._h, None, None, None, C.byref(d)))
+        return d.value
+
+    def out_count(self, n: int) -> int:
+        return int(lib().tsdgpu_ola_out_count(self._h, int(n)))
+
+    def step(self, x, out=None):
+        b = Batch(x, np.complex64, self.nchan)
+        cnt = self.out_count(b.n)
+        if out is None:
+            y = empty_like_batch(b, np.complex64, cnt)
+        else:
+            y = out if out.ndim == 2 else out[None]
+        if b.n == 0:
+            return restore_shape(y[:, :0], b.ndim)
+        yb = Batch(y, np.complex64, self.nchan, "y")
+        no = C.c_longlong()
+        check(lib().tsdgpu_ola_step(self._h, b.ptr, b.stride, b.n, yb.ptr if cnt else None, max(yb.stride, 1),
+                                    C.byref(no), b.mem))
+        assert no.value == cnt
+        return restore_shape(yb.arr[:, :cnt], b.ndim)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                lib().tsdgpu_ola_destroy(h)
+            except Exception:
+                pass
+
+
+def filtre_fft(config: FiltreFFTConfig, nchan: int = 1):
+    """tuple<sptr<Filtre<cfloat,cfloat,FiltreFFTConfig>>, entier> filtre_fft(config)
+    (fourier.hpp:370, fourier.cc:935-940): returns (filter, N)."""
+    f = OLA(config, nchan)
+    return f, f.N
+
+
+filter_fft = filtre_fft
+
+
+def ola_make_H(h, N: int) -> np.ndarray:
+    """H of the FiltreFFTRIF convention (fourier.cc:962-965): h2.tail(K) = h; H = fft(h2) * sqrt(N).
+    Set-up helper evaluated in float64 on the host."""
+    h = np.asarray(h, np.float64)
+    h2 = np.zeros(N, np.float64)
+    h2[N - len(h):] = h
+    return np.fft.fft(h2).astype(np.complex64)
+
+
+class FiltreFFTRIF(FiltreGen):
+    """filtre_rif_fft<T>(h) (fourier.cc:946-990).  ``Ne`` defaults to the reference's 512; the
+    reference is only defined for K <= 512 (with more taps N_zeros > Ne and it indexes before its
+    buffer, fourier.cc:870), so longer filters must pass a larger ``Ne`` explicitly.
+    ``compat_real_output`` reproduces the reference's ``real(...)`` of the output (fourier.cc:976)."""
+
+    def __init__(self, h, Ne: int = 0, nchan: int = 1, compat_real_output: bool = False):
+        h = np.ascontiguousarray(h, np.float32)
+        K = len(h)
+        ne = Ne if Ne > 0 else 512
+        N = prochaine_puissance_de_2(ne + K)
+        cfg = FiltreFFTConfig(dim_blocs_temporel=Ne, nb_zeros_min=K, H=ola_make_H(h, N), fir_len=K)
+        self.ola = OLA(cfg, nchan)
+        self.nchan = nchan
+        self.compat_real_output = compat_real_output
+
+    def step(self, x):
+        y = self.ola.step(x)
+        if self.compat_real_output:
+            y = y.real.astype(np.complex64) if isinstance(y, np.ndarray) else (y.real + 0j)
+        return y
+
+
+def filtre_rif_fft(h, Ne: int = 0, nchan: int = 1, compat_real_output: bool = False) -> FiltreFFTRIF:
+    return FiltreFFTRIF(h, Ne, nchan, compat_real_output)
+
+
+filter_fir_fft = filtre_rif_fft

@@ -1,0 +1,352 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): index / length / state bookkeeping bit-exact; cf32 samples within
+max |y_gpu - y_ref| <= 1e-5 * rms(signal).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+
+
+def cn(rng, *shape):
+    return (rng.standard_normal(shape) + 1j * rng.standard_normal(shape)).astype(np.complex64)
+
+
+def rms(a):
+    return float(np.sqrt(np.mean(np.abs(a.astype(np.complex128)) ** 2)))
+
+
+def rel_err(y, yref, scale):
+    assert y.shape == yref.shape, (y.shape, yref.shape)
+    if y.size == 0:
+        return 0.0
+    return float(np.max(np.abs(y.astype(np.complex128) - yref.astype(np.complex128))) / scale)
+
+
+@pytest.fixture(scope="module")
+def tsd():
+    import libtsd_b200
+    libtsd_b200.init(0)
+    return libtsd_b200
+
+
+# ------------------------------------------------------------------------------------- FIR
+def test_readme_example(tsd, cpu_oracle):
+    """BASELINE config 1: design_fir_wnd(31,"lp",0.25), filter() on 500 float samples (README.md:27-33)."""
+    from libtsd_b200 import filtrage as F
+    h = cpu_oracle.design_rif_fen(31, "lp", 0.25)
+    rng = np.random.default_rng(0x7D5D0001)
+    x = (np.cos(2 * np.pi * 0.01 * np.arange(500)) + 0.1 * rng.standard_normal(500)).astype(np.float32)
+    y = F.filtrer(h, x)
+    yref = cpu_oracle.fir(0, h).step(x)
+    assert y.dtype == np.float32 and len(y) == 500
+    assert rel_err(y, yref, rms(x)) <= TOL
+
+
+def test_fir_impulse_response(tsd):
+    """test_filtre_rif (reference test-filtres.cc:479-511): impulse response equals the taps."""
+    from libtsd_b200 import filtrage as F
+    h = np.arange(1, 32, dtype=np.float32)
+    x = np.zeros(100, np.float32)
+    x[0] = 1
+    y = F.filtre_rif(h, np.float32).step(x)
+    assert len(y) == len(x)
+    assert np.max(np.abs(y[:31] - h)) <= 1e-7 and np.all(y[31:] == 0)
+
+
+@pytest.mark.parametrize("kind,K", [(0, 31), (1, 1), (1, 2), (1, 31), (1, 127), (1, 128), (1, 1000), (2, 63)])
+def test_fir_streaming_blocks(tsd, cpu_oracle, kind, K):
+    """Block-partition independence + state carried across step() (filtre_par_bloc, test-filtres.cc:9-31)."""
+    from libtsd_b200 import filtrage as F
+    rng = np.random.default_rng(100 + K + kind)
+    taps = cn(rng, K) if kind == 2 else rng.standard_normal(K).astype(np.float32)
+    dt = np.float32 if kind == 0 else np.complex64
+    nchan = 3
+    g = F.filtre_rif(taps, dt, nchan)
+    refs = [cpu_oracle.fir(kind, taps) for _ in range(nchan)]
+    for n in (1, 7, 100, 126, 127, 128, 1000, 2304, 2305, 5000, 2):
+        x = rng.standard_normal((nchan, n)).astype(np.float32) if kind == 0 else cn(rng, nchan, n)
+        y = g.step(x)
+        yref = np.stack([r.step(x[c]) for c, r in enumerate(refs)])
+        assert y.shape == (nchan, n)
+        assert rel_err(y, yref, rms(x) * np.sqrt(np.sum(np.abs(taps) ** 2))) <= TOL
+    # bookkeeping: same ring index as the reference object (filtre-rt.cc:89)
+    total = 1 + 7 + 100 + 126 + 127 + 128 + 1000 + 2304 + 2305 + 5000 + 2
+    assert g.index == total % K
+    if hasattr(refs[0], "index"):
+        assert g.index == refs[0].index
+
+
+def test_fir_state_roundtrip_and_inplace(tsd, port):
+    import torch
+    from libtsd_b200 import filtrage as F
+    rng = np.random.default_rng(5)
+    taps = rng.standard_normal(127).astype(np.float32)
+    a = F.filtre_rif(taps, np.complex64, 2)
+    x1, x2 = cn(rng, 2, 777), cn(rng, 2, 4000)
+    a.step(x1)
+    fen, idx = a.get_state()
+    assert idx == 777 % 127
+    # reference ring content (filtre-rt.cc:56-64): fen[(t-1-j) % K] = x[t-1-j]
+    for j in range(127):
+        assert np.array_equal(fen[:, (777 - 1 - j) % 127], x1[:, 777 - 1 - j])
+    b = F.filtre_rif(taps, np.complex64, 2)
+    b.set_state(fen, idx)
+    ya, yb = a.step(x2), b.step(x2)
+    assert np.array_equal(ya, yb)
+    # in place on the device (x.data() == y.data() is allowed by the reference, filtre-rt.cc:76-80)
+    c = F.filtre_rif(taps, np.complex64, 2)
+    c.step(x1)
+    xt = torch.from_numpy(x2).cuda()
+    yt = c.step(xt, out=xt)
+    tsd.synchronize()
+    assert yt.data_ptr() == xt.data_ptr()
+    assert np.array_equal(yt.cpu().numpy(), ya)
+
+
+def test_fir_config3_shape_subset(tsd, cpu_oracle):
+    """BASELINE config 3 shape: 127-tap low-pass, 64 Ki-sample step() blocks, channel subset."""
+    import torch
+    from libtsd_b200 import filtrage as F
+    h = cpu_oracle.design_rif_fen(127, "lp", 0.1)
+    nchan, blocks, bl = 4, 3, 65536
+    rng = np.random.default_rng(0x7D5D0003)
+    x = cn(rng, nchan, blocks * bl)
+    g = F.filtre_rif(h, np.complex64, nchan)
+    xt = torch.from_numpy(x).cuda()
+    yt = torch.empty_like(xt)
+    for b in range(blocks):
+        g.step(xt[:, b * bl:(b + 1) * bl], out=yt[:, b * bl:(b + 1) * bl])
+    tsd.synchronize()
+    y = yt.cpu().numpy()
+    refs = [cpu_oracle.fir(1, h) for _ in range(nchan)]
+    yref = np.stack([np.concatenate([r.step(x[c, b * bl:(b + 1) * bl]) for b in range(blocks)]) for c, r in enumerate(refs)])
+    assert rel_err(y, yref, rms(x)) <= TOL
+
+
+def test_fir_errors(tsd):
+    from libtsd_b200 import filtrage as F
+    with pytest.raises(tsd.TsdGpuError):
+        F.filtre_rif(np.zeros(0, np.float32))
+    f = F.filtre_rif(np.ones(3, np.float32), np.complex64, 2)
+    with pytest.raises(tsd.TsdGpuError):
+        f.step(np.zeros((3, 10), np.complex64))
+    assert f.step(np.zeros((2, 0), np.complex64)).shape == (2, 0)
+
+
+# ------------------------------------------------------------------------------------- FFT
+@pytest.mark.parametrize("n", [1, 2, 4, 8, 16, 128, 1024, 4096, 65536])
+def test_fft_vs_oracle(tsd, cpu_oracle, n):
+    """fft/ifft against the reference plan (sizes of test_fft_valide, test-fourier.cc:263, pow2 subset + 65536)."""
+    from libtsd_b200 import fourier as Fo
+    rng = np.random.default_rng(n)
+    batch = 5 if n < 65536 else 3
+    x = cn(rng, batch, n)
+    plan = Fo.tfrplan_creation(n, batch=batch)
+    ref = cpu_oracle.fft(n)
+    X = plan.step(x, True)
+    Xref = np.stack([ref.step(x[b], True) for b in range(batch)])
+    assert rel_err(X, Xref, rms(x)) <= TOL
+    x2 = plan.step(X, False)
+    x2ref = np.stack([ref.step(Xref[b], False) for b in range(batch)])
+    assert rel_err(x2, x2ref, rms(x)) <= TOL
+    # unitary + round trip (test-fourier.cc:287-312: RMS error <= 5e-6)
+    assert abs(rms(X) / rms(x) - 1) < 1e-5
+    assert rms(x2 - x) / rms(x) <= 5e-6
+
+
+def test_fft_vs_float64_dft(tsd):
+    from libtsd_b200 import fourier as Fo
+    rng = np.random.default_rng(3)
+    x = cn(rng, 2, 65536)
+    X = Fo.fft(x)
+    Xt = np.fft.fft(x.astype(np.complex128), axis=1) / 256.0
+    assert np.max(np.abs(X - Xt)) / rms(Xt) <= 2e-6
+
+
+def test_fft_device_inplace_and_many(tsd):
+    import torch
+    from libtsd_b200 import fourier as Fo
+    rng = np.random.default_rng(4)
+    batch = 200   # more transforms than scratch ring slots: exercises slot reuse
+    x = cn(rng, batch, 65536)
+    xt = torch.from_numpy(x).cuda()
+    plan = Fo.tfrplan_creation(65536, batch=batch)
+    Xt = plan.step(xt, True)
+    back = plan.step(Xt, False, out=Xt)   # in place
+    tsd.synchronize()
+    assert back.data_ptr() == Xt.data_ptr()
+    assert rms(back.cpu().numpy() - x) / rms(x) <= 5e-6
+    Xref = np.fft.fft(x[-1].astype(np.complex128)) / 256.0
+    X1 = plan.step(xt, True)
+    tsd.synchronize()
+    assert np.max(np.abs(X1[-1].cpu().numpy() - Xref)) / rms(Xref) <= 2e-6
+
+
+def test_fft_replan_and_errors(tsd):
+    from libtsd_b200 import fourier as Fo
+    rng = np.random.default_rng(6)
+    p = Fo.tfrplan_creation(16)
+    for n in (16, 64, 16):
+        x = cn(rng, n)
+        X = p.step(x)
+        assert np.max(np.abs(X - np.fft.fft(x.astype(np.complex128)) / np.sqrt(n))) <= 1e-5
+    with pytest.raises(tsd.TsdGpuError):
+        Fo.tfrplan_creation(12)   # non power of two: not in this version
+
+
+# ------------------------------------------------------------------------------------- OLA
+def _ola_pair(cpu_oracle, Ne, nzmin, h, nchan, fir_len):
+    from libtsd_b200 import fourier as Fo
+    N = cpu_oracle.p2((Ne if Ne > 0 else 512) + nzmin)
+    H = cpu_oracle.ola_make_H(h, N) if h is not None else None
+    g, Ng = Fo.filtre_fft(Fo.FiltreFFTConfig(dim_blocs_temporel=Ne, nb_zeros_min=nzmin, H=H, fir_len=fir_len), nchan)
+    refs = [cpu_oracle.ola(Ne, nzmin, H) for _ in range(nchan)]
+    assert Ng == N == refs[0].N
+    return g, refs
+
+
+@pytest.mark.parametrize("Ne,K,fir", [(0, 127, 0), (1500, 127, 0), (4000, 33, 0)])
+def test_ola_small_unfused(tsd, cpu_oracle, Ne, K, fir):
+    rng = np.random.default_rng(Ne + K)
+    h = cpu_oracle.design_rif_fen(K, "lp", 0.1)
+    nchan = 3
+    g, refs = _ola_pair(cpu_oracle, Ne, K, h, nchan, fir)
+    for n in (100, 1000, g.Ne, 5000, 3, 0, 20000):
+        x = cn(rng, nchan, n)
+        y = g.step(x)
+        yref = np.stack([r.step(x[c]) for c, r in enumerate(refs)])
+        assert y.shape == yref.shape          # per-call output length: bit-exact bookkeeping
+        if n:
+            assert rel_err(y, yref, 1.0) <= TOL
+        assert g.residual == refs[0].residual if hasattr(refs[0], "residual") else True
+
+
+@pytest.mark.parametrize("fir", [4095, 0])
+def test_ola_config4_shape(tsd, cpu_oracle, fir):
+    """BASELINE config 4 shape on a channel subset: K = 4095, Ne = 61441, N = 65536, both output forms,
+    one-shot and 64 Ki-chunked (exercises the re-blocking)."""
+    rng = np.random.default_rng(0x7D5D0004 + fir)
+    K, Ne = 4095, 61441
+    h = cpu_oracle.design_rif_fen(K, "lp", 0.1)
+    nchan, n = 2, 400000
+    x = cn(rng, nchan, n)
+    g, refs = _ola_pair(cpu_oracle, Ne, K, h, nchan, fir)
+    assert (g.Ne, g.N, g.N_zeros) == (61441, 65536, 4095)
+    y = g.step(x)
+    yref = np.stack([r.step(x[c]) for c, r in enumerate(refs)])
+    assert y.shape == yref.shape == (nchan, 6 * Ne)
+    assert rel_err(y, yref, rms(x)) <= TOL
+    # delay Ne - K: exact zeros before, FIR output after
+    assert np.all(yref[:, : Ne - K] == 0)
+    assert np.max(np.abs(y[:, : Ne - K])) <= TOL * rms(x)
+    # chunked: per-call lengths 61441 x6 then 0 for the 6784-sample tail
+    g2, refs2 = _ola_pair(cpu_oracle, Ne, K, h, nchan, fir)
+    outs, lens = [], []
+    for i in range(0, n, 65536):
+        o = g2.step(x[:, i:i + 65536])
+        lens.append(o.shape[1])
+        outs.append(o)
+    lens_ref = [len(refs2[0].step(x[0, i:i + 65536])) for i in range(0, n, 65536)]
+    assert lens == lens_ref == [61441] * 6 + [0]
+    y2 = np.concatenate(outs, axis=1)
+    assert rel_err(y2, yref, rms(x)) <= TOL
+
+
+def test_ola_generic_H(tsd, cpu_oracle):
+    """Arbitrary spectral gain (not FIR-derived): true overlap-add semantics must be kept."""
+    from libtsd_b200 import fourier as Fo
+    rng = np.random.default_rng(11)
+    Ne, nz = 61441, 4095
+    N = 65536
+    H = cn(rng, N) * 0.5
+    g, _ = Fo.filtre_fft(Fo.FiltreFFTConfig(Ne, nz, H=H, fir_len=0), 2)
+    refs = [cpu_oracle.ola(Ne, nz, H) for _ in range(2)]
+    for n in (200000, 100000, 50000):
+        x = cn(rng, 2, n)
+        y = g.step(x)
+        yref = np.stack([r.step(x[c]) for c, r in enumerate(refs)])
+        assert y.shape == yref.shape
+        if y.size:
+            assert rel_err(y, yref, rms(yref)) <= TOL
+    # identity callback
+    g, _ = Fo.filtre_fft(Fo.FiltreFFTConfig(Ne, nz), 1)
+    r = cpu_oracle.ola(Ne, nz, None)
+    x = cn(rng, 1, 130000)
+    assert rel_err(g.step(x), r.step(x[0])[None], rms(x)) <= TOL
+
+
+def test_ola_errors(tsd):
+    from libtsd_b200 import fourier as Fo
+    with pytest.raises(tsd.TsdGpuError):
+        Fo.filtre_fft(Fo.FiltreFFTConfig(1000, 127))     # N_zeros > Ne: reference is out of bounds there
+    with pytest.raises(tsd.TsdGpuError):
+        Fo.filtre_fft(Fo.FiltreFFTConfig(512, 127, H=np.zeros(8, np.complex64)))
+
+
+def test_rif_vs_rif_fft(tsd, cpu_oracle):
+    """test_rif_vs_rif_fft (test-filtres.cc:514-554): 127 taps, direct FIR vs FFT FIR after alignment."""
+    from libtsd_b200 import filtrage as F, fourier as Fo
+    rng = np.random.default_rng(12)
+    h = cpu_oracle.design_rif_fen(127, "lp", 0.2)
+    x = cn(rng, 10000)
+    y1 = F.filtre_rif(h, np.complex64).step(x)
+    y2 = Fo.filtre_rif_fft(h).step(x)
+    d = 512 - 127
+    n = len(y2) - d
+    assert np.max(np.abs(y2[d:d + n] - y1[:n])) <= 2e-6 * max(1.0, rms(x))
+
+
+# ------------------------------------------------------------------------------------- resampler
+@pytest.mark.parametrize("ratio,K,fcut", [(147 / 160, 64, 0.4), (1.5, 127, 0.5), (0.5, 15, 0.25), (1.9999, 15, 0.4),
+                                          (np.pi / 2, 31, 0.4), (1.0, 15, 0.4), (0.3, 16, 0.15), (3.7, 8, 0.4)])
+def test_itrp_vs_oracle(tsd, port, cpu_oracle, ratio, K, fcut):
+    """filtre_itrp with a sinc LUT: output counts / phase bit-exact, samples within tolerance, any block partition."""
+    from libtsd_b200 import filtrage as F
+    rng = np.random.default_rng(int(ratio * 1000) + K)
+    lut = cpu_oracle.itrp_sinc_lut(K, 256, fcut)
+    nchan = 3
+    g = F.filtre_itrp(ratio, F.InterpolateurLUT(lut), nchan)
+    refs = [port.itrp(ratio, lut, 256) for _ in range(nchan)]
+    for n in (1, 10, 1000, 65536, 0, 777, 3):
+        x = cn(rng, nchan, n)
+        y = g.step(x)
+        yref = np.stack([r.step(x[c]) for c, r in enumerate(refs)]) if n else np.zeros((nchan, 0), np.complex64)
+        assert y.shape == yref.shape
+        if y.size:
+            assert rel_err(y, yref, max(rms(x), 1e-3) * np.sqrt(K)) <= TOL
+        assert np.float32(g.phase) == np.float32(refs[0].phase)
+
+
+def test_itrp_vs_reference_object(tsd, ref):
+    """Same comparison against the reference's own filtre_itrp + itrp_sinc objects (config 5 parameters)."""
+    from libtsd_b200 import filtrage as F
+    rng = np.random.default_rng(0x7D5D0005)
+    g = F.filtre_itrp(147.0 / 160.0, F.itrp_sinc(F.InterpolateurSincConfig(64, 256, 0.4, "hn")), 2)
+    refs = [ref.itrp(147.0 / 160.0, 64, 256, 0.4) for _ in range(2)]
+    lens = []
+    for _ in range(3):
+        x = cn(rng, 2, 65536)
+        y = g.step(x)
+        yref = np.stack([r.step(x[c]) for c, r in enumerate(refs)])
+        lens.append(y.shape[1])
+        assert y.shape == yref.shape
+        assert rel_err(y, yref, rms(x)) <= TOL
+    assert lens == [60212, 60211, 60211]
+
+
+def test_reechan_stock(tsd, cpu_oracle):
+    """resample()/rééchan for a ratio in [0.5, 2): 15 taps x 257 phases, fcut = min(0.4, r/2) (ra.cc:136-152)."""
+    from libtsd_b200 import filtrage as F
+    rng = np.random.default_rng(13)
+    x = cn(rng, 50000)
+    y = F.reechan(x, 147.0 / 160.0)
+    if hasattr(cpu_oracle, "reechan"):
+        yref = cpu_oracle.reechan(147.0 / 160.0).step(x)
+        assert y.shape == yref.shape
+        assert rel_err(y, yref, rms(x)) <= TOL
+    assert abs(len(y) - 50000 * 147 / 160) <= 2
+    assert np.array_equal(F.reechan(x, 1.0), x)
