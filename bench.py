@@ -357,6 +357,9 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     import libtsd_b200
     libtsd_b200.init(local_rank)
+    # every launch of the library and the timing events go to ONE explicit (non-default) stream
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     libtsd_b200.use_torch_stream()
 
     wl = GpuWorkload(args.workload, args.scale)
@@ -377,10 +380,10 @@ def main():
     libtsd_b200._lib.timing_enable(True)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    ev0.record()
+    ev0.record(stream)
     for _ in range(args.steps):
         wl.step()
-    ev1.record()
+    ev1.record(stream)
     barrier()
     elapsed_ms = ev0.elapsed_time(ev1)
     kern_ms, kern_launches = libtsd_b200._lib.timing_read()

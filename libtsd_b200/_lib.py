@@ -89,7 +89,11 @@ def init(device: int = 0) -> None:
 def use_torch_stream() -> None:
     """Enqueue the library's launches on torch's current CUDA stream."""
     import torch
-    check(lib().tsdgpu_set_stream(_vp(torch.cuda.current_stream().cuda_stream)))
+    h = torch.cuda.current_stream().cuda_stream
+    if not h:
+        raise TsdGpuError("use_torch_stream: torch's current stream is the legacy default stream (handle 0), which the "
+                          "C ABI reads as 'library stream'; make a torch.cuda.Stream() current first")
+    check(lib().tsdgpu_set_stream(_vp(h)))
 
 
 def synchronize() -> None:

@@ -71,78 +71,66 @@ struct Fft64kParams
 constexpr int FFT_NT = 256;
 
 template<bool INV>
-__global__ void __launch_bounds__(FFT_NT, 2) fft64k_kernel(Fft64kParams p)
+__global__ void __launch_bounds__(FFT_NT, 3) fft64k_kernel(Fft64kParams p)
 {
   __shared__ float2 sm[4096];
-  __shared__ unsigned s_ticket;
+  __shared__ float2 tw[256];
+  __shared__ unsigned s_ticket[2];
   const int tid = threadIdx.x, hi = tid >> 4, lo = tid & 15;
   const float inv256 = 1.0f / 256.0f;
-  const float2 w256_hi = twiddle<false>((unsigned) hi, 2.0f / 256.0f);
-  const float2 w256_lo = twiddle<false>((unsigned) lo, 2.0f / 256.0f);
   const unsigned total = (unsigned) (p.batch + p.lag) * 32u;
+  const unsigned full = 16u * ITEM_WARPS;
+  fill_tw256(tw, tid);
+  if(tid == 0) s_ticket[0] = atomicAdd(p.ticket, 1u);
+  __syncthreads();
 
-  for(;;)
+  for(int it = 0;; it ^= 1)
   {
-    __syncthreads();   // previous item's shared-memory reads are finished
-    if(tid == 0) s_ticket = atomicAdd(p.ticket, 1u);
-    __syncthreads();
-    const unsigned ticket = s_ticket;
+    const unsigned ticket = s_ticket[it];
     if(ticket >= total) break;
-    const int s = (int) (ticket >> 5), sub = (int) (ticket & 31u);
-    const int g = sub & 15;
-    if(sub < 16)
+    const int s = (int) (ticket >> 5), sub = (int) (ticket & 31u), g = sub & 15;
+    const bool is_a = sub < 16;
+    const int t = is_a ? s : s - p.lag;
+    const bool valid = t >= 0 && t < p.batch;
+    if(tid == 0)
+    {
+      s_ticket[it ^ 1] = atomicAdd(p.ticket, 1u);   // next item, fetched early
+      if(valid)
+      {
+        if(!is_a) spin_until(p.done_a + t, full);                       // all 16 column tiles written
+        else if(t >= p.ring) spin_until(p.done_b + (t - p.ring), full); // ring slot free again
+      }
+    }
+    __syncthreads();
+    if(!valid) continue;
+    float2 v[16];
+    if(is_a)
     {
       // ---- stage A: columns n2 in [16g, 16g+16), transform over n1
-      const int t = s;
-      if(t >= p.batch) continue;
-      if(t >= p.ring)
-      {
-        if(tid == 0)
-          while(ld_acquire(p.done_b + (t - p.ring)) < 16u) __nanosleep(64);
-        __syncthreads();
-      }
-      const float2 *x = p.x + (long long) t * p.x_stride + 16 * g + lo;
-      float2 v[16];
+      const float2 *x = p.x + (long long) t * p.x_stride + hi * 256 + 16 * g + lo;
 #pragma unroll
-      for(int j = 0; j < 16; j++) v[j] = ldg_stream(x + (16 * j + hi) * 256);
-      fft256_cols<INV>(v, sm, hi, lo, w256_hi);
+      for(int j = 0; j < 16; j++) v[j] = ldg_stream(x + j * 4096);
+      fft256_cols<INV>(v, sm, tw, hi, lo);
       // v[p2] = Y[k1 = hi + 16 p2][n2]; four-step twiddle W_N^(n2*k1)
       const unsigned n2 = (unsigned) (16 * g + lo);
       mul_geometric(v, twiddle<INV>(n2 * (unsigned) hi, 2.0f / 65536.0f), twiddle<INV>(16u * n2, 2.0f / 65536.0f));
-      float2 *sc = p.scratch + (long long) (t % p.ring) * 65536 + 16 * g + lo;
+      float2 *sc = p.scratch + (long long) (t % p.ring) * 65536 + hi * 256 + 16 * g + lo;
 #pragma unroll
-      for(int p2 = 0; p2 < 16; p2++) sc[(hi + 16 * p2) * 256] = v[p2];
-      __syncthreads();
-      if(tid == 0)
-      {
-        __threadfence();
-        red_release_add(p.done_a + t, 1u);
-      }
+      for(int p2 = 0; p2 < 16; p2++) sc[p2 * 4096] = v[p2];
+      warp_release(p.done_a + t);
     }
     else
     {
       // ---- stage B: rows k1 in [16g, 16g+16), transform over n2, natural-order output
-      const int t = s - p.lag;
-      if(t < 0 || t >= p.batch) continue;
-      if(tid == 0)
-        while(ld_acquire(p.done_a + t) < 16u) __nanosleep(64);
-      __syncthreads();
       const float2 *sc = p.scratch + (long long) (t % p.ring) * 65536 + (16 * g + hi) * 256 + lo;
-      float2 v[16];
 #pragma unroll
       for(int j = 0; j < 16; j++) v[j] = __ldcg(sc + 16 * j);
-      fft256_rows_a<INV>(v, sm, hi, lo, w256_lo);
+      fft256_rows_a<INV>(v, sm, tw, hi, lo);
       // thread (hi = k', lo = r): v[k2] = X[(16g + r) + 256*(k' + 16*k2)]
-      float2 *y = p.y + (long long) t * p.y_stride + 16 * g + lo;
+      float2 *y = p.y + (long long) t * p.y_stride + hi * 256 + 16 * g + lo;
 #pragma unroll
-      for(int k2 = 0; k2 < 16; k2++)
-        stg_stream(y + (hi + 16 * k2) * 256, make_float2(v[k2].x * inv256, v[k2].y * inv256));
-      __syncthreads();
-      if(tid == 0)
-      {
-        __threadfence();
-        red_release_add(p.done_b + t, 1u);
-      }
+      for(int k2 = 0; k2 < 16; k2++) stg_stream(y + k2 * 4096, make_float2(v[k2].x * inv256, v[k2].y * inv256));
+      warp_release(p.done_b + t);
     }
   }
 }

@@ -11,8 +11,9 @@
 //
 // Arithmetic: the reference computes a unitary radix-2 DFT in float32 with double-generated
 // twiddles (fourier.cc:32-46,61-121).  Here the same DFT is evaluated with radix-16 butterflies;
-// twiddles come from sincospif on exact dyadic angles and short power trees (depth <= 4), so the
-// result differs from the reference by float rounding only (tests: <= 1e-5 of signal RMS).
+// local twiddles come from a 256-entry shared table (sincospif on exact dyadic angles), the W_N
+// four-step twiddles from sincospif + a power tree of depth <= 4, so the result differs from the
+// reference by float rounding only (tests: <= 1e-5 of signal RMS).
 #pragma once
 #include "common.cuh"
 
@@ -93,48 +94,52 @@ template<bool INV> __device__ __forceinline__ void fft16(float2 (&v)[16])
 #undef TSD_SWAP
 }
 
-// v[k] *= base * step^k for k = 0..15 (power tree, depth <= 4)
+// v[k] *= base * step^k for k = 0..15.  Power tree of depth <= 4 arranged so that only a handful of
+// temporaries are live at a time (register pressure decides the CTAs per SM).
 __device__ __forceinline__ void mul_geometric(float2 (&v)[16], float2 base, float2 step)
 {
-  float2 s2 = cmul(step, step), s4 = cmul(s2, s2), s8 = cmul(s4, s4);
-  float2 t[16];
+  const float2 s2 = cmul(step, step), s4 = cmul(s2, s2), s8 = cmul(s4, s4);
+  float2 t[4];
   t[0] = base;
-  t[1] = cmul(t[0], step);
-  t[2] = cmul(t[0], s2);
+  t[1] = cmul(base, step);
+  t[2] = cmul(base, s2);
   t[3] = cmul(t[1], s2);
 #pragma unroll
-  for(int k = 0; k < 4; k++) t[4 + k] = cmul(t[k], s4);
-#pragma unroll
-  for(int k = 0; k < 8; k++) t[8 + k] = cmul(t[k], s8);
-#pragma unroll
-  for(int k = 0; k < 16; k++) v[k] = cmul(v[k], t[k]);
+  for(int i = 0; i < 4; i++)
+  {
+    v[i] = cmul(v[i], t[i]);
+    v[4 + i] = cmul(v[4 + i], cmul(t[i], s4));
+    const float2 u = cmul(t[i], s8);
+    v[8 + i] = cmul(v[8 + i], u);
+    v[12 + i] = cmul(v[12 + i], cmul(u, s4));
+  }
 }
-// v[k] *= step^k for k = 0..15
-__device__ __forceinline__ void mul_powers(float2 (&v)[16], float2 step)
+
+// Local twiddles of a 256-point transform from the shared table tw[k*16 + i] = exp(-2 pi i * i*k / 256),
+// i, k in [0,16): v[k] *= tw[k][idx] (conjugated for the inverse).  For a fixed k the 16 lanes of a
+// half-warp read either one entry (idx = hi: broadcast) or 16 consecutive entries (idx = lo).
+template<bool INV> __device__ __forceinline__ void mul_table(float2 (&v)[16], const float2 *tw, int idx)
 {
-  float2 s2 = cmul(step, step), s4 = cmul(s2, s2), s8 = cmul(s4, s4);
-  float2 t[16];
-  t[1] = step;
-  t[2] = s2;
-  t[3] = cmul(step, s2);
-  t[4] = s4;
 #pragma unroll
-  for(int k = 1; k < 4; k++) t[4 + k] = cmul(t[k], s4);
-  t[8] = s8;
-#pragma unroll
-  for(int k = 1; k < 8; k++) t[8 + k] = cmul(t[k], s8);
-#pragma unroll
-  for(int k = 1; k < 16; k++) v[k] = cmul(v[k], t[k]);
+  for(int k = 1; k < 16; k++)
+  {
+    const float2 w = tw[k * 16 + idx];
+    v[k] = INV ? cmulc(v[k], w) : cmul(v[k], w);
+  }
+}
+__device__ __forceinline__ void fill_tw256(float2 *tw, int tid)
+{
+  // 256 threads, one entry each: tw[k*16 + i] = W256^(i*k)
+  tw[tid] = twiddle<false>((unsigned) ((tid >> 4) * (tid & 15)), 2.0f / 256.0f);
 }
 
 // ---- 256-point transform, COLS pattern -------------------------------------------------------
 // in : thread (hi = tid>>4, lo = tid&15) holds v[j] = x_lo[16*j + hi]
 // out: thread (hi, lo) holds v[k2] = X_lo[hi + 16*k2]
-// w256_hi = exp(-2 pi i hi / 256) (forward value; conjugated here when INV)
-template<bool INV> __device__ __forceinline__ void fft256_cols(float2 (&v)[16], float2 *sm, int hi, int lo, float2 w256_hi)
+template<bool INV> __device__ __forceinline__ void fft256_cols(float2 (&v)[16], float2 *sm, const float2 *tw, int hi, int lo)
 {
   fft16<INV>(v);
-  mul_powers(v, INV ? make_float2(w256_hi.x, -w256_hi.y) : w256_hi);   // W256^(hi*k1)
+  mul_table<INV>(v, tw, hi);   // W256^(hi*k1)
 #pragma unroll
   for(int k1 = 0; k1 < 16; k1++) sm[(hi * 16 + k1) * 16 + lo] = v[k1];
   __syncthreads();
@@ -146,11 +151,10 @@ template<bool INV> __device__ __forceinline__ void fft256_cols(float2 (&v)[16], 
 // ---- 256-point transform, ROWS pattern -------------------------------------------------------
 // in : thread (hi = row r, lo = b) holds v[j] = x_r[16*j + b]
 // out: thread (hi = k1, lo = row r) holds v[k2] = X_r[k1 + 16*k2]
-// w256_lo = exp(-2 pi i lo / 256)
-template<bool INV> __device__ __forceinline__ void fft256_rows_a(float2 (&v)[16], float2 *sm, int hi, int lo, float2 w256_lo)
+template<bool INV> __device__ __forceinline__ void fft256_rows_a(float2 (&v)[16], float2 *sm, const float2 *tw, int hi, int lo)
 {
   fft16<INV>(v);
-  mul_powers(v, INV ? make_float2(w256_lo.x, -w256_lo.y) : w256_lo);   // W256^(b*k1)
+  mul_table<INV>(v, tw, lo);   // W256^(b*k1)
 #pragma unroll
   for(int k1 = 0; k1 < 16; k1++) sm[k1 * 256 + lo * 16 + ((hi + lo) & 15)] = v[k1];
   __syncthreads();
@@ -160,17 +164,34 @@ template<bool INV> __device__ __forceinline__ void fft256_rows_a(float2 (&v)[16]
 }
 // in : thread (hi = k1, lo = row r) holds v[k2] = X_r[k1 + 16*k2]
 // out: thread (hi = row r, lo = q) holds v[p] = x_r[16*p + q]
-// w256_hi = exp(-2 pi i hi / 256)
-template<bool INV> __device__ __forceinline__ void fft256_rows_b(float2 (&v)[16], float2 *sm, int hi, int lo, float2 w256_hi)
+template<bool INV> __device__ __forceinline__ void fft256_rows_b(float2 (&v)[16], float2 *sm, const float2 *tw, int hi, int lo)
 {
-  fft16<INV>(v);                                                       // over k2 -> q
-  mul_powers(v, INV ? make_float2(w256_hi.x, -w256_hi.y) : w256_hi);   // W256^(k1*q)
+  fft16<INV>(v);               // over k2 -> q
+  mul_table<INV>(v, tw, hi);   // W256^(k1*q)
 #pragma unroll
   for(int q = 0; q < 16; q++) sm[hi * 256 + q * 16 + ((lo + q) & 15)] = v[q];
   __syncthreads();
 #pragma unroll
   for(int k1 = 0; k1 < 16; k1++) v[k1] = sm[k1 * 256 + lo * 16 + ((hi + lo) & 15)];
-  fft16<INV>(v);                                                       // over k1 -> p
+  fft16<INV>(v);               // over k1 -> p
+}
+
+// ---- persistent-kernel plumbing ---------------------------------------------------------------
+// Every warp publishes its own completion (its stores -> __syncwarp -> fence -> red.release), so no
+// CTA-wide barrier is needed at the end of an item; a finished item counts ITEM_WARPS per tile.
+constexpr unsigned ITEM_WARPS = 8;
+__device__ __forceinline__ void warp_release(unsigned *flag)
+{
+  __syncwarp();
+  if((threadIdx.x & 31) == 0)
+  {
+    __threadfence();
+    red_release_add(flag, 1u);
+  }
+}
+__device__ __forceinline__ void spin_until(const unsigned *flag, unsigned target)
+{
+  while(ld_acquire(flag) < target) __nanosleep(32);
 }
 
 } // namespace tsdgpu

@@ -60,110 +60,111 @@ __device__ __forceinline__ void red_add_f2(float2 *p, float2 v)
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(&p->y), "f"(v.y) : "memory");
 }
 
-__global__ void __launch_bounds__(OLA_NT, 2) ola64k_kernel(OlaParams p)
+__global__ void __launch_bounds__(OLA_NT, 3) ola64k_kernel(OlaParams p)
 {
   __shared__ float2 sm[4096];
-  __shared__ unsigned s_ticket;
+  __shared__ float2 tw[256];
+  __shared__ unsigned s_ticket[2];
   const int tid = threadIdx.x, hi = tid >> 4, lo = tid & 15;
-  const float2 w256_hi = twiddle<false>((unsigned) hi, 2.0f / 256.0f);
-  const float2 w256_lo = twiddle<false>((unsigned) lo, 2.0f / 256.0f);
   const unsigned total = (unsigned) (p.Q + 2 * p.lag) * 48u;
+  const unsigned full = 16u * ITEM_WARPS;
+  fill_tw256(tw, tid);
+  if(tid == 0) s_ticket[0] = atomicAdd(p.ticket, 1u);
+  __syncthreads();
 
-  for(;;)
+  for(int it = 0;; it ^= 1)
   {
-    __syncthreads();
-    if(tid == 0) s_ticket = atomicAdd(p.ticket, 1u);
-    __syncthreads();
-    const unsigned ticket = s_ticket;
+    const unsigned ticket = s_ticket[it];
     if(ticket >= total) break;
     const int s = (int) (ticket / 48u), sub = (int) (ticket - (unsigned) s * 48u);
     const int g = sub & 15, stage = sub >> 4;
     const int q = s - stage * p.lag;
-    if(q < 0 || q >= p.Q) continue;
+    const bool valid = q >= 0 && q < p.Q;
+    if(tid == 0)
+    {
+      s_ticket[it ^ 1] = atomicAdd(p.ticket, 1u);   // next item, fetched early
+      if(valid)
+      {
+        if(stage == 1) spin_until(p.done_a + q, full);
+        else if(stage == 2) spin_until(p.done_b + q, full);
+        else if(q >= p.ring) spin_until(p.done_c + (q - p.ring), full);   // ring slot free again
+      }
+    }
+    __syncthreads();
+    if(!valid) continue;
     const int chan = q / p.nblocks, blk = q - chan * p.nblocks;
     float2 *sc = p.scratch + (long long) (q % p.ring) * 65536;
     float2 v[16];
 
     if(stage == 0)
     {
-      if(q >= p.ring)
-      {
-        if(tid == 0)
-          while(ld_acquire(p.done_c + (q - p.ring)) < 16u) __nanosleep(64);
-        __syncthreads();
-      }
       // window element n sits at position pos0 + n relative to x[0]
       const long long pos0 = (long long) blk * p.Ne - p.residual + p.base_off;
       const float2 *x = p.x + (long long) chan * p.x_stride;
-      const float2 *cr = p.carry + (long long) chan * p.carry_len + p.carry_len;
-#pragma unroll
-      for(int j = 0; j < 16; j++)
+      const int n0 = hi * 256 + 16 * g + lo;
+      if(pos0 >= 0 && p.zero_below == 0)
       {
-        const int n = (16 * j + hi) * 256 + 16 * g + lo;
-        const long long pos = pos0 + n;
-        float2 val = make_float2(0.f, 0.f);
-        if(n >= p.zero_below) val = (pos >= 0) ? ldg_stream(x + pos) : __ldg(cr + pos);
-        v[j] = val;
+        const float2 *xw = x + pos0 + n0;
+#pragma unroll
+        for(int j = 0; j < 16; j++) v[j] = ldg_stream(xw + j * 4096);
       }
-      fft256_cols<false>(v, sm, hi, lo, w256_hi);
+      else
+      {
+        // block at the start of the call: part of the window is carried history or zero padding
+        const float2 *cr = p.carry + (long long) chan * p.carry_len + p.carry_len;
+#pragma unroll
+        for(int j = 0; j < 16; j++)
+        {
+          const int n = n0 + j * 4096;
+          const long long pos = pos0 + n;
+          float2 val = make_float2(0.f, 0.f);
+          if(n >= p.zero_below) val = (pos >= 0) ? ldg_stream(x + pos) : __ldg(cr + pos);
+          v[j] = val;
+        }
+      }
+      fft256_cols<false>(v, sm, tw, hi, lo);
       const unsigned n2 = (unsigned) (16 * g + lo);
       mul_geometric(v, twiddle<false>(n2 * (unsigned) hi, 2.0f / 65536.0f), twiddle<false>(16u * n2, 2.0f / 65536.0f));
+      float2 *dst = sc + n0;
 #pragma unroll
-      for(int p2 = 0; p2 < 16; p2++) sc[(hi + 16 * p2) * 256 + 16 * g + lo] = v[p2];
-      __syncthreads();
-      if(tid == 0)
-      {
-        __threadfence();
-        red_release_add(p.done_a + q, 1u);
-      }
+      for(int p2 = 0; p2 < 16; p2++) dst[p2 * 4096] = v[p2];
+      warp_release(p.done_a + q);
     }
     else if(stage == 1)
     {
-      if(tid == 0)
-        while(ld_acquire(p.done_a + q) < 16u) __nanosleep(64);
-      __syncthreads();
       float2 *row = sc + (16 * g + hi) * 256 + lo;
 #pragma unroll
       for(int j = 0; j < 16; j++) v[j] = __ldcg(row + 16 * j);
-      fft256_rows_a<false>(v, sm, hi, lo, w256_lo);
+      fft256_rows_a<false>(v, sm, tw, hi, lo);
       // thread (hi = k', lo = r): v[k2] = X[k], k = (16g + r) + 256*(k' + 16*k2)
-      const float2 *H = p.H + 16 * g + lo;
+      const float2 *H = p.H + hi * 256 + 16 * g + lo;
 #pragma unroll
-      for(int k2 = 0; k2 < 16; k2++) v[k2] = cmul(v[k2], __ldg(H + (hi + 16 * k2) * 256));
+      for(int k2 = 0; k2 < 16; k2++) v[k2] = cmul(v[k2], __ldg(H + k2 * 4096));
       __syncthreads();   // exchange buffer is reused
-      fft256_rows_b<true>(v, sm, hi, lo, w256_hi);
+      fft256_rows_b<true>(v, sm, tw, hi, lo);
       // thread (hi = r, lo = q'): v[pp] = b[k1 = 16g + r][n2 = 16*pp + q']; conj four-step twiddle
       const unsigned k1 = (unsigned) (16 * g + hi);
       mul_geometric(v, twiddle<true>(k1 * (unsigned) lo, 2.0f / 65536.0f), twiddle<true>(16u * k1, 2.0f / 65536.0f));
 #pragma unroll
       for(int pp = 0; pp < 16; pp++) row[16 * pp] = v[pp];
-      __syncthreads();
-      if(tid == 0)
-      {
-        __threadfence();
-        red_release_add(p.done_b + q, 1u);
-      }
+      warp_release(p.done_b + q);
     }
     else
     {
-      if(tid == 0)
-        while(ld_acquire(p.done_b + q) < 16u) __nanosleep(64);
-      __syncthreads();
-      const float2 *col = sc + 16 * g + lo;
+      const float2 *col = sc + hi * 256 + 16 * g + lo;
 #pragma unroll
-      for(int j = 0; j < 16; j++) v[j] = __ldcg(col + (16 * j + hi) * 256);
-      fft256_cols<true>(v, sm, hi, lo, w256_hi);
+      for(int j = 0; j < 16; j++) v[j] = __ldcg(col + j * 4096);
+      fft256_cols<true>(v, sm, tw, hi, lo);
       // thread (hi = p1, lo): v[p2] = x2[256*(p1 + 16*p2) + 16g + lo]
       float2 *y = p.y + (long long) chan * p.y_stride;
+      const int j0 = hi * 256 + 16 * g + lo;
       if(!p.ola_form)
       {
-        float2 *yb = y + (long long) blk * p.Ne;
+        const int i0 = j0 - p.out_shift;
+        float2 *yb = y + (long long) blk * p.Ne + i0;
 #pragma unroll
         for(int p2 = 0; p2 < 16; p2++)
-        {
-          const int i = (hi + 16 * p2) * 256 + 16 * g + lo - p.out_shift;
-          if(i >= 0 && i < p.Ne) stg_stream(yb + i, v[p2]);
-        }
+          if((unsigned) (i0 + p2 * 4096) < (unsigned) p.Ne) stg_stream(yb + p2 * 4096, v[p2]);
       }
       else
       {
@@ -172,7 +173,7 @@ __global__ void __launch_bounds__(OLA_NT, 2) ola64k_kernel(OlaParams p)
 #pragma unroll
         for(int p2 = 0; p2 < 16; p2++)
         {
-          const int j = (hi + 16 * p2) * 256 + 16 * g + lo;
+          const int j = j0 + p2 * 4096;
           if(j < p.Nz)
             red_add_f2(y + (long long) blk * p.Ne + (p.Ne - p.Nz) + j, v[p2]);   // tail of block blk
           else if(last)
@@ -183,12 +184,7 @@ __global__ void __launch_bounds__(OLA_NT, 2) ola64k_kernel(OlaParams p)
             red_add_f2(y + (long long) (blk + 1) * p.Ne + (j - p.Nz), v[p2]);     // meets head of block blk+1
         }
       }
-      __syncthreads();
-      if(tid == 0)
-      {
-        __threadfence();
-        red_release_add(p.done_c + q, 1u);
-      }
+      warp_release(p.done_c + q);
     }
   }
 }
