@@ -71,87 +71,69 @@ struct Fft64kParams
 
 constexpr int FFT_NT = 256;
 
-template<bool INV> struct Fft64kPolicy
+template<bool INV>
+__global__ void __launch_bounds__(FFT_NT, 3) fft64k_kernel(Fft64kParams p)
 {
-  const Fft64kParams &p;
-  __device__ explicit Fft64kPolicy(const Fft64kParams &q) : p(q) {}
-  struct Item
+  __shared__ float2 sm[4096];
+  __shared__ float2 tw[256];
+  __shared__ unsigned s_ticket[2];
+  const int tid = threadIdx.x, hi = tid >> 4, lo = tid & 15;
+  const float inv256 = 1.0f / 256.0f;
+  const unsigned total = (unsigned) (p.batch + p.lag) * 32u;
+  const unsigned full = 16u * ITEM_WARPS;
+  fill_tw256(tw, tid);
+  if(tid == 0) s_ticket[0] = atomicAdd(p.ticket, 1u);
+  __syncthreads();
+
+  for(int it = 0;; it ^= 1)
   {
-    bool valid, is_a;
-    int t, g;
-  };
-  __device__ __forceinline__ Item decode(unsigned ticket) const
-  {
-    Item i;
-    const int s = (int) (ticket >> 5), sub = (int) (ticket & 31u);
-    i.g = sub & 15;
-    i.is_a = sub < 16;
-    i.t = i.is_a ? s : s - p.lag;
-    i.valid = i.t >= 0 && i.t < p.batch;
-    return i;
-  }
-  __device__ __forceinline__ const unsigned *dependency(const Item &i) const
-  {
-    if(!i.is_a) return p.done_a + i.t;                        // all 16 column tiles written
-    if(i.t >= p.ring) return p.done_b + (i.t - p.ring);       // ring slot free again
-    return nullptr;
-  }
-  __device__ __forceinline__ void fetch(const Item &i, float2 *st, int tid) const
-  {
-    const int hi = tid >> 4, lo = tid & 15;
-    if(i.is_a)
+    const unsigned ticket = s_ticket[it];
+    if(ticket >= total) break;
+    const int s = (int) (ticket >> 5), sub = (int) (ticket & 31u), g = sub & 15;
+    const bool is_a = sub < 16;
+    const int t = is_a ? s : s - p.lag;
+    const bool valid = t >= 0 && t < p.batch;
+    if(tid == 0)
     {
-      const float2 *x = p.x + (long long) i.t * p.x_stride + hi * 256 + 16 * i.g + lo;
-#pragma unroll
-      for(int j = 0; j < 16; j++) cp_async8(st + j * 256 + tid, x + j * 4096);
+      s_ticket[it ^ 1] = atomicAdd(p.ticket, 1u);   // next item, fetched early
+      if(valid)
+      {
+        if(!is_a) spin_until(p.done_a + t, full);                       // all 16 column tiles written
+        else if(t >= p.ring) spin_until(p.done_b + (t - p.ring), full); // ring slot free again
+      }
     }
-    else
-    {
-      const float2 *sc = p.scratch + (long long) (i.t % p.ring) * 65536 + (16 * i.g + hi) * 256 + lo;
-#pragma unroll
-      for(int j = 0; j < 16; j++) cp_async8(st + j * 256 + tid, sc + 16 * j);
-    }
-  }
-  __device__ __forceinline__ unsigned *process(const Item &i, float2 (&v)[16], float2 *sm, const float2 *tw, int tid,
-                                               unsigned *pending) const
-  {
-    const int hi = tid >> 4, lo = tid & 15, g = i.g;
-    if(i.is_a)
+    __syncthreads();
+    if(!valid) continue;
+    float2 v[16];
+    if(is_a)
     {
       // ---- stage A: columns n2 in [16g, 16g+16), transform over n1
+      const float2 *x = p.x + (long long) t * p.x_stride + hi * 256 + 16 * g + lo;
+#pragma unroll
+      for(int j = 0; j < 16; j++) v[j] = ldg_stream(x + j * 4096);
       fft256_cols<INV>(v, sm, tw, hi, lo);
       // v[p2] = Y[k1 = hi + 16 p2][n2]; four-step twiddle W_N^(n2*k1)
       const unsigned n2 = (unsigned) (16 * g + lo);
       mul_geometric(v, twiddle<INV>(n2 * (unsigned) hi, 2.0f / 65536.0f), twiddle<INV>(16u * n2, 2.0f / 65536.0f));
-      if(pending) warp_release(pending);
-      float2 *sc = p.scratch + (long long) (i.t % p.ring) * 65536 + hi * 256 + 16 * g + lo;
+      float2 *sc = p.scratch + (long long) (t % p.ring) * 65536 + hi * 256 + 16 * g + lo;
 #pragma unroll
       for(int p2 = 0; p2 < 16; p2++) sc[p2 * 4096] = v[p2];
-      return p.done_a + i.t;
+      warp_release(p.done_a + t);
     }
-    // ---- stage B: rows k1 in [16g, 16g+16), transform over n2, natural-order output
-    fft256_rows_a<INV>(v, sm, tw, hi, lo);
-    // thread (hi = k', lo = r): v[k2] = X[(16g + r) + 256*(k' + 16*k2)]
-    if(pending) warp_release(pending);
-    const float inv256 = 1.0f / 256.0f;
-    float2 *y = p.y + (long long) i.t * p.y_stride + hi * 256 + 16 * g + lo;
+    else
+    {
+      // ---- stage B: rows k1 in [16g, 16g+16), transform over n2, natural-order output
+      const float2 *sc = p.scratch + (long long) (t % p.ring) * 65536 + (16 * g + hi) * 256 + lo;
 #pragma unroll
-    for(int k2 = 0; k2 < 16; k2++) stg_stream(y + k2 * 4096, make_float2(v[k2].x * inv256, v[k2].y * inv256));
-    return p.done_b + i.t;
+      for(int j = 0; j < 16; j++) v[j] = __ldcg(sc + 16 * j);
+      fft256_rows_a<INV>(v, sm, tw, hi, lo);
+      // thread (hi = k', lo = r): v[k2] = X[(16g + r) + 256*(k' + 16*k2)]
+      float2 *y = p.y + (long long) t * p.y_stride + hi * 256 + 16 * g + lo;
+#pragma unroll
+      for(int k2 = 0; k2 < 16; k2++) stg_stream(y + k2 * 4096, make_float2(v[k2].x * inv256, v[k2].y * inv256));
+      warp_release(p.done_b + t);
+    }
   }
-};
-
-constexpr int TILE_SMEM_BYTES = (4096 + 4096 + 256) * (int) sizeof(float2);
-
-template<bool INV>
-__global__ void __launch_bounds__(FFT_NT, 3) fft64k_kernel(Fft64kParams p)
-{
-  extern __shared__ __align__(16) float2 dyn_smem[];
-  __shared__ unsigned s_ticket[2], s_ready[2];
-  float2 *sm = dyn_smem, *staging = dyn_smem + 4096, *tw = dyn_smem + 8192;
-  fill_tw256(tw, threadIdx.x);
-  Fft64kPolicy<INV> pol(p);
-  run_items(pol, p.ticket, (unsigned) (p.batch + p.lag) * 32u, sm, staging, tw, s_ticket, s_ready);
 }
 
 } // namespace tsdgpu
@@ -189,10 +171,8 @@ int fft_plan_create(int n, int batch, tsdgpu_fft_s **out)
       return fail("tsdgpu_fft_plan: out of device memory");
     }
     int occ_f = 0, occ_i = 0;
-    cudaFuncSetAttribute(fft64k_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES);
-    cudaFuncSetAttribute(fft64k_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, fft64k_kernel<false>, FFT_NT, TILE_SMEM_BYTES);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_i, fft64k_kernel<true>, FFT_NT, TILE_SMEM_BYTES);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, fft64k_kernel<false>, FFT_NT, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_i, fft64k_kernel<true>, FFT_NT, 0);
     p->ctas = rt().num_sms * std::max(1, std::min(occ_f, occ_i));
   }
   *out = p;
@@ -254,8 +234,8 @@ int fft_exec_device(tsdgpu_fft_s *p, const float2 *x, long long xs, float2 *y, l
     const int grid = std::min(p->ctas, (batch + p->lag) * 32);
     {
       KernelTimer timer;
-      if(forward) fft64k_kernel<false><<<grid, FFT_NT, TILE_SMEM_BYTES, r.stream>>>(q);
-      else fft64k_kernel<true><<<grid, FFT_NT, TILE_SMEM_BYTES, r.stream>>>(q);
+      if(forward) fft64k_kernel<false><<<grid, FFT_NT, 0, r.stream>>>(q);
+      else fft64k_kernel<true><<<grid, FFT_NT, 0, r.stream>>>(q);
       TSD_LAUNCH_CHECK();
     }
     return 0;

@@ -177,127 +177,19 @@ template<bool INV> __device__ __forceinline__ void fft256_rows_b(float2 (&v)[16]
 }
 
 // ---- persistent-kernel plumbing ---------------------------------------------------------------
-// Items (4096-point tiles) are drawn from a global ticket counter.  An item may depend on a
-// per-transform completion counter bumped by earlier tickets; it only ever waits on SMALLER tickets,
-// so the schedule makes progress for any number of resident CTAs.
-//
-// Software pipeline inside a CTA (one item in flight in registers, the next one in flight in memory):
-//   * the 4096 inputs of the NEXT item are fetched with per-thread cp.async (LDGSTS, 8 B) into a
-//     staging buffer while the current item is being computed; every thread fetches exactly the 16
-//     elements it will consume itself, so cp.async.wait_group is the only synchronisation needed;
-//   * every warp publishes its own completion (stores -> __syncwarp -> red.release.gpu); the
-//     release of item i is issued just before the stores of item i+1, when the stores of item i
-//     have long reached L2, so the implied MEMBAR does not stall;
-//   * a CTA never blocks on a dependency while it still holds an unpublished item.
+// Every warp publishes its own completion (its stores -> __syncwarp -> fence -> red.release), so no
+// CTA-wide barrier is needed at the end of an item; a finished item counts ITEM_WARPS per tile.
 constexpr unsigned ITEM_WARPS = 8;
-constexpr unsigned ITEM_FULL = 16u * ITEM_WARPS;   // counter value when all 16 tiles of a stage are done
-
 __device__ __forceinline__ void warp_release(unsigned *flag)
 {
   __syncwarp();
-  if((threadIdx.x & 31) == 0) red_release_add(flag, 1u);   // release: orders the warp's prior stores (cumulative)
+  // red.release.gpu orders every store that happens-before it (the warp's, via __syncwarp) — no extra
+  // __threadfence, which would add a second MEMBAR and an L1 invalidate (CCTL.IVALL) per item
+  if((threadIdx.x & 31) == 0) red_release_add(flag, 1u);
 }
 __device__ __forceinline__ void spin_until(const unsigned *flag, unsigned target)
 {
   while(ld_acquire(flag) < target) __nanosleep(32);
-}
-__device__ __forceinline__ void cp_async8(float2 *dst_smem, const float2 *src)
-{
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
-// Policy P provides:
-//   struct Item { bool valid; ... };
-//   Item decode(unsigned ticket) const;
-//   const unsigned *dependency(const Item &) const;        // nullptr = none
-//   void fetch(const Item &, float2 *staging, int tid);    // cp.async of the thread's own 16 inputs
-//   unsigned *process(const Item &, float2 (&v)[16], float2 *sm, const float2 *tw, int tid, unsigned *pending);
-//       computes the item from v (exchanges through sm), publishes `pending` (the previous item)
-//       right before its own stores, stores, and returns this item's completion flag.
-template<class P>
-__device__ __forceinline__ void run_items(P &pol, unsigned *ticket_ctr, unsigned total, float2 *sm, float2 *staging,
-                                          const float2 *tw, unsigned *s_ticket, unsigned *s_ready)
-{
-  const int tid = threadIdx.x;
-  unsigned *pending = nullptr;
-  // prologue: first item
-  if(tid == 0) s_ticket[0] = atomicAdd(ticket_ctr, 1u);
-  __syncthreads();
-  unsigned ticket = s_ticket[0];
-  if(ticket >= total) return;
-  typename P::Item cur = pol.decode(ticket);
-  {
-    const unsigned *dep = cur.valid ? pol.dependency(cur) : nullptr;
-    if(dep)
-    {
-      if(tid == 0) spin_until(dep, ITEM_FULL);
-      __syncthreads();
-    }
-    if(cur.valid) pol.fetch(cur, staging, tid);
-    cp_async_commit();
-  }
-  for(int it = 0;; it ^= 1)
-  {
-    // next ticket and a single look at its dependency
-    if(tid == 0)
-    {
-      const unsigned nt = atomicAdd(ticket_ctr, 1u);
-      s_ticket[it ^ 1] = nt;
-      unsigned ready = 1u;
-      if(nt < total)
-      {
-        const typename P::Item ni = pol.decode(nt);
-        const unsigned *dep = ni.valid ? pol.dependency(ni) : nullptr;
-        if(dep && ld_acquire(dep) < ITEM_FULL) ready = 0u;
-      }
-      s_ready[it ^ 1] = ready;
-    }
-    // this item's inputs: staging -> registers (own elements only)
-    float2 v[16];
-    cp_async_wait_all();
-    if(cur.valid)
-    {
-#pragma unroll
-      for(int j = 0; j < 16; j++) v[j] = staging[j * 256 + tid];
-    }
-    __syncthreads();   // next ticket visible; previous item's exchange reads are over
-    const unsigned nticket = s_ticket[it ^ 1];
-    const bool more = nticket < total;
-    typename P::Item nxt = cur;
-    bool fetched = false;
-    if(more)
-    {
-      nxt = pol.decode(nticket);
-      if(nxt.valid && s_ready[it ^ 1])
-      {
-        pol.fetch(nxt, staging, tid);   // overlaps with the computation below
-        fetched = true;
-      }
-    }
-    cp_async_commit();
-    if(cur.valid) pending = pol.process(cur, v, sm, tw, tid, pending);
-    else if(pending)
-    {
-      warp_release(pending);   // nothing to overlap with
-      pending = nullptr;
-    }
-    if(!more) break;
-    if(nxt.valid && !fetched)
-    {
-      // dependency not there yet: publish what we hold, then wait, then fetch
-      if(pending) warp_release(pending);
-      pending = nullptr;
-      const unsigned *dep = pol.dependency(nxt);
-      if(tid == 0) spin_until(dep, ITEM_FULL);
-      __syncthreads();
-      pol.fetch(nxt, staging, tid);
-      cp_async_commit();
-    }
-    cur = nxt;
-  }
-  if(pending) warp_release(pending);
 }
 
 } // namespace tsdgpu

@@ -61,95 +61,81 @@ __device__ __forceinline__ void red_add_f2(float2 *p, float2 v)
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(&p->y), "f"(v.y) : "memory");
 }
 
-struct Ola64kPolicy
+__global__ void __launch_bounds__(OLA_NT, 3) ola64k_kernel(OlaParams p)
 {
-  const OlaParams &p;
-  __device__ explicit Ola64kPolicy(const OlaParams &q) : p(q) {}
-  struct Item
+  __shared__ float2 sm[4096];
+  __shared__ float2 tw[256];
+  __shared__ unsigned s_ticket[2];
+  const int tid = threadIdx.x, hi = tid >> 4, lo = tid & 15;
+  const unsigned total = (unsigned) (p.Q + 2 * p.lag) * 48u;
+  const unsigned full = 16u * ITEM_WARPS;
+  fill_tw256(tw, tid);
+  if(tid == 0) s_ticket[0] = atomicAdd(p.ticket, 1u);
+  __syncthreads();
+
+  for(int it = 0;; it ^= 1)
   {
-    bool valid;
-    int stage, g, q, chan, blk;
-  };
-  __device__ __forceinline__ Item decode(unsigned ticket) const
-  {
-    Item i;
+    const unsigned ticket = s_ticket[it];
+    if(ticket >= total) break;
     const int s = (int) (ticket / 48u), sub = (int) (ticket - (unsigned) s * 48u);
-    i.g = sub & 15;
-    i.stage = sub >> 4;
-    i.q = s - i.stage * p.lag;
-    i.valid = i.q >= 0 && i.q < p.Q;
-    i.chan = i.valid ? i.q / p.nblocks : 0;
-    i.blk = i.q - i.chan * p.nblocks;
-    return i;
-  }
-  __device__ __forceinline__ const unsigned *dependency(const Item &i) const
-  {
-    if(i.stage == 1) return p.done_a + i.q;
-    if(i.stage == 2) return p.done_b + i.q;
-    if(i.q >= p.ring) return p.done_c + (i.q - p.ring);   // ring slot free again
-    return nullptr;
-  }
-  __device__ __forceinline__ void fetch(const Item &i, float2 *st, int tid) const
-  {
-    const int hi = tid >> 4, lo = tid & 15, g = i.g;
-    const float2 *sc = p.scratch + (long long) (i.q % p.ring) * 65536;
-    if(i.stage == 0)
+    const int g = sub & 15, stage = sub >> 4;
+    const int q = s - stage * p.lag;
+    const bool valid = q >= 0 && q < p.Q;
+    if(tid == 0)
+    {
+      s_ticket[it ^ 1] = atomicAdd(p.ticket, 1u);   // next item, fetched early
+      if(valid)
+      {
+        if(stage == 1) spin_until(p.done_a + q, full);
+        else if(stage == 2) spin_until(p.done_b + q, full);
+        else if(q >= p.ring) spin_until(p.done_c + (q - p.ring), full);   // ring slot free again
+      }
+    }
+    __syncthreads();
+    if(!valid) continue;
+    const int chan = q / p.nblocks, blk = q - chan * p.nblocks;
+    float2 *sc = p.scratch + (long long) (q % p.ring) * 65536;
+    float2 v[16];
+
+    if(stage == 0)
     {
       // window element n sits at position pos0 + n relative to x[0]
-      const long long pos0 = (long long) i.blk * p.Ne - p.residual + p.base_off;
-      const float2 *x = p.x + (long long) i.chan * p.x_stride;
+      const long long pos0 = (long long) blk * p.Ne - p.residual + p.base_off;
+      const float2 *x = p.x + (long long) chan * p.x_stride;
       const int n0 = hi * 256 + 16 * g + lo;
       if(pos0 >= 0 && p.zero_below == 0)
       {
         const float2 *xw = x + pos0 + n0;
 #pragma unroll
-        for(int j = 0; j < 16; j++) cp_async8(st + j * 256 + tid, xw + j * 4096);
+        for(int j = 0; j < 16; j++) v[j] = ldg_stream(xw + j * 4096);
       }
       else
       {
         // block at the start of the call: part of the window is carried history or zero padding
-        const float2 *cr = p.carry + (long long) i.chan * p.carry_len + p.carry_len;
+        const float2 *cr = p.carry + (long long) chan * p.carry_len + p.carry_len;
 #pragma unroll
         for(int j = 0; j < 16; j++)
         {
           const int n = n0 + j * 4096;
           const long long pos = pos0 + n;
-          if(n < p.zero_below) st[j * 256 + tid] = make_float2(0.f, 0.f);   // read back by this thread only
-          else cp_async8(st + j * 256 + tid, (pos >= 0) ? (x + pos) : (cr + pos));
+          float2 val = make_float2(0.f, 0.f);
+          if(n >= p.zero_below) val = (pos >= 0) ? ldg_stream(x + pos) : __ldg(cr + pos);
+          v[j] = val;
         }
       }
-    }
-    else if(i.stage == 1)
-    {
-      const float2 *row = sc + (16 * g + hi) * 256 + lo;
-#pragma unroll
-      for(int j = 0; j < 16; j++) cp_async8(st + j * 256 + tid, row + 16 * j);
-    }
-    else
-    {
-      const float2 *col = sc + hi * 256 + 16 * g + lo;
-#pragma unroll
-      for(int j = 0; j < 16; j++) cp_async8(st + j * 256 + tid, col + j * 4096);
-    }
-  }
-  __device__ __forceinline__ unsigned *process(const Item &i, float2 (&v)[16], float2 *sm, const float2 *tw, int tid,
-                                               unsigned *pending) const
-  {
-    const int hi = tid >> 4, lo = tid & 15, g = i.g;
-    float2 *sc = p.scratch + (long long) (i.q % p.ring) * 65536;
-    if(i.stage == 0)
-    {
       fft256_cols<false>(v, sm, tw, hi, lo);
       const unsigned n2 = (unsigned) (16 * g + lo);
       mul_geometric(v, twiddle<false>(n2 * (unsigned) hi, 2.0f / 65536.0f), twiddle<false>(16u * n2, 2.0f / 65536.0f));
-      if(pending) warp_release(pending);
-      float2 *dst = sc + hi * 256 + 16 * g + lo;
+      float2 *dst = sc + n0;
 #pragma unroll
       for(int p2 = 0; p2 < 16; p2++) dst[p2 * 4096] = v[p2];
-      return p.done_a + i.q;
+      warp_release(p.done_a + q);
     }
-    if(i.stage == 1)
+    else if(stage == 1)
     {
+      float2 *row = sc + (16 * g + hi) * 256 + lo;
+#pragma unroll
+      for(int j = 0; j < 16; j++) v[j] = __ldcg(row + 16 * j);
       fft256_rows_a<false>(v, sm, tw, hi, lo);
       // thread (hi = k', lo = r): v[k2] = X[k], k = (16g + r) + 256*(k' + 16*k2)
       const float2 *H = p.H + hi * 256 + 16 * g + lo;
@@ -160,57 +146,48 @@ struct Ola64kPolicy
       // thread (hi = r, lo = q'): v[pp] = b[k1 = 16g + r][n2 = 16*pp + q']; conj four-step twiddle
       const unsigned k1 = (unsigned) (16 * g + hi);
       mul_geometric(v, twiddle<true>(k1 * (unsigned) lo, 2.0f / 65536.0f), twiddle<true>(16u * k1, 2.0f / 65536.0f));
-      if(pending) warp_release(pending);
-      float2 *row = sc + (16 * g + hi) * 256 + lo;
 #pragma unroll
       for(int pp = 0; pp < 16; pp++) row[16 * pp] = v[pp];
-      return p.done_b + i.q;
-    }
-    fft256_cols<true>(v, sm, tw, hi, lo);
-    // thread (hi = p1, lo): v[p2] = x2[256*(p1 + 16*p2) + 16g + lo]
-    if(pending) warp_release(pending);
-    float2 *y = p.y + (long long) i.chan * p.y_stride;
-    const int j0 = hi * 256 + 16 * g + lo;
-    if(!p.ola_form)
-    {
-      const int i0 = j0 - p.out_shift;
-      float2 *yb = y + (long long) i.blk * p.Ne + i0;
-#pragma unroll
-      for(int p2 = 0; p2 < 16; p2++)
-        if((unsigned) (i0 + p2 * 4096) < (unsigned) p.Ne) stg_stream(yb + p2 * 4096, v[p2]);
+      warp_release(p.done_b + q);
     }
     else
     {
-      const bool last = (i.blk + 1 == p.nblocks);
-      float2 *svg = p.svg + (long long) i.chan * p.Ne;
+      const float2 *col = sc + hi * 256 + 16 * g + lo;
 #pragma unroll
-      for(int p2 = 0; p2 < 16; p2++)
+      for(int j = 0; j < 16; j++) v[j] = __ldcg(col + j * 4096);
+      fft256_cols<true>(v, sm, tw, hi, lo);
+      // thread (hi = p1, lo): v[p2] = x2[256*(p1 + 16*p2) + 16g + lo]
+      float2 *y = p.y + (long long) chan * p.y_stride;
+      const int j0 = hi * 256 + 16 * g + lo;
+      if(!p.ola_form)
       {
-        const int j = j0 + p2 * 4096;
-        if(j < p.Nz)
-          red_add_f2(y + (long long) i.blk * p.Ne + (p.Ne - p.Nz) + j, v[p2]);   // tail of block blk
-        else if(last)
-          svg[j - p.Nz] = v[p2];                                                   // carried (fourier.cc:872)
-        else if(j < p.Ne)
-          stg_stream(y + (long long) (i.blk + 1) * p.Ne + (j - p.Nz), v[p2]);
-        else
-          red_add_f2(y + (long long) (i.blk + 1) * p.Ne + (j - p.Nz), v[p2]);     // meets head of block blk+1
+        const int i0 = j0 - p.out_shift;
+        float2 *yb = y + (long long) blk * p.Ne + i0;
+#pragma unroll
+        for(int p2 = 0; p2 < 16; p2++)
+          if((unsigned) (i0 + p2 * 4096) < (unsigned) p.Ne) stg_stream(yb + p2 * 4096, v[p2]);
       }
+      else
+      {
+        const bool last = (blk + 1 == p.nblocks);
+        float2 *svg = p.svg + (long long) chan * p.Ne;
+#pragma unroll
+        for(int p2 = 0; p2 < 16; p2++)
+        {
+          const int j = j0 + p2 * 4096;
+          if(j < p.Nz)
+            red_add_f2(y + (long long) blk * p.Ne + (p.Ne - p.Nz) + j, v[p2]);   // tail of block blk
+          else if(last)
+            svg[j - p.Nz] = v[p2];                                                 // carried (fourier.cc:872)
+          else if(j < p.Ne)
+            stg_stream(y + (long long) (blk + 1) * p.Ne + (j - p.Nz), v[p2]);
+          else
+            red_add_f2(y + (long long) (blk + 1) * p.Ne + (j - p.Nz), v[p2]);     // meets head of block blk+1
+        }
+      }
+      warp_release(p.done_c + q);
     }
-    return p.done_c + i.q;
   }
-};
-
-constexpr int OLA_SMEM_BYTES = (4096 + 4096 + 256) * (int) sizeof(float2);
-
-__global__ void __launch_bounds__(OLA_NT, 3) ola64k_kernel(OlaParams p)
-{
-  extern __shared__ __align__(16) float2 dyn_smem[];
-  __shared__ unsigned s_ticket[2], s_ready[2];
-  float2 *sm = dyn_smem, *staging = dyn_smem + 4096, *tw = dyn_smem + 8192;
-  fill_tw256(tw, threadIdx.x);
-  Ola64kPolicy pol(p);
-  run_items(pol, p.ticket, (unsigned) (p.Q + 2 * p.lag) * 48u, sm, staging, tw, s_ticket, s_ready);
 }
 
 // OLA form: y[0..Ne) of every channel starts as the carried svg; the other two-addend regions
@@ -308,7 +285,7 @@ struct tsdgpu_ola_s
   float2 *scratch = nullptr;
   unsigned *flags = nullptr;
   size_t flags_cap = 0;
-  int ring = 64, lag = 16, ctas = 0;
+  int ring = 80, lag = 24, ctas = 0;
   // unfused
   tsdgpu_fft_s *plan = nullptr;
   float2 *work = nullptr;
@@ -372,7 +349,7 @@ static int ola_run_fused(tsdgpu_ola_s *f, const float2 *x, long long xs, float2 
   const int grid = (int) std::min<long long>(f->ctas, tickets);
   {
     KernelTimer timer;
-    ola64k_kernel<<<grid, OLA_NT, OLA_SMEM_BYTES, r.stream>>>(p);
+    ola64k_kernel<<<grid, OLA_NT, 0, r.stream>>>(p);
     TSD_LAUNCH_CHECK();
   }
   return 0;
@@ -492,14 +469,13 @@ int tsdgpu_ola_create(int dim_blocs_temporel, int nb_zeros_min, const float *H, 
   }
   if(e == cudaSuccess && f->fused)
   {
-    // pipeline depth knobs (experiments): lag = slots between dependent stages, ring = scratch slots
+    // pipeline depth knobs (tuning experiments): lag = slots between dependent stages, ring = scratch slots
     if(const char *v = getenv("TSDGPU_OLA_LAG")) f->lag = std::max(1, atoi(v));
-    if(const char *v = getenv("TSDGPU_OLA_RING")) f->ring = std::max(2 * f->lag + 1, atoi(v));
+    if(const char *v = getenv("TSDGPU_OLA_RING")) f->ring = atoi(v);
     if(f->ring <= 2 * f->lag) f->ring = 2 * f->lag + 16;
     e = cudaMalloc(&f->scratch, (size_t) f->ring * 65536 * sizeof(float2));
     int occ = 0;
-    cudaFuncSetAttribute(ola64k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OLA_SMEM_BYTES);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ola64k_kernel, OLA_NT, OLA_SMEM_BYTES);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ola64k_kernel, OLA_NT, 0);
     f->ctas = rt().num_sms * std::max(1, occ);
   }
   if(e == cudaSuccess) e = cudaStreamSynchronize(rt().stream);
