@@ -12,7 +12,9 @@
 #include "common.cuh"
 #include "tsdgpu.h"
 
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 namespace tsdgpu {
@@ -31,7 +33,7 @@ struct ResampParams
 
 constexpr int RS_NT = 128;
 
-// v1: one thread per output, window and LUT column read through L1
+// generic fallback: one thread per output, window and LUT column read through L1
 __global__ void __launch_bounds__(RS_NT) resamp_lut_kernel(ResampParams p)
 {
   const int j = blockIdx.x * RS_NT + threadIdx.x;
@@ -68,6 +70,129 @@ __global__ void __launch_bounds__(RS_NT) resamp_lut_kernel(ResampParams p)
   p.y[(long long) chan * p.y_stride + p.out0 + j] = make_float2(sr, si);
 }
 
+// ---- main kernel: channel-batched banded product ----------------------------------------------
+// All channels share the schedule, so a tile of 16 consecutive outputs is a small banded matrix
+//   A[s][jj] = lut[lut_idx[j]][s - d_jj]  (0 <= s - d_jj < K, else 0),  d_jj = window start of output jj
+// applied to every channel: out[c][j] = sum_s A[s][jj] * x[c][b + s].  One warp owns 16 outputs x 64
+// channels (lane = channel, 2 channels per lane): per window sample it reads 16 coefficients with
+// four broadcast LDS.128 and its two samples with two LDS.64, and issues 64 FFMA -> FP32-FMA bound.
+// A CTA = 4 warps = 64 consecutive outputs x 64 channels; the input window is staged once in shared
+// memory as [sample][channel] (row pitch 65 float2: conflict-free transposing stores).
+// s ascending == tap index ascending, i.e. the reference's accumulation order
+// (filtrage.hpp:1877-1879); the zero coefficients outside the band only add +0.
+constexpr int RS2_RJ = 16, RS2_WARPS = 4, RS2_CH = 64, RS2_J = RS2_RJ * RS2_WARPS, RS2_PITCH = RS2_CH + 1;
+
+struct Resamp2Params
+{
+  ResampParams b;
+  int nchan, s_cta_max, s_w_max;
+};
+
+__global__ void __launch_bounds__(RS2_WARPS * 32) resamp_banded_kernel(Resamp2Params q)
+{
+  const ResampParams &p = q.b;
+  extern __shared__ __align__(16) unsigned char rs_smem[];
+  float2 *tile = reinterpret_cast<float2 *>(rs_smem);                                        // [s_cta_max][65]
+  float *Aall = reinterpret_cast<float *>(rs_smem + (((size_t) q.s_cta_max * RS2_PITCH * sizeof(float2) + 15) & ~(size_t) 15));   // [4][s_w_max][16]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int j0 = blockIdx.x * RS2_J;                       // first output of this CTA within the chunk
+  const int c0 = blockIdx.y * RS2_CH;                      // first channel
+  const int jlast = min(j0 + RS2_J, p.n_out_chunk) - 1;
+  const int K = p.K;
+  const int b_first = p.sched[j0].x - (K - 1);             // oldest input needed by the CTA
+  const int s_cta = p.sched[jlast].x - b_first + 1;
+
+  // ---- stage the window asynchronously: tile[s][c] = stream_c[b_first + s]   (LDGSTS, transposing)
+  for(int c = warp; c < RS2_CH; c += RS2_WARPS)
+  {
+    const int chan = c0 + c;
+    const bool ok = chan < q.nchan;
+    const float2 *x = p.x + (long long) chan * p.x_stride;
+    const float2 *hist = p.hist + (long long) chan * p.hist_len + p.hist_len;
+    for(int sidx = lane; sidx < s_cta; sidx += 32)
+    {
+      const int t = b_first + sidx;
+      float2 *dst = tile + sidx * RS2_PITCH + c;
+      if(ok) cp_async8(dst, (t >= 0) ? (x + t) : (hist + t));
+      else *dst = make_float2(0.f, 0.f);
+    }
+  }
+  cp_async_commit();
+  // ---- meanwhile: this warp's banded coefficient matrix.  Lane l fills output jj = l & 15 for the
+  //      window samples s = (l >> 4), (l >> 4) + 2, ... : a strided walk down one LUT column.
+  float *A = Aall + (size_t) warp * q.s_w_max * RS2_RJ;
+  const int jw0 = j0 + warp * RS2_RJ;
+  const bool warp_active = jw0 <= jlast;
+  int b_w = 0, s_w = 0;
+  if(warp_active)
+  {
+    const int jw_last = min(jw0 + RS2_RJ - 1, jlast);
+    b_w = p.sched[jw0].x - (K - 1);
+    s_w = p.sched[jw_last].x - b_w + 1;
+    const int jj = lane & 15;
+    const bool have = jw0 + jj <= jlast;
+    const int2 sc = have ? p.sched[jw0 + jj] : make_int2(0, 0);
+    const int d = sc.x - (K - 1) - b_w;
+    const float *colp = p.lut + (size_t) sc.y * K;
+#pragma unroll 8
+    for(int sidx = lane >> 4; sidx < s_w; sidx += 2)
+    {
+      const int i = sidx - d;
+      float a = 0.f;
+      if(have && i >= 0 && i < K) a = __ldg(colp + i);
+      A[sidx * RS2_RJ + jj] = a;
+    }
+  }
+  cp_async_wait_all();
+  __syncthreads();
+  if(!warp_active) return;
+
+  // ---- 16 outputs x 2 channels per lane
+  float2 acc0[RS2_RJ], acc1[RS2_RJ];
+#pragma unroll
+  for(int jj = 0; jj < RS2_RJ; jj++) acc0[jj] = acc1[jj] = make_float2(0.f, 0.f);
+  const float2 *col = tile + (size_t) (b_w - b_first) * RS2_PITCH + lane;
+  for(int sidx = 0; sidx < s_w; sidx++)
+  {
+    const float4 *a4 = reinterpret_cast<const float4 *>(A + sidx * RS2_RJ);
+    const float2 x0 = col[sidx * RS2_PITCH], x1 = col[sidx * RS2_PITCH + 32];
+    float cf[RS2_RJ];
+#pragma unroll
+    for(int k = 0; k < 4; k++)
+    {
+      const float4 t = a4[k];
+      cf[4 * k] = t.x; cf[4 * k + 1] = t.y; cf[4 * k + 2] = t.z; cf[4 * k + 3] = t.w;
+    }
+#pragma unroll
+    for(int jj = 0; jj < RS2_RJ; jj++)
+    {
+      acc0[jj].x = fmaf(x0.x, cf[jj], acc0[jj].x);
+      acc0[jj].y = fmaf(x0.y, cf[jj], acc0[jj].y);
+      acc1[jj].x = fmaf(x1.x, cf[jj], acc1[jj].x);
+      acc1[jj].y = fmaf(x1.y, cf[jj], acc1[jj].y);
+    }
+  }
+  // ---- transpose through the warp's (now dead) coefficient area so that each half-warp stores 16
+  //      consecutive outputs (128 B) of one channel
+  __syncwarp();
+  float2 *patch = reinterpret_cast<float2 *>(A);   // [32 channels][17]  (needs s_w_max*16*4 >= 32*17*8 bytes)
+  const int nout_w = min(RS2_RJ, jlast - jw0 + 1);
+#pragma unroll
+  for(int half = 0; half < 2; half++)
+  {
+#pragma unroll
+    for(int jj = 0; jj < RS2_RJ; jj++) patch[lane * 17 + jj] = half ? acc1[jj] : acc0[jj];
+    __syncwarp();
+    const int jj = lane & 15;
+    for(int cc = lane >> 4; cc < 32; cc += 2)
+    {
+      const int chan = c0 + half * 32 + cc;
+      if(chan < q.nchan && jj < nout_w) p.y[(long long) chan * p.y_stride + p.out0 + jw0 + jj] = patch[cc * 17 + jj];
+    }
+    __syncwarp();
+  }
+}
+
 // new_hist = last hist_len samples of (old_hist ++ x[0..n))
 __global__ void resamp_hist_kernel(const float2 *x, long long x_stride, int n, const float2 *o, float2 *d, int hl)
 {
@@ -97,6 +222,7 @@ struct tsdgpu_resamp_s
   cudaEvent_t ev[NBUF] = {nullptr, nullptr, nullptr};
   size_t sched_cap = 0;
   int next_buf = 0;
+  size_t smem_set = 0;
 };
 
 // The reference recurrence (ra.cc:58-73), verbatim in float32.  Processes inputs [i0, i1) of the
@@ -179,8 +305,45 @@ static int resamp_run_device(tsdgpu_resamp_s *f, const float2 *x, long long xs, 
     p.n_out_chunk = (int) cnt;
     p.K = f->K;
     p.hist_len = f->hist_len;
-    dim3 grid((unsigned) ((cnt + RS_NT - 1) / RS_NT), f->nchan);
+    // window extents of the banded kernel's tiles (exact, from the schedule just computed)
+    int s_cta_max = 0, s_w_max = 0;
     {
+      const int2 *sc = f->h_sched[b];
+      for(size_t j = 0; j < cnt; j += RS2_RJ)
+      {
+        const size_t jl = std::min(cnt - 1, j + RS2_RJ - 1);
+        s_w_max = std::max(s_w_max, sc[jl].x - sc[j].x + f->K);
+      }
+      for(size_t j = 0; j < cnt; j += RS2_J)
+      {
+        const size_t jl = std::min(cnt - 1, j + RS2_J - 1);
+        s_cta_max = std::max(s_cta_max, sc[jl].x - sc[j].x + f->K);
+      }
+      s_w_max = std::max(s_w_max, 68);   // the output transpose patch (32 x 17 float2 = 4352 B) reuses this area
+    }
+    const size_t smem2 = (((size_t) s_cta_max * RS2_PITCH * sizeof(float2) + 15) & ~(size_t) 15) + (size_t) RS2_WARPS * s_w_max * RS2_RJ * sizeof(float);
+    if(smem2 <= 200 * 1024 && !getenv("TSDGPU_RESAMP_V1"))
+    {
+      Resamp2Params q;
+      q.b = p;
+      q.nchan = f->nchan;
+      q.s_cta_max = s_cta_max;
+      q.s_w_max = s_w_max;
+      static size_t smem_set = 0;   // the attribute is per function, not per filter object
+      if(smem2 > smem_set)
+      {
+        TSD_CUDA(cudaFuncSetAttribute(resamp_banded_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(smem2, 64 * 1024)));
+        smem_set = std::max<size_t>(smem2, 64 * 1024);
+      }
+      dim3 grid((unsigned) ((cnt + RS2_J - 1) / RS2_J), (unsigned) ((f->nchan + RS2_CH - 1) / RS2_CH));
+      KernelTimer timer;
+      resamp_banded_kernel<<<grid, RS2_WARPS * 32, smem2, r.stream>>>(q);
+      TSD_LAUNCH_CHECK();
+    }
+    else
+    {
+      // generic fallback (very small ratios: the window of 64 outputs does not fit in shared memory)
+      dim3 grid((unsigned) ((cnt + RS_NT - 1) / RS_NT), f->nchan);
       KernelTimer timer;
       resamp_lut_kernel<<<grid, RS_NT, 0, r.stream>>>(p);
       TSD_LAUNCH_CHECK();
