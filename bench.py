@@ -255,7 +255,7 @@ class GpuWorkload:
             raise SystemExit(f"unknown workload {name}")
 
 
-def e2e_measure(name, steps, warmup):
+def e2e_measure(name, steps, warmup, barrier=None):
     """Same metric through the C ABI with pinned HOST buffers (H2D + D2H inside the timed region)."""
     import torch
     import oracle
@@ -297,21 +297,23 @@ def e2e_measure(name, steps, warmup):
         step = lambda: flt.step(x, out=y)   # noqa: E731
         out_per_step = n
     else:
-        nchan, n = 32, 1 << 22
+        nchan, n = 128, 1 << 20
         flt = F.filtre_itrp(147.0 / 160.0, F.InterpolateurLUT(O.itrp_sinc_lut(64, 256, 0.4)), nchan)
         tx, x = pinned(nchan, n)
         step = lambda: flt.step(x)   # noqa: E731
         out_per_step = int(n * 147 / 160)
     for _ in range(warmup):
         step()
+    if barrier is not None:
+        barrier()
     t0 = time.perf_counter()
     for _ in range(steps):
         step()   # host-memory calls return when y is valid on the host
     dt = (time.perf_counter() - t0) / steps
     samples = nchan * (n if name != "fft" else n // 2)
-    return {"value": samples / dt / 1e9, "unit": "Gsamples/s", "h2d_bytes_per_step": int(nchan * n * 8),
+    return {"samples_per_step": samples, "seconds_per_step": dt, "unit": "Gsamples/s", "h2d_bytes_per_step": int(nchan * n * 8),
             "d2h_bytes_per_step": int(nchan * out_per_step * 8),
-            "sample": f"{nchan} channels x {n if name != 'fft' else n // 2} cf32 in pinned host memory per step"}
+            "sample": f"{nchan} channels x {n if name != 'fft' else n // 2} cf32 in pinned host memory per step and per GPU"}
 
 
 def main():
@@ -396,30 +398,45 @@ def main():
         elapsed_ms = float(t.item())
     total_samples = float(wl.samples_per_step) * world * args.steps
     value = total_samples / (elapsed_ms * 1e-3) / 1e9
+    samples_per_step = wl.samples_per_step
+
+    # end to end through the C ABI with pinned host buffers: every rank drives its own GPU, same metric
+    e2e = None
+    if not args.no_e2e:
+        del wl
+        torch.cuda.empty_cache()
+        m = e2e_measure(args.workload, 3, 1, barrier if world > 1 else None)
+        sec = m.pop("seconds_per_step")
+        smp = m.pop("samples_per_step")
+        if world > 1:
+            t = torch.tensor([sec], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sec = float(t.item())
+        e2e = dict(value=smp * world / sec / 1e9, **m)
 
     if rank == 0:
         peaks, peak_kind = load_peaks()
         peak = float(peaks["hbm_gbs"])
         # dominant kernel: algorithmic bytes of one rank's launches / summed CUDA-event duration
-        achieved = bytes_per_sample * wl.samples_per_step * args.steps / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else None
+        achieved = bytes_per_sample * samples_per_step * args.steps / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else None
         kernel_name = {"ola": "ola64k_kernel", "fft": "fft64k_kernel", "fir": "fir_direct_kernel", "resample": "resamp_lut_kernel"}[args.workload]
         roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_kind,
                     "algorithmic_bytes_per_sample": bytes_per_sample, "kernel_ms_per_step": kern_ms / args.steps,
                     "kernel_launches": kern_launches}
+        # DRAM bytes per launch from the committed ncu capture (measured at a reduced size, scaled per sample)
         traffic_file = os.path.join(ROOT, "profiles", f"traffic_{args.workload}.json")
-        if os.path.exists(traffic_file):
+        if os.path.exists(traffic_file) and kern_launches:
             with open(traffic_file) as f:
-                roofline["traffic"] = json.load(f).get("dram_bytes_per_launch")
+                per_sample = json.load(f).get("dram_bytes_per_sample")
+            if per_sample:
+                launches_per_sample_pass = 2 if args.workload == "fft" else 1   # fwd + inv are two launches over the same samples
+                roofline["traffic"] = per_sample * samples_per_step * args.steps * launches_per_sample_pass / kern_launches
+                roofline["algorithmic_bytes_per_launch"] = bytes_per_sample * samples_per_step * args.steps / kern_launches
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             v, ms, threads, kind, sample = cpu_run(args.workload, 2, 1)
             cpu = {"value": v, "unit": "Gsamples/s", "cores": threads, "kind": kind, "sample": sample}
-        e2e = None
-        if not args.no_e2e:
-            del wl
-            torch.cuda.empty_cache()
-            e2e = e2e_measure(args.workload, 3, 1)
         line = {"metric": "Gsamples/s filtered (cf32)", "value": value, "unit": "Gsamples/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",

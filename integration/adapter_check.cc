@@ -1,0 +1,89 @@
+// Drop-in proof: drives the reference's OWN interfaces (FiltreGen<T>::step, FFTPlan, fft()) once through
+// the reference CPU classes and once through the adapters of tsd_gpu_adapters.hpp, on the same inputs.
+// Built here by oracle/Makefile target `adapter` against /root/reference headers + the Tab shim; the
+// binary (oracle/_ref/adapter_check) travels to the GPU box.  Exit code 0 = all within 1e-5 of RMS.
+#include "tsd_gpu_adapters.hpp"
+#include <cstdio>
+#include <random>
+
+using namespace tsd;
+using namespace tsd::filtrage;
+using namespace tsd::fourier;
+
+static Veccf bruit(entier n, unsigned seed)
+{
+  std::mt19937 g(seed);
+  std::normal_distribution<float> d(0, 1);
+  Veccf x(n);
+  pour(auto i = 0; i < n; i++) x(i) = cfloat(d(g), d(g));
+  retourne x;
+}
+static double ecart(const Veccf &a, const Veccf &b, const Veccf &x)
+{
+  si(a.rows() != b.rows()) retourne 1e9;
+  double m = 0, e = 0;
+  pour(auto i = 0; i < a.rows(); i++) m = std::max(m, (double) std::abs(a(i) - b(i)));
+  pour(auto i = 0; i < x.rows(); i++) e += std::norm(x(i));
+  retourne m / std::sqrt(e / std::max(1, x.rows()));
+}
+
+int main()
+{
+  get_logger() = [](const char *, entier, entier niveau, cstring s) { if(niveau >= 4) throw std::runtime_error(s); };
+  int bad = 0;
+  try
+  {
+    // filtre_rif<float,cfloat>, streaming in blocks (test-filtres.cc:9-31 pattern)
+    soit h = design_rif_fen(127, "lp", 0.1);
+    soit x = bruit(20000, 1);
+    soit fc = filtre_rif<float, cfloat>(h);
+    soit fg = tsd::gpu::filtre_rif_gpu<float, cfloat>(h);
+    pour(auto i = 0; i < 20000; i += 5000)
+    {
+      Veccf xb = x.segment(i, 5000).clone();
+      soit e = ecart(fg->step(xb), fc->step(xb), xb);
+      printf("filtre_rif   bloc %5d : ecart %.2e\n", i, e);
+      bad += e > 1e-5;
+    }
+    // fft()/ifft() through the global plan hook
+    soit xf = bruit(65536, 2);
+    soit Xc = fft(xf);
+    tsd::gpu::installe_fftplan_gpu();
+    soit Xg = fft(xf);
+    soit e1 = ecart(Xg, Xc, xf), e2 = ecart(ifft(Xg), xf, xf);
+    printf("fft 65536 via fftplan_defaut : ecart %.2e, aller-retour %.2e\n", e1, e2);
+    bad += (e1 > 1e-5) + (e2 > 1e-5);
+    // filtre_fft, K = 4095, Ne = 61441
+    soit h4 = design_rif_fen(4095, "lp", 0.1);
+    FiltreFFTConfig cfg;
+    cfg.dim_blocs_temporel = 61441;
+    cfg.nb_zeros_min = 4095;
+    Veccf H;
+    {
+      soit h2 = Vecf::zeros(65536);
+      h2.tail(4095) = h4;
+      H = fft(h2);          // GPU plan is installed; rfft path of the reference on top of it
+      H *= sqrt(65536.0f);
+    }
+    cfg.traitement_freq = [&](Veccf &X) { X *= H; };
+    soit [oc, Nc] = filtre_fft(cfg);
+    soit [og, Ng] = tsd::gpu::filtre_fft_gpu(cfg, H, 4095);
+    soit xo = bruit(200000, 3);
+    soit yc = oc->step(xo), yg = og->step(xo);
+    soit e3 = ecart(yg, yc, xo);
+    printf("filtre_fft   N %d/%d, %d/%d echantillons : ecart %.2e\n", Nc, Ng, yc.rows(), yg.rows(), e3);
+    bad += (e3 > 1e-5) + (Nc != Ng);
+    // filtre_itrp 147/160, sinc 64 x 257
+    soit it = itrp_sinc<cfloat>({64, 256, 0.4f, "hn"});
+    soit rc = filtre_itrp<cfloat>(147.0f / 160.0f, it);
+    soit rg = tsd::gpu::filtre_itrp_gpu(147.0f / 160.0f, it, 256);
+    soit xr = bruit(50000, 4);
+    soit e4 = ecart(rg->step(xr), rc->step(xr), xr);
+    printf("filtre_itrp  147/160 : ecart %.2e\n", e4);
+    bad += e4 > 1e-5;
+  }
+  catch(const std::exception &e) { printf("exception: %s\n", e.what()); retourne 2; }
+  catch(const std::string &s) { printf("exception: %s\n", s.c_str()); retourne 2; }
+  printf(bad ? "ADAPTER CHECK FAILED\n" : "ADAPTER CHECK OK\n");
+  retourne bad ? 1 : 0;
+}

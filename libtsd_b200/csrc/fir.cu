@@ -10,6 +10,7 @@
 // window loads (R*8 B) is bank-conflict free.  Results go back through shared memory so that the
 // global stores are fully coalesced.
 #include "common.cuh"
+#include "host_pipe.cuh"
 #include "tsdgpu.h"
 
 #include <cstring>
@@ -305,22 +306,29 @@ int tsdgpu_fir_step(tsdgpu_fir_t f, const void *x, long long xs, int n, void *y,
   if(xs < n || ys < n) return fail("tsdgpu_fir_step: channel stride smaller than n");
   if(mem == TSDGPU_DEVICE) return fir_run_device(f, x, xs, n, y, ys);
   const size_t ssz = (f->DC == 1) ? 4 : 8;
-  void *dx = nullptr, *dy = nullptr;
-  size_t bytes = (size_t) f->nchan * n * ssz;
-  TSD_CUDA(cudaMalloc(&dx, bytes));
-  if(cudaMalloc(&dy, bytes) != cudaSuccess) { cudaFree(dx); return fail("tsdgpu_fir_step: out of device memory"); }
-  int rc = 0;
-  cudaError_t e = cudaMemcpy2DAsync(dx, (size_t) n * ssz, x, (size_t) xs * ssz, (size_t) n * ssz, f->nchan,
-                                    cudaMemcpyHostToDevice, rt().stream);
-  if(e == cudaSuccess) rc = fir_run_device(f, dx, n, n, dy, n);
-  if(e == cudaSuccess && !rc)
-    e = cudaMemcpy2DAsync(y, (size_t) ys * ssz, dy, (size_t) n * ssz, (size_t) n * ssz, f->nchan,
-                          cudaMemcpyDeviceToHost, rt().stream);
-  if(e == cudaSuccess) e = cudaStreamSynchronize(rt().stream);
-  cudaFree(dx);
-  cudaFree(dy);
-  if(e != cudaSuccess) return fail(std::string("tsdgpu_fir_step: ") + cudaGetErrorString(e));
-  return rc;
+  const long long chunk = host_chunk_len(f->nchan, ssz, n, 4);
+  if(host_stage_reserve((size_t) f->nchan * chunk * ssz, (size_t) f->nchan * chunk * ssz)) return 1;
+  HostStage &hs = host_stage();
+  const char *xh = (const char *) x;
+  char *yh = (char *) y;
+  return host_pipeline(
+    n, chunk,
+    [&](int slot, long long first, long long count) -> int {
+      TSD_CUDA(cudaMemcpy2DAsync(hs.in[slot], (size_t) chunk * ssz, xh + (size_t) first * ssz, (size_t) xs * ssz,
+                                 (size_t) count * ssz, f->nchan, cudaMemcpyHostToDevice, rt().copy_in));
+      return 0;
+    },
+    [&](long long count) { return count; },
+    [&](int slot, long long count, long long *got) -> int {
+      *got = count;
+      return fir_run_device(f, hs.in[slot], chunk, (int) count, hs.out[slot], chunk);
+    },
+    [&](int slot, long long out_first, long long count) -> int {
+      TSD_CUDA(cudaMemcpy2DAsync(yh + (size_t) out_first * ssz, (size_t) ys * ssz, hs.out[slot], (size_t) chunk * ssz,
+                                 (size_t) count * ssz, f->nchan, cudaMemcpyDeviceToHost, rt().copy_out));
+      return 0;
+    },
+    nullptr);
 }
 
 int tsdgpu_fir_get_state(tsdgpu_fir_t f, void *fen_host, int *index)

@@ -22,6 +22,7 @@
 // Other N use an unfused path built on the generic FFT plan (gather, FFT, *H, IFFT, overlap-add).
 #include "fft_tiles.cuh"
 #include "fft_plan.h"
+#include "host_pipe.cuh"
 #include "tsdgpu.h"
 
 #include <algorithm>
@@ -520,25 +521,30 @@ int tsdgpu_ola_step(tsdgpu_ola_t f, const void *x, long long xs, int n, void *y,
     if(x == y) return fail("tsdgpu_ola_step: in-place operation is not supported (neither does the reference, fourier.cc:871)");
     return ola_run_device(f, (const float2 *) x, xs, n, (float2 *) y, ys, n_out);
   }
-  float2 *dx = nullptr, *dy = nullptr;
-  TSD_CUDA(cudaMalloc(&dx, (size_t) f->nchan * n * sizeof(float2)));
-  if(cudaMalloc(&dy, std::max<size_t>(1, (size_t) f->nchan * cnt) * sizeof(float2)) != cudaSuccess)
-  {
-    cudaFree(dx);
-    return fail("tsdgpu_ola_step: out of device memory");
-  }
-  int rc = 0;
-  cudaError_t e = cudaMemcpy2DAsync(dx, (size_t) n * 8, x, (size_t) xs * 8, (size_t) n * 8, f->nchan, cudaMemcpyHostToDevice,
-                                    rt().stream);
-  if(e == cudaSuccess) rc = ola_run_device(f, dx, n, n, dy, std::max(1LL, cnt), n_out);
-  if(e == cudaSuccess && !rc && cnt > 0)
-    e = cudaMemcpy2DAsync(y, (size_t) ys * 8, dy, (size_t) cnt * 8, (size_t) cnt * 8, f->nchan, cudaMemcpyDeviceToHost,
-                          rt().stream);
-  if(e == cudaSuccess) e = cudaStreamSynchronize(rt().stream);
-  cudaFree(dx);
-  cudaFree(dy);
-  if(e != cudaSuccess) return fail(std::string("tsdgpu_ola_step: ") + cudaGetErrorString(e));
-  return rc;
+  (void) cnt;
+  const long long chunk = host_chunk_len(f->nchan, 8, n, 2);
+  const long long out_cap = (chunk / f->Ne + 2) * (long long) f->Ne;
+  if(host_stage_reserve((size_t) f->nchan * chunk * 8, (size_t) f->nchan * out_cap * 8)) return 1;
+  HostStage &hs = host_stage();
+  const float2 *xh = (const float2 *) x;
+  float2 *yh = (float2 *) y;
+  return host_pipeline(
+    n, chunk,
+    [&](int slot, long long first, long long count) -> int {
+      TSD_CUDA(cudaMemcpy2DAsync(hs.in[slot], (size_t) chunk * 8, xh + first, (size_t) xs * 8, (size_t) count * 8, f->nchan,
+                                 cudaMemcpyHostToDevice, rt().copy_in));
+      return 0;
+    },
+    [&](long long count) { return tsdgpu_ola_out_count(f, (int) count); },
+    [&](int slot, long long count, long long *got) -> int {
+      return ola_run_device(f, (const float2 *) hs.in[slot], chunk, (int) count, (float2 *) hs.out[slot], out_cap, got);
+    },
+    [&](int slot, long long out_first, long long count) -> int {
+      TSD_CUDA(cudaMemcpy2DAsync(yh + out_first, (size_t) ys * 8, hs.out[slot], (size_t) out_cap * 8, (size_t) count * 8, f->nchan,
+                                 cudaMemcpyDeviceToHost, rt().copy_out));
+      return 0;
+    },
+    n_out);
 }
 
 int tsdgpu_ola_destroy(tsdgpu_ola_t f)

@@ -10,6 +10,7 @@
 // with i ascending, as InterpolateurRIF::step does.  State across calls: phase (host) and the
 // last K-1 inputs of every channel (device).
 #include "common.cuh"
+#include "host_pipe.cuh"
 #include "tsdgpu.h"
 
 #include <algorithm>
@@ -73,14 +74,14 @@ __global__ void __launch_bounds__(RS_NT) resamp_lut_kernel(ResampParams p)
 // ---- main kernel: channel-batched banded product ----------------------------------------------
 // All channels share the schedule, so a tile of 16 consecutive outputs is a small banded matrix
 //   A[s][jj] = lut[lut_idx[j]][s - d_jj]  (0 <= s - d_jj < K, else 0),  d_jj = window start of output jj
-// applied to every channel: out[c][j] = sum_s A[s][jj] * x[c][b + s].  One warp owns 16 outputs x 64
-// channels (lane = channel, 2 channels per lane): per window sample it reads 16 coefficients with
-// four broadcast LDS.128 and its two samples with two LDS.64, and issues 64 FFMA -> FP32-FMA bound.
-// A CTA = 4 warps = 64 consecutive outputs x 64 channels; the input window is staged once in shared
+// applied to every channel: out[c][j] = sum_s A[s][jj] * x[c][b + s].  One warp owns 8 outputs x 64
+// channels (lane = channel, 2 channels per lane): per window sample it reads 8 coefficients with
+// two broadcast LDS.128 and its two samples with two LDS.64, and issues 32 FFMA -> FP32-FMA bound.
+// A CTA = 8 warps = 64 consecutive outputs x 64 channels; the input window is staged once in shared
 // memory as [sample][channel] (row pitch 65 float2: conflict-free transposing stores).
 // s ascending == tap index ascending, i.e. the reference's accumulation order
 // (filtrage.hpp:1877-1879); the zero coefficients outside the band only add +0.
-constexpr int RS2_RJ = 16, RS2_WARPS = 4, RS2_CH = 64, RS2_J = RS2_RJ * RS2_WARPS, RS2_PITCH = RS2_CH + 1;
+constexpr int RS2_RJ = 8, RS2_WARPS = 8, RS2_CH = 64, RS2_J = RS2_RJ * RS2_WARPS, RS2_PITCH = RS2_CH + 1;
 
 struct Resamp2Params
 {
@@ -118,8 +119,8 @@ __global__ void __launch_bounds__(RS2_WARPS * 32) resamp_banded_kernel(Resamp2Pa
     }
   }
   cp_async_commit();
-  // ---- meanwhile: this warp's banded coefficient matrix.  Lane l fills output jj = l & 15 for the
-  //      window samples s = (l >> 4), (l >> 4) + 2, ... : a strided walk down one LUT column.
+  // ---- meanwhile: this warp's banded coefficient matrix.  Lane l fills output jj = l & 7 for the
+  //      window samples s = (l >> 3), (l >> 3) + 4, ... : a strided walk down one LUT column.
   float *A = Aall + (size_t) warp * q.s_w_max * RS2_RJ;
   const int jw0 = j0 + warp * RS2_RJ;
   const bool warp_active = jw0 <= jlast;
@@ -129,13 +130,13 @@ __global__ void __launch_bounds__(RS2_WARPS * 32) resamp_banded_kernel(Resamp2Pa
     const int jw_last = min(jw0 + RS2_RJ - 1, jlast);
     b_w = p.sched[jw0].x - (K - 1);
     s_w = p.sched[jw_last].x - b_w + 1;
-    const int jj = lane & 15;
+    const int jj = lane & (RS2_RJ - 1);
     const bool have = jw0 + jj <= jlast;
     const int2 sc = have ? p.sched[jw0 + jj] : make_int2(0, 0);
     const int d = sc.x - (K - 1) - b_w;
     const float *colp = p.lut + (size_t) sc.y * K;
 #pragma unroll 8
-    for(int sidx = lane >> 4; sidx < s_w; sidx += 2)
+    for(int sidx = lane / RS2_RJ; sidx < s_w; sidx += 32 / RS2_RJ)
     {
       const int i = sidx - d;
       float a = 0.f;
@@ -158,7 +159,7 @@ __global__ void __launch_bounds__(RS2_WARPS * 32) resamp_banded_kernel(Resamp2Pa
     const float2 x0 = col[sidx * RS2_PITCH], x1 = col[sidx * RS2_PITCH + 32];
     float cf[RS2_RJ];
 #pragma unroll
-    for(int k = 0; k < 4; k++)
+    for(int k = 0; k < RS2_RJ / 4; k++)
     {
       const float4 t = a4[k];
       cf[4 * k] = t.x; cf[4 * k + 1] = t.y; cf[4 * k + 2] = t.z; cf[4 * k + 3] = t.w;
@@ -172,22 +173,22 @@ __global__ void __launch_bounds__(RS2_WARPS * 32) resamp_banded_kernel(Resamp2Pa
       acc1[jj].y = fmaf(x1.y, cf[jj], acc1[jj].y);
     }
   }
-  // ---- transpose through the warp's (now dead) coefficient area so that each half-warp stores 16
-  //      consecutive outputs (128 B) of one channel
+  // ---- transpose through the warp's (now dead) coefficient area so that 8 lanes store the 8
+  //      consecutive outputs (64 B) of one channel
   __syncwarp();
-  float2 *patch = reinterpret_cast<float2 *>(A);   // [32 channels][17]  (needs s_w_max*16*4 >= 32*17*8 bytes)
+  float2 *patch = reinterpret_cast<float2 *>(A);   // [32 channels][RS2_RJ + 1]
   const int nout_w = min(RS2_RJ, jlast - jw0 + 1);
 #pragma unroll
   for(int half = 0; half < 2; half++)
   {
 #pragma unroll
-    for(int jj = 0; jj < RS2_RJ; jj++) patch[lane * 17 + jj] = half ? acc1[jj] : acc0[jj];
+    for(int jj = 0; jj < RS2_RJ; jj++) patch[lane * (RS2_RJ + 1) + jj] = half ? acc1[jj] : acc0[jj];
     __syncwarp();
-    const int jj = lane & 15;
-    for(int cc = lane >> 4; cc < 32; cc += 2)
+    const int jj = lane & (RS2_RJ - 1);
+    for(int cc = lane / RS2_RJ; cc < 32; cc += 32 / RS2_RJ)
     {
       const int chan = c0 + half * 32 + cc;
-      if(chan < q.nchan && jj < nout_w) p.y[(long long) chan * p.y_stride + p.out0 + jw0 + jj] = patch[cc * 17 + jj];
+      if(chan < q.nchan && jj < nout_w) p.y[(long long) chan * p.y_stride + p.out0 + jw0 + jj] = patch[cc * (RS2_RJ + 1) + jj];
     }
     __syncwarp();
   }
@@ -319,7 +320,7 @@ static int resamp_run_device(tsdgpu_resamp_s *f, const float2 *x, long long xs, 
         const size_t jl = std::min(cnt - 1, j + RS2_J - 1);
         s_cta_max = std::max(s_cta_max, sc[jl].x - sc[j].x + f->K);
       }
-      s_w_max = std::max(s_w_max, 68);   // the output transpose patch (32 x 17 float2 = 4352 B) reuses this area
+      s_w_max = std::max(s_w_max, 72);   // the output transpose patch (32 x 9 float2 = 2304 B) reuses this area
     }
     const size_t smem2 = (((size_t) s_cta_max * RS2_PITCH * sizeof(float2) + 15) & ~(size_t) 15) + (size_t) RS2_WARPS * s_w_max * RS2_RJ * sizeof(float);
     if(smem2 <= 200 * 1024 && !getenv("TSDGPU_RESAMP_V1"))
@@ -412,25 +413,29 @@ int tsdgpu_resamp_step(tsdgpu_resamp_t f, const void *x, long long xs, int n, vo
   if(mem == TSDGPU_DEVICE) return resamp_run_device(f, (const float2 *) x, xs, n, (float2 *) y, ys, ycap, n_out);
   const long long cnt = tsdgpu_resamp_out_count(f, n);
   if(cnt > ycap) return fail("tsdgpu_resamp_step: output capacity too small");
-  float2 *dx = nullptr, *dy = nullptr;
-  TSD_CUDA(cudaMalloc(&dx, (size_t) f->nchan * n * sizeof(float2)));
-  if(cudaMalloc(&dy, std::max<size_t>(1, (size_t) f->nchan * cnt) * sizeof(float2)) != cudaSuccess)
-  {
-    cudaFree(dx);
-    return fail("tsdgpu_resamp_step: out of device memory");
-  }
-  int rc = 0;
-  cudaError_t e = cudaMemcpy2DAsync(dx, (size_t) n * 8, x, (size_t) xs * 8, (size_t) n * 8, f->nchan,
-                                    cudaMemcpyHostToDevice, rt().stream);
-  if(e == cudaSuccess) rc = resamp_run_device(f, dx, n, n, dy, cnt, cnt, n_out);
-  if(e == cudaSuccess && !rc && cnt > 0)
-    e = cudaMemcpy2DAsync(y, (size_t) ys * 8, dy, (size_t) cnt * 8, (size_t) cnt * 8, f->nchan, cudaMemcpyDeviceToHost,
-                          rt().stream);
-  if(e == cudaSuccess) e = cudaStreamSynchronize(rt().stream);
-  cudaFree(dx);
-  cudaFree(dy);
-  if(e != cudaSuccess) return fail(std::string("tsdgpu_resamp_step: ") + cudaGetErrorString(e));
-  return rc;
+  const long long chunk = host_chunk_len(f->nchan, 8, n, 2);
+  const long long out_cap = (long long) std::ceil((double) chunk * std::max(1.0f, f->ratio)) + 16;
+  if(host_stage_reserve((size_t) f->nchan * chunk * 8, (size_t) f->nchan * out_cap * 8)) return 1;
+  HostStage &hs = host_stage();
+  const float2 *xh = (const float2 *) x;
+  float2 *yh = (float2 *) y;
+  return host_pipeline(
+    n, chunk,
+    [&](int slot, long long first, long long count) -> int {
+      TSD_CUDA(cudaMemcpy2DAsync(hs.in[slot], (size_t) chunk * 8, xh + first, (size_t) xs * 8, (size_t) count * 8, f->nchan,
+                                 cudaMemcpyHostToDevice, rt().copy_in));
+      return 0;
+    },
+    [&](long long count) { return tsdgpu_resamp_out_count(f, (int) count); },
+    [&](int slot, long long count, long long *got) -> int {
+      return resamp_run_device(f, (const float2 *) hs.in[slot], chunk, (int) count, (float2 *) hs.out[slot], out_cap, out_cap, got);
+    },
+    [&](int slot, long long out_first, long long count) -> int {
+      TSD_CUDA(cudaMemcpy2DAsync(yh + out_first, (size_t) ys * 8, hs.out[slot], (size_t) out_cap * 8, (size_t) count * 8, f->nchan,
+                                 cudaMemcpyDeviceToHost, rt().copy_out));
+      return 0;
+    },
+    n_out);
 }
 
 int tsdgpu_resamp_schedule(float *phase, float ratio, int nphases, int n, int32_t *in_idx, int32_t *lut_idx,

@@ -1,5 +1,6 @@
 // Runtime of libtsdgpu: device selection, the library stream, error reporting, launch counter.
 #include "common.cuh"
+#include "host_pipe.cuh"
 #include "tsdgpu.h"
 
 #include <cmath>
@@ -53,6 +54,51 @@ int ensure_init()
     return 0;
   }
   return init_device(0);
+}
+
+HostStage &host_stage()
+{
+  static HostStage hs;
+  return hs;
+}
+int host_stage_reserve(size_t in_bytes, size_t out_bytes)
+{
+  HostStage &hs = host_stage();
+  Runtime &r = rt();
+  if(!hs.ev_in[0])
+    for(int i = 0; i < 2; i++)
+    {
+      TSD_CUDA(cudaEventCreateWithFlags(&hs.ev_in[i], cudaEventDisableTiming));
+      TSD_CUDA(cudaEventCreateWithFlags(&hs.ev_done[i], cudaEventDisableTiming));
+      TSD_CUDA(cudaEventCreateWithFlags(&hs.ev_out[i], cudaEventDisableTiming));
+    }
+  if(in_bytes > hs.in_bytes || out_bytes > hs.out_bytes)
+  {
+    TSD_CUDA(cudaStreamSynchronize(r.stream));
+    TSD_CUDA(cudaStreamSynchronize(r.copy_in));
+    TSD_CUDA(cudaStreamSynchronize(r.copy_out));
+  }
+  if(in_bytes > hs.in_bytes)
+  {
+    for(int i = 0; i < 2; i++)
+    {
+      if(hs.in[i]) cudaFree(hs.in[i]);
+      hs.in[i] = nullptr;
+      TSD_CUDA(cudaMalloc(&hs.in[i], in_bytes));
+    }
+    hs.in_bytes = in_bytes;
+  }
+  if(out_bytes > hs.out_bytes)
+  {
+    for(int i = 0; i < 2; i++)
+    {
+      if(hs.out[i]) cudaFree(hs.out[i]);
+      hs.out[i] = nullptr;
+      TSD_CUDA(cudaMalloc(&hs.out[i], out_bytes));
+    }
+    hs.out_bytes = out_bytes;
+  }
+  return 0;
 }
 
 KernelTimer::KernelTimer()

@@ -350,3 +350,19 @@ def test_reechan_stock(tsd, cpu_oracle):
         assert rel_err(y, yref, rms(x)) <= TOL
     assert abs(len(y) - 50000 * 147 / 160) <= 2
     assert np.array_equal(F.reechan(x, 1.0), x)
+
+
+# ------------------------------------------------------------------------------------- C++ adapters
+def test_cpp_adapters_drop_in():
+    """integration/adapter_check.cc: the reference's own FiltreGen<T>::step / fft() / filtre_fft / filtre_itrp
+    signatures, once on the reference CPU classes and once through integration/tsd_gpu_adapters.hpp
+    (binary built in the authoring container by `make -C oracle adapter`; needs reference headers)."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "adapter_check")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/adapter_check not built (needs /root/reference)")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    print(r.stdout, r.stderr)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "ADAPTER CHECK OK" in r.stdout
