@@ -50,17 +50,48 @@ int fail(const std::string &s);
   } while(0)
 
 // ---------------------------------------------------------------- device helpers
-__device__ __forceinline__ float2 cmul(float2 a, float2 b)
+// ---- packed FP32x2 arithmetic (Blackwell FADD2 / FMUL2 / FFMA2): one issue slot per complex add.
+// A float2 lives in an aligned 64-bit register pair; scalar broadcast (make_float2(s, s)) and half
+// swap (make_float2(v.y, v.x)) become operand modifiers (.F32 / .F32x2.LO_HI) in SASS.
+__device__ __forceinline__ unsigned long long f2_bits(float2 v) { return *reinterpret_cast<unsigned long long *>(&v); }
+__device__ __forceinline__ float2 bits_f2(unsigned long long u) { return *reinterpret_cast<float2 *>(&u); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b)
 {
-  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+  return bits_f2(d);
 }
+__device__ __forceinline__ float2 sub2(float2 a, float2 b)
+{
+  unsigned long long d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+  return bits_f2(d);
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b)
+{
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+  return bits_f2(d);
+}
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c)
+{
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)), "l"(f2_bits(c)));
+  return bits_f2(d);
+}
+__device__ __forceinline__ float2 bcast2(float s) { return make_float2(s, s); }
+// i * w
+__device__ __forceinline__ float2 rot90(float2 w) { return make_float2(-w.y, w.x); }
+// a * w given w and rw = i*w : (a.x*w.x - a.y*w.y, a.x*w.y + a.y*w.x) in two packed instructions
+__device__ __forceinline__ float2 cmul_rot(float2 a, float2 w, float2 rw) { return fma2(bcast2(a.y), rw, mul2(bcast2(a.x), w)); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return cmul_rot(a, b, rot90(b)); }
 // a * conj(b)
 __device__ __forceinline__ float2 cmulc(float2 a, float2 b)
 {
-  return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+  return cmul_rot(a, make_float2(b.x, -b.y), make_float2(b.y, b.x));
 }
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return add2(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return sub2(a, b); }
 
 // exp(-+ 2*pi*i * num/den), den a power of two <= 2^24, 0 <= num: exact angle in revolutions.
 template<bool INV> __device__ __forceinline__ float2 twiddle(unsigned num, float two_over_den)

@@ -72,10 +72,10 @@ struct Fft64kParams
 constexpr int FFT_NT = 256;
 
 template<bool INV>
-__global__ void __launch_bounds__(FFT_NT, 3) fft64k_kernel(Fft64kParams p)
+__global__ void __launch_bounds__(FFT_NT, 4) fft64k_kernel(Fft64kParams p)
 {
   __shared__ float2 sm[4096];
-  __shared__ float2 tw[256];
+  __shared__ float4 tw[256];
   __shared__ unsigned s_ticket[2];
   const int tid = threadIdx.x, hi = tid >> 4, lo = tid & 15;
   const float inv256 = 1.0f / 256.0f;
@@ -160,7 +160,7 @@ int fft_plan_create(int n, int batch, tsdgpu_fft_s **out)
   if(n == 65536)
   {
     p->ring = 64;
-    p->lag = 24;
+    p->lag = 32;
     if(const char *v = getenv("TSDGPU_FFT_LAG")) p->lag = std::max(1, atoi(v));
     if(const char *v = getenv("TSDGPU_FFT_RING")) p->ring = atoi(v);
     if(p->ring <= p->lag) p->ring = p->lag + 16;

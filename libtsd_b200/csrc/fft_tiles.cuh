@@ -23,41 +23,37 @@ namespace tsdgpu {
 #define TSD_S1 0.38268343236508977f   // sin(pi/8)
 #define TSD_R2 0.70710678118654752f   // sqrt(1/2)
 
+// 4-point DFT, natural order in and out: 6 packed add/sub + 2 packed FMA.
+// (-i)*d = (d.y, -d.x) is folded into an FFMA2 on the half-swapped operand: s1 + swap(d) * (1, -1).
+template<bool INV> __device__ __forceinline__ void fft4(float2 &a0, float2 &a1, float2 &a2, float2 &a3)
+{
+  const float2 s0 = add2(a0, a2), s1 = sub2(a0, a2), s2 = add2(a1, a3), d = sub2(a1, a3);
+  const float2 ds = make_float2(d.y, d.x);
+  const float2 j = INV ? make_float2(-1.f, 1.f) : make_float2(1.f, -1.f);
+  const float2 nj = INV ? make_float2(1.f, -1.f) : make_float2(-1.f, 1.f);
+  a0 = add2(s0, s2);
+  a2 = sub2(s0, s2);
+  a1 = fma2(ds, j, s1);
+  a3 = fma2(ds, nj, s1);
+}
 // multiply by -i (forward) / +i (inverse)
 template<bool INV> __device__ __forceinline__ float2 mul_mi(float2 a)
 {
-  return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
+  return mul2(make_float2(a.y, a.x), INV ? make_float2(-1.f, 1.f) : make_float2(1.f, -1.f));
 }
 
-// 4-point DFT, natural order in and out
-template<bool INV> __device__ __forceinline__ void fft4(float2 &a0, float2 &a1, float2 &a2, float2 &a3)
-{
-  float2 s0 = cadd(a0, a2), s1 = csub(a0, a2), s2 = cadd(a1, a3), s3 = mul_mi<INV>(csub(a1, a3));
-  a0 = cadd(s0, s2);
-  a2 = csub(s0, s2);
-  a1 = cadd(s1, s3);
-  a3 = csub(s1, s3);
-}
-
-// v *= W16^m (forward) or conj (inverse), m a compile-time constant in {1,2,3,6,9}
+// v *= W16^m (forward) or conj (inverse), m a compile-time constant in {1,2,3,6,9}: the twiddle and its
+// 90-degree rotation are immediates, the product is FMUL2 + FFMA2
 template<bool INV, int M> __device__ __forceinline__ float2 mul_w16(float2 v)
 {
-  if(M == 2)
-  {
-    // (1 - i)/sqrt2 forward, (1 + i)/sqrt2 inverse
-    return INV ? make_float2((v.x - v.y) * TSD_R2, (v.x + v.y) * TSD_R2) : make_float2((v.x + v.y) * TSD_R2, (v.y - v.x) * TSD_R2);
-  }
-  if(M == 6)
-  {
-    // (-1 - i)/sqrt2 forward, (-1 + i)/sqrt2 inverse
-    return INV ? make_float2(-(v.x + v.y) * TSD_R2, (v.x - v.y) * TSD_R2) : make_float2((v.y - v.x) * TSD_R2, -(v.x + v.y) * TSD_R2);
-  }
   float wr, wi;   // forward value of W16^M = exp(-2 pi i M / 16)
   if(M == 1) { wr = TSD_C1; wi = -TSD_S1; }
+  else if(M == 2) { wr = TSD_R2; wi = -TSD_R2; }
   else if(M == 3) { wr = TSD_S1; wi = -TSD_C1; }
+  else if(M == 6) { wr = -TSD_R2; wi = -TSD_R2; }
   else { wr = -TSD_C1; wi = TSD_S1; }   // M == 9
   if(INV) wi = -wi;
-  return make_float2(v.x * wr - v.y * wi, v.x * wi + v.y * wr);
+  return cmul_rot(v, make_float2(wr, wi), make_float2(-wi, wr));
 }
 
 // 16-point DFT of v[0..15], natural order in and out, all indices static
@@ -115,28 +111,30 @@ __device__ __forceinline__ void mul_geometric(float2 (&v)[16], float2 base, floa
   }
 }
 
-// Local twiddles of a 256-point transform from the shared table tw[k*16 + i] = exp(-2 pi i * i*k / 256),
-// i, k in [0,16): v[k] *= tw[k][idx] (conjugated for the inverse).  For a fixed k the 16 lanes of a
-// half-warp read either one entry (idx = hi: broadcast) or 16 consecutive entries (idx = lo).
-template<bool INV> __device__ __forceinline__ void mul_table(float2 (&v)[16], const float2 *tw, int idx)
+// Local twiddles of a 256-point transform from the shared table tw[k*16 + i] = {w, i*w} with
+// w = exp(-2 pi i * i*k / 256), i, k in [0,16): v[k] *= w (conjugated for the inverse), one LDS.128 +
+// FMUL2 + FFMA2 each.  For a fixed k the 16 lanes of a half-warp read either one entry (idx = hi:
+// broadcast) or 16 consecutive entries (idx = lo).
+template<bool INV> __device__ __forceinline__ void mul_table(float2 (&v)[16], const float4 *tw, int idx)
 {
 #pragma unroll
   for(int k = 1; k < 16; k++)
   {
-    const float2 w = tw[k * 16 + idx];
-    v[k] = INV ? cmulc(v[k], w) : cmul(v[k], w);
+    const float4 t = tw[k * 16 + idx];   // {w.x, w.y, -w.y, w.x}
+    v[k] = INV ? cmul_rot(v[k], make_float2(t.x, t.z), make_float2(t.y, t.x)) : cmul_rot(v[k], make_float2(t.x, t.y), make_float2(t.z, t.w));
   }
 }
-__device__ __forceinline__ void fill_tw256(float2 *tw, int tid)
+__device__ __forceinline__ void fill_tw256(float4 *tw, int tid)
 {
-  // 256 threads, one entry each: tw[k*16 + i] = W256^(i*k)
-  tw[tid] = twiddle<false>((unsigned) ((tid >> 4) * (tid & 15)), 2.0f / 256.0f);
+  // 256 threads, one entry each
+  const float2 w = twiddle<false>((unsigned) ((tid >> 4) * (tid & 15)), 2.0f / 256.0f);
+  tw[tid] = make_float4(w.x, w.y, -w.y, w.x);
 }
 
 // ---- 256-point transform, COLS pattern -------------------------------------------------------
 // in : thread (hi = tid>>4, lo = tid&15) holds v[j] = x_lo[16*j + hi]
 // out: thread (hi, lo) holds v[k2] = X_lo[hi + 16*k2]
-template<bool INV> __device__ __forceinline__ void fft256_cols(float2 (&v)[16], float2 *sm, const float2 *tw, int hi, int lo)
+template<bool INV> __device__ __forceinline__ void fft256_cols(float2 (&v)[16], float2 *sm, const float4 *tw, int hi, int lo)
 {
   fft16<INV>(v);
   mul_table<INV>(v, tw, hi);   // W256^(hi*k1)
@@ -151,7 +149,7 @@ template<bool INV> __device__ __forceinline__ void fft256_cols(float2 (&v)[16], 
 // ---- 256-point transform, ROWS pattern -------------------------------------------------------
 // in : thread (hi = row r, lo = b) holds v[j] = x_r[16*j + b]
 // out: thread (hi = k1, lo = row r) holds v[k2] = X_r[k1 + 16*k2]
-template<bool INV> __device__ __forceinline__ void fft256_rows_a(float2 (&v)[16], float2 *sm, const float2 *tw, int hi, int lo)
+template<bool INV> __device__ __forceinline__ void fft256_rows_a(float2 (&v)[16], float2 *sm, const float4 *tw, int hi, int lo)
 {
   fft16<INV>(v);
   mul_table<INV>(v, tw, lo);   // W256^(b*k1)
@@ -164,7 +162,7 @@ template<bool INV> __device__ __forceinline__ void fft256_rows_a(float2 (&v)[16]
 }
 // in : thread (hi = k1, lo = row r) holds v[k2] = X_r[k1 + 16*k2]
 // out: thread (hi = row r, lo = q) holds v[p] = x_r[16*p + q]
-template<bool INV> __device__ __forceinline__ void fft256_rows_b(float2 (&v)[16], float2 *sm, const float2 *tw, int hi, int lo)
+template<bool INV> __device__ __forceinline__ void fft256_rows_b(float2 (&v)[16], float2 *sm, const float4 *tw, int hi, int lo)
 {
   fft16<INV>(v);               // over k2 -> q
   mul_table<INV>(v, tw, hi);   // W256^(k1*q)

@@ -65,7 +65,7 @@ __device__ __forceinline__ void red_add_f2(float2 *p, float2 v)
 __global__ void __launch_bounds__(OLA_NT, 3) ola64k_kernel(OlaParams p)
 {
   __shared__ float2 sm[4096];
-  __shared__ float2 tw[256];
+  __shared__ float4 tw[256];
   __shared__ unsigned s_ticket[2];
   const int tid = threadIdx.x, hi = tid >> 4, lo = tid & 15;
   const unsigned total = (unsigned) (p.Q + 2 * p.lag) * 48u;
@@ -140,8 +140,12 @@ __global__ void __launch_bounds__(OLA_NT, 3) ola64k_kernel(OlaParams p)
       fft256_rows_a<false>(v, sm, tw, hi, lo);
       // thread (hi = k', lo = r): v[k2] = X[k], k = (16g + r) + 256*(k' + 16*k2)
       const float2 *H = p.H + hi * 256 + 16 * g + lo;
+#ifndef TSD_EXPERIMENT_NO_H
 #pragma unroll
       for(int k2 = 0; k2 < 16; k2++) v[k2] = cmul(v[k2], __ldg(H + k2 * 4096));
+#else
+      (void) H;   // TIMING EXPERIMENT ONLY: no spectral gain
+#endif
       __syncthreads();   // exchange buffer is reused
       fft256_rows_b<true>(v, sm, tw, hi, lo);
       // thread (hi = r, lo = q'): v[pp] = b[k1 = 16g + r][n2 = 16*pp + q']; conj four-step twiddle
