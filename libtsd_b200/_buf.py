@@ -5,7 +5,7 @@ import ctypes as C
 
 import numpy as np
 
-from ._lib import DEVICE, HOST, TsdGpuError
+from ._lib import DEVICE, HOST, TsdGpuError, bind_torch_stream
 
 try:  # torch is only needed for device-resident buffers
     import torch
@@ -38,6 +38,7 @@ class Batch:
             self.stride = int(x.stride(0)) if x.shape[0] > 1 else max(self.n, 1)
             self.ptr = C.c_void_p(x.data_ptr())
             self.mem = DEVICE
+            bind_torch_stream()   # stream-ordered with the producer / consumer kernels of the tensor
         else:
             a = np.asarray(x)
             if a.dtype != dtype:

@@ -96,6 +96,15 @@ def use_torch_stream() -> None:
     check(lib().tsdgpu_set_stream(_vp(h)))
 
 
+def bind_torch_stream() -> None:
+    """Device-resident (torch) buffers: run the library on torch's CURRENT stream so that the call is ordered after the
+    kernels that produced its inputs and before the consumers of its outputs (torch's legacy default stream has handle 0,
+    which the C ABI reads as "library stream"; cudaStreamLegacy = 1 names it explicitly)."""
+    import torch
+    h = torch.cuda.current_stream().cuda_stream or 1
+    check(lib().tsdgpu_set_stream(_vp(h)))
+
+
 def synchronize() -> None:
     check(lib().tsdgpu_synchronize())
 

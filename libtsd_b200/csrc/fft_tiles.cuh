@@ -134,9 +134,10 @@ __device__ __forceinline__ void fill_tw256(float4 *tw, int tid)
 // ---- 256-point transform, COLS pattern -------------------------------------------------------
 // in : thread (hi = tid>>4, lo = tid&15) holds v[j] = x_lo[16*j + hi]
 // out: thread (hi, lo) holds v[k2] = X_lo[hi + 16*k2]
-template<bool INV> __device__ __forceinline__ void fft256_cols(float2 (&v)[16], float2 *sm, const float4 *tw, int hi, int lo)
+// The *_tail variants expect the first radix-16 pass (fft16 over j) to have been done by the caller, so
+// that the software-pipelined kernels can issue the next item's global loads right after it.
+template<bool INV> __device__ __forceinline__ void fft256_cols_tail(float2 (&v)[16], float2 *sm, const float4 *tw, int hi, int lo)
 {
-  fft16<INV>(v);
   mul_table<INV>(v, tw, hi);   // W256^(hi*k1)
 #pragma unroll
   for(int k1 = 0; k1 < 16; k1++) sm[(hi * 16 + k1) * 16 + lo] = v[k1];
@@ -145,13 +146,17 @@ template<bool INV> __device__ __forceinline__ void fft256_cols(float2 (&v)[16], 
   for(int a = 0; a < 16; a++) v[a] = sm[(a * 16 + hi) * 16 + lo];
   fft16<INV>(v);
 }
+template<bool INV> __device__ __forceinline__ void fft256_cols(float2 (&v)[16], float2 *sm, const float4 *tw, int hi, int lo)
+{
+  fft16<INV>(v);
+  fft256_cols_tail<INV>(v, sm, tw, hi, lo);
+}
 
 // ---- 256-point transform, ROWS pattern -------------------------------------------------------
 // in : thread (hi = row r, lo = b) holds v[j] = x_r[16*j + b]
 // out: thread (hi = k1, lo = row r) holds v[k2] = X_r[k1 + 16*k2]
-template<bool INV> __device__ __forceinline__ void fft256_rows_a(float2 (&v)[16], float2 *sm, const float4 *tw, int hi, int lo)
+template<bool INV> __device__ __forceinline__ void fft256_rows_a_tail(float2 (&v)[16], float2 *sm, const float4 *tw, int hi, int lo)
 {
-  fft16<INV>(v);
   mul_table<INV>(v, tw, lo);   // W256^(b*k1)
 #pragma unroll
   for(int k1 = 0; k1 < 16; k1++) sm[k1 * 256 + lo * 16 + ((hi + lo) & 15)] = v[k1];
@@ -159,6 +164,11 @@ template<bool INV> __device__ __forceinline__ void fft256_rows_a(float2 (&v)[16]
 #pragma unroll
   for(int b = 0; b < 16; b++) v[b] = sm[hi * 256 + b * 16 + ((lo + b) & 15)];
   fft16<INV>(v);
+}
+template<bool INV> __device__ __forceinline__ void fft256_rows_a(float2 (&v)[16], float2 *sm, const float4 *tw, int hi, int lo)
+{
+  fft16<INV>(v);
+  fft256_rows_a_tail<INV>(v, sm, tw, hi, lo);
 }
 // in : thread (hi = k1, lo = row r) holds v[k2] = X_r[k1 + 16*k2]
 // out: thread (hi = row r, lo = q) holds v[p] = x_r[16*p + q]
@@ -188,6 +198,13 @@ __device__ __forceinline__ void warp_release(unsigned *flag)
 __device__ __forceinline__ void spin_until(const unsigned *flag, unsigned target)
 {
   while(ld_acquire(flag) < target) __nanosleep(32);
+}
+// global load that bypasses L1 (data written by other SMs in the same launch, or touched once)
+__device__ __forceinline__ float2 ld_cg(const float2 *p)
+{
+  float2 v;
+  asm volatile("ld.global.cg.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+  return v;
 }
 
 } // namespace tsdgpu
