@@ -17,6 +17,12 @@ struct Runtime
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;     // stream every launch goes to
   cudaStream_t copy_in = nullptr, copy_out = nullptr;
+  // auxiliary compute streams: the staged FFT / FFT-filter paths spread their chunks over them so that
+  // the stage kernels of different chunks overlap (fork from / join into `stream` with events)
+  static constexpr int MAX_AUX = 8;
+  cudaStream_t aux[MAX_AUX] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[MAX_AUX] = {};
+  float4 *tw256 = nullptr;           // [512] local twiddles of the 256-point transforms: forward, then conjugated
   long long launches = 0;
   // optional device-side timing of the dominant kernels (tsdgpu_timing_*)
   bool timing = false;
@@ -31,6 +37,9 @@ struct KernelTimer
 };
 Runtime &rt();
 int ensure_init();
+int aux_init();          // creates the auxiliary streams, their events and the twiddle table (idempotent)
+int aux_fork(int n);     // aux[0..n) wait for everything enqueued so far on rt().stream
+int aux_join(int n);     // rt().stream waits for everything enqueued on aux[0..n)
 void set_error(const std::string &s);
 int fail(const std::string &s);
 
@@ -139,6 +148,11 @@ __device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, u
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
                "r"(bytes)
                : "memory");
+}
+// hint: bring [src, src + bytes) into L2 (both 16-byte aligned); no completion to wait for
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src_gmem, unsigned bytes)
+{
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }

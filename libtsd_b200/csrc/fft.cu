@@ -136,6 +136,58 @@ __global__ void __launch_bounds__(FFT_NT, 4) fft64k_kernel(Fft64kParams p)
   }
 }
 
+// ---- staged form (default): one kernel per stage and chunk of transforms, chunks round-robin over the
+// auxiliary streams; the hand-over between the stages is the kernel boundary (see ola.cu).
+struct Fft64kStageParams
+{
+  const float2 *x;
+  float2 *y;
+  long long x_stride, y_stride;
+  float2 *scratch;        // this chunk's scratch, [gridDim.y][65536]
+  const float4 *tw;       // rt().tw256
+  int t0;                 // first transform of the chunk
+};
+
+template<bool INV, int STAGE> __global__ void __launch_bounds__(FFT_NT, 4) fft64k_stage(Fft64kStageParams p)
+{
+  __shared__ float2 sm[4096];
+  __shared__ float4 tw[256];
+  const int tid = threadIdx.x, hi = tid >> 4, lo = tid & 15;
+  const int g = blockIdx.x, t = p.t0 + blockIdx.y;
+  float2 *sc = p.scratch + (long long) blockIdx.y * 65536;
+  float2 v[16];
+  if(STAGE == 0)
+  {
+    // columns n2 in [16g, 16g+16), transform over n1, four-step twiddle W_N^(n2*k1)
+    const float2 *x = p.x + (long long) t * p.x_stride + hi * 256 + 16 * g + lo;
+#pragma unroll
+    for(int j = 0; j < 16; j++) v[j] = ldg_stream(x + j * 4096);
+    fill_tw256_from(tw, p.tw, tid, INV);
+    __syncthreads();
+    fft256_cols<INV, true>(v, sm, tw, hi, lo);
+    const unsigned n2 = (unsigned) (16 * g + lo);
+    mul_geometric(v, twiddle<INV>(n2 * (unsigned) hi, 2.0f / 65536.0f), twiddle<INV>(16u * n2, 2.0f / 65536.0f));
+    float2 *dst = sc + hi * 256 + 16 * g + lo;
+#pragma unroll
+    for(int p2 = 0; p2 < 16; p2++) dst[p2 * 4096] = v[p2];
+  }
+  else
+  {
+    // rows k1 in [16g, 16g+16), transform over n2, natural-order output, unitary scaling
+    const float2 *row = sc + (16 * g + hi) * 256 + lo;
+#pragma unroll
+    for(int j = 0; j < 16; j++) v[j] = __ldcg(row + 16 * j);
+    fill_tw256_from(tw, p.tw, tid, INV);
+    __syncthreads();
+    fft256_rows_a<INV, true>(v, sm, tw, hi, lo);
+    // thread (hi = k', lo = r): v[k2] = X[(16g + r) + 256*(k' + 16*k2)]
+    const float inv256 = 1.0f / 256.0f;
+    float2 *y = p.y + (long long) t * p.y_stride + hi * 256 + 16 * g + lo;
+#pragma unroll
+    for(int k2 = 0; k2 < 16; k2++) stg_stream(y + k2 * 4096, make_float2(v[k2].x * inv256, v[k2].y * inv256));
+  }
+}
+
 } // namespace tsdgpu
 
 using namespace tsdgpu;
@@ -161,10 +213,16 @@ int fft_plan_create(int n, int batch, tsdgpu_fft_s **out)
   {
     p->ring = 64;
     p->lag = 32;
+    p->staged = 1;
+    if(const char *v = getenv("TSDGPU_FFT_MODE")) p->staged = v[0] == 'p' ? 0 : 1;
+    if(const char *v = getenv("TSDGPU_FFT_CHUNK")) p->chunk = std::max(1, atoi(v));
+    if(const char *v = getenv("TSDGPU_FFT_STREAMS")) p->nstreams = std::min((int) Runtime::MAX_AUX, std::max(1, atoi(v)));
+    if(p->staged && aux_init()) { fft_plan_destroy(p); return 1; }
     if(const char *v = getenv("TSDGPU_FFT_LAG")) p->lag = std::max(1, atoi(v));
     if(const char *v = getenv("TSDGPU_FFT_RING")) p->ring = atoi(v);
     if(p->ring <= p->lag) p->ring = p->lag + 16;
-    if(cudaMalloc(&p->scratch, (size_t) p->ring * 65536 * sizeof(float2)) != cudaSuccess ||
+    const size_t slots = p->staged ? (size_t) p->chunk * p->nstreams : (size_t) p->ring;
+    if(cudaMalloc(&p->scratch, slots * 65536 * sizeof(float2)) != cudaSuccess ||
        cudaMalloc(&p->flags, ((size_t) 2 * batch + 1) * sizeof(unsigned)) != cudaSuccess)
     {
       fft_plan_destroy(p);
@@ -217,6 +275,41 @@ int fft_exec_device(tsdgpu_fft_s *p, const float2 *x, long long xs, float2 *y, l
     {
       // stage B of transform t overwrites y[t] while stage A items of the same transform have
       // long finished, but A reads x[t] == y[t] only before B(t) starts: in place is safe.
+    }
+    if(p->staged)
+    {
+      KernelTimer timer;
+      if(aux_fork(p->nstreams)) return 1;
+      Fft64kStageParams sp;
+      sp.x = x;
+      sp.y = y;
+      sp.x_stride = xs;
+      sp.y_stride = ys;
+      sp.tw = r.tw256;
+      int c = 0;
+      for(int t0 = 0; t0 < batch; t0 += p->chunk, c++)
+      {
+        const int s = c % p->nstreams;
+        const dim3 grid(16, std::min(p->chunk, batch - t0));
+        sp.t0 = t0;
+        sp.scratch = p->scratch + (size_t) s * p->chunk * 65536;
+        if(forward)
+        {
+          fft64k_stage<false, 0><<<grid, FFT_NT, 0, r.aux[s]>>>(sp);
+          TSD_LAUNCH_CHECK();
+          fft64k_stage<false, 1><<<grid, FFT_NT, 0, r.aux[s]>>>(sp);
+          TSD_LAUNCH_CHECK();
+        }
+        else
+        {
+          fft64k_stage<true, 0><<<grid, FFT_NT, 0, r.aux[s]>>>(sp);
+          TSD_LAUNCH_CHECK();
+          fft64k_stage<true, 1><<<grid, FFT_NT, 0, r.aux[s]>>>(sp);
+          TSD_LAUNCH_CHECK();
+        }
+      }
+      if(aux_join(p->nstreams)) return 1;
+      return 0;
     }
     TSD_CUDA(cudaMemsetAsync(p->flags, 0, ((size_t) 2 * batch + 1) * sizeof(unsigned), r.stream));
     Fft64kParams q;

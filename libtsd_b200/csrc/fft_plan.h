@@ -9,6 +9,7 @@ struct tsdgpu_fft_s
   float2 *scratch = nullptr;   // ring of L2-resident intermediates
   unsigned *flags = nullptr;   // done_a[batch], done_b[batch], ticket
   int ring = 0, lag = 0, ctas = 0;
+  int staged = 1, chunk = 32, nstreams = 4;   // staged form: transforms per stage kernel, auxiliary streams
   // generic radix-2 path
   float2 *work[2] = {nullptr, nullptr};
 };

@@ -115,14 +115,21 @@ __device__ __forceinline__ void mul_geometric(float2 (&v)[16], float2 base, floa
 // w = exp(-2 pi i * i*k / 256), i, k in [0,16): v[k] *= w (conjugated for the inverse), one LDS.128 +
 // FMUL2 + FFMA2 each.  For a fixed k the 16 lanes of a half-warp read either one entry (idx = hi:
 // broadcast) or 16 consecutive entries (idx = lo).
-template<bool INV> __device__ __forceinline__ void mul_table(float2 (&v)[16], const float4 *tw, int idx)
+// With TBL = true the table already holds the twiddles of this direction (conjugated for the inverse,
+// fill_tw256_from), so that {w, i*w} are two aligned register pairs of the LDS.128 and no MOVs are needed.
+template<bool INV, bool TBL = false> __device__ __forceinline__ void mul_table(float2 (&v)[16], const float4 *tw, int idx)
 {
 #pragma unroll
   for(int k = 1; k < 16; k++)
   {
     const float4 t = tw[k * 16 + idx];   // {w.x, w.y, -w.y, w.x}
-    v[k] = INV ? cmul_rot(v[k], make_float2(t.x, t.z), make_float2(t.y, t.x)) : cmul_rot(v[k], make_float2(t.x, t.y), make_float2(t.z, t.w));
+    v[k] = (INV && !TBL) ? cmul_rot(v[k], make_float2(t.x, t.z), make_float2(t.y, t.x)) : cmul_rot(v[k], make_float2(t.x, t.y), make_float2(t.z, t.w));
   }
+}
+// host-built tables (tw256_host_table): [0..256) forward, [256..512) conjugated
+__device__ __forceinline__ void fill_tw256_from(float4 *tw, const float4 *global_table, int tid, bool inverse)
+{
+  tw[tid] = __ldg(global_table + (inverse ? 256 : 0) + tid);
 }
 __device__ __forceinline__ void fill_tw256(float4 *tw, int tid)
 {
@@ -136,9 +143,9 @@ __device__ __forceinline__ void fill_tw256(float4 *tw, int tid)
 // out: thread (hi, lo) holds v[k2] = X_lo[hi + 16*k2]
 // The *_tail variants expect the first radix-16 pass (fft16 over j) to have been done by the caller, so
 // that the software-pipelined kernels can issue the next item's global loads right after it.
-template<bool INV> __device__ __forceinline__ void fft256_cols_tail(float2 (&v)[16], float2 *sm, const float4 *tw, int hi, int lo)
+template<bool INV, bool TBL = false> __device__ __forceinline__ void fft256_cols_tail(float2 (&v)[16], float2 *sm, const float4 *tw, int hi, int lo)
 {
-  mul_table<INV>(v, tw, hi);   // W256^(hi*k1)
+  mul_table<INV, TBL>(v, tw, hi);   // W256^(hi*k1)
 #pragma unroll
   for(int k1 = 0; k1 < 16; k1++) sm[(hi * 16 + k1) * 16 + lo] = v[k1];
   __syncthreads();
@@ -146,18 +153,18 @@ template<bool INV> __device__ __forceinline__ void fft256_cols_tail(float2 (&v)[
   for(int a = 0; a < 16; a++) v[a] = sm[(a * 16 + hi) * 16 + lo];
   fft16<INV>(v);
 }
-template<bool INV> __device__ __forceinline__ void fft256_cols(float2 (&v)[16], float2 *sm, const float4 *tw, int hi, int lo)
+template<bool INV, bool TBL = false> __device__ __forceinline__ void fft256_cols(float2 (&v)[16], float2 *sm, const float4 *tw, int hi, int lo)
 {
   fft16<INV>(v);
-  fft256_cols_tail<INV>(v, sm, tw, hi, lo);
+  fft256_cols_tail<INV, TBL>(v, sm, tw, hi, lo);
 }
 
 // ---- 256-point transform, ROWS pattern -------------------------------------------------------
 // in : thread (hi = row r, lo = b) holds v[j] = x_r[16*j + b]
 // out: thread (hi = k1, lo = row r) holds v[k2] = X_r[k1 + 16*k2]
-template<bool INV> __device__ __forceinline__ void fft256_rows_a_tail(float2 (&v)[16], float2 *sm, const float4 *tw, int hi, int lo)
+template<bool INV, bool TBL = false> __device__ __forceinline__ void fft256_rows_a_tail(float2 (&v)[16], float2 *sm, const float4 *tw, int hi, int lo)
 {
-  mul_table<INV>(v, tw, lo);   // W256^(b*k1)
+  mul_table<INV, TBL>(v, tw, lo);   // W256^(b*k1)
 #pragma unroll
   for(int k1 = 0; k1 < 16; k1++) sm[k1 * 256 + lo * 16 + ((hi + lo) & 15)] = v[k1];
   __syncthreads();
@@ -165,17 +172,17 @@ template<bool INV> __device__ __forceinline__ void fft256_rows_a_tail(float2 (&v
   for(int b = 0; b < 16; b++) v[b] = sm[hi * 256 + b * 16 + ((lo + b) & 15)];
   fft16<INV>(v);
 }
-template<bool INV> __device__ __forceinline__ void fft256_rows_a(float2 (&v)[16], float2 *sm, const float4 *tw, int hi, int lo)
+template<bool INV, bool TBL = false> __device__ __forceinline__ void fft256_rows_a(float2 (&v)[16], float2 *sm, const float4 *tw, int hi, int lo)
 {
   fft16<INV>(v);
-  fft256_rows_a_tail<INV>(v, sm, tw, hi, lo);
+  fft256_rows_a_tail<INV, TBL>(v, sm, tw, hi, lo);
 }
 // in : thread (hi = k1, lo = row r) holds v[k2] = X_r[k1 + 16*k2]
 // out: thread (hi = row r, lo = q) holds v[p] = x_r[16*p + q]
-template<bool INV> __device__ __forceinline__ void fft256_rows_b(float2 (&v)[16], float2 *sm, const float4 *tw, int hi, int lo)
+template<bool INV, bool TBL = false> __device__ __forceinline__ void fft256_rows_b(float2 (&v)[16], float2 *sm, const float4 *tw, int hi, int lo)
 {
   fft16<INV>(v);               // over k2 -> q
-  mul_table<INV>(v, tw, hi);   // W256^(k1*q)
+  mul_table<INV, TBL>(v, tw, hi);   // W256^(k1*q)
 #pragma unroll
   for(int q = 0; q < 16; q++) sm[hi * 256 + q * 16 + ((lo + q) & 15)] = v[q];
   __syncthreads();

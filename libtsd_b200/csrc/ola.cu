@@ -52,6 +52,7 @@ struct OlaParams
   int out_shift;          // OLS: output i = j - out_shift
   int ola_form;           // 0 overlap-save, 1 overlap-add
   int ring, lag;
+  int n;                  // samples per channel in this call
 };
 
 constexpr int OLA_NT = 256;
@@ -195,6 +196,138 @@ __global__ void __launch_bounds__(OLA_NT, 3) ola64k_kernel(OlaParams p)
   }
 }
 
+// ---- staged form: the hand-over between stages is a kernel boundary ---------------------------------
+// Same three tile stages as the persistent kernel, but without tickets, flags, spins or fences on the
+// math warps: a chunk of `chunk` blocks runs one kernel per stage, back to back on one auxiliary stream,
+// with its own L2-resident scratch (chunk x 512 KiB); consecutive chunks go round-robin to `nstreams`
+// streams so that the kernels of different chunks overlap and fill each other's tails.  Stages A and C
+// run at 64 registers (4 CTAs per SM), stage B at 80 (3 CTAs per SM).
+// Measured alternatives: A/B/C of different chunks chained by events on three prioritised
+// streams (CPU-bound on the event calls), the same captured in a CUDA graph (node-to-node dependency latency
+// eats the gain), one launch per pipeline slot with interleaved A/B/C CTAs on one stream (tail at every
+// launch boundary), L2 bulk prefetch of the next chunks' input from stage B (no gain).
+struct OlaRole
+{
+  float2 *scratch;        // this chunk's scratch, [nb][65536]
+  int q0, nb;             // first block (channel-major block index) and number of blocks of the chunk
+};
+struct OlaStageParams
+{
+  OlaParams o;
+  const float4 *tw;       // rt().tw256
+  OlaRole role[1];
+};
+
+template<int STAGE>
+__device__ __forceinline__ void ola_stage_body(const OlaParams &p, const float4 *gtw, float2 *sc, int q, int g, float2 *sm, float4 *tw)
+{
+  const int tid = threadIdx.x, hi = tid >> 4, lo = tid & 15;
+  const int chan = q / p.nblocks, blk = q - chan * p.nblocks;
+  float2 v[16];
+  if(STAGE == 0)
+  {
+    // window element n sits at position pos0 + n relative to x[0]
+    const long long pos0 = (long long) blk * p.Ne - p.residual + p.base_off;
+    const float2 *x = p.x + (long long) chan * p.x_stride;
+    const int n0 = hi * 256 + 16 * g + lo;
+    if(pos0 >= 0 && p.zero_below == 0)
+    {
+      const float2 *xw = x + pos0 + n0;
+#pragma unroll
+      for(int j = 0; j < 16; j++) v[j] = ldg_stream(xw + j * 4096);
+    }
+    else
+    {
+      // block at the start of the call: part of the window is carried history or zero padding
+      const float2 *cr = p.carry + (long long) chan * p.carry_len + p.carry_len;
+#pragma unroll
+      for(int j = 0; j < 16; j++)
+      {
+        const int n = n0 + j * 4096;
+        const long long pos = pos0 + n;
+        float2 val = make_float2(0.f, 0.f);
+        if(n >= p.zero_below) val = (pos >= 0) ? ldg_stream(x + pos) : __ldg(cr + pos);
+        v[j] = val;
+      }
+    }
+    fill_tw256_from(tw, gtw, tid, false);
+    __syncthreads();
+    fft256_cols<false, true>(v, sm, tw, hi, lo);
+    const unsigned n2 = (unsigned) (16 * g + lo);
+    mul_geometric(v, twiddle<false>(n2 * (unsigned) hi, 2.0f / 65536.0f), twiddle<false>(16u * n2, 2.0f / 65536.0f));
+    float2 *dst = sc + n0;
+#pragma unroll
+    for(int p2 = 0; p2 < 16; p2++) dst[p2 * 4096] = v[p2];
+  }
+  else if(STAGE == 1)
+  {
+    float2 *row = sc + (16 * g + hi) * 256 + lo;
+#pragma unroll
+    for(int j = 0; j < 16; j++) v[j] = __ldcg(row + 16 * j);
+    fill_tw256_from(tw, gtw, tid, false);
+    fill_tw256_from(tw + 256, gtw, tid, true);
+    __syncthreads();
+    fft256_rows_a<false, true>(v, sm, tw, hi, lo);
+    // thread (hi = k', lo = r): v[k2] = X[k], k = (16g + r) + 256*(k' + 16*k2)
+    const float2 *H = p.H + hi * 256 + 16 * g + lo;
+#pragma unroll
+    for(int k2 = 0; k2 < 16; k2++) v[k2] = cmul(v[k2], __ldg(H + k2 * 4096));
+    __syncthreads();   // exchange buffer is reused
+    fft256_rows_b<true, true>(v, sm, tw + 256, hi, lo);
+    // thread (hi = r, lo = q'): v[pp] = b[k1 = 16g + r][n2 = 16*pp + q']; conj four-step twiddle
+    const unsigned k1 = (unsigned) (16 * g + hi);
+    mul_geometric(v, twiddle<true>(k1 * (unsigned) lo, 2.0f / 65536.0f), twiddle<true>(16u * k1, 2.0f / 65536.0f));
+#pragma unroll
+    for(int pp = 0; pp < 16; pp++) row[16 * pp] = v[pp];
+  }
+  else
+  {
+    const float2 *col = sc + hi * 256 + 16 * g + lo;
+#pragma unroll
+    for(int j = 0; j < 16; j++) v[j] = __ldcg(col + j * 4096);
+    fill_tw256_from(tw, gtw, tid, true);
+    __syncthreads();
+    fft256_cols<true, true>(v, sm, tw, hi, lo);
+    // thread (hi = p1, lo): v[p2] = x2[256*(p1 + 16*p2) + 16g + lo]
+    float2 *y = p.y + (long long) chan * p.y_stride;
+    const int j0 = hi * 256 + 16 * g + lo;
+    if(!p.ola_form)
+    {
+      const int i0 = j0 - p.out_shift;
+      float2 *yb = y + (long long) blk * p.Ne + i0;
+#pragma unroll
+      for(int p2 = 0; p2 < 16; p2++)
+        if((unsigned) (i0 + p2 * 4096) < (unsigned) p.Ne) stg_stream(yb + p2 * 4096, v[p2]);
+    }
+    else
+    {
+      const bool last = (blk + 1 == p.nblocks);
+      float2 *svg = p.svg + (long long) chan * p.Ne;
+#pragma unroll
+      for(int p2 = 0; p2 < 16; p2++)
+      {
+        const int j = j0 + p2 * 4096;
+        if(j < p.Nz)
+          red_add_f2(y + (long long) blk * p.Ne + (p.Ne - p.Nz) + j, v[p2]);   // tail of block blk
+        else if(last)
+          svg[j - p.Nz] = v[p2];                                                 // carried (fourier.cc:872)
+        else if(j < p.Ne)
+          stg_stream(y + (long long) (blk + 1) * p.Ne + (j - p.Nz), v[p2]);
+        else
+          red_add_f2(y + (long long) (blk + 1) * p.Ne + (j - p.Nz), v[p2]);     // meets head of block blk+1
+      }
+    }
+  }
+}
+
+template<int STAGE> __global__ void __launch_bounds__(OLA_NT, STAGE == 1 ? 3 : 4) ola64k_stage(OlaStageParams sp)
+{
+  __shared__ float2 sm[4096];
+  __shared__ float4 tw[STAGE == 1 ? 512 : 256];
+  const OlaRole &r = sp.role[0];
+  ola_stage_body<STAGE>(sp.o, sp.tw, r.scratch + (long long) blockIdx.y * 65536, r.q0 + blockIdx.y, blockIdx.x, sm, tw);
+}
+
 // OLA form: y[0..Ne) of every channel starts as the carried svg; the other two-addend regions
 // [b*Ne + Ne - Nz, (b+1)*Ne), b >= 1, start at zero.
 __global__ void ola_prepare_kernel(float2 *y, long long y_stride, const float2 *svg, int Ne, int Nz, int nblocks)
@@ -291,19 +424,22 @@ struct tsdgpu_ola_s
   unsigned *flags = nullptr;
   size_t flags_cap = 0;
   int ring = 80, lag = 24, ctas = 0;
+  // staged form (default): blocks per stage kernel, number of auxiliary streams
+  // 1 = staged kernels over auxiliary streams (default), 0 = single persistent kernel
+  int staged = 1, chunk = 32, nslots = 4;
   // unfused
   tsdgpu_fft_s *plan = nullptr;
   float2 *work = nullptr;
   int plan_batch = 0;
 };
 
-static int ola_run_fused(tsdgpu_ola_s *f, const float2 *x, long long xs, float2 *y, long long ys, int B)
+static int ola_run_fused(tsdgpu_ola_s *f, const float2 *x, long long xs, int n, float2 *y, long long ys, int B)
 {
   Runtime &r = rt();
   const long long Q = (long long) f->nchan * B;
   if(Q > (1LL << 25)) return fail("tsdgpu_ola_step: too many blocks in one call (split the call)");
   const size_t need = (size_t) 3 * Q + 1;
-  if(need > f->flags_cap)
+  if(!f->staged && need > f->flags_cap)
   {
     if(f->flags) cudaFree(f->flags);
     f->flags = nullptr;
@@ -311,7 +447,7 @@ static int ola_run_fused(tsdgpu_ola_s *f, const float2 *x, long long xs, float2 
     TSD_CUDA(cudaMalloc(&f->flags, need * sizeof(unsigned)));
     f->flags_cap = need;
   }
-  TSD_CUDA(cudaMemsetAsync(f->flags, 0, need * sizeof(unsigned), r.stream));
+  if(!f->staged) TSD_CUDA(cudaMemsetAsync(f->flags, 0, need * sizeof(unsigned), r.stream));
   OlaParams p;
   p.x = x;
   p.y = y;
@@ -333,6 +469,7 @@ static int ola_run_fused(tsdgpu_ola_s *f, const float2 *x, long long xs, float2 
   p.residual = f->residual;
   p.ring = f->ring;
   p.lag = f->lag;
+  p.n = n;
   if(f->K > 0)
   {
     p.ola_form = 0;
@@ -349,6 +486,34 @@ static int ola_run_fused(tsdgpu_ola_s *f, const float2 *x, long long xs, float2 
     dim3 grid(std::min(1024LL, ((long long) f->Ne + (long long) (B - 1) * f->Nz + 255) / 256), f->nchan);
     ola_prepare_kernel<<<grid, 256, 0, r.stream>>>(y, ys, f->d_svg, f->Ne, f->Nz, B);
     TSD_LAUNCH_CHECK();
+  }
+  if(f->staged)
+  {
+    KernelTimer timer;
+    OlaStageParams sp;
+    sp.o = p;
+    sp.tw = r.tw256;
+    const int C = f->chunk;
+    const int nchunks = (int) ((Q + C - 1) / C);
+    // streams schedule
+    if(aux_fork(f->nslots)) return 1;
+    for(int c = 0; c < nchunks; c++)
+    {
+      const int s = c % f->nslots;
+      OlaRole &ro = sp.role[0];
+      ro.q0 = c * C;
+      ro.nb = (int) std::min<long long>(C, Q - (long long) c * C);
+      ro.scratch = f->scratch + (size_t) s * C * 65536;
+      const dim3 grid(16, ro.nb);
+      ola64k_stage<0><<<grid, OLA_NT, 0, r.aux[s]>>>(sp);
+      TSD_LAUNCH_CHECK();
+      ola64k_stage<1><<<grid, OLA_NT, 0, r.aux[s]>>>(sp);
+      TSD_LAUNCH_CHECK();
+      ola64k_stage<2><<<grid, OLA_NT, 0, r.aux[s]>>>(sp);
+      TSD_LAUNCH_CHECK();
+    }
+    if(aux_join(f->nslots)) return 1;
+    return 0;
   }
   const long long tickets = (Q + 2LL * f->lag) * 48;
   const int grid = (int) std::min<long long>(f->ctas, tickets);
@@ -415,7 +580,7 @@ static int ola_run_device(tsdgpu_ola_s *f, const float2 *x, long long xs, int n,
   if(B > 0)
   {
     if(ys < *n_out) return fail("tsdgpu_ola_step: output stride smaller than the emitted count");
-    int rc = f->fused ? ola_run_fused(f, x, xs, y, ys, B) : ola_run_unfused(f, x, xs, y, ys, B);
+    int rc = f->fused ? ola_run_fused(f, x, xs, n, y, ys, B) : ola_run_unfused(f, x, xs, y, ys, B);
     if(rc) return rc;
   }
   dim3 grid((f->carry_len + 255) / 256, f->nchan);
@@ -478,7 +643,13 @@ int tsdgpu_ola_create(int dim_blocs_temporel, int nb_zeros_min, const float *H, 
     if(const char *v = getenv("TSDGPU_OLA_LAG")) f->lag = std::max(1, atoi(v));
     if(const char *v = getenv("TSDGPU_OLA_RING")) f->ring = atoi(v);
     if(f->ring <= 2 * f->lag) f->ring = 2 * f->lag + 16;
-    e = cudaMalloc(&f->scratch, (size_t) f->ring * 65536 * sizeof(float2));
+    // TSDGPU_OLA_MODE=persistent selects the single persistent kernel; default = staged kernels
+    if(const char *v = getenv("TSDGPU_OLA_MODE")) f->staged = v[0] == 'p' ? 0 : 1;
+    if(const char *v = getenv("TSDGPU_OLA_CHUNK")) f->chunk = std::max(1, atoi(v));
+    if(const char *v = getenv("TSDGPU_OLA_STREAMS")) f->nslots = std::min((int) Runtime::MAX_AUX, std::max(1, atoi(v)));
+    if(f->staged && aux_init()) e = cudaErrorUnknown;
+    const size_t slots = f->staged ? (size_t) f->chunk * f->nslots : (size_t) f->ring;
+    if(e == cudaSuccess) e = cudaMalloc(&f->scratch, slots * 65536 * sizeof(float2));
     int occ = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ola64k_kernel, OLA_NT, 0);
     f->ctas = rt().num_sms * std::max(1, occ);
@@ -550,6 +721,7 @@ int tsdgpu_ola_step(tsdgpu_ola_t f, const void *x, long long xs, int n, void *y,
     },
     n_out);
 }
+
 
 int tsdgpu_ola_destroy(tsdgpu_ola_t f)
 {

@@ -3,7 +3,9 @@
 #include "host_pipe.cuh"
 #include "tsdgpu.h"
 
+#include <algorithm>
 #include <cmath>
+#include <vector>
 
 namespace tsdgpu {
 
@@ -37,6 +39,7 @@ static int init_device(int device)
     return fail("libtsdgpu: built for sm_100a (Blackwell B200) only; found compute capability " +
                 std::to_string(prop.major) + "." + std::to_string(prop.minor));
   r.device = device;
+  r.tw256 = nullptr;   // auxiliary streams and tables belong to a device: rebuilt on demand (aux_init)
   r.num_sms = prop.multiProcessorCount;
   TSD_CUDA(cudaStreamCreateWithFlags(&r.own_stream, cudaStreamNonBlocking));
   TSD_CUDA(cudaStreamCreateWithFlags(&r.copy_in, cudaStreamNonBlocking));
@@ -54,6 +57,54 @@ int ensure_init()
     return 0;
   }
   return init_device(0);
+}
+
+int aux_init()
+{
+  Runtime &r = rt();
+  if(r.tw256) return 0;
+  // aux[i] has a higher scheduling priority than aux[i-1]: the staged pipelines put their LAST stage on the
+  // highest-priority stream so that blocks are drained before new ones are started
+  int least = 0, greatest = 0;
+  TSD_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+  for(int i = 0; i < Runtime::MAX_AUX; i++)
+  {
+    TSD_CUDA(cudaStreamCreateWithPriority(&r.aux[i], cudaStreamNonBlocking, std::max(greatest, least - i)));
+    TSD_CUDA(cudaEventCreateWithFlags(&r.ev_join[i], cudaEventDisableTiming));
+  }
+  TSD_CUDA(cudaEventCreateWithFlags(&r.ev_fork, cudaEventDisableTiming));
+  // tw[k*16 + i] = {w, i*w}, w = exp(-2 pi i * i*k / 256) (double on the host, like the reference's
+  // twiddle generation fourier.cc:32-46), then the same for conj(w)
+  std::vector<float4> h(512);
+  for(int t = 0; t < 256; t++)
+  {
+    const double a = -2.0 * M_PI * (double) ((t >> 4) * (t & 15)) / 256.0;
+    const float c = (float) cos(a), s = (float) sin(a);
+    h[t] = make_float4(c, s, -s, c);
+    h[256 + t] = make_float4(c, -s, s, c);
+  }
+  float4 *d = nullptr;
+  TSD_CUDA(cudaMalloc(&d, 512 * sizeof(float4)));
+  TSD_CUDA(cudaMemcpy(d, h.data(), 512 * sizeof(float4), cudaMemcpyHostToDevice));
+  r.tw256 = d;
+  return 0;
+}
+int aux_fork(int n)
+{
+  Runtime &r = rt();
+  TSD_CUDA(cudaEventRecord(r.ev_fork, r.stream));
+  for(int i = 0; i < n; i++) TSD_CUDA(cudaStreamWaitEvent(r.aux[i], r.ev_fork, 0));
+  return 0;
+}
+int aux_join(int n)
+{
+  Runtime &r = rt();
+  for(int i = 0; i < n; i++)
+  {
+    TSD_CUDA(cudaEventRecord(r.ev_join[i], r.aux[i]));
+    TSD_CUDA(cudaStreamWaitEvent(r.stream, r.ev_join[i], 0));
+  }
+  return 0;
 }
 
 HostStage &host_stage()

@@ -279,6 +279,33 @@ def test_ola_generic_H(tsd, cpu_oracle):
     assert rel_err(g.step(x), r.step(x[0])[None], rms(x)) <= TOL
 
 
+@pytest.mark.parametrize("mode", ["persistent", "staged"])
+def test_64k_schedules(tsd, cpu_oracle, mode, monkeypatch):
+    """N = 65536 has two schedules of the same tile stages (one persistent kernel with flags / one kernel per
+    stage and chunk over auxiliary streams, chosen when the object is created): both against the oracle, with a
+    chunk size that leaves a ragged last chunk."""
+    from libtsd_b200 import fourier as Fo
+    monkeypatch.setenv("TSDGPU_OLA_MODE", mode)
+    monkeypatch.setenv("TSDGPU_FFT_MODE", mode)
+    monkeypatch.setenv("TSDGPU_OLA_CHUNK", "5")
+    monkeypatch.setenv("TSDGPU_FFT_CHUNK", "3")
+    rng = np.random.default_rng(77)
+    K, Ne, nchan, n = 4095, 61441, 3, 500000
+    h = cpu_oracle.design_rif_fen(K, "lp", 0.1)
+    x = cn(rng, nchan, n)
+    for fir in (K, 0):
+        g, refs = _ola_pair(cpu_oracle, Ne, K, h, nchan, fir)
+        yref = np.stack([r.step(x[c]) for c, r in enumerate(refs)])
+        assert rel_err(g.step(x), yref, rms(x)) <= TOL
+    plan = Fo.tfrplan_creation(65536, batch=7)
+    ref = cpu_oracle.fft(65536)
+    z = cn(rng, 7, 65536)
+    for fwd in (True, False):
+        Z = plan.step(z, fwd)
+        Zr = np.stack([ref.step(z[c], fwd) for c in range(7)])
+        assert rel_err(Z, Zr, rms(z)) <= TOL
+
+
 def test_ola_errors(tsd):
     from libtsd_b200 import fourier as Fo
     with pytest.raises(tsd.TsdGpuError):
