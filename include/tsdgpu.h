@@ -39,6 +39,7 @@ typedef struct tsdgpu_fir_s    *tsdgpu_fir_t;
 typedef struct tsdgpu_fft_s    *tsdgpu_fft_t;
 typedef struct tsdgpu_ola_s    *tsdgpu_ola_t;
 typedef struct tsdgpu_resamp_s *tsdgpu_resamp_t;
+typedef struct tsdgpu_poly_s   *tsdgpu_poly_t;
 
 /* ---- runtime ------------------------------------------------------------------------------ */
 /* Selects the CUDA device for the calling thread and creates the library stream. */
@@ -60,6 +61,11 @@ int tsdgpu_timing_read(double *total_ms, long long *launches);
 /* Bookkeeping shared with the reference, computed on the host with the same expressions:
  * prochaine_puissance_de_2 (tsd.cc:287-291). */
 int tsdgpu_p2(int i);
+/* Cost model of the block filter (fourier.cc:708-735): FLOP per input sample for pattern length M and block
+ * length Ne, and the block length 2^k - (M-1) that minimises it (what filtre_rif_fft-style callers use to pick
+ * dim_blocs_temporel).  Host arithmetic, same expressions as the reference. */
+int tsdgpu_ola_complexite(int M, int Ne, float *C, int *Nf, int *Nz);
+int tsdgpu_ola_complexite_optimise(int M, float *C, int *Nf, int *Nz, int *Ne);
 
 /* ---- direct-form FIR: replaces filtre_rif<Tc,T>(h) and FiltreRIF::step ---------------------- */
 /* (filtrage.hpp:1367-1368, filtre-rt.cc:53-109,171-175).  State per channel = the last K-1
@@ -123,6 +129,24 @@ int tsdgpu_resamp_destroy(tsdgpu_resamp_t f);
  * updates *phase.  in_idx / lut_idx may be NULL to count only. */
 int tsdgpu_resamp_schedule(float *phase, float ratio, int nphases, int n, int32_t *in_idx,
                            int32_t *lut_idx, long long capacity, long long *n_out);
+
+/* ---- polyphase rate-change stages: replace filtre_rif_ups / filtre_rif_demi_bande / filtre_rif_decim ---- */
+/* (filtrage.hpp polyphase factories; polyphase.cc:54-149 half-band decimator, :156-239 FIR + decimation by R,
+ * :246-341 xR polyphase interpolator, factories :344-360) — the stages filtre_reechan puts in front of the LUT
+ * interpolator when the ratio leaves [0.5, 2) (ra.cc:124-141).  Real coefficients; data float (data_complex = 0)
+ * or cfloat.  State per channel: the reference's delay line (K samples, K'/R for the interpolator) kept on the
+ * device, plus the decimation counter (`odd` / `cnt`), which decides the number of outputs of a call. */
+#define TSDGPU_POLY_UPS        0   /* filtre_rif_ups<float,T>(c, R): n*R outputs, coefficients scaled by R, zero-padded */
+#define TSDGPU_POLY_DEMI_BANDE 1   /* filtre_rif_demi_bande<float,T>(c): R = 2, even coefficients + literal 0.5 centre */
+#define TSDGPU_POLY_DECIM      2   /* filtre_rif_decim<float,T>(c, R): (n + cnt) / R outputs */
+int tsdgpu_poly_create(int kind, const float *coefs, int K, int R, int data_complex, int nchan,
+                       tsdgpu_poly_t *out);
+long long tsdgpu_poly_out_count(tsdgpu_poly_t f, int n);
+/* ring index ((samples so far) mod delay-line length) and decimation counter of the reference object */
+int tsdgpu_poly_state(tsdgpu_poly_t f, int *index, int *cnt);
+int tsdgpu_poly_step(tsdgpu_poly_t f, const void *x, long long x_stride, int n,
+                     void *y, long long y_stride, long long *n_out, int mem);
+int tsdgpu_poly_destroy(tsdgpu_poly_t f);
 
 #ifdef __cplusplus
 }

@@ -34,6 +34,8 @@ _SIGS = {
     "tsdgpu_last_error": (C.c_char_p, []),
     "tsdgpu_launch_count": (_ll, [_i]),
     "tsdgpu_p2": (_i, [_i]),
+    "tsdgpu_ola_complexite": (_i, [_i, _i, C.POINTER(_f), C.POINTER(_i), C.POINTER(_i)]),
+    "tsdgpu_ola_complexite_optimise": (_i, [_i, C.POINTER(_f), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "tsdgpu_timing_enable": (_i, [_i]),
     "tsdgpu_timing_read": (_i, [C.POINTER(C.c_double), C.POINTER(_ll)]),
     "tsdgpu_fir_create": (_i, [_i, _vp, _i, _i, C.POINTER(_vp)]),
@@ -54,6 +56,11 @@ _SIGS = {
     "tsdgpu_resamp_phase": (_f, [_vp]),
     "tsdgpu_resamp_step": (_i, [_vp, _vp, _ll, _i, _vp, _ll, _ll, C.POINTER(_ll), _i]),
     "tsdgpu_resamp_destroy": (_i, [_vp]),
+    "tsdgpu_poly_create": (_i, [_i, _vp, _i, _i, _i, _i, C.POINTER(_vp)]),
+    "tsdgpu_poly_out_count": (_ll, [_vp, _i]),
+    "tsdgpu_poly_state": (_i, [_vp, C.POINTER(_i), C.POINTER(_i)]),
+    "tsdgpu_poly_step": (_i, [_vp, _vp, _ll, _i, _vp, _ll, C.POINTER(_ll), _i]),
+    "tsdgpu_poly_destroy": (_i, [_vp]),
     "tsdgpu_resamp_schedule": (_i, [C.POINTER(_f), _f, _i, _i, _vp, _vp, _ll, C.POINTER(_ll)]),
 }
 

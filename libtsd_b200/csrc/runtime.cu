@@ -233,4 +233,42 @@ int tsdgpu_p2(int i)
   return (int) (1l << lg2);
 }
 
+// fourier.cc:708-713 ola_complexité: same float expressions (log of a float is logf, evaluated left to right)
+int tsdgpu_ola_complexite(int M, int Ne, float *C, int *Nf, int *Nz)
+{
+  if(Ne <= 0 || M <= 0) return fail("tsdgpu_ola_complexite: M and Ne must be > 0");
+  const int nf = tsdgpu_p2(Ne + M - 1);
+  if(Nf) *Nf = nf;
+  if(Nz) *Nz = nf - Ne;
+  if(C) *C = (1.0f / Ne) * 2 * 5 * nf * logf(1.0f * nf) / logf(2.0f);
+  return 0;
+}
+
+// fourier.cc:715-735 ola_complexité_optimise: kmin from a DOUBLE log (integer argument), 20 candidates
+int tsdgpu_ola_complexite_optimise(int M, float *C_, int *Nf_, int *Nz_, int *Ne_)
+{
+  if(M <= 0) return fail("tsdgpu_ola_complexite_optimise: M must be > 0");
+  const int kmin = (int) ceil(log((double) M) / log(2.0));
+  float best = 0;
+  int bnf = 0, bne = 0;
+  for(int k = kmin; (k < kmin + 20) && (k < 31); k++)
+  {
+    const int Ne = (1 << k) - (M - 1);
+    float C;
+    int Nf, Nz;
+    tsdgpu_ola_complexite(M, Ne, &C, &Nf, &Nz);
+    if((k == kmin) || (C < best))
+    {
+      bnf = Nf;
+      bne = Ne;
+      best = C;
+    }
+  }
+  if(C_) *C_ = best;
+  if(Nf_) *Nf_ = bnf;
+  if(Nz_) *Nz_ = bnf - bne;
+  if(Ne_) *Ne_ = bne;
+  return 0;
+}
+
 } // extern "C"

@@ -170,6 +170,17 @@ def filtrer(h, x):
 filter = filtrer  # noqa: A001  (dsp::filter, dsp/filter.hpp:1662-1666)
 
 
+def convol(h, x):
+    """tsd::filtrage::convol(h, x) (filtrage.hpp:1774-1780): filtre_rif<Tc,T>(h)->step(x), as many outputs as inputs."""
+    return filtrer(h, x)
+
+
+def filtfilt(h, x):
+    """tsd::filtrage::filtfilt(h, x) (filtrage.hpp:1761-1765): filtrer(h, filtrer(h, x).reverse()).reverse()."""
+    rev = (lambda a: a.flip(-1)) if hasattr(x, "is_cuda") else (lambda a: np.ascontiguousarray(a[..., ::-1]))
+    return rev(filtrer(h, rev(filtrer(h, x))))
+
+
 # ----------------------------------------------------------------------------- interpolators
 @dataclass
 class InterpolateurSincConfig:
@@ -272,12 +283,85 @@ def filtre_itrp(ratio: float, itrp, nchan: int = 1) -> AdaptationRythmeSimple:
 filter_itrp = filtre_itrp
 
 
-class AdaptationRythmeArbitraire(FiltreGen):
-    """filtre_reechan<cfloat>(ratio) (ra.cc:84-183): stage planner + arbitrary-ratio interpolator.
+# ----------------------------------------------------------------------------- polyphase stages
+POLY_UPS, POLY_DEMI_BANDE, POLY_DECIM = 0, 1, 2
 
-    Ratios whose post-interpolation factor needs half-band / x2 stages (ratio outside [0.5, 2))
-    are not built yet and raise.
-    """
+
+class FiltrePolyphase(FiltreGen):
+    """GPU counterpart of FiltreRIFUps / FiltreRIFDemiBande / FiltreRIFDecim (polyphase.cc:54-341)."""
+
+    def __init__(self, kind: int, coefs, R: int = 2, T=np.complex64, nchan: int = 1):
+        T = np.dtype(T).type
+        if T not in (np.float32, np.complex64):
+            raise TsdGpuError("filtre polyphase: T doit être float32 ou complex64")
+        self.kind, self.dtype, self.nchan = int(kind), T, int(nchan)
+        self.R = 2 if kind == POLY_DEMI_BANDE else int(R)
+        self.coefs = np.ascontiguousarray(coefs, np.float32)
+        h = _vp()
+        check(lib().tsdgpu_poly_create(self.kind, self.coefs.ctypes.data_as(_vp), int(self.coefs.shape[0]), self.R,
+                                       1 if T is np.complex64 else 0, self.nchan, C.byref(h)))
+        self._h = h
+
+    def out_count(self, n: int) -> int:
+        return int(lib().tsdgpu_poly_out_count(self._h, int(n)))
+
+    @property
+    def state(self):
+        """(ring index, decimation counter) of the reference object (`index`, `odd` / `cnt`)."""
+        i, c = C.c_int(), C.c_int()
+        check(lib().tsdgpu_poly_state(self._h, C.byref(i), C.byref(c)))
+        return i.value, c.value
+
+    def step(self, x):
+        b = Batch(x, self.dtype, self.nchan)
+        cnt = self.out_count(b.n)
+        y = empty_like_batch(b, self.dtype, cnt)
+        if b.n == 0:
+            return restore_shape(y, b.ndim)
+        yb = Batch(y, self.dtype, self.nchan, "y")
+        no = C.c_longlong()
+        check(lib().tsdgpu_poly_step(self._h, b.ptr, b.stride, b.n, yb.ptr if cnt else None, max(yb.stride, 1),
+                                     C.byref(no), b.mem))
+        assert no.value == cnt
+        return restore_shape(y, b.ndim)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                lib().tsdgpu_poly_destroy(h)
+            except Exception:
+                pass
+
+
+def filtre_rif_ups(coefs, R: int, T=np.complex64, nchan: int = 1) -> FiltrePolyphase:
+    """filtre_rif_ups<float,T>(c, R) (polyphase.cc:246-341,356-360): xR polyphase interpolator."""
+    return FiltrePolyphase(POLY_UPS, coefs, R, T, nchan)
+
+
+def filtre_rif_demi_bande(coefs, T=np.complex64, nchan: int = 1) -> FiltrePolyphase:
+    """filtre_rif_demi_bande<float,T>(c) (polyphase.cc:54-149,350-354): half-band decimator by 2."""
+    return FiltrePolyphase(POLY_DEMI_BANDE, coefs, 2, T, nchan)
+
+
+def filtre_rif_decim(coefs, R: int, T=np.complex64, nchan: int = 1) -> FiltrePolyphase:
+    """filtre_rif_decim<float,T>(c, R) (polyphase.cc:156-239,344-348): FIR followed by decimation by R."""
+    return FiltrePolyphase(POLY_DECIM, coefs, R, T, nchan)
+
+
+def filtre_rif_ups_delais(nc: int, R: int) -> float:
+    """filtre_rif_ups_délais (polyphase.cc:363-369)."""
+    pad = (R - (nc % R)) if (nc % R) else 0
+    return (nc - 1) / 2.0 + pad
+
+
+filter_fir_ups, filter_fir_half_band, filter_fir_decim = filtre_rif_ups, filtre_rif_demi_bande, filtre_rif_decim
+
+
+class AdaptationRythmeArbitraire(FiltreGen):
+    """filtre_reechan<cfloat>(ratio) (ra.cc:84-183): half-band decimators while the factor is < 0.5, x2 polyphase
+    interpolators while it is >= 2 (both on design_rif_fen(15, "lp", 0.25, "hn")), then the arbitrary-ratio LUT
+    interpolator itrp_sinc({15, 256, min(0.4, f/2), "hn"}) unless |f - 1| < 1e-6."""
 
     def __init__(self, ratio: float, nchan: int = 1):
         r = np.float32(ratio)
@@ -295,17 +379,25 @@ class AdaptationRythmeArbitraire(FiltreGen):
             self.nb_surechantillonneurs += 1
             f = np.float32(f / 2)
         self.facteur_post_interpolation = float(f)
-        if self.nb_decimateurs or self.nb_surechantillonneurs:
-            raise TsdGpuError("filtre_reechan: ratio hors de [0.5, 2[ — étages demi-bande / x2 pas encore disponibles")
+        coefs = design_rif_fen(15, "lp", 0.25, "hn")                      # ra.cc:135
+        self.decimateurs = [filtre_rif_demi_bande(coefs, np.complex64, nchan) for _ in range(self.nb_decimateurs)]
+        self.surechantillonneurs = [filtre_rif_ups(coefs, 2, np.complex64, nchan) for _ in range(self.nb_surechantillonneurs)]
         fcut = min(np.float32(0.4), np.float32(f / 2))
         self.interpolateur = filtre_itrp(float(f), itrp_sinc(InterpolateurSincConfig(15, 256, float(fcut), "hn")), nchan)
 
     def step(self, x):
         if self.ratio == 1:                        # ra.cc:162-163
             return x.clone() if hasattr(x, "clone") else np.array(x, np.complex64)
+        y = x
+        for d in self.decimateurs:                 # ra.cc:166-167
+            y = d.step(y)
+        for s in self.surechantillonneurs:         # ra.cc:169-170
+            y = s.step(y)
         if abs(np.float32(self.facteur_post_interpolation) - 1) < 1e-6:   # ra.cc:173-174
-            return x.clone() if hasattr(x, "clone") else np.array(x, np.complex64)
-        return self.interpolateur.step(x)
+            if y is x:
+                return x.clone() if hasattr(x, "clone") else np.array(x, np.complex64)
+            return y
+        return self.interpolateur.step(y)
 
 
 def filtre_reechan(ratio: float, nchan: int = 1) -> AdaptationRythmeArbitraire:

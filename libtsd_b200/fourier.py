@@ -20,6 +20,23 @@ def prochaine_puissance_de_2(i: int) -> int:
     return int(lib().tsdgpu_p2(int(i)))
 
 
+def ola_complexite(M: int, Ne: int):
+    """ola_complexité(M, Ne) -> (C, Nf, Nz) (fourier.cc:708-713): FLOP per input sample of the block filter."""
+    c, nf, nz = C.c_float(), C.c_int(), C.c_int()
+    check(lib().tsdgpu_ola_complexite(int(M), int(Ne), C.byref(c), C.byref(nf), C.byref(nz)))
+    return c.value, nf.value, nz.value
+
+
+def ola_complexite_optimise(M: int):
+    """ola_complexité_optimise(M) -> (C, Nf, Nz, Ne) (fourier.cc:715-735): block length 2^k - (M-1) of least cost."""
+    c, nf, nz, ne = C.c_float(), C.c_int(), C.c_int(), C.c_int()
+    check(lib().tsdgpu_ola_complexite_optimise(int(M), C.byref(c), C.byref(nf), C.byref(nz), C.byref(ne)))
+    return c.value, nf.value, nz.value, ne.value
+
+
+ola_complexity, ola_complexity_optimize = ola_complexite, ola_complexite_optimise
+
+
 class FFTPlan:
     """tsd::fourier::FFTPlan (fourier.hpp:19-32) backed by the GPU plan.
 
@@ -91,6 +108,44 @@ def fft(x):
 def ifft(X):
     """tsd::fourier::ifft (fourier.hpp:199-205): unitary inverse DFT."""
     return FFTPlan().step(X, False)
+
+
+def _tfr_rotation(n: int) -> np.ndarray:
+    """tfr_rotation<float>(n) (fourier.cc:32-46): cdouble recurrence r *= w0, stored as cfloat."""
+    w0 = np.exp(-2j * np.pi / n)
+    out = np.empty(n, np.complex64)
+    r = 1.0 + 0.0j
+    for i in range(n):
+        out[i] = r
+        r *= w0
+    return out
+
+
+def rfft(x):
+    """tsd::fourier::rfft (fourier.hpp:116-122) = RTFRPlan<float>::step (fourier.cc:280-355): n real samples ->
+    n complex bins of the unitary DFT.  Even n: one n/2-point complex transform (GPU plan) of the packed signal, the
+    reference's post-twiddle, then csym_forçage (fourier.hpp:264-282); odd n: plain complex transform.
+    Set-up path (it builds H for filtre_rif_fft, fourier.cc:962-965): host numpy around the GPU plan."""
+    x = np.ascontiguousarray(x, np.float32)
+    n = x.shape[0]
+    if n == 0:
+        raise TsdGpuError("Echec assertion : x.rows() > 0.")
+    if n & 1:
+        return FFTPlan().step(x.astype(np.complex64), True)
+    h = n // 2
+    Xt = FFTPlan().step((x[0::2] + 1j * x[1::2]).astype(np.complex64), True)
+    rot = _tfr_rotation(n)
+    i = np.arange(h + 1)
+    X1 = np.where(i == h, Xt[0], Xt[np.minimum(i, h - 1)])
+    X2 = np.where(i > 0, Xt[(h - i) % h], Xt[0])
+    j2, r2 = np.complex64(1j * 0.5 / np.sqrt(2)), np.complex64(0.5 / np.sqrt(2))
+    y = np.zeros(n, np.complex64)
+    y[: h + 1] = (r2 * (X1 + np.conj(X2)) - j2 * (X1 - np.conj(X2)) * rot[: h + 1]).astype(np.complex64)
+    y[0] = y[0].real
+    y[h] = y[h].real
+    if h > 1:
+        y[n - (h - 1):] = np.conj(y[1:h][::-1])
+    return y
 
 
 @dataclass

@@ -49,7 +49,7 @@ class _Port:
         if not os.path.exists(PORT_SO):
             build()
         L = C.CDLL(PORT_SO)
-        for name in ("tsdo_fir_new", "tsdo_fft_new", "tsdo_ola_new", "tsdo_itrp_new"):
+        for name in ("tsdo_fir_new", "tsdo_fft_new", "tsdo_ola_new", "tsdo_itrp_new", "tsdo_poly_new"):
             getattr(L, name).restype = _vp
         L.tsdo_itrp_phase.restype = _f
         self.L = L
@@ -100,6 +100,10 @@ class _Port:
 
     def itrp(self, ratio: float, lut: np.ndarray, nphases: int):
         return _PortItrp(self.L, ratio, lut, nphases)
+
+    def polyphase(self, kind: int, taps, R: int = 2, cplx: bool = True):
+        """kind 0: filtre_rif_ups(c, R), 1: filtre_rif_demi_bande(c), 2: filtre_rif_decim(c, R) (polyphase.cc)."""
+        return _PortPoly(self.L, kind, taps, R, cplx)
 
     def itrp_schedule(self, phase: float, ratio: float, nphases: int, n: int):
         cap = int(np.ceil(np.float32(ratio) * n) + 10)
@@ -188,6 +192,33 @@ class _PortOla:
     def __del__(self):
         if getattr(self, "h", None):
             self.L.tsdo_ola_free(self.h)
+
+
+class _PortPoly:
+    def __init__(self, L, kind, taps, R, cplx):
+        self.L, self.cplx = L, bool(cplx)
+        t = _f32(taps)
+        self.h = _vp(L.tsdo_poly_new(_i(kind), _ptr(t), _i(len(t)), _i(R), _i(1 if cplx else 0)))
+        if not self.h:
+            raise ValueError("tsdo_poly_new: bad arguments")
+
+    @property
+    def index(self):
+        return self.L.tsdo_poly_index(self.h)
+
+    @property
+    def cnt(self):
+        return self.L.tsdo_poly_cnt(self.h)
+
+    def step(self, x):
+        x = _c64(x) if self.cplx else _f32(x)
+        y = np.empty(self.L.tsdo_poly_out_count(self.h, _i(len(x))), x.dtype)
+        self.L.tsdo_poly_step(self.h, _ptr(x), _i(len(x)), _ptr(y))
+        return y
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.tsdo_poly_free(self.h)
 
 
 class _PortItrp:

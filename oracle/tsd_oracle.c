@@ -565,3 +565,107 @@ void tsdo_reechan_plan(float ratio_, int *ndec, int *nups, float *post, float *f
   *fcut = fminf(0.4f, f / 2);
   *use_itrp = (ratio != 1) && !(fabsf(f - 1) < 1e-6f);
 }
+
+/* ------------------------------------------------------------------ polyphase rate-change stages */
+
+/* polyphase.cc:54-341.  kind 0: FiltreRIFUps<T,float>(c, R) (:246-341), 1: FiltreRIFDemiBande<T,float>(c) (:54-149),
+ * 2: FiltreRIFDecim<T,float>(c, R) (:156-239); cplx selects T = cfloat (else float).  The loops below are the
+ * reference's, pointer walk included (ring `fenêtre`, `index`, counter `odd` / `cnt`). */
+typedef struct
+{
+  int kind, cplx, K, R, index, cnt;
+  float *coefs; /* K floats (ups: scaled by R and zero-padded to a multiple of R, :259-269) */
+  float *fen;   /* ring: K (decimators) or K/R (ups) samples of T */
+} tsdo_poly;
+
+tsdo_poly *tsdo_poly_new(int kind, const float *taps, int K, int R, int cplx)
+{
+  if(K <= 0 || kind < 0 || kind > 2) return NULL;
+  if(kind == 1) R = 2; /* :60 */
+  if(R < 1) return NULL;
+  tsdo_poly *f = (tsdo_poly *) calloc(1, sizeof(*f));
+  f->kind = kind;
+  f->cplx = cplx;
+  f->R = R;
+  int Kp = K;
+  if(kind == 0 && (K % R) != 0) Kp = K + (R - (K % R)); /* :264-268 */
+  f->K = Kp;
+  f->coefs = (float *) calloc(Kp, sizeof(float));
+  for(int i = 0; i < K; i++) f->coefs[i] = (kind == 0) ? taps[i] * R : taps[i]; /* coefs = c * R (:258) */
+  const int W = (kind == 0) ? Kp / R : Kp;
+  f->fen = (float *) calloc((size_t) W * (cplx ? 2 : 1), sizeof(float));
+  return f;
+}
+void tsdo_poly_free(tsdo_poly *f)
+{
+  if(!f) return;
+  free(f->coefs);
+  free(f->fen);
+  free(f);
+}
+int tsdo_poly_index(const tsdo_poly *f) { return f->index; }
+int tsdo_poly_cnt(const tsdo_poly *f) { return f->cnt; }
+/* y.resize(n*R) (:290) / y.resize((n + cnt) / R) (:78,181) */
+int tsdo_poly_out_count(const tsdo_poly *f, int n) { return f->kind == 0 ? n * f->R : (n + f->cnt) / f->R; }
+
+#define TSDO_POLY_BODY(T)                                                                                  \
+  const T *iptr = (const T *) x;                                                                           \
+  T *optr = (T *) y;                                                                                       \
+  T *fen = (T *) f->fen;                                                                                   \
+  const int K = f->K, R = f->R;                                                                            \
+  if(f->kind == 0)                                                                                         \
+  {                                                                                                        \
+    const int W = K / R;                                                                                   \
+    for(int j = 0; j < n; j++)                                                                             \
+    {                                                                                                      \
+      fen[f->index] = *iptr++;                                                                             \
+      f->index = (f->index + 1) % W;                                                                       \
+      for(int i = 0; i < R; i++)                                                                           \
+      {                                                                                                    \
+        T sum = 0;                                                                                         \
+        const float *cptr = f->coefs + (R - 1) - i;                                                        \
+        const T *wptr = fen + f->index;                                                                    \
+        const int K1 = W - f->index, K2 = W - K1;                                                          \
+        for(int k = 0; k < K1; k++) { sum += *wptr++ * *cptr; cptr += R; }                                 \
+        wptr = fen;                                                                                        \
+        for(int k = 0; k < K2; k++) { sum += *wptr++ * *cptr; cptr += R; }                                 \
+        *optr++ = sum;                                                                                     \
+      }                                                                                                    \
+    }                                                                                                      \
+  }                                                                                                        \
+  else                                                                                                     \
+  {                                                                                                        \
+    for(int j = 0; j < n; j++)                                                                             \
+    {                                                                                                      \
+      const float *cptr = f->coefs;                                                                        \
+      T somme = 0;                                                                                         \
+      fen[f->index] = *iptr++;                                                                             \
+      f->index = (f->index + 1) % K;                                                                       \
+      if(f->cnt < R - 1) { f->cnt++; continue; }                                                           \
+      f->cnt = 0;                                                                                          \
+      const T *wptr = fen + f->index;                                                                      \
+      const int K1 = K - f->index, K2 = K - K1;                                                            \
+      if(f->kind == 2)                                                                                     \
+      {                                                                                                    \
+        for(int i = 0; i < K1; i++) somme += *wptr++ * *cptr++;                                            \
+        wptr = fen;                                                                                        \
+        for(int i = 0; i < K2; i++) somme += *wptr++ * *cptr++;                                            \
+      }                                                                                                    \
+      else                                                                                                 \
+      {                                                                                                    \
+        int i;                                                                                             \
+        for(i = 0; i < K1; i += 2) { somme += *wptr * *cptr; wptr += 2; cptr += 2; }                       \
+        i = i - K1;                                                                                        \
+        wptr = fen + i;                                                                                    \
+        for(; i < K2; i += 2) { somme += *wptr * *cptr; wptr += 2; cptr += 2; }                            \
+        somme += 0.5f * fen[(f->index + K / 2) % K];                                                       \
+      }                                                                                                    \
+      *optr++ = somme;                                                                                     \
+    }                                                                                                      \
+  }
+
+void tsdo_poly_step(tsdo_poly *f, const float *x, int n, float *y)
+{
+  if(f->cplx) { TSDO_POLY_BODY(cf32) }
+  else { TSDO_POLY_BODY(float) }
+}

@@ -120,6 +120,29 @@ def main():
     z = np.zeros(65536, np.complex64)
     out["rs_counts_64k"] = np.array([len(r.step(z)) for _ in range(6)], np.int32)
 
+    # polyphase stages (polyphase.cc) on design_rif_fen(15, "lp", 0.25): x2 interpolator, half-band, decimator by 3,
+    # blocks 1000/1/777 (ref driver kinds: 0 demi-bande, 1 ups, 2 decim)
+    h15 = R.design_rif_fen(15, "lp", 0.25)
+    out["h15"] = h15
+    x = cn(np.random.default_rng(0x7D5D0006), 1778)
+    out["poly_x"] = x
+    out["poly_blocks"] = np.array([1000, 1, 777], np.int32)
+    for name, kind, rr in (("ups2", 1, 2), ("demi", 0, 2), ("decim3", 2, 3)):
+        f = R.polyphase(kind, h15, rr)
+        ys = [f.step(x[:1000], cap=4096), f.step(x[1000:1001], cap=64), f.step(x[1001:], cap=4096)]
+        out[f"poly_{name}_lens"] = np.array([len(v) for v in ys], np.int32)
+        out[f"poly_{name}_y"] = np.concatenate(ys)
+    # full resample() chains: ratio 0.1 (3 half-bands + interpolator 0.8) and 7.3 (2 x2 stages + interpolator 1.825)
+    for name, ratio in (("r0p1", 0.1), ("r7p3", 7.3)):
+        f = R.reechan(ratio)
+        ys = [f.step(x[:1000], cap=16384), f.step(x[1000:1001], cap=64), f.step(x[1001:], cap=16384)]
+        out[f"reechan_{name}_lens"] = np.array([len(v) for v in ys], np.int32)
+        out[f"reechan_{name}_y"] = np.concatenate(ys)
+    # rfft (RTFRPlan, fourier.cc:280-355)
+    xr = np.random.default_rng(0x7D5D0007).standard_normal(1024).astype(np.float32)
+    out["rfft_x"] = xr
+    out["rfft_X"] = R.rfft(xr)
+
     # integer bookkeeping
     out["p2_in"] = np.array([1, 2, 3, 5, 127, 512, 639, 1024, 1025, 65535, 65536, 65537, 61441 + 4095, 1 << 20], np.int32)
     out["p2_out"] = np.array([R.p2(int(v)) for v in out["p2_in"]], np.int32)

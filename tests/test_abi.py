@@ -31,6 +31,11 @@ def test_host_only_entries(port):
     L = _lib.lib()
     for i in (1, 2, 3, 100, 65536, 65537, 61441 + 4095):
         assert L.tsdgpu_p2(i) == port.p2(i)
+    # cost model of the block filter (fourier.cc:708-735)
+    from libtsd_b200 import fourier as Fo
+    for M in (3, 127, 512, 2560, 4095):
+        assert Fo.ola_complexite_optimise(M) == port.ola_complexite_optimise(M)
+    assert Fo.ola_complexite_optimise(4095)[1:] == (65536, 4094, 61442)
     # resampler schedule == the oracle's recurrence, for several ratios and block partitions
     for ratio in (147 / 160, 1.5, 0.5, 1.9999, 3.7, 0.3):
         phase_g, phase_o = ctypes.c_float(0), 0.0

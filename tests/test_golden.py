@@ -103,3 +103,29 @@ def test_resampler(port):
     r = port.itrp(147.0 / 160.0, G["lut64"], 256)
     z = np.zeros(65536, np.complex64)
     assert [len(r.step(z)) for _ in range(6)] == list(G["rs_counts_64k"]) == [60212, 60211, 60211, 60211, 60211, 60212]
+
+
+def test_polyphase_and_chains(port):
+    """polyphase.cc stages and full filtre_reechan chains against vectors produced by the reference build."""
+    x, blocks = G["poly_x"], list(G["poly_blocks"])
+    for name, kind, rr in (("ups2", 0, 2), ("demi", 1, 2), ("decim3", 2, 3)):   # port kinds: 0 ups, 1 demi-bande, 2 decim
+        f = port.polyphase(kind, G["h15"], rr)
+        ys, i = [], 0
+        for n in blocks:
+            ys.append(f.step(x[i:i + n]))
+            i += n
+        assert [len(v) for v in ys] == list(G[f"poly_{name}_lens"])
+        assert np.array_equal(np.concatenate(ys), G[f"poly_{name}_y"])
+    for name, ratio in (("r0p1", 0.1), ("r7p3", 7.3)):
+        nd, nu, post, fcut, use = port.reechan_plan(ratio)
+        stages = [port.polyphase(1, G["h15"]) for _ in range(nd)] + [port.polyphase(0, G["h15"], 2) for _ in range(nu)]
+        itrp = port.itrp(post, port.itrp_sinc_lut(15, 256, fcut), 256) if use else None
+        ys, i = [], 0
+        for n in blocks:
+            y = x[i:i + n]
+            i += n
+            for st in stages:
+                y = st.step(y)
+            ys.append(itrp.step(y) if itrp is not None else y)
+        assert [len(v) for v in ys] == list(G[f"reechan_{name}_lens"])
+        assert np.array_equal(np.concatenate(ys), G[f"reechan_{name}_y"])

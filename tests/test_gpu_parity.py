@@ -380,6 +380,108 @@ def test_reechan_stock(tsd, cpu_oracle):
 
 
 # ------------------------------------------------------------------------------------- C++ adapters
+@pytest.mark.parametrize("kind,K,R", [(0, 15, 2), (0, 15, 3), (0, 64, 4), (1, 15, 2), (1, 17, 2), (1, 127, 2), (2, 15, 2), (2, 31, 3), (2, 1, 2)])
+@pytest.mark.parametrize("cplx", [True, False])
+def test_polyphase_vs_oracle(tsd, port, kind, K, R, cplx):
+    """filtre_rif_ups / filtre_rif_demi_bande / filtre_rif_decim (polyphase.cc) on a batch, streamed in ragged
+    blocks (including empty and 1-sample calls): per-call output counts, ring index and decimation counter
+    bit-exact, samples within tolerance."""
+    from libtsd_b200 import filtrage as F
+    rng = np.random.default_rng(1000 * kind + 10 * K + R + cplx)
+    taps = rng.standard_normal(K).astype(np.float32) / np.sqrt(K)
+    nchan = 3
+    T = np.complex64 if cplx else np.float32
+    g = F.FiltrePolyphase(kind, taps, R, T, nchan)
+    refs = [port.polyphase(kind, taps, R, cplx) for _ in range(nchan)]
+    for n in (1, 2, 0, 1000, 7, 65536, 3, 1):
+        x = cn(rng, nchan, n) if cplx else rng.standard_normal((nchan, n)).astype(np.float32)
+        y = g.step(x)
+        yr = np.stack([r.step(x[c]) for c, r in enumerate(refs)])
+        assert y.shape == yr.shape
+        assert g.state == (refs[0].index, refs[0].cnt)
+        if y.size:
+            assert rel_err(y, yr, max(rms(x), 1e-30)) <= TOL
+
+
+def test_polyphase_device_buffers(tsd, port):
+    import torch
+    from libtsd_b200 import filtrage as F
+    rng = np.random.default_rng(3)
+    taps = port.design_rif_fen(15, "lp", 0.25)
+    x = cn(rng, 4, 100001)
+    for kind in (0, 1, 2):
+        yd = F.FiltrePolyphase(kind, taps, 2, np.complex64, 4).step(torch.from_numpy(x).cuda())
+        yh = F.FiltrePolyphase(kind, taps, 2, np.complex64, 4).step(x)
+        tsd.synchronize()
+        assert np.array_equal(yd.cpu().numpy(), yh)
+
+
+@pytest.mark.parametrize("ratio", [0.1, 0.25, 0.3, 3.0, 4.0, 7.3, 2.0, 0.5, 1.0, 147 / 160])
+def test_reechan_full_chain(tsd, cpu_oracle, port, ratio):
+    """rééchan / filtre_reechan<cfloat>(ratio) for ratios that need half-band and x2 stages (ra.cc:104-177):
+    per-call output counts equal the reference object's, samples within tolerance."""
+    from libtsd_b200 import filtrage as F
+    rng = np.random.default_rng(int(ratio * 1000))
+    nchan = 2
+    g = F.filtre_reechan(ratio, nchan)
+    if hasattr(cpu_oracle, "reechan"):
+        refs = [cpu_oracle.reechan(ratio) for _ in range(nchan)]
+        step = lambda r, x: r.step(x, cap=int(len(x) * max(ratio, 1) * 2 + 64))   # noqa: E731
+    else:
+        pytest.skip("needs the reference build")
+    assert (g.nb_decimateurs, g.nb_surechantillonneurs) == port.reechan_plan(ratio)[:2]
+    for n in (5000, 37, 4096, 1, 513):
+        x = cn(rng, nchan, n)
+        y = g.step(x)
+        yr = np.stack([step(r, x[c]) for c, r in enumerate(refs)])
+        assert y.shape == yr.shape, (ratio, n)
+        if y.size:
+            assert rel_err(y, yr, rms(x)) <= TOL
+
+
+def test_rfft_convol_filtfilt(tsd, cpu_oracle):
+    """rfft (RTFRPlan, fourier.cc:280-355) against the reference; convol / filtfilt wrappers (filtrage.hpp:1761-1780)."""
+    from libtsd_b200 import filtrage as F, fourier as Fo
+    rng = np.random.default_rng(9)
+    if hasattr(cpu_oracle, "rfft"):
+        for n in (2, 8, 64, 1024, 65536, 131072):   # n/2 must be a power of two (non-2^k plans: SURVEY §8f-3)
+            x = rng.standard_normal(n).astype(np.float32)
+            X, Xr = Fo.rfft(x), cpu_oracle.rfft(x)
+            assert rel_err(X, Xr, rms(x)) <= TOL
+    h = cpu_oracle.design_rif_fen(31, "lp", 0.25)
+    x = rng.standard_normal(2000).astype(np.float32)
+    y1 = cpu_oracle.fir(0, h).step(x)
+    assert rel_err(F.convol(h, x), y1, rms(x)) <= TOL
+    y2 = cpu_oracle.fir(0, h).step(np.ascontiguousarray(y1[::-1]))[::-1]
+    assert rel_err(F.filtfilt(h, x), y2, rms(x)) <= TOL
+
+
+def test_golden_polyphase_chains_rfft(tsd):
+    """The CUDA path against the committed vectors produced by the reference build (tests/golden/make_golden.py):
+    polyphase stages, full resample() chains, rfft — no oracle involved."""
+    import os
+    from libtsd_b200 import filtrage as F, fourier as Fo
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_vectors.npz"))
+    x, blocks = G["poly_x"], list(G["poly_blocks"])
+
+    def run(f):
+        ys, i = [], 0
+        for n in blocks:
+            ys.append(f.step(x[i:i + n]))
+            i += n
+        return ys
+    for name, mk in (("ups2", lambda: F.filtre_rif_ups(G["h15"], 2)), ("demi", lambda: F.filtre_rif_demi_bande(G["h15"])),
+                     ("decim3", lambda: F.filtre_rif_decim(G["h15"], 3))):
+        ys = run(mk())
+        assert [len(v) for v in ys] == list(G[f"poly_{name}_lens"])
+        assert rel_err(np.concatenate(ys), G[f"poly_{name}_y"], rms(x)) <= TOL
+    for name, ratio in (("r0p1", 0.1), ("r7p3", 7.3)):
+        ys = run(F.filtre_reechan(ratio))
+        assert [len(v) for v in ys] == list(G[f"reechan_{name}_lens"])
+        assert rel_err(np.concatenate(ys), G[f"reechan_{name}_y"], rms(x)) <= TOL
+    assert rel_err(Fo.rfft(G["rfft_x"]), G["rfft_X"], rms(G["rfft_x"])) <= TOL
+
+
 def test_cpp_adapters_drop_in():
     """integration/adapter_check.cc: the reference's own FiltreGen<T>::step / fft() / filtre_fft / filtre_itrp
     signatures, once on the reference CPU classes and once through integration/tsd_gpu_adapters.hpp

@@ -84,6 +84,45 @@ def test_itrp_bit_exact(port, ref, ratio, K, fc):
         assert len(ya) == len(yb) and np.array_equal(ya, yb)
 
 
+# ref driver numbering (ref_driver.cc:171-183): 0 demi-bande, 1 ups, 2 decim; port / C ABI: 0 ups, 1 demi-bande, 2 decim
+_REF_KIND = {0: 1, 1: 0, 2: 2}
+
+
+@pytest.mark.parametrize("kind,K,R", [(0, 15, 2), (0, 15, 3), (0, 16, 4), (0, 7, 5), (1, 15, 2), (1, 17, 2), (1, 31, 2), (1, 8, 2),
+                                      (2, 15, 2), (2, 31, 3), (2, 5, 7), (2, 1, 2)])
+def test_polyphase_bit_exact(port, ref, kind, K, R):
+    """FiltreRIFUps / FiltreRIFDemiBande / FiltreRIFDecim (polyphase.cc): output counts per call and samples."""
+    rng = np.random.default_rng(100 * kind + K + R)
+    taps = rng.standard_normal(K).astype(np.float32) if K not in (15, 31) else ref.design_rif_fen(K, "lp", 0.25)
+    a, b = port.polyphase(kind, taps, R), ref.polyphase(_REF_KIND[kind], taps, R)
+    for n in (1, 2, 3, 10, 0, 1000, 7, 4096, 1):
+        x = cn(rng, n)
+        ya, yb = a.step(x), b.step(x, cap=n * max(R, 1) + 16)
+        assert len(ya) == len(yb) and np.array_equal(ya, yb)
+
+
+def test_reechan_chain_matches_reference(port, ref):
+    """filtre_reechan<cfloat>(ratio) (ra.cc:104-177) rebuilt from the port's stages equals the reference object,
+    per call, for ratios that need half-band / x2 stages."""
+    rng = np.random.default_rng(5)
+    for ratio in (0.1, 0.25, 0.3, 3.0, 4.0, 7.3, 2.0, 0.5, 1.0):
+        nd, nu, post, fcut, use = port.reechan_plan(ratio)
+        coefs = ref.design_rif_fen(15, "lp", 0.25)
+        stages = [port.polyphase(1, coefs) for _ in range(nd)] + [port.polyphase(0, coefs, 2) for _ in range(nu)]
+        itrp = port.itrp(post, ref.itrp_sinc_lut(15, 256, fcut), 256) if use else None
+        r = ref.reechan(ratio)
+        for n in (1000, 37, 4096, 1, 513):
+            x = cn(rng, n)
+            y = x
+            if ratio != 1:
+                for st in stages:
+                    y = st.step(y)
+                if itrp is not None:
+                    y = itrp.step(y)
+            yr = r.step(x, cap=int(n * max(ratio, 1) * 2 + 64))
+            assert len(y) == len(yr) and np.array_equal(y, yr), ratio
+
+
 def test_reference_quirks(ref):
     """filtre_rif_fft<cfloat> drops the imaginary part; delay Ne - K."""
     rng = np.random.default_rng(0)
