@@ -81,6 +81,22 @@ int main()
     soit e4 = ecart(rg->step(xr), rc->step(xr), xr);
     printf("filtre_itrp  147/160 : ecart %.2e\n", e4);
     bad += e4 > 1e-5;
+    // polyphase stages and full resample() chains (ratios outside [0.5, 2) use half-band / x2 stages)
+    soit h15 = design_rif_fen(15, "lp", 0.25);
+    soit xp = bruit(30001, 5);
+    {
+      soit e5 = ecart(tsd::gpu::filtre_rif_ups_gpu<cfloat>(h15, 2)->step(xp), filtre_rif_ups<float, cfloat>(h15, 2)->step(xp), xp);
+      soit e6 = ecart(tsd::gpu::filtre_rif_demi_bande_gpu<cfloat>(h15)->step(xp), filtre_rif_demi_bande<float, cfloat>(h15)->step(xp), xp);
+      soit e7 = ecart(tsd::gpu::filtre_rif_decim_gpu<cfloat>(h15, 3)->step(xp), filtre_rif_decim<float, cfloat>(h15, 3)->step(xp), xp);
+      printf("polyphase    ups %.2e, demi-bande %.2e, decim %.2e\n", e5, e6, e7);
+      bad += (e5 > 1e-5) + (e6 > 1e-5) + (e7 > 1e-5);
+    }
+    pour(float ratio: {0.1f, 7.3f, 147.0f / 160.0f})
+    {
+      soit e8 = ecart(tsd::gpu::filtre_reechan_gpu(ratio)->step(xp), filtre_reechan<cfloat>(ratio)->step(xp), xp);
+      printf("filtre_reechan %.4f : ecart %.2e\n", ratio, e8);
+      bad += e8 > 1e-5;
+    }
   }
   catch(const std::exception &e) { printf("exception: %s\n", e.what()); retourne 2; }
   catch(const std::string &s) { printf("exception: %s\n", s.c_str()); retourne 2; }

@@ -11,6 +11,8 @@
 //   filtre_fft(config)             core/src/fourier/fourier.cc:935-940      -> tsd::gpu::filtre_fft_gpu(config, H, K)
 //   filtre_itrp<cfloat>(r, itrp)   core/src/reechan/ra.cc:185-188           -> tsd::gpu::filtre_itrp_gpu(r, itrp)
 //   fftplan_defaut (global hook)   core/src/fourier/fourier.cc:469-472      -> tsd::gpu::installe_fftplan_gpu()
+//   filtre_rif_ups / _demi_bande / _decim   core/src/reechan/polyphase.cc:344-360 -> tsd::gpu::filtre_rif_*_gpu<T>(c[, R])
+//   filtre_reechan<cfloat>(ratio)  core/src/reechan/ra.cc:180-183           -> tsd::gpu::filtre_reechan_gpu(ratio)
 #pragma once
 #include "tsd/tsd.hpp"
 #include "tsd/filtrage.hpp"
@@ -143,6 +145,73 @@ struct AdaptationRythmeGpu: FiltreGen<cfloat>
 inline sptr<FiltreGen<cfloat>> filtre_itrp_gpu(float ratio, sptr<tsd::filtrage::InterpolateurRIF<cfloat>> itrp, entier nphases = 256)
 {
   retourne std::make_shared<AdaptationRythmeGpu>(ratio, itrp, nphases);
+}
+
+// polyphase.cc stages: filtre_rif_ups<float,T>(c, R), filtre_rif_demi_bande<float,T>(c), filtre_rif_decim<float,T>(c, R)
+template<typename T> struct FiltrePolyphaseGpu: FiltreGen<T>
+{
+  tsdgpu_poly_t h = nullptr;
+  FiltrePolyphaseGpu(int kind, const Vecf &c, entier R)
+  {
+    verifie(tsdgpu_poly_create(kind, c.data(), c.rows(), R, std::is_same<T, cfloat>::value ? 1 : 0, 1, &h), "filtre polyphase (gpu)");
+  }
+  ~FiltrePolyphaseGpu() { tsdgpu_poly_destroy(h); }
+  void step(const Vecteur<T> &x, Vecteur<T> &y) override
+  {
+    soit n = x.rows();
+    y.resize((entier) tsdgpu_poly_out_count(h, n));
+    long long n_out = 0;
+    verifie(tsdgpu_poly_step(h, x.data(), n, n, y.rows() ? y.data() : nullptr, std::max(1, y.rows()), &n_out, TSDGPU_HOST),
+            "filtre polyphase::step (gpu)");
+  }
+};
+template<typename T> sptr<FiltreGen<T>> filtre_rif_ups_gpu(const Vecf &c, entier R)
+{
+  retourne std::make_shared<FiltrePolyphaseGpu<T>>(TSDGPU_POLY_UPS, c, R);
+}
+template<typename T> sptr<FiltreGen<T>> filtre_rif_demi_bande_gpu(const Vecf &c)
+{
+  retourne std::make_shared<FiltrePolyphaseGpu<T>>(TSDGPU_POLY_DEMI_BANDE, c, 2);
+}
+template<typename T> sptr<FiltreGen<T>> filtre_rif_decim_gpu(const Vecf &c, entier R)
+{
+  retourne std::make_shared<FiltrePolyphaseGpu<T>>(TSDGPU_POLY_DECIM, c, R);
+}
+
+// filtre_reechan<cfloat>(ratio): the reference's own planner (ra.cc:104-156) with every stage on the GPU
+struct AdaptationRythmeArbitraireGpu: Filtre<cfloat, cfloat, float>
+{
+  std::vector<sptr<FiltreGen<cfloat>>> etages;
+  float ratio = 1;
+  AdaptationRythmeArbitraireGpu(float r) { Configurable<float>::configure(r); }
+  void configure_impl(const float &ratio_) override
+  {
+    ratio = ratio_;
+    si((ratio <= 0) || std::isinf(ratio) || (ratio >= 1e9))
+    {
+      msg_erreur("filtre_reechan (gpu) : facteur de décimation invalide : {}.", ratio);
+      ratio = 1;
+    }
+    etages.clear();
+    float f = ratio;
+    soit coefs = tsd::filtrage::design_rif_fen(15, "lp", 0.25, "hn");
+    tantque(f < 0.5) { etages.push_back(filtre_rif_demi_bande_gpu<cfloat>(coefs)); f *= 2; }
+    std::vector<sptr<FiltreGen<cfloat>>> ups;
+    tantque(f >= 2) { ups.push_back(filtre_rif_ups_gpu<cfloat>(coefs, 2)); f /= 2; }
+    etages.insert(etages.end(), ups.begin(), ups.end());
+    si(!(std::abs(f - 1) < 1e-6f))
+      etages.push_back(filtre_itrp_gpu(f, tsd::filtrage::itrp_sinc<cfloat>({15, 256, std::min(0.4f, f / 2), "hn"}), 256));
+  }
+  void step(const Veccf &x, Veccf &y) override
+  {
+    y = x;
+    si(ratio == 1) retourne;
+    pour(auto &e: etages) y = e->step(y);
+  }
+};
+inline sptr<Filtre<cfloat, cfloat, float>> filtre_reechan_gpu(float ratio)
+{
+  retourne std::make_shared<AdaptationRythmeArbitraireGpu>(ratio);
 }
 
 } // namespace tsd::gpu
