@@ -82,7 +82,9 @@ int tsdgpu_fir_destroy(tsdgpu_fir_t f);
 
 /* ---- FFT plan: replaces FFTPlan / tfrplan_création / fft() / ifft() ------------------------- */
 /* (fourier.hpp:19-32,69,163-205; fourier.cc:360-481).  Always unitary: the reference ignores
- * `normalize` (fourier.cc:119-120,362).  n must be a power of two >= 1 in this version. */
+ * `normalize` (fourier.cc:119-120,362).  Any n >= 1 like TFRPlanDefaut::configure (fourier.cc:372-405): powers of two
+ * directly, even n through two transforms of n/2 (fourier.cc:438-462), odd n through the chirp-z plan of size
+ * p2(2n-1) with the reference's float32 chirp (fourier.cc:237-255,392-398). */
 int tsdgpu_fft_plan(int n, int batch, tsdgpu_fft_t *out);
 /* y[b] = unitary DFT (forward != 0) or inverse DFT of x[b], b in [0,batch). x == y allowed. */
 int tsdgpu_fft_exec(tsdgpu_fft_t p, const void *x, long long x_stride,

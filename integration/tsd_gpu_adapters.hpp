@@ -76,7 +76,7 @@ struct FFTPlanGpu: FiltreGen<cfloat>, tsd::fourier::FFTPlan
     verifie(tsdgpu_fft_exec(h, x.data(), n, y.data(), n, av ? 1 : 0, TSDGPU_HOST), "tfrplan::step (gpu)");
   }
 };
-// every fft()/ifft()/rfft()/Spectrum in the library then uses the GPU plan (power-of-two sizes)
+// every fft()/ifft()/rfft()/Spectrum in the library then uses the GPU plan (any n: 2^k, even split, chirp-z)
 inline void installe_fftplan_gpu()
 {
   tsd::fourier::fftplan_defaut = []() -> sptr<tsd::fourier::FFTPlan> { retourne std::make_shared<FFTPlanGpu>(); };

@@ -19,6 +19,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <string>
+#include <vector>
 
 namespace tsdgpu {
 
@@ -53,6 +55,186 @@ __global__ void copy_strided(const float2 *in, long long in_stride, float2 *out,
   {
     const int b = (int) (idx / n), i = (int) (idx - (long long) b * n);
     out[(long long) b * out_stride + i] = in[(long long) b * in_stride + i];
+  }
+}
+
+// ------------------------------------------------------------------ n not a power of two
+// even n (fourier.cc:438-462): xe(i) = x(2i), xo(i) = x(2i+1); E, O = transforms of n/2;
+// y.head = E + rot.head * O, y.tail = E + rot.tail * O (conj(rot) for the inverse); y *= 1/sqrt(2)
+__global__ void fft_even_split(const float2 *x, long long x_stride, float2 *w, int m, int batch)
+{
+  const long long total = (long long) 2 * m * batch;
+  for(long long idx = (long long) blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long) gridDim.x * blockDim.x)
+  {
+    const int b = (int) (idx / (2 * m)), i = (int) (idx - (long long) b * 2 * m);
+    w[((long long) 2 * b + (i & 1)) * m + (i >> 1)] = x[(long long) b * x_stride + i];
+  }
+}
+__global__ void fft_even_combine(const float2 *w, const float2 *rot, float2 *y, long long y_stride, int m, int batch, int inverse)
+{
+  const long long total = (long long) 2 * m * batch;
+  const float s = 1.0f / sqrtf(2.0f);
+  for(long long idx = (long long) blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long) gridDim.x * blockDim.x)
+  {
+    const int b = (int) (idx / (2 * m)), k = (int) (idx - (long long) b * 2 * m), kk = k < m ? k : k - m;
+    const float2 E = w[(long long) 2 * b * m + kk], O = w[((long long) 2 * b + 1) * m + kk];
+    float2 r = rot[k];
+    if(inverse) r.y = -r.y;
+    const float2 v = cadd(E, cmul(r, O));
+    y[(long long) b * y_stride + k] = make_float2(v.x * s, v.y * s);
+  }
+}
+// odd n (tfr_czt_impl, fourier.cc:237-255): xp.head(n) = x * chirp.tail(n), zero-padded to n2
+__global__ void fft_czt_pre(const float2 *x, long long x_stride, const float2 *chirp_tail, float2 *w, int n, int n2, int batch)
+{
+  const long long total = (long long) n2 * batch;
+  for(long long idx = (long long) blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long) gridDim.x * blockDim.x)
+  {
+    const int b = (int) (idx / n2), i = (int) (idx - (long long) b * n2);
+    w[idx] = i < n ? cmul(x[(long long) b * x_stride + i], chirp_tail[i]) : make_float2(0.f, 0.f);
+  }
+}
+__global__ void fft_mul_vec(float2 *w, const float2 *v, int n2, long long total)
+{
+  for(long long idx = (long long) blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long) gridDim.x * blockDim.x)
+    w[idx] = cmul(w[idx], v[idx % n2]);
+}
+// y = y2.segment(n-1, n) * chirp.tail(n) * (sqrt(n2) / sqrt(n)); inverse: Y(0) = X(0), Y(k) = X(n-k) (tfr2itfr, fourier.cc:258-277)
+__global__ void fft_czt_post(const float2 *w, const float2 *chirp_tail, float2 *y, long long y_stride, int n, int n2, int batch, float scale,
+                             int inverse)
+{
+  const long long total = (long long) n * batch;
+  for(long long idx = (long long) blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long) gridDim.x * blockDim.x)
+  {
+    const int b = (int) (idx / n), k = (int) (idx - (long long) b * n);
+    const float2 v = cmul(w[(long long) b * n2 + n - 1 + k], chirp_tail[k]);
+    const int ko = (inverse && k) ? n - k : k;
+    y[(long long) b * y_stride + ko] = make_float2(v.x * scale, v.y * scale);
+  }
+}
+
+// ------------------------------------------------------------------ 16 <= N <= 16384: one launch, shared memory
+// Stockham autosort with 16 points per thread: radix-16 passes (fft16 in registers), then one radix-4 and/or one
+// radix-2 pass for the remaining factor.  Pass with sub-transform length Ns and radix R, butterfly j:
+//   k = j mod Ns;  v[t] = in[j + t*N/R] * W_(Ns*R)^(k*t);  DFT_R;  out[(j - k)*R + k + t*Ns] = v[t]
+// All inputs of a pass are read into registers before any output is written (barrier in between), so one buffer
+// of N points per transform is enough; the first pass reads global memory and the last one writes it, both fully
+// coalesced.  N/16 threads per transform; CTAs of 256 threads pack 4096/N transforms when N < 4096.
+template<bool INV>
+__global__ void __launch_bounds__(1024, 1) fft_smem_kernel(const float2 *x, long long x_stride, float2 *y, long long y_stride, int N, int batch,
+                                                           float scale)
+{
+  extern __shared__ float2 fft_sm[];
+  const int T = N >> 4;
+  const int local = threadIdx.x / T, j = threadIdx.x - local * T;
+  const long long b = (long long) blockIdx.x * (blockDim.x / T) + local;
+  const bool active = b < batch;
+  float2 *sm = fft_sm + (size_t) local * N;
+  const float2 *in = x + b * x_stride;
+  float2 *out = y + b * y_stride;
+  float2 v[16];
+  int Ns = 1, rem = N;
+  bool first = true;
+  // ---- radix-16 passes
+  while(rem >= 16)
+  {
+    rem >>= 4;
+    const bool last = rem == 1;
+    if(active)
+    {
+#pragma unroll
+      for(int t = 0; t < 16; t++) v[t] = first ? in[j + t * T] : sm[j + t * T];
+    }
+    if(!first) __syncthreads();
+    const int k = j & (Ns - 1);
+    if(Ns > 1) mul_geometric(v, make_float2(1.f, 0.f), twiddle<INV>((unsigned) k, 2.0f / (float) (Ns * 16)));
+    fft16<INV>(v);
+    const int j0 = (j - k) * 16 + k;
+    if(active)
+    {
+      if(last)
+      {
+#pragma unroll
+        for(int t = 0; t < 16; t++) out[j0 + t * Ns] = make_float2(v[t].x * scale, v[t].y * scale);
+      }
+      else
+      {
+#pragma unroll
+        for(int t = 0; t < 16; t++) sm[j0 + t * Ns] = v[t];
+      }
+    }
+    if(!last) __syncthreads();
+    Ns <<= 4;
+    first = false;
+  }
+  // ---- one radix-4 pass (remaining factor 4 or 8): 4 butterflies per thread
+  if(rem >= 4)
+  {
+    rem >>= 2;
+    const bool last = rem == 1;
+    const int Q = N >> 2;
+    if(active)
+    {
+#pragma unroll
+      for(int m = 0; m < 4; m++)
+#pragma unroll
+        for(int t = 0; t < 4; t++) v[4 * m + t] = first ? in[j + m * T + t * Q] : sm[j + m * T + t * Q];
+    }
+    if(!first) __syncthreads();
+#pragma unroll
+    for(int m = 0; m < 4; m++)
+    {
+      const int jj = j + m * T, k = jj & (Ns - 1);
+      if(Ns > 1)
+      {
+        const float2 w = twiddle<INV>((unsigned) k, 2.0f / (float) (Ns * 4)), w2 = cmul(w, w);
+        v[4 * m + 1] = cmul(v[4 * m + 1], w);
+        v[4 * m + 2] = cmul(v[4 * m + 2], w2);
+        v[4 * m + 3] = cmul(v[4 * m + 3], cmul(w2, w));
+      }
+      fft4<INV>(v[4 * m], v[4 * m + 1], v[4 * m + 2], v[4 * m + 3]);
+      const int j0 = (jj - k) * 4 + k;
+      if(active)
+      {
+#pragma unroll
+        for(int t = 0; t < 4; t++)
+        {
+          if(last) out[j0 + t * Ns] = make_float2(v[4 * m + t].x * scale, v[4 * m + t].y * scale);
+          else sm[j0 + t * Ns] = v[4 * m + t];
+        }
+      }
+    }
+    if(!last) __syncthreads();
+    Ns <<= 2;
+    first = false;
+  }
+  // ---- one radix-2 pass (remaining factor 2): 8 butterflies per thread, always the last pass
+  if(rem == 2)
+  {
+    const int Hh = N >> 1;
+    if(active)
+    {
+#pragma unroll
+      for(int m = 0; m < 8; m++)
+      {
+        v[2 * m] = first ? in[j + m * T] : sm[j + m * T];
+        v[2 * m + 1] = first ? in[j + m * T + Hh] : sm[j + m * T + Hh];
+      }
+    }
+    // no barrier needed: this pass writes global memory only
+#pragma unroll
+    for(int m = 0; m < 8; m++)
+    {
+      const int jj = j + m * T, k = jj & (Ns - 1);
+      const float2 wb = Ns > 1 ? cmul(v[2 * m + 1], twiddle<INV>((unsigned) k, 2.0f / (float) (Ns * 2))) : v[2 * m + 1];
+      const float2 a = cadd(v[2 * m], wb), d = csub(v[2 * m], wb);
+      const int j0 = (jj - k) * 2 + k;
+      if(active)
+      {
+        out[j0] = make_float2(a.x * scale, a.y * scale);
+        out[j0 + Ns] = make_float2(d.x * scale, d.y * scale);
+      }
+    }
   }
 }
 
@@ -203,12 +385,74 @@ namespace tsdgpu {
 
 int fft_plan_create(int n, int batch, tsdgpu_fft_s **out)
 {
-  if(n <= 0 || (n & (n - 1))) return fail("tsdgpu_fft_plan: n must be a power of two >= 1 in this version");
+  if(n <= 0) return fail("tsdgpu_fft_plan: n must be >= 1");
   if(batch <= 0) return fail("tsdgpu_fft_plan: batch must be > 0");
   if(n > (1 << 24)) return fail("tsdgpu_fft_plan: n > 2^24 not supported");
   auto *p = new tsdgpu_fft_s;
   p->n = n;
   p->batch = batch;
+  if(n & (n - 1))
+  {
+    cudaError_t e = cudaSuccess;
+    if((n & 1) == 0)
+    {
+      // even: decompose while even (fourier.cc:385-389); rotations = tfr_rotation<float>(n): cdouble recurrence (fourier.cc:32-46)
+      const int m = n / 2;
+      if((long long) 2 * batch > (1LL << 30) || fft_plan_create(m, 2 * batch, &p->sub)) { fft_plan_destroy(p); return 1; }
+      std::vector<float2> rot((size_t) n);
+      double rr = 1.0, ri = 0.0;
+      const double wr = cos(-2.0 * M_PI / n), wi = sin(-2.0 * M_PI / n);
+      for(int i = 0; i < n; i++)
+      {
+        rot[i] = make_float2((float) rr, (float) ri);
+        const double t = rr * wr - ri * wi;
+        ri = rr * wi + ri * wr;
+        rr = t;
+      }
+      e = cudaMalloc(&p->d_rot, (size_t) n * sizeof(float2));
+      if(e == cudaSuccess) e = cudaMemcpy(p->d_rot, rot.data(), (size_t) n * sizeof(float2), cudaMemcpyHostToDevice);
+      if(e == cudaSuccess) e = cudaMalloc(&p->nwork, (size_t) 2 * batch * m * sizeof(float2));
+    }
+    else
+    {
+      // odd: chirp-z.  n2 = p2(2n-1); t = square(linspace(-(n-1), n-1, 2n-1)) / 2; t *= -2*pi/n; chirp = polar(t)
+      // (fourier.cc:392-398) -- float arithmetic reproduced operation by operation: for large n the reference's own
+      // chirp carries float phase errors far above 1e-5, and parity is against the reference.
+      if(2LL * n - 1 > (1 << 24)) { fft_plan_destroy(p); return fail("tsdgpu_fft_plan: odd n too large for the chirp-z plan"); }
+      p->n2 = tsdgpu_p2(2 * n - 1);
+      if(fft_plan_create(p->n2, batch, &p->sub)) { fft_plan_destroy(p); return 1; }
+      const float c = (float) (-2.0 * M_PI / n);
+      std::vector<float2> chirp((size_t) 2 * n - 1), icp((size_t) p->n2, make_float2(0.f, 0.f));
+      for(int i = 0; i < 2 * n - 1; i++)
+      {
+        const float lin = (float) (-(double) (n - 1) + (double) i);
+        float t = (lin * lin) / 2.0f;
+        t = t * c;
+        chirp[i] = make_float2(1.0f * cosf(t), 1.0f * sinf(t));      // std::polar((float) 1, t)
+        icp[i] = make_float2(chirp[i].x, -chirp[i].y);               // icp.head(2n-1) = chirp.conjugate() (fourier.cc:246-247)
+      }
+      e = cudaMalloc(&p->d_chirp, (size_t) n * sizeof(float2));
+      if(e == cudaSuccess) e = cudaMemcpy(p->d_chirp, chirp.data() + (n - 1), (size_t) n * sizeof(float2), cudaMemcpyHostToDevice);
+      if(e == cudaSuccess) e = cudaMalloc(&p->d_Xc, (size_t) p->n2 * sizeof(float2));
+      if(e == cudaSuccess) e = cudaMemcpy(p->d_Xc, icp.data(), (size_t) p->n2 * sizeof(float2), cudaMemcpyHostToDevice);
+      if(e == cudaSuccess) e = cudaMalloc(&p->nwork, (size_t) batch * p->n2 * sizeof(float2));
+      if(e == cudaSuccess)
+      {
+        // Xc = unitary transform of icp, computed once (the reference redoes it at every call, fourier.cc:252)
+        tsdgpu_fft_s *one = nullptr;
+        if(fft_plan_create(p->n2, 1, &one) || fft_exec_device(one, p->d_Xc, p->n2, p->d_Xc, p->n2, true)) { fft_plan_destroy(one); fft_plan_destroy(p); return 1; }
+        e = cudaStreamSynchronize(rt().stream);
+        fft_plan_destroy(one);
+      }
+    }
+    if(e != cudaSuccess)
+    {
+      fft_plan_destroy(p);
+      return fail(std::string("tsdgpu_fft_plan: ") + cudaGetErrorString(e));
+    }
+    *out = p;
+    return 0;
+  }
   if(n == 65536)
   {
     p->ring = 64;
@@ -240,6 +484,11 @@ int fft_plan_create(int n, int batch, tsdgpu_fft_s **out)
 void fft_plan_destroy(tsdgpu_fft_s *p)
 {
   if(!p) return;
+  if(p->sub) fft_plan_destroy(p->sub);
+  if(p->d_rot) cudaFree(p->d_rot);
+  if(p->d_chirp) cudaFree(p->d_chirp);
+  if(p->d_Xc) cudaFree(p->d_Xc);
+  if(p->nwork) cudaFree(p->nwork);
   if(p->scratch) cudaFree(p->scratch);
   if(p->flags) cudaFree(p->flags);
   if(p->work[0]) cudaFree(p->work[0]);
@@ -258,6 +507,32 @@ int fft_exec_device(tsdgpu_fft_s *p, const float2 *x, long long xs, float2 *y, l
 {
   Runtime &r = rt();
   const int N = p->n, batch = p->batch;
+  if(p->sub && p->n2 == 0)
+  {
+    const int m = N / 2;
+    const int grid = grid_for((long long) N * batch, 256);
+    fft_even_split<<<grid, 256, 0, r.stream>>>(x, xs, p->nwork, m, batch);
+    TSD_LAUNCH_CHECK();
+    if(fft_exec_device(p->sub, p->nwork, m, p->nwork, m, forward)) return 1;
+    fft_even_combine<<<grid, 256, 0, r.stream>>>(p->nwork, p->d_rot, y, ys, m, batch, forward ? 0 : 1);
+    TSD_LAUNCH_CHECK();
+    return 0;
+  }
+  if(p->sub)
+  {
+    const int n2 = p->n2;
+    const long long total = (long long) n2 * batch;
+    fft_czt_pre<<<grid_for(total, 256), 256, 0, r.stream>>>(x, xs, p->d_chirp, p->nwork, N, n2, batch);
+    TSD_LAUNCH_CHECK();
+    if(fft_exec_device(p->sub, p->nwork, n2, p->nwork, n2, true)) return 1;
+    fft_mul_vec<<<grid_for(total, 256), 256, 0, r.stream>>>(p->nwork, p->d_Xc, n2, total);
+    TSD_LAUNCH_CHECK();
+    if(fft_exec_device(p->sub, p->nwork, n2, p->nwork, n2, false)) return 1;
+    fft_czt_post<<<grid_for((long long) N * batch, 256), 256, 0, r.stream>>>(p->nwork, p->d_chirp, y, ys, N, n2, batch,
+                                                                              sqrtf((float) n2) / sqrtf((float) N), forward ? 0 : 1);
+    TSD_LAUNCH_CHECK();
+    return 0;
+  }
   if(N == 1)
   {
     if(x != y || xs != ys)
@@ -331,6 +606,24 @@ int fft_exec_device(tsdgpu_fft_s *p, const float2 *x, long long xs, float2 *y, l
       else fft64k_kernel<true><<<grid, FFT_NT, 0, r.stream>>>(q);
       TSD_LAUNCH_CHECK();
     }
+    return 0;
+  }
+  if(N >= 16 && N <= 16384)
+  {
+    const int T = N / 16, threads = std::max(256, T), per_cta = threads / T;
+    const size_t smem = (size_t) per_cta * N * sizeof(float2);
+    const float scale = 1.0f / sqrtf((float) N);
+    const unsigned grid = (unsigned) ((batch + per_cta - 1) / per_cta);
+    if(smem > 48 * 1024 && !p->smem_optin)
+    {
+      TSD_CUDA(cudaFuncSetAttribute(fft_smem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+      TSD_CUDA(cudaFuncSetAttribute(fft_smem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+      p->smem_optin = true;
+    }
+    KernelTimer timer;
+    if(forward) fft_smem_kernel<false><<<grid, threads, smem, r.stream>>>(x, xs, y, ys, N, batch, scale);
+    else fft_smem_kernel<true><<<grid, threads, smem, r.stream>>>(x, xs, y, ys, N, batch, scale);
+    TSD_LAUNCH_CHECK();
     return 0;
   }
   // ---- generic: log2(N) radix-2 passes, ping-pong so that the last pass lands in y

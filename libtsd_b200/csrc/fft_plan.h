@@ -10,8 +10,17 @@ struct tsdgpu_fft_s
   unsigned *flags = nullptr;   // done_a[batch], done_b[batch], ticket
   int ring = 0, lag = 0, ctas = 0;
   int staged = 1, chunk = 32, nstreams = 4;   // staged form: transforms per stage kernel, auxiliary streams
+  bool smem_optin = false;     // shared-memory kernel: > 48 KiB of dynamic shared memory enabled
   // generic radix-2 path
   float2 *work[2] = {nullptr, nullptr};
+  // n not a power of two (TFRPlanDefaut::configure, fourier.cc:372-405): even n -> two transforms of n/2 + one
+  // radix-2 combine (fourier.cc:438-462); odd n -> chirp-z through a power-of-two plan of n2 = p2(2n-1) (fourier.cc:237-255)
+  tsdgpu_fft_s *sub = nullptr;
+  int n2 = 0;
+  float2 *d_rot = nullptr;     // even n: tfr_rotation(n), [n]
+  float2 *d_chirp = nullptr;   // odd n: chirp.tail(n), [n]
+  float2 *d_Xc = nullptr;      // odd n: unitary transform of conj(chirp) zero-padded to n2, [n2]
+  float2 *nwork = nullptr;     // [2*batch][n/2] or [batch][n2]
 };
 
 namespace tsdgpu {

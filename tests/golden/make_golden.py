@@ -143,6 +143,14 @@ def main():
     out["rfft_x"] = xr
     out["rfft_X"] = R.rfft(xr)
 
+    # FFT plans for n not a power of two: even split (fourier.cc:438-462) and chirp-z (fourier.cc:237-255)
+    for n in (12, 15, 1000, 12345):
+        xx = cn(np.random.default_rng(1000 + n), n)
+        pl = R.fft(n)
+        out[f"fftnp{n}_x"] = xx
+        out[f"fftnp{n}_X"] = pl.step(xx, True)
+        out[f"fftnp{n}_xi"] = pl.step(xx, False)
+
     # integer bookkeeping
     out["p2_in"] = np.array([1, 2, 3, 5, 127, 512, 639, 1024, 1025, 65535, 65536, 65537, 61441 + 4095, 1 << 20], np.int32)
     out["p2_out"] = np.array([R.p2(int(v)) for v in out["p2_in"]], np.int32)
