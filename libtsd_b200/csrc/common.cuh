@@ -23,6 +23,9 @@ struct Runtime
   cudaStream_t aux[MAX_AUX] = {};
   cudaEvent_t ev_fork = nullptr, ev_join[MAX_AUX] = {};
   float4 *tw256 = nullptr;           // [512] local twiddles of the 256-point transforms: forward, then conjugated
+  // four-step twiddles of the 65536-point transform, W = exp(-2 pi i / 65536) (host-built in double):
+  // [0, 4096) W^(n2*hi) at [hi*256 + n2]; [4096, 8192) the same values at [k1*16 + lo]; [8192, 8448) W^(16*n)
+  float2 *tw4 = nullptr;
   long long launches = 0;
   // optional device-side timing of the dominant kernels (tsdgpu_timing_*)
   bool timing = false;

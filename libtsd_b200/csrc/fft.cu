@@ -249,6 +249,7 @@ struct Fft64kParams
   unsigned *done_b;       // [batch]
   unsigned *ticket;
   int batch, ring, lag;
+  const float2 *tw4;      // rt().tw4: four-step twiddle tables
 };
 
 constexpr int FFT_NT = 256;
@@ -295,8 +296,7 @@ __global__ void __launch_bounds__(FFT_NT, 4) fft64k_kernel(Fft64kParams p)
       for(int j = 0; j < 16; j++) v[j] = ldg_stream(x + j * 4096);
       fft256_cols<INV>(v, sm, tw, hi, lo);
       // v[p2] = Y[k1 = hi + 16 p2][n2]; four-step twiddle W_N^(n2*k1)
-      const unsigned n2 = (unsigned) (16 * g + lo);
-      mul_geometric(v, twiddle<INV>(n2 * (unsigned) hi, 2.0f / 65536.0f), twiddle<INV>(16u * n2, 2.0f / 65536.0f));
+      mul_fourstep_cols<INV>(v, p.tw4, 16 * g + lo, hi);
       float2 *sc = p.scratch + (long long) (t % p.ring) * 65536 + hi * 256 + 16 * g + lo;
 #pragma unroll
       for(int p2 = 0; p2 < 16; p2++) sc[p2 * 4096] = v[p2];
@@ -327,6 +327,7 @@ struct Fft64kStageParams
   long long x_stride, y_stride;
   float2 *scratch;        // this chunk's scratch, [gridDim.y][65536]
   const float4 *tw;       // rt().tw256
+  const float2 *tw4;      // rt().tw4
   int t0;                 // first transform of the chunk
 };
 
@@ -345,10 +346,10 @@ template<bool INV, int STAGE> __global__ void __launch_bounds__(FFT_NT, 4) fft64
 #pragma unroll
     for(int j = 0; j < 16; j++) v[j] = ldg_stream(x + j * 4096);
     fill_tw256_from(tw, p.tw, tid, INV);
+    const float2 tb = tw4_load<INV>(p.tw4 + hi * 256 + 16 * g + lo), ts = tw4_load<INV>(p.tw4 + 8192 + 16 * g + lo);
     __syncthreads();
     fft256_cols<INV, true>(v, sm, tw, hi, lo);
-    const unsigned n2 = (unsigned) (16 * g + lo);
-    mul_geometric(v, twiddle<INV>(n2 * (unsigned) hi, 2.0f / 65536.0f), twiddle<INV>(16u * n2, 2.0f / 65536.0f));
+    mul_geometric(v, tb, ts);   // four-step twiddle W_N^(n2*k1)
     float2 *dst = sc + hi * 256 + 16 * g + lo;
 #pragma unroll
     for(int p2 = 0; p2 < 16; p2++) dst[p2 * 4096] = v[p2];
@@ -461,7 +462,7 @@ int fft_plan_create(int n, int batch, tsdgpu_fft_s **out)
     if(const char *v = getenv("TSDGPU_FFT_MODE")) p->staged = v[0] == 'p' ? 0 : 1;
     if(const char *v = getenv("TSDGPU_FFT_CHUNK")) p->chunk = std::max(1, atoi(v));
     if(const char *v = getenv("TSDGPU_FFT_STREAMS")) p->nstreams = std::min((int) Runtime::MAX_AUX, std::max(1, atoi(v)));
-    if(p->staged && aux_init()) { fft_plan_destroy(p); return 1; }
+    if(aux_init()) { fft_plan_destroy(p); return 1; }   // twiddle tables (and the auxiliary streams of the staged form)
     if(const char *v = getenv("TSDGPU_FFT_LAG")) p->lag = std::max(1, atoi(v));
     if(const char *v = getenv("TSDGPU_FFT_RING")) p->ring = atoi(v);
     if(p->ring <= p->lag) p->ring = p->lag + 16;
@@ -561,6 +562,7 @@ int fft_exec_device(tsdgpu_fft_s *p, const float2 *x, long long xs, float2 *y, l
       sp.x_stride = xs;
       sp.y_stride = ys;
       sp.tw = r.tw256;
+      sp.tw4 = r.tw4;
       int c = 0;
       for(int t0 = 0; t0 < batch; t0 += p->chunk, c++)
       {
@@ -596,6 +598,7 @@ int fft_exec_device(tsdgpu_fft_s *p, const float2 *x, long long xs, float2 *y, l
     q.done_a = p->flags;
     q.done_b = p->flags + batch;
     q.ticket = p->flags + 2 * batch;
+    q.tw4 = r.tw4;
     q.batch = batch;
     q.ring = p->ring;
     q.lag = p->lag;

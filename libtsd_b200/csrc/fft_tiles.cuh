@@ -111,6 +111,23 @@ __device__ __forceinline__ void mul_geometric(float2 (&v)[16], float2 base, floa
   }
 }
 
+// Four-step twiddles from the host-built tables (Runtime::tw4): stage A, thread (hi, column n2): v[p2] *= W^(n2*(hi + 16 p2));
+// row stage of the inverse, thread (row k1, lo): v[pp] *= conj(W)^(k1*(lo + 16 pp)).  Two coalesced 8-byte loads
+// replace two sincospif evaluations.
+template<bool INV> __device__ __forceinline__ float2 tw4_load(const float2 *p)
+{
+  const float2 w = __ldg(p);
+  return INV ? make_float2(w.x, -w.y) : w;
+}
+template<bool INV> __device__ __forceinline__ void mul_fourstep_cols(float2 (&v)[16], const float2 *tw4, int n2, int hi)
+{
+  mul_geometric(v, tw4_load<INV>(tw4 + hi * 256 + n2), tw4_load<INV>(tw4 + 8192 + n2));
+}
+template<bool INV> __device__ __forceinline__ void mul_fourstep_rows(float2 (&v)[16], const float2 *tw4, int k1, int lo)
+{
+  mul_geometric(v, tw4_load<INV>(tw4 + 4096 + k1 * 16 + lo), tw4_load<INV>(tw4 + 8192 + k1));
+}
+
 // Local twiddles of a 256-point transform from the shared table tw[k*16 + i] = {w, i*w} with
 // w = exp(-2 pi i * i*k / 256), i, k in [0,16): v[k] *= w (conjugated for the inverse), one LDS.128 +
 // FMUL2 + FFMA2 each.  For a fixed k the 16 lanes of a half-warp read either one entry (idx = hi:

@@ -53,6 +53,7 @@ struct OlaParams
   int ola_form;           // 0 overlap-save, 1 overlap-add
   int ring, lag;
   int n;                  // samples per channel in this call
+  const float2 *tw4;      // rt().tw4: four-step twiddle tables
 };
 
 constexpr int OLA_NT = 256;
@@ -126,8 +127,7 @@ __global__ void __launch_bounds__(OLA_NT, 3) ola64k_kernel(OlaParams p)
         }
       }
       fft256_cols<false>(v, sm, tw, hi, lo);
-      const unsigned n2 = (unsigned) (16 * g + lo);
-      mul_geometric(v, twiddle<false>(n2 * (unsigned) hi, 2.0f / 65536.0f), twiddle<false>(16u * n2, 2.0f / 65536.0f));
+      mul_fourstep_cols<false>(v, p.tw4, 16 * g + lo, hi);
       float2 *dst = sc + n0;
 #pragma unroll
       for(int p2 = 0; p2 < 16; p2++) dst[p2 * 4096] = v[p2];
@@ -150,8 +150,7 @@ __global__ void __launch_bounds__(OLA_NT, 3) ola64k_kernel(OlaParams p)
       __syncthreads();   // exchange buffer is reused
       fft256_rows_b<true>(v, sm, tw, hi, lo);
       // thread (hi = r, lo = q'): v[pp] = b[k1 = 16g + r][n2 = 16*pp + q']; conj four-step twiddle
-      const unsigned k1 = (unsigned) (16 * g + hi);
-      mul_geometric(v, twiddle<true>(k1 * (unsigned) lo, 2.0f / 65536.0f), twiddle<true>(16u * k1, 2.0f / 65536.0f));
+      mul_fourstep_rows<true>(v, p.tw4, 16 * g + hi, lo);
 #pragma unroll
       for(int pp = 0; pp < 16; pp++) row[16 * pp] = v[pp];
       warp_release(p.done_b + q);
@@ -251,10 +250,10 @@ __device__ __forceinline__ void ola_stage_body(const OlaParams &p, const float4 
       }
     }
     fill_tw256_from(tw, gtw, tid, false);
+    const float2 tb = tw4_load<false>(p.tw4 + hi * 256 + 16 * g + lo), ts = tw4_load<false>(p.tw4 + 8192 + 16 * g + lo);
     __syncthreads();
     fft256_cols<false, true>(v, sm, tw, hi, lo);
-    const unsigned n2 = (unsigned) (16 * g + lo);
-    mul_geometric(v, twiddle<false>(n2 * (unsigned) hi, 2.0f / 65536.0f), twiddle<false>(16u * n2, 2.0f / 65536.0f));
+    mul_geometric(v, tb, ts);   // four-step twiddle W_N^(n2*k1)
     float2 *dst = sc + n0;
 #pragma unroll
     for(int p2 = 0; p2 < 16; p2++) dst[p2 * 4096] = v[p2];
@@ -266,6 +265,7 @@ __device__ __forceinline__ void ola_stage_body(const OlaParams &p, const float4 
     for(int j = 0; j < 16; j++) v[j] = __ldcg(row + 16 * j);
     fill_tw256_from(tw, gtw, tid, false);
     fill_tw256_from(tw + 256, gtw, tid, true);
+    const float2 tb = tw4_load<true>(p.tw4 + 4096 + (16 * g + hi) * 16 + lo), ts = tw4_load<true>(p.tw4 + 8192 + 16 * g + hi);
     __syncthreads();
     fft256_rows_a<false, true>(v, sm, tw, hi, lo);
     // thread (hi = k', lo = r): v[k2] = X[k], k = (16g + r) + 256*(k' + 16*k2)
@@ -275,8 +275,7 @@ __device__ __forceinline__ void ola_stage_body(const OlaParams &p, const float4 
     __syncthreads();   // exchange buffer is reused
     fft256_rows_b<true, true>(v, sm, tw + 256, hi, lo);
     // thread (hi = r, lo = q'): v[pp] = b[k1 = 16g + r][n2 = 16*pp + q']; conj four-step twiddle
-    const unsigned k1 = (unsigned) (16 * g + hi);
-    mul_geometric(v, twiddle<true>(k1 * (unsigned) lo, 2.0f / 65536.0f), twiddle<true>(16u * k1, 2.0f / 65536.0f));
+    mul_geometric(v, tb, ts);
 #pragma unroll
     for(int pp = 0; pp < 16; pp++) row[16 * pp] = v[pp];
   }
@@ -470,6 +469,7 @@ static int ola_run_fused(tsdgpu_ola_s *f, const float2 *x, long long xs, int n, 
   p.ring = f->ring;
   p.lag = f->lag;
   p.n = n;
+  p.tw4 = r.tw4;
   if(f->K > 0)
   {
     p.ola_form = 0;
@@ -495,15 +495,22 @@ static int ola_run_fused(tsdgpu_ola_s *f, const float2 *x, long long xs, int n, 
     sp.tw = r.tw256;
     const int C = f->chunk;
     const int nchunks = (int) ((Q + C - 1) / C);
-    // streams schedule
-    if(aux_fork(f->nslots)) return 1;
-    for(int c = 0; c < nchunks; c++)
+    // TSDGPU_OLA_SKEW=d gives stream s chunks of C + d*(s - (S-1)/2) blocks (<= C) so that the streams drift out of
+    // lock-step: +1..2 % (measured; marking the scratch as an L2 persisting window instead costs 15 %)
+    static const int skew = getenv("TSDGPU_OLA_SKEW") ? atoi(getenv("TSDGPU_OLA_SKEW")) : 0;
+    const int S = f->nslots;
+    if(aux_fork(S)) return 1;
+    long long q0 = 0;
+    for(int c = 0; q0 < Q; c++)
     {
-      const int s = c % f->nslots;
+      const int s = c % S;
+      int cs = C + (skew * (2 * s - (S - 1))) / 2;
+      cs = std::max(1, std::min(cs, C));
       OlaRole &ro = sp.role[0];
-      ro.q0 = c * C;
-      ro.nb = (int) std::min<long long>(C, Q - (long long) c * C);
+      ro.q0 = (int) q0;
+      ro.nb = (int) std::min<long long>(cs, Q - q0);
       ro.scratch = f->scratch + (size_t) s * C * 65536;
+      q0 += ro.nb;
       const dim3 grid(16, ro.nb);
       ola64k_stage<0><<<grid, OLA_NT, 0, r.aux[s]>>>(sp);
       TSD_LAUNCH_CHECK();
@@ -647,7 +654,7 @@ int tsdgpu_ola_create(int dim_blocs_temporel, int nb_zeros_min, const float *H, 
     if(const char *v = getenv("TSDGPU_OLA_MODE")) f->staged = v[0] == 'p' ? 0 : 1;
     if(const char *v = getenv("TSDGPU_OLA_CHUNK")) f->chunk = std::max(1, atoi(v));
     if(const char *v = getenv("TSDGPU_OLA_STREAMS")) f->nslots = std::min((int) Runtime::MAX_AUX, std::max(1, atoi(v)));
-    if(f->staged && aux_init()) e = cudaErrorUnknown;
+    if(aux_init()) e = cudaErrorUnknown;   // twiddle tables (and the auxiliary streams of the staged form)
     const size_t slots = f->staged ? (size_t) f->chunk * f->nslots : (size_t) f->ring;
     if(e == cudaSuccess) e = cudaMalloc(&f->scratch, slots * 65536 * sizeof(float2));
     int occ = 0;

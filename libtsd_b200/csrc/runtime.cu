@@ -86,6 +86,22 @@ int aux_init()
   float4 *d = nullptr;
   TSD_CUDA(cudaMalloc(&d, 512 * sizeof(float4)));
   TSD_CUDA(cudaMemcpy(d, h.data(), 512 * sizeof(float4), cudaMemcpyHostToDevice));
+  std::vector<float2> h4(8448);
+  for(int a = 0; a < 16; a++)
+    for(int n = 0; n < 256; n++)
+    {
+      const double ang = -2.0 * M_PI * (double) (a * n) / 65536.0;
+      h4[a * 256 + n] = h4[4096 + n * 16 + a] = make_float2((float) cos(ang), (float) sin(ang));
+    }
+  for(int n = 0; n < 256; n++)
+  {
+    const double ang = -2.0 * M_PI * (double) (16 * n) / 65536.0;
+    h4[8192 + n] = make_float2((float) cos(ang), (float) sin(ang));
+  }
+  float2 *d4 = nullptr;
+  TSD_CUDA(cudaMalloc(&d4, h4.size() * sizeof(float2)));
+  TSD_CUDA(cudaMemcpy(d4, h4.data(), h4.size() * sizeof(float2), cudaMemcpyHostToDevice));
+  r.tw4 = d4;
   r.tw256 = d;
   return 0;
 }
