@@ -10,9 +10,11 @@
 // window loads (R*8 B) is bank-conflict free.  Results go back through shared memory so that the
 // global stores are fully coalesced.
 #include "common.cuh"
+#include "fir_tc.h"
 #include "host_pipe.cuh"
 #include "tsdgpu.h"
 
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -252,7 +254,27 @@ static int fir_run_device(tsdgpu_fir_s *f, const void *x, long long xs, int n, v
   const int unit = (int) (16 / ssz);
   p.use_tma = (((uintptr_t) src & 15) == 0) && (src_stride % unit == 0) && (n % unit == 0) && (f->halo % unit == 0);
   int rc;
-  if(f->kind == TSDGPU_FIR_F32_F32) rc = fir_launch<1, 1, 9>(f, p);
+  // cf32 data, <= 127 real taps: banded Toeplitz GEMM on the tensor cores (3xTF32, fir_tc.cu); TSDGPU_FIR_TC=0 keeps FP32 FMA
+  static const bool tc_on = getenv("TSDGPU_FIR_TC") && atoi(getenv("TSDGPU_FIR_TC")) != 0;
+  if(tc_on && fir_tc_eligible(f->kind == TSDGPU_FIR_CF32_F32, f->K, src, src_stride, hist_old, f->halo))
+  {
+    FirTcParams t;
+    t.x = (const float2 *) src;
+    t.y = (float2 *) y;
+    t.hist = (const float2 *) hist_old;
+    t.taps_rev = (const float *) f->d_taps;
+    t.x_stride = src_stride;
+    t.y_stride = ys;
+    t.n = n;
+    t.K = f->K;
+    t.halo = f->halo;
+    t.nchan = f->nchan;
+    {
+      KernelTimer timer;
+      rc = fir_tc_launch(t);
+    }
+  }
+  else if(f->kind == TSDGPU_FIR_F32_F32) rc = fir_launch<1, 1, 9>(f, p);
   else if(f->kind == TSDGPU_FIR_CF32_F32) rc = fir_launch<2, 1, 9>(f, p);
   else rc = fir_launch<2, 2, 7>(f, p);
   if(rc) return rc;
