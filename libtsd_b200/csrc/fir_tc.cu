@@ -10,17 +10,19 @@
 // fp32 accuracy from tf32 inputs: x = x_hi + x_lo, h = h_hi + h_lo (each part rounded to tf32), three MMAs
 // h_hi*x_hi + h_lo*x_hi + h_hi*x_lo accumulated in fp32 by the tensor core (error ~2^-21 per product).
 //
-// One CTA (288 threads, 1 per SM) = 64 channels x `span` tiles, input-stationary: every input chunk is loaded,
+// One CTA (416 threads, 1 per SM) = 64 channels x `span` tiles, input-stationary: every input chunk is loaded,
 // split and stored to shared memory ONCE (K-major, 128-byte swizzle, the canonical UMMA layout) and feeds the
 // two output tiles it overlaps, whose accumulators are live in TMEM at the same time (3 regions of 128 columns:
 // two accumulating, one being drained).  Warp roles: warps 0-3 epilogue (tcgen05.ld -> coalesced float2 stores),
-// warps 4-7 producers (LDG.128 -> cvt.rna.tf32 split -> STS, 3-stage ring, mbarrier full/empty), warp 8 lane 0
-// issues the MMAs (24 per chunk: 2 tiles x 4 K-steps of 8 x 3 split terms) and the commits.
+// warps 4-11 producers (two groups alternating chunks: LDG.128 one chunk ahead -> cvt.rna.tf32 split -> STS, 3-stage
+// ring, mbarrier full/empty), warp 12 lane 0 issues the MMAs (24 per chunk: 2 tiles x 4 K-steps of 8 x 3 split terms) and the commits.
 // Per chunk of 2048 complex samples: 24 MMAs x 64 cycles = 1536 cycles  =>  tensor bound 0.75 cycle per sample
 // per SM (~375 Gsamples/s at 1.9 GHz) against 16 B/sample of HBM traffic (410 Gsamples/s): HBM / tensor balanced,
 // where the FP32 FMA formulation (fir.cu) is capped at 146 Gsamples/s.
 #include "common.cuh"
 #include "fir_tc.h"
+
+#include <cstdlib>
 
 namespace tsdgpu {
 namespace tc {
@@ -35,7 +37,9 @@ constexpr int G_BYTES = GROWS * 128; // per split part (multiple of 1024)
 constexpr int PART_BYTES = NCOL * 128;          // one split part of one chunk: 128 rows x 32 tf32
 constexpr int STAGE_BYTES = 2 * PART_BYTES;     // hi + lo
 constexpr int SMEM_BYTES = 2 * G_BYTES + NSTAGE * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
-constexpr int NTHREADS = 288;
+constexpr int NGROUP = 2;              // producer groups (4 warps each)
+constexpr int MMA_WARP = 4 + 4 * NGROUP;
+constexpr int NTHREADS = 32 * (MMA_WARP + 1);
 constexpr int TMEM_COLS = 512;
 
 __device__ __forceinline__ uint32_t swz(uint32_t off) { return off ^ (((off >> 7) & 7u) << 4); }   // Swizzle<3,4,3>
@@ -71,6 +75,12 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ bool elect_one()
+{
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -97,7 +107,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc_kernel(FirTcParams p)
     for(int i = 0; i < 3; i++) { mbar_init(tfull + i, 1); mbar_init(tempty + i, 4); }
     mbar_fence_init();
   }
-  if(warp == 8)
+  if(warp == MMA_WARP)
   {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -117,18 +127,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc_kernel(FirTcParams p)
   fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if(warp >= 4 && warp < 8)
+  if(warp >= 4 && warp < 4 + 4 * NGROUP)
   {
-    // ===== producers: chunk it covers inputs [32 c, 32 c + 32), c = 4 ts - 4 + it, of 64 channels
-    const int pw = warp - 4;
+    // ===== producers: NGROUP groups of 4 warps, group g takes chunks it = g, g + NGROUP, ...  Chunk it covers inputs
+    // [32 c, 32 c + 32), c = 4 ts - 4 + it, of 64 channels.  The global loads of a group's NEXT chunk are issued
+    // before the current one is converted (they do not depend on the ring), so that NGROUP + ... chunks are in flight.
+    const int pw = (warp - 4) & 3, grp = (warp - 4) >> 2;
     const int sp = lane & 15, half = lane >> 4;
-    for(int it = 0; it < nchunks; it++)
-    {
-      const int stage = it % NSTAGE;
-      mbar_wait(empty + stage, (unsigned) (((it / NSTAGE) & 1) ^ 1));
-      unsigned char *bhi = stages + stage * STAGE_BYTES, *blo = bhi + PART_BYTES;
+    auto load_chunk = [&](int it, float4 (&v)[8]) {
       const long long pos = (long long) (4 * ts - 4 + it) * CHUNK + 2 * sp;   // first of this lane's two samples
-      float4 v[8];
 #pragma unroll
       for(int i = 0; i < 8; i++)
       {
@@ -145,6 +152,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc_kernel(FirTcParams p)
           else if(pos >= -(long long) p.halo) v[i] = __ldg(reinterpret_cast<const float4 *>(p.hist + (long long) chan * p.halo + p.halo + pos));
         }
       }
+    };
+    auto store_chunk = [&](int it, const float4 (&v)[8]) {
+      const int stage = it % NSTAGE;
+      mbar_wait(empty + stage, (unsigned) (((it / NSTAGE) & 1) ^ 1));
+      unsigned char *bhi = stages + stage * STAGE_BYTES, *blo = bhi + PART_BYTES;
 #pragma unroll
       for(int i = 0; i < 8; i++)
       {
@@ -160,44 +172,75 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc_kernel(FirTcParams p)
       fence_proxy_async();
       __syncwarp();
       if(lane == 0) mbar_arrive(full + stage);
+    };
+    // three register sets per thread: the loads of a group's next TWO chunks are in flight while one is converted
+    float4 va[8], vb[8], vc[8];
+    const int G = NGROUP;
+    int it = grp;
+    if(it < nchunks) load_chunk(it, va);
+    if(it + G < nchunks) load_chunk(it + G, vb);
+    for(; it < nchunks; it += 3 * G)
+    {
+      if(it + 2 * G < nchunks) load_chunk(it + 2 * G, vc);
+      store_chunk(it, va);
+      if(it + G >= nchunks) break;
+      if(it + 3 * G < nchunks) load_chunk(it + 3 * G, va);
+      store_chunk(it + G, vb);
+      if(it + 2 * G >= nchunks) break;
+      if(it + 4 * G < nchunks) load_chunk(it + 4 * G, vb);
+      store_chunk(it + 2 * G, vc);
     }
   }
-  else if(warp == 8)
+  else if(warp == MMA_WARP)
   {
-    // ===== MMA issuer (one thread)
-    if(lane == 0)
+    // ===== MMA issuer: the whole warp runs the loop on warp-uniform values (so that descriptors live in uniform
+    // registers) and one elected lane issues the 24 MMAs + commits of a chunk in a single block.  The issue loop
+    // is the critical path of the kernel: keep it free of per-MMA address arithmetic and branches.
+    const uint32_t ghi = base, glo = base + G_BYTES, st0 = base + 2 * G_BYTES;
+    const uint64_t dbase = smem_desc(0);
+    const int ntl = te - ts;
+    for(int it = 0; it < nchunks; it++)
     {
-      const uint32_t ghi = base, glo = base + G_BYTES, st0 = base + 2 * G_BYTES;
-      for(int it = 0; it < nchunks; it++)
+      const int stage = it % NSTAGE;
+      mbar_wait(full + stage, (unsigned) ((it / NSTAGE) & 1));
+      // chunk c = 4 ts - 4 + it feeds tiles ts + (it / 4) - 1 (d = 4 t - c = -(it % 4)) and ts + it / 4 (d = 4 - it % 4)
+      const int q4 = it >> 2, r4 = it & 3;
+      const int tl0 = q4 - 1, tl1 = q4;
+      const bool on0 = tl0 >= 0 && tl0 < ntl, on1 = tl1 < ntl;
+      if(on1 && r4 == 0) mbar_wait(tempty + tl1 % 3, (unsigned) (((tl1 / 3) & 1) ^ 1));   // accumulator region drained
+      fence_after();
+      const uint32_t bhi = st0 + stage * STAGE_BYTES;
+      const uint64_t bh0 = dbase + (bhi >> 4), bl0 = bh0 + (PART_BYTES >> 4);
+      const uint32_t arow0 = (uint32_t) ((96 - 32 * r4) * 128), arow1 = (uint32_t) ((224 - 32 * r4) * 128);
+      const uint64_t ah0 = dbase + ((ghi + arow0) >> 4), al0 = dbase + ((glo + arow0) >> 4);
+      const uint64_t ah1 = dbase + ((ghi + arow1) >> 4), al1 = dbase + ((glo + arow1) >> 4);
+      const uint32_t d0 = tmem + (uint32_t) ((tl0 + 3) % 3 * NCOL), d1 = tmem + (uint32_t) (tl1 % 3 * NCOL);
+      if(elect_one())
       {
-        const int stage = it % NSTAGE;
-        mbar_wait(full + stage, (unsigned) ((it / NSTAGE) & 1));
-        fence_after();
-        const uint32_t bhi = st0 + stage * STAGE_BYTES, blo = bhi + PART_BYTES;
-        // chunk c = 4 ts - 4 + it feeds tiles ts + (it / 4) - 1 (d = 4 t - c = -(it % 4)) and ts + it / 4 (d = 4 - it % 4)
-#pragma unroll
-        for(int which = 0; which < 2; which++)
+        if(on0)
         {
-          const int tl = it / 4 - 1 + which;              // tile index relative to ts
-          if(tl < 0 || tl >= te - ts) continue;
-          const int d = which ? 4 - (it & 3) : -(it & 3);
-          const int region = tl % 3;
-          const uint32_t dcol = tmem + (uint32_t) (region * NCOL);
-          if(d == 4) { mbar_wait(tempty + region, (unsigned) (((tl / 3) & 1) ^ 1)); fence_after(); }   // accumulator drained
-          const uint32_t arow = (uint32_t) ((32 * d + 96) * 128);
 #pragma unroll
           for(int ks = 0; ks < 4; ks++)
           {
-            const uint64_t ah = smem_desc(ghi + arow + ks * 32), al = smem_desc(glo + arow + ks * 32);
-            const uint64_t bh = smem_desc(bhi + ks * 32), bl = smem_desc(blo + ks * 32);
-            mma_tf32(dcol, al, bh, (d == 4 && ks == 0) ? 0u : 1u);
-            mma_tf32(dcol, ah, bl, 1u);
-            mma_tf32(dcol, ah, bh, 1u);
+            mma_tf32(d0, al0 + 2 * ks, bh0 + 2 * ks, 1u);
+            mma_tf32(d0, ah0 + 2 * ks, bl0 + 2 * ks, 1u);
+            mma_tf32(d0, ah0 + 2 * ks, bh0 + 2 * ks, 1u);
           }
-          if(d == -3) mma_commit(tfull + region);         // last chunk of this tile: accumulator complete
+          if(r4 == 3) mma_commit(tfull + tl0 % 3);          // d = -3: last chunk of tile tl0, accumulator complete
         }
-        mma_commit(empty + stage);                        // the stage may be refilled once these MMAs have read it
+        if(on1)
+        {
+#pragma unroll
+          for(int ks = 0; ks < 4; ks++)
+          {
+            mma_tf32(d1, al1 + 2 * ks, bh0 + 2 * ks, (r4 == 0 && ks == 0) ? 0u : 1u);   // d = 4: first chunk of tile tl1
+            mma_tf32(d1, ah1 + 2 * ks, bl0 + 2 * ks, 1u);
+            mma_tf32(d1, ah1 + 2 * ks, bh0 + 2 * ks, 1u);
+          }
+        }
+        mma_commit(empty + stage);                          // the stage may be refilled once these MMAs have read it
       }
+      __syncwarp();
     }
   }
   else
@@ -243,7 +286,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc_kernel(FirTcParams p)
   // ---- teardown
   fence_before();
   __syncthreads();
-  if(warp == 8)
+  if(warp == MMA_WARP)
   {
     fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS) : "memory");
@@ -271,8 +314,16 @@ int fir_tc_launch(const FirTcParams &p0)
   p.ntiles = (p.n + tc::TILE - 1) / tc::TILE;
   const int groups = (p.nchan + tc::CH - 1) / tc::CH;
   // tiles per CTA: long spans amortise the 4 halo chunks and the set-up, short spans balance the 148 SMs
-  int span = 16;
-  while(span > 2 && (long long) groups * ((p.ntiles + span - 1) / span) < 4LL * r.num_sms) span /= 2;
+  // every CTA pays one extra tile's worth of halo chunks; pick the span in [4, 32] that minimises waves x (span + 1)
+  int span = 1;
+  long long best = -1;
+  for(int sgs = 1; sgs <= 32; sgs++)
+  {
+    if(sgs < 4 && p.ntiles > 4) continue;
+    const long long ctas = (long long) groups * ((p.ntiles + sgs - 1) / sgs);
+    const long long cost = ((ctas + r.num_sms - 1) / r.num_sms) * (sgs + 1);
+    if(best < 0 || cost < best) { best = cost; span = sgs; }
+  }
   p.span = span;
   dim3 grid((p.ntiles + span - 1) / span, groups);
   tc::fir_tc_kernel<<<grid, tc::NTHREADS, tc::SMEM_BYTES, r.stream>>>(p);
