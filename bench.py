@@ -423,7 +423,7 @@ def main():
         achieved = bytes_per_sample * samples_per_step * args.steps / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else None
         # ola: the block filter runs as three stage kernels per chunk of 32 blocks, overlapped on four streams; the timed
         # unit is the whole pipeline of one step() (events around its first and last launch on the launching stream)
-        kernel_name = {"ola": "ola64k_stage<0|1|2> (stage kernels of one step(), overlapped)", "fft": "fft64k_kernel", "fir": "fir_direct_kernel",
+        kernel_name = {"ola": "ola64k_stage<0|1|2> (stage kernels of one step(), overlapped)", "fft": "fft64k_kernel", "fir": "fir_tc_kernel (tcgen05 3xTF32 Toeplitz GEMM)",
                        "resample": "resamp_banded_kernel"}[args.workload]
         roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_kind,

@@ -2,6 +2,9 @@
 //   y[n] = sum_{k<K} h[k] x[n-k], accumulated oldest sample first (h[K-1] first) like the
 //   reference's loop (filtre-rt.cc:84-104), zeros before the first sample, state = last K-1 inputs.
 //
+// cf32 data with <= 127 real taps (BASELINE config 3) runs as a 3xTF32 banded Toeplitz GEMM on the tensor cores
+// (fir_tc.cu); everything else (real data, complex taps, longer filters, unaligned rows) on the FP32 FMA kernel below.
+//
 // Kernel shape: one CTA = one tile of NT*R consecutive outputs of one channel.  The input tile
 // (+ K-1 halo) is brought into shared memory by the TMA unit as 1-D bulk copies
 // (cp.async.bulk, SASS UBLKCP) when the addresses allow it, the taps sit in shared memory in
@@ -255,8 +258,9 @@ static int fir_run_device(tsdgpu_fir_s *f, const void *x, long long xs, int n, v
   p.use_tma = (((uintptr_t) src & 15) == 0) && (src_stride % unit == 0) && (n % unit == 0) && (f->halo % unit == 0);
   int rc;
   // cf32 data, <= 127 real taps: banded Toeplitz GEMM on the tensor cores (3xTF32, fir_tc.cu); TSDGPU_FIR_TC=0 keeps FP32 FMA
-  static const bool tc_on = getenv("TSDGPU_FIR_TC") && atoi(getenv("TSDGPU_FIR_TC")) != 0;
-  if(tc_on && fir_tc_eligible(f->kind == TSDGPU_FIR_CF32_F32, f->K, src, src_stride, hist_old, f->halo))
+  const char *tc_env = getenv("TSDGPU_FIR_TC");
+  const bool tc_on = !(tc_env && atoi(tc_env) == 0);
+  if(tc_on && fir_tc_eligible(f->kind == TSDGPU_FIR_CF32_F32, f->K, src, src_stride, y, ys, hist_old, f->halo))
   {
     FirTcParams t;
     t.x = (const float2 *) src;

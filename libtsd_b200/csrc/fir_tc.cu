@@ -3,22 +3,25 @@
 // Replaces the inner product of FiltreRIF<cfloat,float>::step (reference filtre-rt.cc:82-107) for K <= 127 real
 // taps on cf32 data.  For a tile of 128 consecutive outputs t and a chunk of 32 consecutive inputs c,
 //   y[128 t + j] += sum_kk h[(128 t + j) - (32 c + kk)] * x[32 c + kk]
-// is D[j][n] += A[j][kk] * B[n][kk] with D in tensor memory (128 lanes x 128 columns, n = 2*channel + re/im of
-// 64 channels), A[j][kk] = h[j - kk + 32 d], d = 4 t - c in [-3, 4], and B the de-interleaved input chunk.
-// All eight A blocks are row-shifted views G[j + 32 d][kk] of ONE generator matrix G[r][kk] = h[r - kk]
-// (352 rows x 32 columns), so the Toeplitz operand costs 44 KiB of shared memory per split part instead of 128 KiB.
+// is D[n][j] += X[n][kk] * T[j][kk]: D in tensor memory (lane n = one of the 128 real rows {re, im} x 64 channels,
+// column j = output), X the de-interleaved input chunk (A operand) and T[j][kk] = h[j - kk + 32 d], d = 4 t - c in
+// [-3, 4], the Toeplitz block (B operand).  All eight blocks are row-shifted views G[j + 32 d][kk] of ONE generator
+// matrix G[r][kk] = h[r - kk] (352 rows x 32 columns, 44 KiB per split part), and because the outputs are the N
+// dimension each block only spends tensor time on the output columns its band touches (N = 32, 64, 96, 128, 128,
+// 96, 64, 32 for K = 127: 62.5 % of the dense work).
 // fp32 accuracy from tf32 inputs: x = x_hi + x_lo, h = h_hi + h_lo (each part rounded to tf32), three MMAs
-// h_hi*x_hi + h_lo*x_hi + h_hi*x_lo accumulated in fp32 by the tensor core (error ~2^-21 per product).
+// x_hi*h_lo + x_lo*h_hi + x_hi*h_hi accumulated in fp32 by the tensor core (measured error 3.7e-6 of the signal RMS).
 //
 // One CTA (416 threads, 1 per SM) = 64 channels x `span` tiles, input-stationary: every input chunk is loaded,
 // split and stored to shared memory ONCE (K-major, 128-byte swizzle, the canonical UMMA layout) and feeds the
 // two output tiles it overlaps, whose accumulators are live in TMEM at the same time (3 regions of 128 columns:
-// two accumulating, one being drained).  Warp roles: warps 0-3 epilogue (tcgen05.ld -> coalesced float2 stores),
-// warps 4-11 producers (two groups alternating chunks: LDG.128 one chunk ahead -> cvt.rna.tf32 split -> STS, 3-stage
-// ring, mbarrier full/empty), warp 12 lane 0 issues the MMAs (24 per chunk: 2 tiles x 4 K-steps of 8 x 3 split terms) and the commits.
-// Per chunk of 2048 complex samples: 24 MMAs x 64 cycles = 1536 cycles  =>  tensor bound 0.75 cycle per sample
-// per SM (~375 Gsamples/s at 1.9 GHz) against 16 B/sample of HBM traffic (410 Gsamples/s): HBM / tensor balanced,
-// where the FP32 FMA formulation (fir.cu) is capped at 146 Gsamples/s.
+// two accumulating, one being drained and re-zeroed).  Warp roles: warps 0-3 epilogue (tcgen05.ld 16x256b -> one
+// 16-byte store of two complex outputs per register quad, then tcgen05.st zeros), warps 4-11 producers (two groups
+// alternating chunks: LDG.128 two chunks ahead -> cvt.rna.tf32 split -> STS, 3-stage ring, mbarrier full/empty),
+// warp 12 issues the MMAs (one elected lane, <= 24 per chunk) and the commits.
+// Tensor work per chunk of 2048 complex samples at K = 127: 2 tiles x 4 K-steps x 3 terms with N summing to 160 per
+// term and K-step => 960 cycles at the nominal TF32 rate (64 cycles per 128x128x8) against 16 B/sample of HBM
+// traffic: the kernel is HBM / tensor balanced, where the FP32 FMA formulation (fir.cu) is capped at 146 Gsamples/s.
 #include "common.cuh"
 #include "fir_tc.h"
 
@@ -43,29 +46,35 @@ constexpr int NTHREADS = 32 * (MMA_WARP + 1);
 constexpr int TMEM_COLS = 512;
 
 __device__ __forceinline__ uint32_t swz(uint32_t off) { return off ^ (((off >> 7) & 7u) << 4); }   // Swizzle<3,4,3>
-__device__ __forceinline__ float to_tf32(float v)
-{
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-  return __uint_as_float(r);
-}
+// round to the nearest tf32 (10-bit mantissa), ties away from zero like cvt.rna.tf32.f32, with two full-rate integer
+// instructions (the conversion instruction itself issues at a small fraction of the FP32 rate: it made the producers
+// the bottleneck of the kernel)
+__device__ __forceinline__ float to_tf32(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u); }
 // shared-memory matrix descriptor, K-major, SWIZZLE_128B: 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor)
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr)
 {
   return (uint64_t) ((saddr >> 4) & 0x3FFFu) | ((uint64_t) 1 << 16) /* LBO (unused for swizzled K-major) */ |
          ((uint64_t) (1024 >> 4) << 32) /* SBO */ | ((uint64_t) 1 << 46) /* version */ | ((uint64_t) 2 << 61) /* SWIZZLE_128B */;
 }
-// instruction descriptor (cute::UMMA::InstrDescriptor): D = f32, A = B = tf32, both K-major, M = 128, N = 128
-constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t) (NCOL >> 3) << 17) | ((uint32_t) (TILE >> 4) << 24);
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = f32, A = B = tf32, both K-major, M = 128; N (bits 17..22, N >> 3) is added per MMA
+constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t) (NCOL >> 4) << 24);
 
-__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate)
+// D[128][N] += A[128][8] * B[N][8]^T  (always accumulating: the epilogue leaves every region zeroed)
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc)
 {
   asm volatile(
     "{\n\t.reg .pred p;\n\t"
-    "setp.ne.b32 p, %4, 0;\n\t"
+    "setp.ne.b32 p, 1, 0;\n\t"
     "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-    ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate)
+    ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc)
     : "memory");
+}
+// output columns [j0, j0 + nn) of a 128-output tile touched by Toeplitz block d (taps j - kk + 32 d in [0, K)), 16-aligned
+__device__ __forceinline__ void band_cols(int d, int K, int &j0, int &nn)
+{
+  const int jlo = max(0, -32 * d), jhi = min(127, K + 30 - 32 * d);
+  j0 = jlo & ~15;
+  nn = jhi < jlo ? 0 : ((jhi + 16) & ~15) - j0;
 }
 __device__ __forceinline__ void mma_commit(uint64_t *bar)
 {
@@ -84,6 +93,25 @@ __device__ __forceinline__ bool elect_one()
 __device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+#ifdef TSD_TC_PROF
+// timing experiment: per-CTA cycle totals [cta][role 0..15][what 0..3]; role = warp, what: 0 wait A, 1 wait B, 2 work, 3 total
+__device__ long long g_tcprof[1024][16][4];
+#define PROF_DECL long long pf_[4] = {0, 0, 0, 0}; const long long pf_t0 = clock64();
+#define PROF_BEGIN(v) const long long v = clock64();
+#define PROF_ADD(k, v) pf_[k] += clock64() - (v);
+#define PROF_END                                                                                             \
+  if(lane == 0 && blockIdx.y == 0 && blockIdx.x < 1024)                                                      \
+  {                                                                                                          \
+    pf_[3] = clock64() - pf_t0;                                                                              \
+    for(int k = 0; k < 4; k++) g_tcprof[blockIdx.x][warp][k] = pf_[k];                                       \
+  }
+#else
+#define PROF_DECL
+#define PROF_BEGIN(v)
+#define PROF_ADD(k, v)
+#define PROF_END
+#endif
+
 __global__ void __launch_bounds__(NTHREADS, 1) fir_tc_kernel(FirTcParams p)
 {
   extern __shared__ unsigned char raw[];
@@ -96,6 +124,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc_kernel(FirTcParams p)
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * NSTAGE + 6);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#ifdef TSD_TC_PROF
+  const long long pf_entry = clock64();
+#endif
   const int ts = blockIdx.x * p.span, te = min(ts + p.span, p.ntiles);   // tiles [ts, te) of this CTA
   const int c0 = blockIdx.y * CH;                                          // first channel
   const int nchunks = 4 * (te - ts) + 4;                                   // chunks 4 ts - 4 ... 4 te - 1
@@ -126,6 +157,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc_kernel(FirTcParams p)
   __syncthreads();
   fence_after();
   const uint32_t tmem = *tmem_slot;
+#ifdef TSD_TC_PROF
+  const long long pf_setup = clock64();
+#endif
 
   if(warp >= 4 && warp < 4 + 4 * NGROUP)
   {
@@ -153,17 +187,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc_kernel(FirTcParams p)
         }
       }
     };
+    PROF_DECL
     auto store_chunk = [&](int it, const float4 (&v)[8]) {
       const int stage = it % NSTAGE;
+      PROF_BEGIN(t_w)
       mbar_wait(empty + stage, (unsigned) (((it / NSTAGE) & 1) ^ 1));
+      PROF_ADD(0, t_w)
+      PROF_BEGIN(t_c)
       unsigned char *bhi = stages + stage * STAGE_BYTES, *blo = bhi + PART_BYTES;
 #pragma unroll
       for(int i = 0; i < 8; i++)
       {
-        const int cl = pw * 16 + i * 2 + half;            // local channel: rows 2 cl (re) and 2 cl + 1 (im)
+        // local channel cl: re in row 16 (cl / 8) + cl % 8, im 8 rows below (the pairing of the 16x256b TMEM load)
+        const int cl = pw * 16 + i * 2 + half, row = 16 * (cl >> 3) + (cl & 7);
         const float4 x = v[i];                            // (re0, im0, re1, im1)
         const float r0 = to_tf32(x.x), i0 = to_tf32(x.y), r1 = to_tf32(x.z), i1 = to_tf32(x.w);
-        const uint32_t ore = swz((uint32_t) ((2 * cl) * 128 + sp * 8)), oim = swz((uint32_t) ((2 * cl + 1) * 128 + sp * 8));
+        const uint32_t ore = swz((uint32_t) (row * 128 + sp * 8)), oim = swz((uint32_t) ((row + 8) * 128 + sp * 8));
         *reinterpret_cast<float2 *>(bhi + ore) = make_float2(r0, r1);
         *reinterpret_cast<float2 *>(bhi + oim) = make_float2(i0, i1);
         *reinterpret_cast<float2 *>(blo + ore) = make_float2(to_tf32(x.x - r0), to_tf32(x.z - r1));
@@ -172,24 +211,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc_kernel(FirTcParams p)
       fence_proxy_async();
       __syncwarp();
       if(lane == 0) mbar_arrive(full + stage);
+      PROF_ADD(2, t_c)
     };
-    // three register sets per thread: the loads of a group's next TWO chunks are in flight while one is converted
-    float4 va[8], vb[8], vc[8];
+    // two register sets per thread: the loads of a group's next chunk are in flight while one is converted
+    float4 va[8], vb[8];
     const int G = NGROUP;
     int it = grp;
     if(it < nchunks) load_chunk(it, va);
-    if(it + G < nchunks) load_chunk(it + G, vb);
-    for(; it < nchunks; it += 3 * G)
+    for(; it < nchunks; it += 2 * G)
     {
-      if(it + 2 * G < nchunks) load_chunk(it + 2 * G, vc);
+      if(it + G < nchunks) load_chunk(it + G, vb);
       store_chunk(it, va);
       if(it + G >= nchunks) break;
-      if(it + 3 * G < nchunks) load_chunk(it + 3 * G, va);
+      if(it + 2 * G < nchunks) load_chunk(it + 2 * G, va);
       store_chunk(it + G, vb);
-      if(it + 2 * G >= nchunks) break;
-      if(it + 4 * G < nchunks) load_chunk(it + 4 * G, vb);
-      store_chunk(it + 2 * G, vc);
     }
+    PROF_END
   }
   else if(warp == MMA_WARP)
   {
@@ -199,93 +236,152 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc_kernel(FirTcParams p)
     const uint32_t ghi = base, glo = base + G_BYTES, st0 = base + 2 * G_BYTES;
     const uint64_t dbase = smem_desc(0);
     const int ntl = te - ts;
+    PROF_DECL
     for(int it = 0; it < nchunks; it++)
     {
       const int stage = it % NSTAGE;
+      PROF_BEGIN(t_w)
       mbar_wait(full + stage, (unsigned) ((it / NSTAGE) & 1));
+      PROF_ADD(0, t_w)
       // chunk c = 4 ts - 4 + it feeds tiles ts + (it / 4) - 1 (d = 4 t - c = -(it % 4)) and ts + it / 4 (d = 4 - it % 4)
       const int q4 = it >> 2, r4 = it & 3;
       const int tl0 = q4 - 1, tl1 = q4;
       const bool on0 = tl0 >= 0 && tl0 < ntl, on1 = tl1 < ntl;
-      if(on1 && r4 == 0) mbar_wait(tempty + tl1 % 3, (unsigned) (((tl1 / 3) & 1) ^ 1));   // accumulator region drained
+      PROF_BEGIN(t_w2)
+      if(on1 && r4 == 0) mbar_wait(tempty + tl1 % 3, (unsigned) ((tl1 / 3) & 1));   // accumulator region drained and zeroed
+      PROF_ADD(1, t_w2)
+      PROF_BEGIN(t_c)
       fence_after();
       const uint32_t bhi = st0 + stage * STAGE_BYTES;
-      const uint64_t bh0 = dbase + (bhi >> 4), bl0 = bh0 + (PART_BYTES >> 4);
-      const uint32_t arow0 = (uint32_t) ((96 - 32 * r4) * 128), arow1 = (uint32_t) ((224 - 32 * r4) * 128);
-      const uint64_t ah0 = dbase + ((ghi + arow0) >> 4), al0 = dbase + ((glo + arow0) >> 4);
-      const uint64_t ah1 = dbase + ((ghi + arow1) >> 4), al1 = dbase + ((glo + arow1) >> 4);
-      const uint32_t d0 = tmem + (uint32_t) ((tl0 + 3) % 3 * NCOL), d1 = tmem + (uint32_t) (tl1 % 3 * NCOL);
+      const uint64_t xh0 = dbase + (bhi >> 4), xl0 = xh0 + (PART_BYTES >> 4);     // A operand: data chunk, hi / lo
+      int j0a, na, j0b, nb;
+      band_cols(-r4, p.K, j0a, na);
+      band_cols(4 - r4, p.K, j0b, nb);
+      const uint32_t rowa = (uint32_t) ((96 - 32 * r4 + j0a) * 128), rowb = (uint32_t) ((224 - 32 * r4 + j0b) * 128);
+      const uint64_t gha = dbase + ((ghi + rowa) >> 4), gla = dbase + ((glo + rowa) >> 4);   // B operand: Toeplitz rows
+      const uint64_t ghb = dbase + ((ghi + rowb) >> 4), glb = dbase + ((glo + rowb) >> 4);
+      const uint32_t da = tmem + (uint32_t) ((tl0 + 3) % 3 * NCOL + j0a), db = tmem + (uint32_t) (tl1 % 3 * NCOL + j0b);
+      const uint32_t ida = IDESC | ((uint32_t) (na >> 3) << 17), idb = IDESC | ((uint32_t) (nb >> 3) << 17);
       if(elect_one())
       {
-        if(on0)
+        if(on0 && na > 0)
         {
 #pragma unroll
           for(int ks = 0; ks < 4; ks++)
           {
-            mma_tf32(d0, al0 + 2 * ks, bh0 + 2 * ks, 1u);
-            mma_tf32(d0, ah0 + 2 * ks, bl0 + 2 * ks, 1u);
-            mma_tf32(d0, ah0 + 2 * ks, bh0 + 2 * ks, 1u);
+            mma_tf32(da, xh0 + 2 * ks, gla + 2 * ks, ida);
+            mma_tf32(da, xl0 + 2 * ks, gha + 2 * ks, ida);
+            mma_tf32(da, xh0 + 2 * ks, gha + 2 * ks, ida);
           }
-          if(r4 == 3) mma_commit(tfull + tl0 % 3);          // d = -3: last chunk of tile tl0, accumulator complete
         }
-        if(on1)
+        if(on0 && r4 == 3) mma_commit(tfull + tl0 % 3);     // d = -3: last chunk of tile tl0, accumulator complete
+        if(on1 && nb > 0)
         {
 #pragma unroll
           for(int ks = 0; ks < 4; ks++)
           {
-            mma_tf32(d1, al1 + 2 * ks, bh0 + 2 * ks, (r4 == 0 && ks == 0) ? 0u : 1u);   // d = 4: first chunk of tile tl1
-            mma_tf32(d1, ah1 + 2 * ks, bl0 + 2 * ks, 1u);
-            mma_tf32(d1, ah1 + 2 * ks, bh0 + 2 * ks, 1u);
+            mma_tf32(db, xh0 + 2 * ks, glb + 2 * ks, idb);
+            mma_tf32(db, xl0 + 2 * ks, ghb + 2 * ks, idb);
+            mma_tf32(db, xh0 + 2 * ks, ghb + 2 * ks, idb);
           }
         }
         mma_commit(empty + stage);                          // the stage may be refilled once these MMAs have read it
       }
       __syncwarp();
+      PROF_ADD(2, t_c)
     }
+    PROF_END
   }
   else
   {
-    // ===== epilogue: warp w owns TMEM lanes (= output rows) 32 w ... 32 w + 31
-    for(int tl = 0; tl < te - ts; tl++)
-    {
-      const int region = tl % 3;
-      mbar_wait(tfull + region, (unsigned) ((tl / 3) & 1));
-      fence_after();
-      const long long nabs = (long long) (ts + tl) * TILE + warp * 32 + lane;
+    // ===== epilogue: warp w owns TMEM lanes 32 w ... 32 w + 31 = rows of channels 16 w ... 16 w + 15 (re rows and, 8 lanes
+    // below, im rows).  tcgen05.ld.16x256b.x4 hands thread t, for column block i, registers {4i, 4i+1} = lane t/4, columns
+    // 8 i + 2 (t % 4) + {0, 1} and {4i+2, 4i+3} = lane t/4 + 8, same columns: (re, im) of two consecutive outputs of one
+    // channel -> one 16-byte store; a quad of lanes writes 64 contiguous bytes.
+    auto zero_region = [&](int region) {
 #pragma unroll
       for(int q = 0; q < 4; q++)
       {
-        uint32_t r[32];
         const uint32_t taddr = tmem + ((uint32_t) (warp * 32) << 16) + (uint32_t) (region * NCOL + q * 32);
         asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-            "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-            "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-            "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-          : "r"(taddr)
-          : "memory");
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if(nabs < p.n)
-        {
-#pragma unroll
-          for(int cp = 0; cp < 16; cp++)
-          {
-            const int chan = c0 + q * 16 + cp;
-            if(chan < p.nchan)
-              stg_stream(p.y + (long long) chan * p.y_stride + nabs, make_float2(__uint_as_float(r[2 * cp]), __uint_as_float(r[2 * cp + 1])));
-          }
-        }
+          "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, "
+          "%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(0u) : "memory");
       }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    };
+    for(int region = 0; region < 3; region++)
+    {
+      zero_region(region);
       fence_before();
       __syncwarp();
       if(lane == 0) mbar_arrive(tempty + region);
     }
+    PROF_DECL
+    for(int tl = 0; tl < te - ts; tl++)
+    {
+      const int region = tl % 3;
+      PROF_BEGIN(t_w)
+      mbar_wait(tfull + region, (unsigned) ((tl / 3) & 1));
+      PROF_ADD(0, t_w)
+      PROF_BEGIN(t_c)
+      fence_after();
+      const long long n0 = (long long) (ts + tl) * TILE + 2 * (lane & 3);
+#pragma unroll
+      for(int half = 0; half < 2; half++)
+      {
+        const int chan = c0 + 8 * (2 * warp + half) + (lane >> 2);
+        float2 *yrow = p.y + (long long) chan * p.y_stride;
+#pragma unroll
+        for(int cb = 0; cb < 4; cb++)
+        {
+          uint32_t r[16];
+          const uint32_t taddr = tmem + ((uint32_t) (warp * 32 + half * 16) << 16) + (uint32_t) (region * NCOL + cb * 32);
+          asm volatile(
+            "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+              "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+            : "r"(taddr)
+            : "memory");
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if(chan < p.nchan)
+          {
+#pragma unroll
+            for(int i = 0; i < 4; i++)
+            {
+              const long long nabs = n0 + cb * 32 + 8 * i;
+              const float4 o = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 1]),
+                                           __uint_as_float(r[4 * i + 3]));
+              if(nabs + 1 < p.n) __stcs(reinterpret_cast<float4 *>(yrow + nabs), o);
+              else if(nabs < p.n) __stcs(yrow + nabs, make_float2(o.x, o.y));
+            }
+          }
+        }
+      }
+      zero_region(region);
+      fence_before();
+      __syncwarp();
+      if(lane == 0) mbar_arrive(tempty + region);
+      PROF_ADD(2, t_c)
+    }
+    PROF_END
   }
   // ---- teardown
   fence_before();
   __syncthreads();
+#ifdef TSD_TC_PROF
+  if(tid == 0 && blockIdx.y * gridDim.x + blockIdx.x < 1024)
+  {
+    const int bi = blockIdx.y * gridDim.x + blockIdx.x;
+    g_tcprof[bi][14][0] = pf_setup - pf_entry;
+    g_tcprof[bi][14][1] = clock64() - pf_setup;
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    g_tcprof[bi][14][2] = (long long) gt;
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    g_tcprof[bi][14][3] = smid;
+  }
+#endif
   if(warp == MMA_WARP)
   {
     fence_after();
@@ -295,11 +391,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc_kernel(FirTcParams p)
 
 } // namespace tc
 
-bool fir_tc_eligible(int kind_cf32_f32, int K, const void *x, long long x_stride, const void *hist, int halo)
+bool fir_tc_eligible(int kind_cf32_f32, int K, const void *x, long long x_stride, const void *y, long long y_stride, const void *hist, int halo)
 {
-  return kind_cf32_f32 && K >= 1 && K <= 127 && (((uintptr_t) x & 15) == 0) && (x_stride % 2 == 0) && (((uintptr_t) hist & 15) == 0) &&
-         (halo % 2 == 0);
+  return kind_cf32_f32 && K >= 1 && K <= 127 && (((uintptr_t) x & 15) == 0) && (x_stride % 2 == 0) && (((uintptr_t) y & 15) == 0) &&
+         (y_stride % 2 == 0) && (((uintptr_t) hist & 15) == 0) && (halo % 2 == 0);
 }
+
+#ifdef TSD_TC_PROF
+extern "C" int tsdgpu_debug_tcprof_dump(const char *path)
+{
+  cudaDeviceSynchronize();
+  static long long h[1024][16][4];
+  if(cudaMemcpyFromSymbol(h, tc::g_tcprof, sizeof(h)) != cudaSuccess) return 1;
+  FILE *fp = fopen(path, "wb");
+  if(!fp) return 1;
+  fwrite(h, 1, sizeof(h), fp);
+  fclose(fp);
+  return 0;
+}
+#endif
 
 int fir_tc_launch(const FirTcParams &p0)
 {

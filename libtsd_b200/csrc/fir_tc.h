@@ -16,7 +16,7 @@ struct FirTcParams
 };
 
 // 16-byte aligned rows (the producers use 128-bit loads) and K <= 127
-bool fir_tc_eligible(int kind_cf32_f32, int K, const void *x, long long x_stride, const void *hist, int halo);
+bool fir_tc_eligible(int kind_cf32_f32, int K, const void *x, long long x_stride, const void *y, long long y_stride, const void *hist, int halo);
 int fir_tc_launch(const FirTcParams &p);
 
 }

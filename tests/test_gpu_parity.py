@@ -127,6 +127,31 @@ def test_fir_config3_shape_subset(tsd, cpu_oracle):
     assert rel_err(y, yref, rms(x)) <= TOL
 
 
+@pytest.mark.parametrize("K,nchan,n", [(127, 70, 4100), (127, 3, 1000), (100, 64, 65536), (31, 2, 500), (1, 1, 300), (97, 65, 129), (127, 130, 20001)])
+def test_fir_tensor_core_path(tsd, cpu_oracle, monkeypatch, K, nchan, n):
+    """cf32 data, <= 127 real taps: the tcgen05 3xTF32 Toeplitz-GEMM kernel (fir_tc.cu) against the oracle, streamed in
+    ragged blocks (state carried), ragged channel groups and tiles; and against the FP32 FMA kernel on the same input."""
+    from libtsd_b200 import filtrage as F
+    rng = np.random.default_rng(K * 1000 + nchan)
+    h = (rng.standard_normal(K) / np.sqrt(K)).astype(np.float32)
+    monkeypatch.setenv("TSDGPU_FIR_TC", "1")
+    f_tc = F.filtre_rif(h, np.complex64, nchan)
+    refs = [cpu_oracle.fir(1, h) for _ in range(min(nchan, 3))]
+    outs_tc, xs = [], []
+    for blk in (n, 130, 7, 1):
+        x = cn(rng, nchan, blk)
+        xs.append(x)
+        y = f_tc.step(x)
+        outs_tc.append(y)
+        for c, r in enumerate(refs):
+            assert rel_err(y[c], r.step(x[c]), rms(x)) <= TOL
+    monkeypatch.setenv("TSDGPU_FIR_TC", "0")
+    f_fma = F.filtre_rif(h, np.complex64, nchan)
+    for x, y in zip(xs, outs_tc):
+        assert rel_err(f_fma.step(x), y, rms(x)) <= TOL
+    assert f_tc.index == f_fma.index
+
+
 def test_fir_errors(tsd):
     from libtsd_b200 import filtrage as F
     with pytest.raises(tsd.TsdGpuError):
@@ -346,9 +371,13 @@ def test_ola_errors(tsd):
         Fo.filtre_fft(Fo.FiltreFFTConfig(512, 127, H=np.zeros(8, np.complex64)))
 
 
-def test_rif_vs_rif_fft(tsd, cpu_oracle):
-    """test_rif_vs_rif_fft (test-filtres.cc:514-554): 127 taps, direct FIR vs FFT FIR after alignment."""
+@pytest.mark.parametrize("tc,tol", [("0", 2e-6), ("1", TOL)])
+def test_rif_vs_rif_fft(tsd, cpu_oracle, monkeypatch, tc, tol):
+    """test_rif_vs_rif_fft (test-filtres.cc:514-554): 127 taps, direct FIR vs FFT FIR after alignment.  The FP32 FMA
+    kernel meets the reference's own 1e-6-class bar; the tensor-core kernel (3xTF32, fp32 accumulation inside the
+    tensor core) is held to the north-star bar of 1e-5 of the signal RMS (measured 3.7e-6)."""
     from libtsd_b200 import filtrage as F, fourier as Fo
+    monkeypatch.setenv("TSDGPU_FIR_TC", tc)
     rng = np.random.default_rng(12)
     h = cpu_oracle.design_rif_fen(127, "lp", 0.2)
     x = cn(rng, 10000)
@@ -356,7 +385,7 @@ def test_rif_vs_rif_fft(tsd, cpu_oracle):
     y2 = Fo.filtre_rif_fft(h).step(x)
     d = 512 - 127
     n = len(y2) - d
-    assert np.max(np.abs(y2[d:d + n] - y1[:n])) <= 2e-6 * max(1.0, rms(x))
+    assert np.max(np.abs(y2[d:d + n] - y1[:n])) <= tol * max(1.0, rms(x))
 
 
 # ------------------------------------------------------------------------------------- resampler
