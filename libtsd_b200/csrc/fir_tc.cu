@@ -12,16 +12,24 @@
 // fp32 accuracy from tf32 inputs: x = x_hi + x_lo, h = h_hi + h_lo (each part rounded to tf32), three MMAs
 // x_hi*h_lo + x_lo*h_hi + x_hi*h_hi accumulated in fp32 by the tensor core (measured error 3.7e-6 of the signal RMS).
 //
-// One CTA (416 threads, 1 per SM) = 64 channels x `span` tiles, input-stationary: every input chunk is loaded,
-// split and stored to shared memory ONCE (K-major, 128-byte swizzle, the canonical UMMA layout) and feeds the
-// two output tiles it overlaps, whose accumulators are live in TMEM at the same time (3 regions of 128 columns:
-// two accumulating, one being drained and re-zeroed).  Warp roles: warps 0-3 epilogue (tcgen05.ld 16x256b -> one
-// 16-byte store of two complex outputs per register quad, then tcgen05.st zeros), warps 4-11 producers (two groups
-// alternating chunks: LDG.128 two chunks ahead -> cvt.rna.tf32 split -> STS, 3-stage ring, mbarrier full/empty),
-// warp 12 issues the MMAs (one elected lane, <= 24 per chunk) and the commits.
+// One CTA (448 threads, 1 per SM, all 512 TMEM columns) = 64 channels x `span` tiles, input-stationary: every input
+// chunk crosses shared memory once as raw cf32 rows and tensor memory once as the split A operand, and feeds the two
+// output tiles it overlaps, whose accumulators are live in TMEM together (3 regions of 128 columns: two accumulating,
+// one being drained and re-zeroed; columns 384..511 hold two A stages of x_hi | x_lo).  Warp roles:
+//   13      loader: 16-byte asynchronous copies (LDGSTS) of raw chunks into a 6-slot staging ring, two chunks of a
+//           channel row back to back (512 contiguous bytes per DRAM page visit), completion on the slot's mbarrier
+//   4-11    converters, two groups alternating chunks, one warp per TMEM lane quadrant: each thread reads the 32
+//           samples of its row (channel, re|im) from the staging, splits them into tf32 hi / lo with two integer
+//           instructions per value (cvt.rna.tf32 issues far too slowly) and writes them with tcgen05.st
+//   12      MMA issuer: descriptors are warp-uniform values, one elected lane issues <= 24 tcgen05.mma.kind::tf32
+//           (A from tensor memory, B = generator rows from shared memory) + tcgen05.commit per chunk
+//   0-3     epilogue: tcgen05.ld.16x256b hands a thread (re, im) of two consecutive outputs of one channel -> one
+//           16-byte store (a lane quad writes 64 contiguous bytes), then tcgen05.st zeros the region
 // Tensor work per chunk of 2048 complex samples at K = 127: 2 tiles x 4 K-steps x 3 terms with N summing to 160 per
-// term and K-step => 960 cycles at the nominal TF32 rate (64 cycles per 128x128x8) against 16 B/sample of HBM
-// traffic: the kernel is HBM / tensor balanced, where the FP32 FMA formulation (fir.cu) is capped at 146 Gsamples/s.
+// term and K-step => 960 cycles at the nominal TF32 rate (64 cycles per 128x128x8); operand reads from shared memory
+// 61 KiB per chunk.  Measured (-DTSD_TC_PROF, per-role clock64): MMA warp busy 950 cycles per chunk, compute-only
+// bound 360 Gsamples/s, loads-only or stores-only 280, both 240: the kernel is bound by DRAM efficiency of 64-channel
+// interleaved row pieces, not by the tensor cores; the FP32 FMA formulation (fir.cu) is capped at 146 Gsamples/s.
 #include "common.cuh"
 #include "fir_tc.h"
 
@@ -34,15 +42,19 @@ constexpr int TILE = 128;            // outputs per tile = UMMA M
 constexpr int CH = 64;               // channels per CTA; UMMA N = 2 * CH
 constexpr int NCOL = 2 * CH;
 constexpr int CHUNK = 32;            // input samples per chunk = 4 UMMA K steps of 8 tf32
-constexpr int NSTAGE = 3;
+constexpr int NRAW = 6;               // raw staging ring (chunks in flight from HBM)
+constexpr int LGRP = 2;               // chunks the loader fetches together: 512 contiguous bytes per channel row (4: no further gain)
+constexpr int NSTAGE = 2;             // A-operand stages in tensor memory = producer groups
 constexpr int GROWS = 352;           // generator rows r in [-96, 256)
 constexpr int G_BYTES = GROWS * 128; // per split part (multiple of 1024)
-constexpr int PART_BYTES = NCOL * 128;          // one split part of one chunk: 128 rows x 32 tf32
-constexpr int STAGE_BYTES = 2 * PART_BYTES;     // hi + lo
-constexpr int SMEM_BYTES = 2 * G_BYTES + NSTAGE * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
-constexpr int NGROUP = 2;              // producer groups (4 warps each)
+constexpr int RAW_PITCH = 272;                  // bytes per channel row of the raw staging (256 + 16: conflict-free LDS.128 down a column)
+constexpr int RAW_BYTES = CH * RAW_PITCH;       // one group's staging buffer: 64 channels x 32 cf32 samples
+constexpr int SMEM_BYTES = 2 * G_BYTES + NRAW * RAW_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
+constexpr int ACOL = 3 * NCOL;                  // TMEM columns [ACOL + 64 s, +32) = x_hi, [+32, +64) = x_lo of stage s
+constexpr int NGROUP = 2;              // converter groups (4 warps each, one warp per TMEM lane quadrant)
 constexpr int MMA_WARP = 4 + 4 * NGROUP;
-constexpr int NTHREADS = 32 * (MMA_WARP + 1);
+constexpr int LOAD_WARP = MMA_WARP + 1;
+constexpr int NTHREADS = 32 * (LOAD_WARP + 1);
 constexpr int TMEM_COLS = 512;
 
 __device__ __forceinline__ uint32_t swz(uint32_t off) { return off ^ (((off >> 7) & 7u) << 4); }   // Swizzle<3,4,3>
@@ -59,14 +71,27 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr)
 // instruction descriptor (cute::UMMA::InstrDescriptor): D = f32, A = B = tf32, both K-major, M = 128; N (bits 17..22, N >> 3) is added per MMA
 constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t) (NCOL >> 4) << 24);
 
-// D[128][N] += A[128][8] * B[N][8]^T  (always accumulating: the epilogue leaves every region zeroed)
-__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc)
+// D[128][N] += A[128][8] * B[N][8]^T, A read from tensor memory (lanes 0..127, 8 columns), B from shared memory
+// (always accumulating: the epilogue leaves every region zeroed)
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc)
 {
   asm volatile(
     "{\n\t.reg .pred p;\n\t"
     "setp.ne.b32 p, 1, 0;\n\t"
-    "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-    ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc)
+    "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+    ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc)
+    : "memory");
+}
+__device__ __forceinline__ void named_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+// 16 consecutive TMEM columns of this thread's lane <- 16 registers
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16])
+{
+  asm volatile(
+    "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+    "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])),
+    "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])),
+    "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])), "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])),
+    "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
     : "memory");
 }
 // output columns [j0, j0 + nn) of a 128-output tile touched by Toeplitz block d (taps j - kk + 32 d in [0, K)), 16-aligned
@@ -119,9 +144,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc_kernel(FirTcParams p)
   unsigned char *sm = raw + (base - smem_u32(raw));
   float *Ghi = reinterpret_cast<float *>(sm), *Glo = reinterpret_cast<float *>(sm + G_BYTES);
   unsigned char *stages = sm + 2 * G_BYTES;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(stages + NSTAGE * STAGE_BYTES);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(stages + NRAW * RAW_BYTES);
   uint64_t *full = bars, *empty = bars + NSTAGE, *tfull = bars + 2 * NSTAGE, *tempty = bars + 2 * NSTAGE + 3;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * NSTAGE + 6);
+  uint64_t *rfull = bars + 2 * NSTAGE + 6, *rempty = rfull + NRAW;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(rempty + NRAW);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 #ifdef TSD_TC_PROF
@@ -136,6 +162,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc_kernel(FirTcParams p)
   {
     for(int i = 0; i < NSTAGE; i++) { mbar_init(full + i, 4); mbar_init(empty + i, 1); }
     for(int i = 0; i < 3; i++) { mbar_init(tfull + i, 1); mbar_init(tempty + i, 4); }
+    for(int i = 0; i < NRAW; i++) { mbar_init(rfull + i, 32); mbar_init(rempty + i, 4); }
     mbar_fence_init();
   }
   if(warp == MMA_WARP)
@@ -161,70 +188,112 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc_kernel(FirTcParams p)
   const long long pf_setup = clock64();
 #endif
 
-  if(warp >= 4 && warp < 4 + 4 * NGROUP)
+  if(warp == LOAD_WARP)
   {
-    // ===== producers: NGROUP groups of 4 warps, group g takes chunks it = g, g + NGROUP, ...  Chunk it covers inputs
-    // [32 c, 32 c + 32), c = 4 ts - 4 + it, of 64 channels.  The global loads of a group's NEXT chunk are issued
-    // before the current one is converted (they do not depend on the ring), so that NGROUP + ... chunks are in flight.
-    const int pw = (warp - 4) & 3, grp = (warp - 4) >> 2;
-    const int sp = lane & 15, half = lane >> 4;
-    auto load_chunk = [&](int it, float4 (&v)[8]) {
-      const long long pos = (long long) (4 * ts - 4 + it) * CHUNK + 2 * sp;   // first of this lane's two samples
-#pragma unroll
-      for(int i = 0; i < 8; i++)
+    // ===== loader: raw chunk it (inputs [32 c, 32 c + 32), c = 4 ts - 4 + it, of 64 channels) -> staging slot it % NRAW,
+    // one 256-byte row per channel, with 16-byte asynchronous copies (LDGSTS): no registers, NRAW chunks in flight,
+    // completion counted on the slot's mbarrier (cp.async.mbarrier.arrive.noinc, one arrival per lane).  Lane l copies
+    // pieces k = l + 32 j: channel (l / 16) + 2 j, sample pair l % 16 -> every warp instruction moves two 256-byte rows.
+    // Chunks that touch the history, the end of the call or a ragged channel group use the zero-filling form
+    // (src-size 0 / 8 / 16) on the same path.
+    const int sp = lane & 15, clb = lane >> 4;
+    auto one_chunk = [&](int it) {
+      const int slot = it % NRAW;
+      const uint32_t dst0 = smem_u32(stages + slot * RAW_BYTES + clb * RAW_PITCH + sp * 16);
+      const long long pos = (long long) (4 * ts - 4 + it) * CHUNK + 2 * sp;
+      for(int j = 0; j < 32; j++)
       {
-        const int chan = c0 + pw * 16 + i * 2 + half;
-        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int chan = c0 + clb + 2 * j;
+        const float2 *src = p.x;   // any valid address when nothing is read
+        unsigned bytes = 0;
         if(chan < p.nchan)
         {
           if(pos >= 0)
           {
-            const float2 *src = p.x + (long long) chan * p.x_stride + pos;
-            if(pos + 1 < p.n) v[i] = __ldcs(reinterpret_cast<const float4 *>(src));
-            else if(pos < p.n) { const float2 a = __ldcs(src); v[i] = make_float4(a.x, a.y, 0.f, 0.f); }
+            if(pos < p.n) { src = p.x + (long long) chan * p.x_stride + pos; bytes = pos + 1 < p.n ? 16u : 8u; }
           }
-          else if(pos >= -(long long) p.halo) v[i] = __ldg(reinterpret_cast<const float4 *>(p.hist + (long long) chan * p.halo + p.halo + pos));
+          else if(pos >= -(long long) p.halo) { src = p.hist + (long long) chan * p.halo + p.halo + pos; bytes = 16u; }
         }
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + j * 2 * RAW_PITCH), "l"(src), "r"(bytes) : "memory");
       }
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(rfull + slot)) : "memory");
     };
+    for(int it = 0; it < nchunks;)
+    {
+      const long long pos0 = (long long) (4 * ts - 4 + it) * CHUNK;
+      const bool group = it + LGRP <= nchunks && pos0 >= 0 && pos0 + LGRP * CHUNK <= p.n && c0 + CH <= p.nchan;
+      mbar_wait(rempty + it % NRAW, (unsigned) (((it / NRAW) & 1) ^ 1));
+      if(!group)
+      {
+        one_chunk(it);
+        it += 1;
+        continue;
+      }
+      // LGRP interior chunks at once: the LGRP 256-byte pieces of a channel row are adjacent in DRAM (one 1 KiB page visit)
+#pragma unroll
+      for(int g = 1; g < LGRP; g++) mbar_wait(rempty + (it + g) % NRAW, (unsigned) ((((it + g) / NRAW) & 1) ^ 1));
+      uint32_t dst[LGRP];
+#pragma unroll
+      for(int g = 0; g < LGRP; g++) dst[g] = smem_u32(stages + ((it + g) % NRAW) * RAW_BYTES + clb * RAW_PITCH + sp * 16);
+      const float2 *src = p.x + (long long) (c0 + clb) * p.x_stride + pos0 + 2 * sp;
+#pragma unroll 4
+      for(int j = 0; j < 32; j++)
+      {
+        const float2 *sj = src + (long long) j * 2 * p.x_stride;
+#pragma unroll
+        for(int g = 0; g < LGRP; g++)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst[g] + j * 2 * RAW_PITCH), "l"(sj + g * CHUNK) : "memory");
+      }
+#pragma unroll
+      for(int g = 0; g < LGRP; g++)
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(rfull + (it + g) % NRAW)) : "memory");
+      it += LGRP;
+    }
+  }
+  else if(warp >= 4 && warp < 4 + 4 * NGROUP)
+  {
+    // ===== converters: group g takes chunks it = g, g + 2, ... and owns A stage g in tensor memory.  This thread's TMEM
+    // lane 32 pw + lane is row (cl, ri): channel cl = 8 (lane / 16 + 2 pw) + lane % 8, ri = (lane / 8) % 2 (re rows and,
+    // 8 lanes below, im rows: the pairing the 16x256b epilogue load wants).  It reads the 32 samples of its row out of the
+    // staging (16 LDS.128), splits its component into tf32 hi / lo and writes both straight into tensor memory.
+    const int pw = (warp - 4) & 3, grp = (warp - 4) >> 2;
+    const int my_cl = 8 * (2 * pw + (lane >> 4)) + (lane & 7), my_ri = (lane >> 3) & 1;
+    const uint32_t my_a = tmem + ((uint32_t) (pw * 32) << 16) + (uint32_t) (ACOL + 64 * grp);
     PROF_DECL
-    auto store_chunk = [&](int it, const float4 (&v)[8]) {
-      const int stage = it % NSTAGE;
+    for(int it = grp; it < nchunks; it += NGROUP)
+    {
+      const int slot = it % NRAW;
       PROF_BEGIN(t_w)
-      mbar_wait(empty + stage, (unsigned) (((it / NSTAGE) & 1) ^ 1));
+      mbar_wait(rfull + slot, (unsigned) ((it / NRAW) & 1));
+      mbar_wait(empty + grp, (unsigned) (((it / NSTAGE) & 1) ^ 1));   // the MMAs of chunk it - 2 have read this A stage
       PROF_ADD(0, t_w)
       PROF_BEGIN(t_c)
-      unsigned char *bhi = stages + stage * STAGE_BYTES, *blo = bhi + PART_BYTES;
+      fence_after();
+      const unsigned char *row = stages + slot * RAW_BYTES + my_cl * RAW_PITCH;
 #pragma unroll
-      for(int i = 0; i < 8; i++)
+      for(int hq = 0; hq < 2; hq++)
       {
-        // local channel cl: re in row 16 (cl / 8) + cl % 8, im 8 rows below (the pairing of the 16x256b TMEM load)
-        const int cl = pw * 16 + i * 2 + half, row = 16 * (cl >> 3) + (cl & 7);
-        const float4 x = v[i];                            // (re0, im0, re1, im1)
-        const float r0 = to_tf32(x.x), i0 = to_tf32(x.y), r1 = to_tf32(x.z), i1 = to_tf32(x.w);
-        const uint32_t ore = swz((uint32_t) (row * 128 + sp * 8)), oim = swz((uint32_t) ((row + 8) * 128 + sp * 8));
-        *reinterpret_cast<float2 *>(bhi + ore) = make_float2(r0, r1);
-        *reinterpret_cast<float2 *>(bhi + oim) = make_float2(i0, i1);
-        *reinterpret_cast<float2 *>(blo + ore) = make_float2(to_tf32(x.x - r0), to_tf32(x.z - r1));
-        *reinterpret_cast<float2 *>(blo + oim) = make_float2(to_tf32(x.y - i0), to_tf32(x.w - i1));
+        float hi[16], lo[16];
+#pragma unroll
+        for(int m = 0; m < 8; m++)
+        {
+          const float4 x = *reinterpret_cast<const float4 *>(row + (hq * 8 + m) * 16);   // (re0, im0, re1, im1)
+          const float a0 = my_ri ? x.y : x.x, a1 = my_ri ? x.w : x.z;
+          hi[2 * m] = to_tf32(a0);
+          hi[2 * m + 1] = to_tf32(a1);
+          lo[2 * m] = to_tf32(a0 - hi[2 * m]);
+          lo[2 * m + 1] = to_tf32(a1 - hi[2 * m + 1]);
+        }
+        tmem_st16(my_a + hq * 16, hi);
+        tmem_st16(my_a + 32 + hq * 16, lo);
       }
-      fence_proxy_async();
       __syncwarp();
-      if(lane == 0) mbar_arrive(full + stage);
+      if(lane == 0) mbar_arrive(rempty + slot);            // staging slot may be refilled
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      fence_before();
+      __syncwarp();
+      if(lane == 0) mbar_arrive(full + grp);
       PROF_ADD(2, t_c)
-    };
-    // two register sets per thread: the loads of a group's next chunk are in flight while one is converted
-    float4 va[8], vb[8];
-    const int G = NGROUP;
-    int it = grp;
-    if(it < nchunks) load_chunk(it, va);
-    for(; it < nchunks; it += 2 * G)
-    {
-      if(it + G < nchunks) load_chunk(it + G, vb);
-      store_chunk(it, va);
-      if(it + G >= nchunks) break;
-      if(it + 2 * G < nchunks) load_chunk(it + 2 * G, va);
-      store_chunk(it + G, vb);
     }
     PROF_END
   }
@@ -233,7 +302,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc_kernel(FirTcParams p)
     // ===== MMA issuer: the whole warp runs the loop on warp-uniform values (so that descriptors live in uniform
     // registers) and one elected lane issues the 24 MMAs + commits of a chunk in a single block.  The issue loop
     // is the critical path of the kernel: keep it free of per-MMA address arithmetic and branches.
-    const uint32_t ghi = base, glo = base + G_BYTES, st0 = base + 2 * G_BYTES;
+    const uint32_t ghi = base, glo = base + G_BYTES;
     const uint64_t dbase = smem_desc(0);
     const int ntl = te - ts;
     PROF_DECL
@@ -252,8 +321,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc_kernel(FirTcParams p)
       PROF_ADD(1, t_w2)
       PROF_BEGIN(t_c)
       fence_after();
-      const uint32_t bhi = st0 + stage * STAGE_BYTES;
-      const uint64_t xh0 = dbase + (bhi >> 4), xl0 = xh0 + (PART_BYTES >> 4);     // A operand: data chunk, hi / lo
+      const uint32_t xh0 = tmem + (uint32_t) (ACOL + 64 * stage), xl0 = xh0 + 32;   // A operand: data chunk in tensor memory, hi / lo
       int j0a, na, j0b, nb;
       band_cols(-r4, p.K, j0a, na);
       band_cols(4 - r4, p.K, j0b, nb);
@@ -269,9 +337,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc_kernel(FirTcParams p)
 #pragma unroll
           for(int ks = 0; ks < 4; ks++)
           {
-            mma_tf32(da, xh0 + 2 * ks, gla + 2 * ks, ida);
-            mma_tf32(da, xl0 + 2 * ks, gha + 2 * ks, ida);
-            mma_tf32(da, xh0 + 2 * ks, gha + 2 * ks, ida);
+            mma_tf32(da, xh0 + 8 * ks, gla + 2 * ks, ida);
+            mma_tf32(da, xl0 + 8 * ks, gha + 2 * ks, ida);
+            mma_tf32(da, xh0 + 8 * ks, gha + 2 * ks, ida);
           }
         }
         if(on0 && r4 == 3) mma_commit(tfull + tl0 % 3);     // d = -3: last chunk of tile tl0, accumulator complete
@@ -280,9 +348,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc_kernel(FirTcParams p)
 #pragma unroll
           for(int ks = 0; ks < 4; ks++)
           {
-            mma_tf32(db, xh0 + 2 * ks, glb + 2 * ks, idb);
-            mma_tf32(db, xl0 + 2 * ks, ghb + 2 * ks, idb);
-            mma_tf32(db, xh0 + 2 * ks, ghb + 2 * ks, idb);
+            mma_tf32(db, xh0 + 8 * ks, glb + 2 * ks, idb);
+            mma_tf32(db, xl0 + 8 * ks, ghb + 2 * ks, idb);
+            mma_tf32(db, xh0 + 8 * ks, ghb + 2 * ks, idb);
           }
         }
         mma_commit(empty + stage);                          // the stage may be refilled once these MMAs have read it
@@ -351,8 +419,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc_kernel(FirTcParams p)
               const long long nabs = n0 + cb * 32 + 8 * i;
               const float4 o = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 1]),
                                            __uint_as_float(r[4 * i + 3]));
-              if(nabs + 1 < p.n) __stcs(reinterpret_cast<float4 *>(yrow + nabs), o);
-              else if(nabs < p.n) __stcs(yrow + nabs, make_float2(o.x, o.y));
+              if(nabs + 1 < p.n) *reinterpret_cast<float4 *>(yrow + nabs) = o;
+              else if(nabs < p.n) yrow[nabs] = make_float2(o.x, o.y);
             }
           }
         }
