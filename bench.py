@@ -424,7 +424,7 @@ def main():
         # ola: the block filter runs as three stage kernels per chunk of 32 blocks, overlapped on four streams; the timed
         # unit is the whole pipeline of one step() (events around its first and last launch on the launching stream)
         kernel_name = {"ola": "ola64k_stage<0|1|2> (stage kernels of one step(), overlapped)", "fft": "fft64k_kernel", "fir": "fir_tc_kernel (tcgen05 3xTF32 Toeplitz GEMM)",
-                       "resample": "resamp_banded_kernel"}[args.workload]
+                       "resample": "resamp_tc_kernel (tcgen05 3xTF32 banded filter-bank GEMM)"}[args.workload]
         roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_kind,
                     "algorithmic_bytes_per_sample": bytes_per_sample, "kernel_ms_per_step": kern_ms / args.steps,

@@ -30,7 +30,7 @@
 // 61 KiB per chunk.  Measured (-DTSD_TC_PROF, per-role clock64): MMA warp busy 950 cycles per chunk, compute-only
 // bound 360 Gsamples/s, loads-only or stores-only 280, both 240: the kernel is bound by DRAM efficiency of 64-channel
 // interleaved row pieces, not by the tensor cores; the FP32 FMA formulation (fir.cu) is capped at 146 Gsamples/s.
-#include "common.cuh"
+#include "tc_common.cuh"
 #include "fir_tc.h"
 
 #include <cstdlib>
@@ -57,43 +57,8 @@ constexpr int LOAD_WARP = MMA_WARP + 1;
 constexpr int NTHREADS = 32 * (LOAD_WARP + 1);
 constexpr int TMEM_COLS = 512;
 
-__device__ __forceinline__ uint32_t swz(uint32_t off) { return off ^ (((off >> 7) & 7u) << 4); }   // Swizzle<3,4,3>
-// round to the nearest tf32 (10-bit mantissa), ties away from zero like cvt.rna.tf32.f32, with two full-rate integer
-// instructions (the conversion instruction itself issues at a small fraction of the FP32 rate: it made the producers
-// the bottleneck of the kernel)
-__device__ __forceinline__ float to_tf32(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u); }
-// shared-memory matrix descriptor, K-major, SWIZZLE_128B: 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor)
-__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr)
-{
-  return (uint64_t) ((saddr >> 4) & 0x3FFFu) | ((uint64_t) 1 << 16) /* LBO (unused for swizzled K-major) */ |
-         ((uint64_t) (1024 >> 4) << 32) /* SBO */ | ((uint64_t) 1 << 46) /* version */ | ((uint64_t) 2 << 61) /* SWIZZLE_128B */;
-}
-// instruction descriptor (cute::UMMA::InstrDescriptor): D = f32, A = B = tf32, both K-major, M = 128; N (bits 17..22, N >> 3) is added per MMA
-constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t) (NCOL >> 4) << 24);
+constexpr uint32_t IDESC = IDESC_M128;
 
-// D[128][N] += A[128][8] * B[N][8]^T, A read from tensor memory (lanes 0..127, 8 columns), B from shared memory
-// (always accumulating: the epilogue leaves every region zeroed)
-__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc)
-{
-  asm volatile(
-    "{\n\t.reg .pred p;\n\t"
-    "setp.ne.b32 p, 1, 0;\n\t"
-    "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
-    ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc)
-    : "memory");
-}
-__device__ __forceinline__ void named_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
-// 16 consecutive TMEM columns of this thread's lane <- 16 registers
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16])
-{
-  asm volatile(
-    "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
-    "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])),
-    "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])),
-    "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])), "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])),
-    "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
-    : "memory");
-}
 // output columns [j0, j0 + nn) of a 128-output tile touched by Toeplitz block d (taps j - kk + 32 d in [0, K)), 16-aligned
 __device__ __forceinline__ void band_cols(int d, int K, int &j0, int &nn)
 {
@@ -101,41 +66,11 @@ __device__ __forceinline__ void band_cols(int d, int K, int &j0, int &nn)
   j0 = jlo & ~15;
   nn = jhi < jlo ? 0 : ((jhi + 16) & ~15) - j0;
 }
-__device__ __forceinline__ void mma_commit(uint64_t *bar)
-{
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
-{
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool elect_one()
-{
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
 #ifdef TSD_TC_PROF
-// timing experiment: per-CTA cycle totals [cta][role 0..15][what 0..3]; role = warp, what: 0 wait A, 1 wait B, 2 work, 3 total
-__device__ long long g_tcprof[1024][16][4];
-#define PROF_DECL long long pf_[4] = {0, 0, 0, 0}; const long long pf_t0 = clock64();
-#define PROF_BEGIN(v) const long long v = clock64();
-#define PROF_ADD(k, v) pf_[k] += clock64() - (v);
-#define PROF_END                                                                                             \
-  if(lane == 0 && blockIdx.y == 0 && blockIdx.x < 1024)                                                      \
-  {                                                                                                          \
-    pf_[3] = clock64() - pf_t0;                                                                              \
-    for(int k = 0; k < 4; k++) g_tcprof[blockIdx.x][warp][k] = pf_[k];                                       \
-  }
-#else
-#define PROF_DECL
-#define PROF_BEGIN(v)
-#define PROF_ADD(k, v)
-#define PROF_END
+__device__ long long g_tcprof[1024][24][4];
+#define PROF_ARRAY g_tcprof
 #endif
+#include "tc_prof.cuh"
 
 __global__ void __launch_bounds__(NTHREADS, 1) fir_tc_kernel(FirTcParams p)
 {
@@ -440,14 +375,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc_kernel(FirTcParams p)
   if(tid == 0 && blockIdx.y * gridDim.x + blockIdx.x < 1024)
   {
     const int bi = blockIdx.y * gridDim.x + blockIdx.x;
-    g_tcprof[bi][14][0] = pf_setup - pf_entry;
-    g_tcprof[bi][14][1] = clock64() - pf_setup;
+    g_tcprof[bi][20][0] = pf_setup - pf_entry;
+    g_tcprof[bi][20][1] = clock64() - pf_setup;
     unsigned long long gt;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-    g_tcprof[bi][14][2] = (long long) gt;
+    g_tcprof[bi][20][2] = (long long) gt;
     unsigned smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    g_tcprof[bi][14][3] = smid;
+    g_tcprof[bi][20][3] = smid;
   }
 #endif
   if(warp == MMA_WARP)
@@ -469,7 +404,7 @@ bool fir_tc_eligible(int kind_cf32_f32, int K, const void *x, long long x_stride
 extern "C" int tsdgpu_debug_tcprof_dump(const char *path)
 {
   cudaDeviceSynchronize();
-  static long long h[1024][16][4];
+  static long long h[1024][24][4];
   if(cudaMemcpyFromSymbol(h, tc::g_tcprof, sizeof(h)) != cudaSuccess) return 1;
   FILE *fp = fopen(path, "wb");
   if(!fp) return 1;

@@ -11,6 +11,7 @@
 // last K-1 inputs of every channel (device).
 #include "common.cuh"
 #include "host_pipe.cuh"
+#include "resamp_tc.h"
 #include "tsdgpu.h"
 
 #include <algorithm>
@@ -232,6 +233,41 @@ static float resamp_schedule(float phase, float increment, int nphases, int i0, 
                              size_t *count, bool *overflow)
 {
   size_t j = 0;
+  // This loop is the host-side critical path of a step() (one float add + one float subtract of dependent latency per
+  // input): keep it free of bounds checks (the caller sizes `out` for ceil((i1 - i0) * max(1, ratio)) + 16 entries,
+  // checked once here) and, for increment >= 1 (at most one output per input), free of the inner loop.
+  const float nph = (float) nphases;
+  if(out && (double) (i1 - i0) / (double) increment + 16.0 <= (double) cap)
+  {
+    if(increment >= 1.0f)
+    {
+      for(int i = i0; i < i1; i++)
+      {
+        if(phase < 1)
+        {
+          out[j] = make_int2(i, (int) (phase * nph));
+          j++;
+          phase += increment;
+        }
+        phase--;
+      }
+    }
+    else
+    {
+      for(int i = i0; i < i1; i++)
+      {
+        while(phase < 1)
+        {
+          out[j] = make_int2(i, (int) (phase * nph));
+          j++;
+          phase += increment;
+        }
+        phase--;
+      }
+    }
+    *count = j;
+    return phase;
+  }
   for(int i = i0; i < i1; i++)
   {
     while(phase < 1)
@@ -323,7 +359,30 @@ static int resamp_run_device(tsdgpu_resamp_s *f, const float2 *x, long long xs, 
       s_w_max = std::max(s_w_max, 72);   // the output transpose patch (32 x 9 float2 = 2304 B) reuses this area
     }
     const size_t smem2 = (((size_t) s_cta_max * RS2_PITCH * sizeof(float2) + 15) & ~(size_t) 15) + (size_t) RS2_WARPS * s_w_max * RS2_RJ * sizeof(float);
-    if(smem2 <= 200 * 1024 && !getenv("TSDGPU_RESAMP_V1"))
+    // banded filter-bank GEMM on the tensor cores (3xTF32, resamp_tc.cu); TSDGPU_RESAMP_TC=0 keeps the FP32 FMA kernels
+    const char *tc_env = getenv("TSDGPU_RESAMP_TC");
+    const bool tc_on = !(tc_env && atoi(tc_env) == 0);
+    if(tc_on && resamp_tc_eligible(f->h_sched[b], (long long) cnt, f->K, x, xs))
+    {
+      ResampTcParams t;
+      t.x = x;
+      t.y = y;
+      t.hist = hist_old;
+      t.lut = f->d_lut;
+      t.sched = f->d_sched[b];
+      t.x_stride = xs;
+      t.y_stride = ys;
+      t.out0 = produced;
+      t.n_out = (long long) cnt;
+      t.n = n;
+      t.K = f->K;
+      t.hist_len = f->hist_len;
+      t.nchan = f->nchan;
+      t.lut_elems = f->K * (f->nphases + 1);
+      KernelTimer timer;
+      if(resamp_tc_launch(t)) return 1;
+    }
+    else if(smem2 <= 200 * 1024 && !getenv("TSDGPU_RESAMP_V1"))
     {
       Resamp2Params q;
       q.b = p;

@@ -256,14 +256,19 @@ class AdaptationRythmeSimple(FiltreGen):
 
     def step(self, x):
         b = Batch(x, np.complex64, self.nchan)
-        cnt = self.out_count(b.n)
-        y = empty_like_batch(b, np.complex64, cnt)
         if b.n == 0:
-            return restore_shape(y, b.ndim)
+            return restore_shape(empty_like_batch(b, np.complex64, 0), b.ndim)
+        # the exact count comes out of the phase recurrence, which the library runs once inside the call: size the
+        # buffer by the bound ceil(n * ratio) + 16 and return the exact-length view (a separate out_count() query would
+        # run the whole recurrence a second time on the host)
+        cap = int(np.ceil(b.n * max(self.ratio, 0.0))) + 16
+        y = empty_like_batch(b, np.complex64, cap)
         yb = Batch(y, np.complex64, self.nchan, "y")
         no = C.c_longlong()
-        check(lib().tsdgpu_resamp_step(self._h, b.ptr, b.stride, b.n, yb.ptr, max(yb.stride, 1), cnt, C.byref(no), b.mem))
-        assert no.value == cnt
+        check(lib().tsdgpu_resamp_step(self._h, b.ptr, b.stride, b.n, yb.ptr, max(yb.stride, 1), cap, C.byref(no), b.mem))
+        y = y[:, : no.value]
+        if not b.torch:
+            y = np.ascontiguousarray(y)
         return restore_shape(y, b.ndim)
 
     def __del__(self):

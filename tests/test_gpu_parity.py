@@ -409,6 +409,28 @@ def test_itrp_vs_oracle(tsd, port, cpu_oracle, ratio, K, fcut):
         assert np.float32(g.phase) == np.float32(refs[0].phase)
 
 
+@pytest.mark.parametrize("tc", ["0", "1"])
+@pytest.mark.parametrize("ratio,K,nchan,n", [(147 / 160, 64, 70, 20000), (1.3, 15, 3, 5000), (0.6, 31, 64, 70001), (147 / 160, 64, 130, 4097)])
+def test_itrp_tensor_core_and_fma_paths(tsd, port, cpu_oracle, monkeypatch, tc, ratio, K, nchan, n):
+    """The tcgen05 banded filter-bank GEMM (resamp_tc.cu) and the FP32 FMA kernel (resamp.cu) on the same ragged input:
+    per-call output counts and final phase bit-exact, samples within tolerance, state carried over ragged calls."""
+    from libtsd_b200 import filtrage as F
+    monkeypatch.setenv("TSDGPU_RESAMP_TC", tc)
+    rng = np.random.default_rng(int(ratio * 100) + K + nchan)
+    lut = cpu_oracle.itrp_sinc_lut(K, 256, 0.4)
+    g = F.filtre_itrp(ratio, F.InterpolateurLUT(lut), nchan)
+    refs = [port.itrp(ratio, lut, 256) for _ in range(min(nchan, 3))]
+    for blk in (n, 131, 1, 4096):
+        x = cn(rng, nchan, blk)
+        y = g.step(x)
+        for c, r in enumerate(refs):
+            yr = r.step(x[c])
+            assert y[c].shape == yr.shape
+            if yr.size:
+                assert rel_err(y[c], yr, rms(x)) <= TOL
+        assert np.float32(g.phase) == np.float32(refs[0].phase)
+
+
 def test_itrp_vs_reference_object(tsd, ref):
     """Same comparison against the reference's own filtre_itrp + itrp_sinc objects (config 5 parameters)."""
     from libtsd_b200 import filtrage as F
