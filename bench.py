@@ -300,7 +300,8 @@ def e2e_measure(name, steps, warmup, barrier=None):
         nchan, n = 128, 1 << 20
         flt = F.filtre_itrp(147.0 / 160.0, F.InterpolateurLUT(O.itrp_sinc_lut(64, 256, 0.4)), nchan)
         tx, x = pinned(nchan, n)
-        step = lambda: flt.step(x)   # noqa: E731
+        ty, y = pinned(nchan, int(n * 147 / 160) + 32)
+        step = lambda: flt.step(x, out=y)   # noqa: E731
         out_per_step = int(n * 147 / 160)
     for _ in range(warmup):
         step()

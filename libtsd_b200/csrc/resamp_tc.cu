@@ -34,8 +34,9 @@ constexpr int MAXSPAN = 16;                      // tiles per CTA: its slice of 
 constexpr int LUT_SMEM_MAX = 66 * 1024;          // the LUT too when it fits (64 taps x 257 phases = 64.25 KiB)
 constexpr int SMEM_BYTES = NT * TB_BYTES + NRAW * RAW_BYTES + MAXSPAN * TILE * 8 + LUT_SMEM_MAX + 1024 + 512 + 2 * MAXSPAN * 4 + 64;
 constexpr int ACOL = 3 * NCOL;
-constexpr int CONV_WARP0 = 4, GEN_WARP0 = 8, NGEN = 8, MMA_WARP = 16, LOAD_WARP = 17;
-constexpr int NTHREADS = 32 * 18;
+constexpr int CONV_WARP0 = 4, GEN_WARP0 = 8, NGEN = 16, MMA_WARP = GEN_WARP0 + NGEN, LOAD_WARP = MMA_WARP + 1;
+constexpr int NTHREADS = 32 * (LOAD_WARP + 1);
+constexpr int GROWS = (TILE + NGEN - 1) / NGEN;   // rows per generator warp and block: j = gw + NGEN * r
 constexpr int TMEM_COLS = 512;
 
 #ifdef TSD_TC_PROF
@@ -249,15 +250,14 @@ template<bool LUTS> __global__ void __launch_bounds__(NTHREADS, 1) resamp_tc_ker
         const int j0 = p.band ? (min(jlo, TILE - 16) & ~15) : 0;
         const int nn = p.band ? max(16, ((jend + 15) & ~15) - j0) : TILE;
         if(gw == 0 && lane == 0) bmeta[slot] = make_int2(j0, nn);
-        // 16 independent, branch-free rows: clamped LUT index, value masked afterwards; lane = column kk
+        // GROWS independent, branch-free rows per warp: clamped LUT index, value masked afterwards; lane = column kk
         const int2 *srow = sched_s + tt[w] * TILE + gw;
         const int tcol = c * CHUNK + lane;
-        const uint32_t off0 = swz((uint32_t) (gw * 128 + lane * 4));   // rows gw + 8 r: same swizzle phase, 1024 bytes apart
-        float v[16];
+        float v[GROWS];
 #pragma unroll
-        for(int r = 0; r < 16; r++)
+        for(int r = 0; r < GROWS; r++)
         {
-          const int2 e = srow[8 * r];                                  // broadcast read
+          const int2 e = srow[min(NGEN * r, TILE - 1 - gw)];           // broadcast read
           const int tap = tcol + e.x;
           const bool ok = (e.y >= 0) & ((unsigned) tap < (unsigned) K);
           const int idx = ok ? e.y + tap : 0;
@@ -265,14 +265,16 @@ template<bool LUTS> __global__ void __launch_bounds__(NTHREADS, 1) resamp_tc_ker
           v[r] = ok ? val : 0.f;
         }
 #pragma unroll
-        for(int r = 0; r < 16; r++)
+        for(int r = 0; r < GROWS; r++)
         {
           // rows outside the band are never read by the MMAs: skip their stores (warp-uniform predicate, no branch)
+          const int j = gw + NGEN * r;
           const float hi = to_tf32(v[r]), lo = to_tf32(v[r] - hi);
-          if((unsigned) (gw + 8 * r - j0) < (unsigned) nn)
+          if(j < TILE && (unsigned) (j - j0) < (unsigned) nn)
           {
-            *reinterpret_cast<float *>(thi + off0 + r * 1024) = hi;
-            *reinterpret_cast<float *>(tlo_ + off0 + r * 1024) = lo;
+            const uint32_t off = swz((uint32_t) (j * 128 + lane * 4));
+            *reinterpret_cast<float *>(thi + off) = hi;
+            *reinterpret_cast<float *>(tlo_ + off) = lo;
           }
         }
         PROF_ADD(2, t_c)

@@ -254,7 +254,9 @@ class AdaptationRythmeSimple(FiltreGen):
     def out_count(self, n: int) -> int:
         return int(lib().tsdgpu_resamp_out_count(self._h, int(n)))
 
-    def step(self, x):
+    def step(self, x, out=None):
+        """``out`` (optional, same memory space as ``x``) needs room for ceil(n * ratio) + 16 samples per channel; the
+        result is the exact-length view of the buffer the samples were written to (no extra host copy)."""
         b = Batch(x, np.complex64, self.nchan)
         if b.n == 0:
             return restore_shape(empty_like_batch(b, np.complex64, 0), b.ndim)
@@ -262,14 +264,18 @@ class AdaptationRythmeSimple(FiltreGen):
         # buffer by the bound ceil(n * ratio) + 16 and return the exact-length view (a separate out_count() query would
         # run the whole recurrence a second time on the host)
         cap = int(np.ceil(b.n * max(self.ratio, 0.0))) + 16
-        y = empty_like_batch(b, np.complex64, cap)
-        yb = Batch(y, np.complex64, self.nchan, "y")
+        if out is None:
+            y = empty_like_batch(b, np.complex64, cap)
+            yb = Batch(y, np.complex64, self.nchan, "y")
+        else:
+            yb = Batch(out, np.complex64, self.nchan, "y")
+            y = yb.arr
+            if yb.mem != b.mem:
+                raise TsdGpuError("filtre_itrp.step: tampon de sortie incompatible")
+            cap = yb.n   # the library reports TSDGPU_ERR_SIZE itself if the exact count does not fit
         no = C.c_longlong()
         check(lib().tsdgpu_resamp_step(self._h, b.ptr, b.stride, b.n, yb.ptr, max(yb.stride, 1), cap, C.byref(no), b.mem))
-        y = y[:, : no.value]
-        if not b.torch:
-            y = np.ascontiguousarray(y)
-        return restore_shape(y, b.ndim)
+        return restore_shape(y[:, : no.value], b.ndim)
 
     def __del__(self):
         h = getattr(self, "_h", None)
