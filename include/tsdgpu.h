@@ -103,9 +103,17 @@ int tsdgpu_fft_destroy(tsdgpu_fft_t p);
  * Fails with the reference's own precondition when N_zeros > Ne (fourier.cc:870). */
 int tsdgpu_ola_create(int dim_blocs_temporel, int nb_zeros_min, const float *H, int fir_len,
                       int nchan, tsdgpu_ola_t *out);
+/* Same object with FiltreFFTConfig::avec_fenetrage = oui (fourier.cc:794-798,884-930): every block is processed
+ * twice — the window [previous half, new half] and the block itself — each multiplied by `fenetre` (Ne floats; the
+ * reference uses fenêtre("hn", Ne, non)), transformed, multiplied by H (NULL = identity), transformed back and
+ * recombined with weights 1/2.  The first block of the stream emits nothing (cnt_ech < 0, :900-903); later blocks
+ * emit Ne samples.  Reproduces the reference as it behaves, including the aliasing of its `svg` buffer with the
+ * inverse-transform output from the second block on (:923).  Even Ne only. */
+int tsdgpu_ola_create_fen(int dim_blocs_temporel, int nb_zeros_min, const float *H, const float *fenetre,
+                          int nchan, tsdgpu_ola_t *out);
 int tsdgpu_ola_dims(tsdgpu_ola_t f, int *Ne, int *N, int *N_zeros, int *residual);
-/* Number of samples the next step(n) will emit: Ne * ((residual + n) / Ne)
- * (TamponNv2 re-blocking, tsd.cc:332-370; fourier.cc:813-833). */
+/* Number of samples the next step(n) will emit: Ne * ((residual + n) / Ne), one block less for the
+ * first block of a windowed filter (TamponNv2 re-blocking, tsd.cc:332-370; fourier.cc:813-833). */
 long long tsdgpu_ola_out_count(tsdgpu_ola_t f, int n);
 /* Feeds n samples per channel; writes *n_out = tsdgpu_ola_out_count(f, n) samples per channel. */
 int tsdgpu_ola_step(tsdgpu_ola_t f, const void *x, long long x_stride, int n,

@@ -73,6 +73,22 @@ int main()
     soit e3 = ecart(yg, yc, xo);
     printf("filtre_fft   N %d/%d, %d/%d echantillons : ecart %.2e\n", Nc, Ng, yc.rows(), yg.rows(), e3);
     bad += (e3 > 1e-5) + (Nc != Ng);
+    {
+      // windowed (Hann, 50 % overlap) mode with the same callback: first block silent, then Ne samples per block
+      FiltreFFTConfig cf2;
+      cf2.dim_blocs_temporel = 4096;
+      cf2.nb_zeros_min = 4096;
+      cf2.avec_fenetrage = oui;
+      Veccf H2 = bruit(8192, 7);
+      cf2.traitement_freq = [&](Veccf &X) { X *= H2; };
+      soit [wc, Nwc] = filtre_fft(cf2);
+      soit [wg, Nwg] = tsd::gpu::filtre_fft_gpu(cf2, H2);
+      soit xw = bruit(50000, 8);
+      soit ywc = wc->step(xw), ywg = wg->step(xw);
+      soit e3b = ywc.rows() == ywg.rows() ? ecart(ywg, ywc, ywc) : 1.0f;
+      printf("filtre_fft   fenetre N %d/%d, %d/%d echantillons : ecart %.2e\n", Nwc, Nwg, ywc.rows(), ywg.rows(), e3b);
+      bad += (e3b > 1e-5) + (Nwc != Nwg);
+    }
     // filtre_itrp 147/160, sinc 64 x 257
     soit it = itrp_sinc<cfloat>({64, 256, 0.4f, "hn"});
     soit rc = filtre_itrp<cfloat>(147.0f / 160.0f, it);

@@ -93,10 +93,18 @@ struct OLAGpu: Filtre<cfloat, cfloat, tsd::fourier::FiltreFFTConfig>
   ~OLAGpu() { tsdgpu_ola_destroy(h); }
   void configure_impl(const tsd::fourier::FiltreFFTConfig &c) override
   {
-    si(c.avec_fenetrage) échec("filtre_fft (gpu) : mode fenêtré non disponible");
     tsdgpu_ola_destroy(h);
-    verifie(tsdgpu_ola_create(c.dim_blocs_temporel, c.nb_zeros_min, H.rows() ? (const float *) H.data() : nullptr, K, 1, &h),
-            "filtre_fft (gpu)");
+    h = nullptr;
+    const float *Hp = H.rows() ? (const float *) H.data() : nullptr;
+    si(c.avec_fenetrage)
+    {
+      // Hann-window 50 % overlap mode (fourier.cc:794-798,884-930): same window as the reference object
+      soit Ne = c.dim_blocs_temporel > 0 ? c.dim_blocs_temporel : 512;
+      Vecf fen = tsd::filtrage::fenêtre("hn", Ne, non);
+      verifie(tsdgpu_ola_create_fen(c.dim_blocs_temporel, c.nb_zeros_min, Hp, fen.data(), 1, &h), "filtre_fft (gpu)");
+    }
+    sinon
+      verifie(tsdgpu_ola_create(c.dim_blocs_temporel, c.nb_zeros_min, Hp, K, 1, &h), "filtre_fft (gpu)");
     tsdgpu_ola_dims(h, nullptr, &N, nullptr, nullptr);
   }
   void step(const Veccf &x, Veccf &y) override

@@ -404,6 +404,89 @@ __global__ void ola_svg_kernel(const float2 *work, float2 *svg, int N, int Ne, i
     svg[(long long) chan * Ne + i] = lastb[Nz + i];
 }
 
+// ---- Hann-window, 50 % overlap mode (fourier.cc:884-930), even Ne ------------------------------
+// Two frames per block g: phase 0 = stream window starting Ne/2 before the block, phase 1 = the block itself, both
+// times the window, zero-padded in front.  Z1_g, Z2_g = the filtered frames.  The reference's svg becomes a VIEW of
+// its x2 buffer at the end of the first block (fourier.cc:923 moves a temporary view into svg, tableau.hpp:545-566),
+// so from block 1 on every frame is folded onto ITSELF:
+//   F(Z)[i] = Z[Nz+i] + (i >= Ne-Nz ? Z[i-(Ne-Nz)] : 0)
+//   S1_g = F(Z1_g), S2_g = F(Z2_g)                                            (g >= 1)
+//   S1_0[i] = i >= Ne-Nz ? Z1_0[i-(Ne-Nz)] : 0 ;  S2_0[i] = Z1_0[Nz+i] + (i >= Ne-Nz ? Z2_0[i-(Ne-Nz)] : 0)
+//   last_g  = [ S1_g.tail(h)/2 + S2_g.head(h)/2 , S2_g.tail(h)/2 ]            (h = Ne/2)
+//   y_g     = [ last_{g-1}.head(h) , last_{g-1}.tail(h) + S1_g.head(h)/2 ]    (g >= 1; block 0 emits nothing)
+// which makes all blocks of a call independent given `last` of the previous call.
+__global__ void ola_gather_fen_kernel(const float2 *x, long long x_stride, const float2 *carry, int carry_len, float2 *work,
+                                      const float *fen, int N, int Ne, int Nz, int nb, int b0, int residual)
+{
+  const int q = blockIdx.y, chan = q / (2 * nb), r = q - chan * 2 * nb, blk = r >> 1, ph = r & 1;
+  const float2 *xc = x + (long long) chan * x_stride;
+  const float2 *cr = carry + (long long) chan * carry_len + carry_len;
+  const long long first = (long long) (b0 + blk) * Ne - residual - (ph == 0 ? Ne / 2 : 0);
+  for(int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x)
+  {
+    float2 v = make_float2(0.f, 0.f);
+    if(n >= Nz)
+    {
+      const long long pos = first + n - Nz;
+      v = (pos >= 0) ? xc[pos] : cr[pos];
+      const float w = fen[n - Nz];
+      v.x *= w;
+      v.y *= w;
+    }
+    work[(long long) q * N + n] = v;
+  }
+}
+__device__ __forceinline__ float2 fen_half(float2 a) { return make_float2(a.x * 0.5f, a.y * 0.5f); }
+__device__ __forceinline__ float2 fen_s1(const float2 *Z1, bool first, int i, int Ne, int Nz)
+{
+  float2 a = first ? make_float2(0.f, 0.f) : Z1[Nz + i];
+  if(i >= Ne - Nz) a = cadd(a, Z1[i - (Ne - Nz)]);
+  return a;
+}
+__device__ __forceinline__ float2 fen_s2(const float2 *Z1, const float2 *Z2, bool first, int i, int Ne, int Nz)
+{
+  float2 a = first ? Z1[Nz + i] : Z2[Nz + i];
+  if(i >= Ne - Nz) a = cadd(a, Z2[i - (Ne - Nz)]);
+  return a;
+}
+// y of the blocks g = g0 + blk >= 1 of this chunk; e0 = emitted-block index of g0 within the call's output
+__global__ void ola_scatter_fen_kernel(const float2 *work, const float2 *last, float2 *y, long long y_stride, int N, int Ne,
+                                       int Nz, int nb, long long g0, long long e0)
+{
+  const int q = blockIdx.y, chan = q / nb, blk = q - chan * nb, h = Ne / 2;
+  const long long g = g0 + blk;
+  if(g < 1) return;
+  const float2 *Z1 = work + ((long long) q * 2) * N;                 // this block, first frame
+  const float2 *P1 = Z1 - 2 * (long long) N, *P2 = P1 + N;           // previous block (blk >= 1)
+  float2 *yb = y + (long long) chan * y_stride + (e0 + blk) * Ne;
+  const float2 *lc = last + (long long) chan * Ne;
+  for(int i = blockIdx.x * blockDim.x + threadIdx.x; i < Ne; i += gridDim.x * blockDim.x)
+  {
+    float2 a;
+    if(blk == 0) a = lc[i];
+    else
+    {
+      a = fen_half(fen_s2(P1, P2, g - 1 == 0, i, Ne, Nz));
+      if(i < h) a = cadd(fen_half(fen_s1(P1, g - 1 == 0, h + i, Ne, Nz)), a);
+    }
+    if(i >= h) a = cadd(a, fen_half(fen_s1(Z1, false, i - h, Ne, Nz)));
+    yb[i] = a;
+  }
+}
+// last = last_g of the chunk's final block
+__global__ void ola_last_fen_kernel(const float2 *work, float2 *last, int N, int Ne, int Nz, int nb, long long g_last)
+{
+  const int chan = blockIdx.y, h = Ne / 2;
+  const float2 *Z1 = work + (((long long) chan * nb + (nb - 1)) * 2) * N, *Z2 = Z1 + N;
+  const bool first = g_last == 0;
+  for(int i = blockIdx.x * blockDim.x + threadIdx.x; i < Ne; i += gridDim.x * blockDim.x)
+  {
+    float2 a = fen_half(fen_s2(Z1, Z2, first, i, Ne, Nz));
+    if(i < h) a = cadd(fen_half(fen_s1(Z1, first, h + i, Ne, Nz)), a);
+    last[(long long) chan * Ne + i] = a;
+  }
+}
+
 } // namespace tsdgpu
 
 using namespace tsdgpu;
@@ -426,6 +509,10 @@ struct tsdgpu_ola_s
   // staged form (default): blocks per stage kernel, number of auxiliary streams
   // 1 = staged kernels over auxiliary streams (default), 0 = single persistent kernel
   int staged = 1, chunk = 32, nslots = 4;
+  // windowed mode (always unfused): window [Ne], `last` of the reference [nchan][Ne]
+  bool fen = false;
+  float *d_fen = nullptr;
+  float2 *d_last = nullptr;
   // unfused
   tsdgpu_fft_s *plan = nullptr;
   float2 *work = nullptr;
@@ -577,17 +664,63 @@ static int ola_run_unfused(tsdgpu_ola_s *f, const float2 *x, long long xs, float
   return 0;
 }
 
+static int ola_run_fen(tsdgpu_ola_s *f, const float2 *x, long long xs, float2 *y, long long ys, int B)
+{
+  Runtime &r = rt();
+  const int N = f->N, Ne = f->Ne, Nz = f->Nz;
+  const long long per_block = 2LL * f->nchan * N * (long long) sizeof(float2);
+  const int nb_max = (int) std::max(1LL, (256LL << 20) / per_block);
+  const long long g0 = f->blocks_done, e_first = std::max(g0, 1LL);
+  for(int b0 = 0; b0 < B; b0 += nb_max)
+  {
+    const int nb = std::min(nb_max, B - b0);
+    const int batch = f->nchan * nb * 2;
+    if(batch > 65535) return fail("tsdgpu_ola_step: 2 * nchan * blocks per chunk > 65535 in the windowed mode");
+    if(!f->plan || f->plan_batch != batch)
+    {
+      if(f->plan) fft_plan_destroy(f->plan);
+      f->plan = nullptr;
+      if(f->work) cudaFree(f->work);
+      f->work = nullptr;
+      if(fft_plan_create(N, batch, &f->plan)) return 1;
+      f->plan_batch = batch;
+      TSD_CUDA(cudaMalloc(&f->work, (size_t) batch * N * sizeof(float2)));
+    }
+    dim3 gg((N + 255) / 256, batch);
+    ola_gather_fen_kernel<<<gg, 256, 0, r.stream>>>(x, xs, f->d_carry[f->cur], f->carry_len, f->work, f->d_fen, N, Ne, Nz, nb,
+                                                   b0, f->residual);
+    TSD_LAUNCH_CHECK();
+    if(fft_exec_device(f->plan, f->work, N, f->work, N, true)) return 1;
+    if(f->d_H)
+    {
+      const long long total = (long long) batch * N;
+      ola_mulH_kernel<<<(int) std::min<long long>((total + 255) / 256, rt().num_sms * 16), 256, 0, r.stream>>>(f->work, f->d_H,
+                                                                                                             N, total);
+      TSD_LAUNCH_CHECK();
+    }
+    if(fft_exec_device(f->plan, f->work, N, f->work, N, false)) return 1;
+    dim3 gs((Ne + 255) / 256, f->nchan * nb);
+    ola_scatter_fen_kernel<<<gs, 256, 0, r.stream>>>(f->work, f->d_last, y, ys, N, Ne, Nz, nb, g0 + b0, g0 + b0 - e_first);
+    TSD_LAUNCH_CHECK();
+    dim3 gv((Ne + 255) / 256, f->nchan);
+    ola_last_fen_kernel<<<gv, 256, 0, r.stream>>>(f->work, f->d_last, N, Ne, Nz, nb, g0 + b0 + nb - 1);
+    TSD_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
 static int ola_run_device(tsdgpu_ola_s *f, const float2 *x, long long xs, int n, float2 *y, long long ys, long long *n_out)
 {
   Runtime &r = rt();
   const long long tot = (long long) f->residual + n;
   const int B = (int) (tot / f->Ne);
-  *n_out = (long long) B * f->Ne;
+  // windowed mode: the first block of the stream emits nothing (cnt_ech < 0, fourier.cc:900-903)
+  *n_out = (long long) (B - ((f->fen && f->blocks_done == 0 && B > 0) ? 1 : 0)) * f->Ne;
   if(n <= 0) return 0;
   if(B > 0)
   {
     if(ys < *n_out) return fail("tsdgpu_ola_step: output stride smaller than the emitted count");
-    int rc = f->fused ? ola_run_fused(f, x, xs, n, y, ys, B) : ola_run_unfused(f, x, xs, y, ys, B);
+    int rc = f->fen ? ola_run_fen(f, x, xs, y, ys, B) : f->fused ? ola_run_fused(f, x, xs, n, y, ys, B) : ola_run_unfused(f, x, xs, y, ys, B);
     if(rc) return rc;
   }
   dim3 grid((f->carry_len + 255) / 256, f->nchan);
@@ -601,7 +734,25 @@ static int ola_run_device(tsdgpu_ola_s *f, const float2 *x, long long xs, int n,
 
 extern "C" {
 
+static int ola_create(int dim_blocs_temporel, int nb_zeros_min, const float *H, int fir_len, const float *fenetre, int nchan,
+                      tsdgpu_ola_t *out);
+
 int tsdgpu_ola_create(int dim_blocs_temporel, int nb_zeros_min, const float *H, int fir_len, int nchan, tsdgpu_ola_t *out)
+{
+  return ola_create(dim_blocs_temporel, nb_zeros_min, H, fir_len, nullptr, nchan, out);
+}
+
+int tsdgpu_ola_create_fen(int dim_blocs_temporel, int nb_zeros_min, const float *H, const float *fenetre, int nchan,
+                          tsdgpu_ola_t *out)
+{
+  if(!fenetre) return fail("tsdgpu_ola_create_fen: null window");
+  return ola_create(dim_blocs_temporel, nb_zeros_min, H, 0, fenetre, nchan, out);
+}
+
+} // extern "C"
+
+static int ola_create(int dim_blocs_temporel, int nb_zeros_min, const float *H, int fir_len, const float *fenetre, int nchan,
+                      tsdgpu_ola_t *out)
 {
   if(ensure_init()) return 1;
   if(!out) return fail("tsdgpu_ola_create: null argument");
@@ -619,12 +770,16 @@ int tsdgpu_ola_create(int dim_blocs_temporel, int nb_zeros_min, const float *H, 
   if(fir_len < 0 || fir_len > Nz)
     return fail("tsdgpu_ola_create: fir_len must be in [1, N_zeros] (or 0 for an arbitrary H)");
   if(fir_len > 0 && !H) return fail("tsdgpu_ola_create: fir_len > 0 needs H");
+  if(fenetre && (Ne & 1))
+    return fail("tsdgpu_ola_create_fen: odd dim_blocs_temporel is not supported in the windowed mode (the reference never "
+                "resets the centre sample of its `last` buffer there, fourier.cc:899-906)");
   auto *f = new tsdgpu_ola_s;
   f->Ne = Ne;
   f->N = N;
   f->Nz = Nz;
   f->nchan = nchan;
-  f->fused = (N == 65536);
+  f->fen = fenetre != nullptr;
+  f->fused = (N == 65536) && !f->fen;
   f->K = f->fused ? fir_len : 0;   // the unfused path always runs the overlap-add form
   f->carry_len = N + Ne;
   cudaError_t e = cudaSuccess;
@@ -635,6 +790,13 @@ int tsdgpu_ola_create(int dim_blocs_temporel, int nb_zeros_min, const float *H, 
   }
   if(e == cudaSuccess) e = cudaMalloc(&f->d_svg, (size_t) nchan * Ne * sizeof(float2));
   if(e == cudaSuccess) e = cudaMemsetAsync(f->d_svg, 0, (size_t) nchan * Ne * sizeof(float2), rt().stream);   // svg.setZero(Ne), fourier.cc:785
+  if(e == cudaSuccess && f->fen)
+  {
+    e = cudaMalloc(&f->d_fen, (size_t) Ne * sizeof(float));
+    if(e == cudaSuccess) e = cudaMemcpy(f->d_fen, fenetre, (size_t) Ne * sizeof(float), cudaMemcpyHostToDevice);
+    if(e == cudaSuccess) e = cudaMalloc(&f->d_last, (size_t) nchan * Ne * sizeof(float2));
+    if(e == cudaSuccess) e = cudaMemsetAsync(f->d_last, 0, (size_t) nchan * Ne * sizeof(float2), rt().stream);   // fourier.cc:784
+  }
   if(e == cudaSuccess && (H || f->fused))
   {
     std::vector<float2> h((size_t) N);
@@ -671,6 +833,8 @@ int tsdgpu_ola_create(int dim_blocs_temporel, int nb_zeros_min, const float *H, 
   return 0;
 }
 
+extern "C" {
+
 int tsdgpu_ola_dims(tsdgpu_ola_t f, int *Ne, int *N, int *Nz, int *residual)
 {
   if(!f) return fail("tsdgpu_ola_dims: null handle");
@@ -684,7 +848,8 @@ int tsdgpu_ola_dims(tsdgpu_ola_t f, int *Ne, int *N, int *Nz, int *residual)
 long long tsdgpu_ola_out_count(tsdgpu_ola_t f, int n)
 {
   if(!f || n < 0) return 0;
-  return (((long long) f->residual + n) / f->Ne) * f->Ne;
+  const long long B = ((long long) f->residual + n) / f->Ne;
+  return (B - ((f->fen && f->blocks_done == 0 && B > 0) ? 1 : 0)) * f->Ne;
 }
 
 int tsdgpu_ola_step(tsdgpu_ola_t f, const void *x, long long xs, int n, void *y, long long ys, long long *n_out, int mem)
@@ -738,6 +903,8 @@ int tsdgpu_ola_destroy(tsdgpu_ola_t f)
   cudaFree(f->d_carry[0]);
   cudaFree(f->d_carry[1]);
   cudaFree(f->d_svg);
+  if(f->d_fen) cudaFree(f->d_fen);
+  if(f->d_last) cudaFree(f->d_last);
   if(f->scratch) cudaFree(f->scratch);
   if(f->flags) cudaFree(f->flags);
   if(f->plan) fft_plan_destroy(f->plan);

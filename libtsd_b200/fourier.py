@@ -162,17 +162,17 @@ class FiltreFFTConfig:
     avec_fenetrage: bool = False
     H: Optional[np.ndarray] = None
     fir_len: int = 0
+    fenetre: Optional[np.ndarray] = None   # windowed mode: the Ne window values as data (default: Hann, periodic)
 
 
 FFTFilterConfig = FiltreFFTConfig
 
 
 class OLA(FiltreGen):
-    """GPU counterpart of OLA<cfloat> (fourier.cc:737-932, plain mode)."""
+    """GPU counterpart of OLA<cfloat> (fourier.cc:737-932): plain mode and, with ``avec_fenetrage``, the
+    Hann-window 50 % overlap mode (:884-930; window = fenêtre("hn", Ne, non), or ``config.fenetre`` as data)."""
 
     def __init__(self, config: FiltreFFTConfig, nchan: int = 1):
-        if config.avec_fenetrage:
-            raise TsdGpuError("filtre_fft: mode fenêtré (Hann 50 %) pas encore disponible sur GPU")
         self.config = config
         self.nchan = int(nchan)
         Ne = config.dim_blocs_temporel if config.dim_blocs_temporel > 0 else 512
@@ -185,8 +185,19 @@ class OLA(FiltreGen):
             Hp = H.ctypes.data_as(_vp)
             self._H = H
         h = _vp()
-        check(lib().tsdgpu_ola_create(int(config.dim_blocs_temporel), int(config.nb_zeros_min), Hp, int(config.fir_len),
-                                      self.nchan, C.byref(h)))
+        if config.avec_fenetrage:
+            w = config.fenetre
+            if w is None:
+                from .filtrage import fenetre
+                w = fenetre("hn", Ne, False)                       # fourier.cc:796
+            w = np.ascontiguousarray(w, np.float32)
+            if w.shape != (Ne,):
+                raise TsdGpuError(f"filtre_fft: la fenêtre doit comporter Ne = {Ne} points")
+            check(lib().tsdgpu_ola_create_fen(int(config.dim_blocs_temporel), int(config.nb_zeros_min), Hp,
+                                              w.ctypes.data_as(_vp), self.nchan, C.byref(h)))
+        else:
+            check(lib().tsdgpu_ola_create(int(config.dim_blocs_temporel), int(config.nb_zeros_min), Hp,
+                                          int(config.fir_len), self.nchan, C.byref(h)))
         self._h = h
         a, b, c, d = C.c_int(), C.c_int(), C.c_int(), C.c_int()
         check(lib().tsdgpu_ola_dims(h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))

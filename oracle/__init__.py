@@ -49,7 +49,7 @@ class _Port:
         if not os.path.exists(PORT_SO):
             build()
         L = C.CDLL(PORT_SO)
-        for name in ("tsdo_fir_new", "tsdo_fft_new", "tsdo_ola_new", "tsdo_itrp_new", "tsdo_poly_new"):
+        for name in ("tsdo_fir_new", "tsdo_fft_new", "tsdo_ola_new", "tsdo_ola_new2", "tsdo_itrp_new", "tsdo_poly_new"):
             getattr(L, name).restype = _vp
         L.tsdo_itrp_phase.restype = _f
         self.L = L
@@ -95,8 +95,14 @@ class _Port:
     def fft(self, n: int):
         return _PortFft(self.L, n)
 
-    def ola(self, Ne: int, nb_zeros_min: int, H=None):
-        return _PortOla(self.L, Ne, nb_zeros_min, H)
+    def ola(self, Ne: int, nb_zeros_min: int, H=None, avec_fenetrage: bool = False):
+        return _PortOla(self.L, Ne, nb_zeros_min, H, avec_fenetrage)
+
+    def fenetre(self, nom: str, n: int, sym: bool = True) -> np.ndarray:
+        w = np.empty(n, np.float32)
+        if self.L.tsdo_fenetre(nom.encode(), _i(n), _i(1 if sym else 0), _ptr(w)):
+            raise ValueError("window not available: " + nom)
+        return w
 
     def itrp(self, ratio: float, lut: np.ndarray, nphases: int):
         return _PortItrp(self.L, ratio, lut, nphases)
@@ -161,10 +167,11 @@ class _PortFft:
 
 
 class _PortOla:
-    def __init__(self, L, Ne, nzmin, H):
+    def __init__(self, L, Ne, nzmin, H, avec_fenetrage=False):
         self.L = L
+        self.fen = bool(avec_fenetrage)
         Hc = None if H is None else _c64(H)
-        self.h = _vp(L.tsdo_ola_new(_i(Ne), _i(nzmin), None if Hc is None else _ptr(Hc)))
+        self.h = _vp(L.tsdo_ola_new2(_i(Ne), _i(nzmin), None if Hc is None else _ptr(Hc), _i(1 if self.fen else 0)))
         if not self.h:
             raise RuntimeError("tsdo_ola_new failed")
         a, b, c, d = _i(), _i(), _i(), _i()
@@ -186,8 +193,8 @@ class _PortOla:
         no = _i()
         if self.L.tsdo_ola_step(self.h, _ptr(x), _i(len(x)), _ptr(y), C.byref(no)):
             raise RuntimeError("OLA: N_zeros > Ne (the reference runs out of its buffers here)")
-        assert no.value == cap
-        return y
+        assert no.value == cap or self.fen   # windowed mode: the first block of the stream emits nothing
+        return y[: no.value]
 
     def __del__(self):
         if getattr(self, "h", None):
@@ -299,7 +306,7 @@ class _Ref:
     def __init__(self):
         L = C.CDLL(REF_SO)
         L.tsdref_last_error.restype = C.c_char_p
-        for name in ("tsdref_fir_new", "tsdref_rif_fft_new", "tsdref_ola_new", "tsdref_itrp_new",
+        for name in ("tsdref_fir_new", "tsdref_rif_fft_new", "tsdref_ola_new", "tsdref_ola_new2", "tsdref_itrp_new",
                      "tsdref_reechan_new", "tsdref_fftplan_new", "tsdref_polyphase_new"):
             getattr(L, name).restype = _vp
         self.L = L
@@ -340,17 +347,23 @@ class _Ref:
             raise ValueError("reference filtre_rif_fft is undefined behaviour for K > 512")
         return _RefFilter(self.L, self.L.tsdref_rif_fft_new(_i(kind), _ptr(t), _i(len(t))), self._err)
 
-    def ola(self, Ne, nb_zeros_min, H=None):
+    def fenetre(self, nom, n, sym=True):
+        w = np.empty(n, np.float32)
+        if self.L.tsdref_fenetre(nom.encode(), _i(n), _i(1 if sym else 0), _ptr(w)):
+            raise RuntimeError(self._err())
+        return w
+
+    def ola(self, Ne, nb_zeros_min, H=None, avec_fenetrage=False):
         N = self.p2((Ne if Ne > 0 else 512) + nb_zeros_min)
         if N - (Ne if Ne > 0 else 512) > (Ne if Ne > 0 else 512):
             raise ValueError("reference OLA is undefined behaviour when N_zeros > Ne")
         no = _i()
         if H is None:
-            h = self.L.tsdref_ola_new(_i(Ne), _i(nb_zeros_min), None, _i(N), C.byref(no))
+            h = self.L.tsdref_ola_new2(_i(Ne), _i(nb_zeros_min), None, _i(N), C.byref(no), _i(1 if avec_fenetrage else 0))
         else:
             Hc = _c64(H)
             assert len(Hc) == N
-            h = self.L.tsdref_ola_new(_i(Ne), _i(nb_zeros_min), _ptr(Hc), _i(N), C.byref(no))
+            h = self.L.tsdref_ola_new2(_i(Ne), _i(nb_zeros_min), _ptr(Hc), _i(N), C.byref(no), _i(1 if avec_fenetrage else 0))
         f = _RefFilter(self.L, h, self._err)
         f.N = no.value
         return f

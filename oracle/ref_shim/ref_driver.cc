@@ -111,13 +111,15 @@ void *tsdref_rif_fft_new(int kind, const float *taps, int K)
 
 // filtre_fft(config) with traitement_freq = "X *= H" (fourier.cc:935-940,956-959).
 // H == NULL gives the identity callback.
-void *tsdref_ola_new(int Ne, int nb_zeros_min, const float *H, int N_expected, int *N_out)
+// avec_fenetrage != 0 selects the Hann-window, 50 % overlap mode (fourier.cc:884-930).
+void *tsdref_ola_new2(int Ne, int nb_zeros_min, const float *H, int N_expected, int *N_out, int avec_fenetrage)
 {
   RefFilter *f = new RefFilter;
   int rc = guarded([&] {
     FiltreFFTConfig cfg;
     cfg.dim_blocs_temporel = Ne;
     cfg.nb_zeros_min = nb_zeros_min;
+    cfg.avec_fenetrage = avec_fenetrage != 0;
     if(H)
     {
       f->H = Veccf::map((const cfloat *) H, N_expected).clone();
@@ -133,6 +135,20 @@ void *tsdref_ola_new(int Ne, int nb_zeros_min, const float *H, int N_expected, i
   });
   if(rc) { delete f; return nullptr; }
   return f;
+}
+
+void *tsdref_ola_new(int Ne, int nb_zeros_min, const float *H, int N_expected, int *N_out)
+{
+  return tsdref_ola_new2(Ne, nb_zeros_min, H, N_expected, N_out, 0);
+}
+
+// fenêtre(nom, n, sym) as the OLA object calls it (fourier.cc:796; built by the shim, tab_shim.cc)
+int tsdref_fenetre(const char *nom, int n, int sym, float *w)
+{
+  return guarded([&] {
+    Vecf v = tsd::filtrage::fenêtre(std::string(nom), n, sym != 0);
+    memcpy(w, v.data(), sizeof(float) * n);
+  });
 }
 
 // H of the FiltreFFTRIF convention (fourier.cc:962-965): h2.tail(K) = h ; H = fft(h2) * sqrt(N)

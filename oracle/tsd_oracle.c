@@ -341,15 +341,30 @@ int tsdo_tampon_blocks(int N, int *windex, int n)
 
 /* ------------------------------------------------------------------ OLA (filtre_fft) */
 
-/* fourier.cc:737-882  OLA<cfloat>, plain mode (avec_fenetrage = non), callback X *= H
- * (fourier.cc:956-959) or identity when H == NULL. */
+/* fourier.cc:737-932  OLA<cfloat>, plain mode (avec_fenetrage = non) and Hann-window 50 % overlap mode
+ * (avec_fenetrage = oui), callback X *= H (fourier.cc:956-959) or identity when H == NULL. */
 typedef struct
 {
-  int Ne, N, Nz, windex;
+  int Ne, N, Nz, windex, avec_fenetrage;
   int64_t cnt_ech;
   tsdo_fft *plan;
-  cf32 *padded, *X, *x2, *svg, *tampon, *H;
+  cf32 *padded, *X, *x2, *svg, *svg_own, *tampon, *H, *last;
+  float *fen;
 } tsdo_ola;
+
+tsdo_ola *tsdo_ola_new(int dim_blocs_temporel, int nb_zeros_min, const float *H);
+
+/* fourier.cc:794-798: fenêtre("hn", Ne, non) */
+tsdo_ola *tsdo_ola_new2(int dim_blocs_temporel, int nb_zeros_min, const float *H, int avec_fenetrage)
+{
+  tsdo_ola *o = tsdo_ola_new(dim_blocs_temporel, nb_zeros_min, H);
+  if(!o || !avec_fenetrage) return o;
+  o->avec_fenetrage = 1;
+  o->last = (cf32 *) calloc(o->Ne, sizeof(cf32));                /* :784 */
+  o->fen = (float *) malloc(sizeof(float) * o->Ne);
+  tsdo_fenetre("hn", o->Ne, 0, o->fen);
+  return o;
+}
 
 tsdo_ola *tsdo_ola_new(int dim_blocs_temporel, int nb_zeros_min, const float *H)
 {
@@ -364,7 +379,7 @@ tsdo_ola *tsdo_ola_new(int dim_blocs_temporel, int nb_zeros_min, const float *H)
   o->padded = (cf32 *) calloc(o->N, sizeof(cf32));
   o->X = (cf32 *) calloc(o->N, sizeof(cf32));
   o->x2 = (cf32 *) calloc(o->N, sizeof(cf32));
-  o->svg = (cf32 *) calloc(o->Ne, sizeof(cf32));
+  o->svg = o->svg_own = (cf32 *) calloc(o->Ne, sizeof(cf32));
   o->tampon = (cf32 *) calloc(o->Ne, sizeof(cf32));
   if(H)
   {
@@ -377,7 +392,7 @@ void tsdo_ola_free(tsdo_ola *o)
 {
   if(!o) return;
   tsdo_fft_free(o->plan);
-  free(o->padded); free(o->X); free(o->x2); free(o->svg); free(o->tampon); free(o->H);
+  free(o->padded); free(o->X); free(o->x2); free(o->svg_own); free(o->tampon); free(o->H); free(o->last); free(o->fen);
   free(o);
 }
 void tsdo_ola_dims(const tsdo_ola *o, int *Ne, int *N, int *Nz, int *residual)
@@ -403,10 +418,100 @@ static int tsdo_ola_block(tsdo_ola *o, const cf32 *x, cf32 *y)
   return 0;
 }
 
+static void tsdo_ola_spectral(tsdo_ola *o)
+{
+  tsdo_fft_step(o->plan, (const float *) o->padded, 1, (float *) o->X);
+  if(o->H)
+    for(int i = 0; i < o->N; i++) o->X[i] *= o->H[i];
+  tsdo_fft_step(o->plan, (const float *) o->X, 0, (float *) o->x2);
+}
+
+/* fourier.cc:884-930 step_interne, windowed branch: two transforms per block (previous half + new half, then the
+ * new block alone), both multiplied by the window, halves recombined through `last`.  *ny = Ne, or 0 for the
+ * blocks seen while cnt_ech < 0 (the first one).
+ * Aliasing of the reference, kept as is: `svg = x2.segment(N_zeros, Ne)` (:923) assigns a temporary VIEW to an
+ * owning vector, which moves the view in (tableau.hpp:545-566): from the end of the first block on, svg IS
+ * x2[N_zeros..N).  x2 is rewritten in place by every inverse transform (resize to the same size keeps the buffer,
+ * tableau.cc:702-705) and the later `svg = ...` assignments copy that memory onto itself (est_reference() and same
+ * dimensions, tableau.hpp:579-590).  So after the first block the "saved" frame is the CURRENT frame: each frame is
+ * folded onto itself (tail(N_zeros) += head(N_zeros)) instead of onto its predecessor. */
+static int tsdo_ola_block_fen(tsdo_ola *o, const cf32 *x, cf32 *y, int *ny)
+{
+  const int Ne = o->Ne, N = o->N, Nz = o->Nz, h = Ne / 2;
+  if(Nz > Ne) return 1;
+  cf32 *tail = o->padded + (N - Ne);
+  /* 1) previous + new */
+  memcpy(o->padded + (N - h), x, sizeof(cf32) * h);                          /* :887 */
+  for(int i = 0; i < Ne; i++) tail[i] *= (cf32) o->fen[i];                    /* :888 (window as complex) */
+  tsdo_ola_spectral(o);
+  for(int i = 0; i < Nz; i++) o->svg[Ne - Nz + i] += o->x2[i];               /* :896 */
+  for(int i = 0; i < h; i++) o->last[Ne - h + i] += o->svg[i] / 2.0f;        /* :899 */
+  if(o->cnt_ech >= 0)
+  {
+    memcpy(y, o->last, sizeof(cf32) * Ne);
+    *ny = Ne;
+  }
+  else
+    *ny = 0;
+  for(int i = 0; i < h; i++) o->last[i] = o->svg[Ne - h + i] / 2.0f;         /* :905 */
+  for(int i = 0; i < h; i++) o->last[Ne - h + i] = 0;                        /* :906 */
+  if(o->svg != o->x2 + Nz) memcpy(o->svg, o->x2 + (N - Ne), sizeof(cf32) * Ne);   /* :909 (self-copy once aliased) */
+  o->cnt_ech += Ne / 2;
+  /* 2) new block alone */
+  for(int i = 0; i < Ne; i++) tail[i] = x[i] * (cf32) o->fen[i];              /* :914 */
+  tsdo_ola_spectral(o);
+  for(int i = 0; i < Nz; i++) o->svg[Ne - Nz + i] += o->x2[i];               /* :921 */
+  for(int i = 0; i < Ne; i++) o->last[i] += o->svg[i] / 2.0f;                /* :922 */
+  o->svg = o->x2 + Nz;                                                       /* :923 svg becomes a view of x2 */
+  o->cnt_ech += Ne / 2;
+  memcpy(o->padded + Nz, x + (Ne - h), sizeof(cf32) * h);                    /* :928 */
+  return 0;
+}
+
+/* Windowed mode through the re-blocking of OLA::step (fourier.cc:813-833).  y must hold Ne * blocks samples;
+ * *n_out receives what was emitted (the first block of the stream emits nothing). */
+int tsdo_ola_step_fen(tsdo_ola *o, const float *xin, int n, float *yout, int *n_out)
+{
+  const cf32 *x = (const cf32 *) xin;
+  cf32 *y = (cf32 *) yout;
+  const int Ne = o->Ne;
+  int produced = 0, i = 0, ny = 0;
+  while(i < n)
+  {
+    const cf32 *blk = NULL;
+    if(o->windex == 0 && n - i >= Ne)
+    {
+      blk = x + i;
+      i += Ne;
+    }
+    else
+    {
+      int take = Ne - o->windex;
+      if(take > n - i) take = n - i;
+      memcpy(o->tampon + o->windex, x + i, sizeof(cf32) * take);
+      o->windex += take;
+      i += take;
+      if(o->windex == Ne)
+      {
+        blk = o->tampon;
+        o->windex = 0;
+      }
+    }
+    if(blk)
+    {
+      if(tsdo_ola_block_fen(o, blk, y + produced, &ny)) return 1;
+      produced += ny;
+    }
+  }
+  *n_out = produced;
+  return 0;
+}
+
 /* fourier.cc:813-833 OLA::step + tsd.cc:332-370 TamponNv2::step.  y must hold
  * Ne * ((residual + n) / Ne) samples; *n_out receives that count. */
 int tsdo_ola_step(tsdo_ola *o, const float *xin, int n, float *yout, int *n_out)
 {
+  if(o->avec_fenetrage) return tsdo_ola_step_fen(o, xin, n, yout, n_out);
   const cf32 *x = (const cf32 *) xin;
   cf32 *y = (cf32 *) yout;
   const int Ne = o->Ne;

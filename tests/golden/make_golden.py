@@ -87,6 +87,25 @@ def main():
     out["ola_small_lens"] = np.array(lens, np.int32)
     out["ola_small_y"] = np.concatenate(ys)
 
+    # OLA, Hann-window 50 % overlap mode (fourier.cc:884-930): Ne = 512, N = 1024, random spectral gain
+    rng = np.random.default_rng(78)
+    x = cn(rng, 6000)
+    H = cn(rng, 1024)
+    o = R.ola(512, 512, H, True)
+    chunks = [512, 100, 1000, 512, 3888]
+    ys, lens, i = [], [], 0
+    for c in chunks:
+        y = o.step(x[i:i + c], cap=8192)
+        i += c
+        ys.append(y)
+        lens.append(len(y))
+    out["ola_fen_x"] = x
+    out["ola_fen_H"] = H
+    out["ola_fen_w"] = R.fenetre("hn", 512, False)
+    out["ola_fen_chunks"] = np.array(chunks, np.int32)
+    out["ola_fen_lens"] = np.array(lens, np.int32)
+    out["ola_fen_y"] = np.concatenate(ys)
+
     # OLA config-4 shape: K = 4095, Ne = 61441, N = 65536, 200000 samples, sub-sampled output
     rng = np.random.default_rng(0x7D5D0004)
     x = cn(rng, 200000)

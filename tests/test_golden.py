@@ -73,6 +73,19 @@ def test_ola_small(port):
     assert np.array_equal(np.concatenate(ys), G["ola_small_y"])
 
 
+def test_ola_fenetre(port):
+    assert np.array_equal(port.fenetre("hn", 512, False), G["ola_fen_w"])
+    o = port.ola(512, 512, G["ola_fen_H"], True)
+    x, i, ys, lens = G["ola_fen_x"], 0, [], []
+    for n in G["ola_fen_chunks"]:
+        y = o.step(x[i:i + n])
+        i += n
+        ys.append(y)
+        lens.append(len(y))
+    assert lens == list(G["ola_fen_lens"])
+    assert np.array_equal(np.concatenate(ys), G["ola_fen_y"])
+
+
 def test_ola_big(port):
     x = cn(np.random.default_rng(int(G["ola_big_seed"][0])), 200000)
     H = port.ola_make_H(G["h4095"], 65536)

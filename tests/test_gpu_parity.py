@@ -313,6 +313,48 @@ def test_ola_config4_shape(tsd, cpu_oracle, fir):
     assert rel_err(y2, yref, rms(x)) <= TOL
 
 
+@pytest.mark.parametrize("Ne,nz,useH", [(512, 0, False), (512, 512, True), (100, 28, True), (1000, 24, True),
+                                        (61440, 4096, True)])
+def test_ola_fenetre(tsd, cpu_oracle, Ne, nz, useH):
+    """Hann-window 50 % overlap mode (fourier.cc:884-930): per-call lengths bit-exact (first block silent),
+    samples vs the reference object, arbitrary chunking, several channels."""
+    from libtsd_b200 import fourier as Fo
+    rng = np.random.default_rng(Ne * 7 + nz)
+    N = cpu_oracle.p2(Ne + nz)
+    H = cn(rng, N) if useH else None
+    nchan = 3
+    w = cpu_oracle.fenetre("hn", Ne, False)
+    g, Ng = Fo.filtre_fft(Fo.FiltreFFTConfig(Ne, nz, avec_fenetrage=True, H=H, fenetre=w), nchan)
+    assert Ng == N
+    refs = [cpu_oracle.ola(Ne, nz, H, True) for _ in range(nchan)]
+    for n in (Ne, Ne, 37, 3 * Ne + 5, 1, Ne - 1, 6 * Ne):
+        x = cn(rng, nchan, n)
+        y = g.step(x)
+        yref = np.stack([r.step(x[c], **({"cap": 8 * Ne + n} if hasattr(r, "cplx") else {})) for c, r in enumerate(refs)])
+        assert y.shape == yref.shape
+        if y.size:
+            assert rel_err(y, yref, max(rms(yref), 1e-30)) <= TOL
+    # default window of the mirror = the reference's fenêtre("hn", Ne, non) within float rounding
+    from libtsd_b200.filtrage import fenetre
+    assert np.max(np.abs(fenetre("hn", Ne, False) - w)) <= 2e-7
+
+
+def test_ola_fenetre_golden(tsd):
+    import os
+    from libtsd_b200 import fourier as Fo
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_vectors.npz"))
+    g, _ = Fo.filtre_fft(Fo.FiltreFFTConfig(512, 512, avec_fenetrage=True, H=G["ola_fen_H"], fenetre=G["ola_fen_w"]), 1)
+    x, i, ys, lens = G["ola_fen_x"], 0, [], []
+    for n in G["ola_fen_chunks"]:
+        y = g.step(x[i:i + n])
+        i += n
+        ys.append(y)
+        lens.append(len(y))
+    assert lens == list(G["ola_fen_lens"])
+    yref = G["ola_fen_y"]
+    assert rel_err(np.concatenate(ys), yref, rms(yref)) <= TOL
+
+
 def test_ola_generic_H(tsd, cpu_oracle):
     """Arbitrary spectral gain (not FIR-derived): true overlap-add semantics must be kept."""
     from libtsd_b200 import fourier as Fo

@@ -66,6 +66,24 @@ def test_ola_bit_exact(port, ref, Ne, nz, K):
         assert len(ya) == len(yb) and np.array_equal(ya, yb)
 
 
+@pytest.mark.parametrize("Ne,nz,useH", [(512, 0, False), (512, 512, True), (100, 28, True), (1000, 24, True),
+                                        (101, 27, True), (33, 31, False), (61440, 4096, True)])
+def test_ola_fenetre_bit_exact(port, ref, Ne, nz, useH):
+    """Hann-window 50 % overlap mode (fourier.cc:884-930), incl. odd Ne and the svg/x2 aliasing of the reference."""
+    rng = np.random.default_rng(Ne * 7 + nz)
+    N = ref.p2(Ne + nz)
+    H = cn(rng, N) if useH else None
+    assert np.array_equal(port.fenetre("hn", Ne, False), ref.fenetre("hn", Ne, False))
+    a, b = port.ola(Ne, nz, H, True), ref.ola(Ne, nz, H, True)
+    lens = []
+    for n in (Ne, Ne, 37, 3 * Ne + 5, 1, Ne - 1, 2 * Ne):
+        x = cn(rng, n)
+        ya, yb = a.step(x), b.step(x, cap=8 * Ne + n)
+        lens.append(len(yb))
+        assert len(ya) == len(yb) and np.array_equal(ya, yb)
+    assert lens[0] == 0 and lens[1] == Ne     # the first block of the stream emits nothing (:900-903)
+
+
 def test_ola_make_H_close(port, ref):
     h = ref.design_rif_fen(4095, "lp", 0.1)
     Ha, Hb = port.ola_make_H(h, 65536), ref.ola_make_H(h, 65536)
