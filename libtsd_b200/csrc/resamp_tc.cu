@@ -18,6 +18,7 @@
 #include "resamp_tc.h"
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 
 namespace tsdgpu {
@@ -40,12 +41,76 @@ constexpr int GROWS = (TILE + NGEN - 1) / NGEN;   // rows per generator warp and
 constexpr int TMEM_COLS = 512;
 
 #ifdef TSD_TC_PROF
-__device__ long long g_rtcprof[1024][24][4];
+__device__ long long g_rtcprof[1024][32][4];
 #define PROF_ARRAY g_rtcprof
 #endif
 #include "tc_prof.cuh"
 
-__device__ __forceinline__ int floor_div32(int v) { return v >> 5; }   // arithmetic shift: floor for negatives too
+__device__ __forceinline__ int floor_div32(int v) { return v >> 5; }
+
+// ---- CTA pair (cta_group::2): two CTAs of a cluster = two groups of 64 channels over the same tiles.  The leader
+// (cluster rank 0) issues M = 256 MMAs that read each CTA's own A rows from its tensor memory and half of the
+// coefficient block from each CTA's shared memory, so every CTA generates only half of the block's rows.
+constexpr uint32_t IDESC_M256 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t) (256 >> 4) << 24);
+__device__ __forceinline__ uint32_t cluster_rank()
+{
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the LEADER's copy of a barrier (same offset in the shared memory of cluster rank 0)
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t *bar)
+{
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(ra) : "r"(smem_u32(bar)));
+  // default semantics (release at CTA scope): what the peer's tensor core / the leader's MMA must see lives in THIS CTA's
+  // shared / tensor memory and has been performed there before the arrive leaves; a cluster-scope release costs ~1 us
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, unsigned parity)
+{
+  asm volatile(
+    "{\n\t.reg .pred p;\n\t"
+    "WAIT_%=:\n\t"
+    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+    "@p bra DONE_%=;\n\t"
+    "bra WAIT_%=;\n\t"
+    "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mma_tf32_pair(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc)
+{
+  asm volatile(
+    "{\n\t.reg .pred p;\n\t"
+    "setp.ne.b32 p, 1, 0;\n\t"
+    "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+    ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc)
+    : "memory");
+}
+// completion of all MMAs issued so far -> the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void mma_commit_pair(uint64_t *bar)
+{
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((unsigned short) 3) : "memory");
+}
+template<bool PAIR> __device__ __forceinline__ void arrive_to_mma(uint64_t *bar)
+{
+  if(PAIR) mbar_arrive_leader(bar);
+  else mbar_arrive(bar);
+}
+template<bool PAIR> __device__ __forceinline__ void commit_from_mma(uint64_t *bar)
+{
+  if(PAIR) mma_commit_pair(bar);
+  else mma_commit(bar);
+}
+template<bool PAIR> __device__ __forceinline__ void wait_in_mma(uint64_t *bar, unsigned parity)
+{
+  if(PAIR) mbar_wait_cluster(bar, parity);
+  else mbar_wait(bar, parity);
+}   // arithmetic shift: floor for negatives too
 
 // the (chunk, tile) block sequence: for chunk c, the tiles it feeds (at most two, consecutive)
 struct Walk
@@ -60,8 +125,9 @@ struct Walk
   }
 };
 
-template<bool LUTS> __global__ void __launch_bounds__(NTHREADS, 1) resamp_tc_kernel(ResampTcParams p)
+template<bool LUTS, bool PAIR> __global__ void __launch_bounds__(NTHREADS, 1) resamp_tc_kernel(ResampTcParams p)
 {
+  const uint32_t rank = PAIR ? cluster_rank() : 0u;
   extern __shared__ unsigned char raw[];
   const uint32_t base = (smem_u32(raw) + 1023u) & ~1023u;
   unsigned char *sm = raw + (base - smem_u32(raw));
@@ -77,22 +143,34 @@ template<bool LUTS> __global__ void __launch_bounds__(NTHREADS, 1) resamp_tc_ker
   int2 *bmeta = reinterpret_cast<int2 *>(cB + MAXSPAN);      // per coefficient-block slot: {first output column, columns}
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int ts = blockIdx.x * p.span, te = min(ts + p.span, p.ntiles), T = te - ts;
-  const int c0 = blockIdx.y * CH;
+  // pair: 1-D grid, consecutive CTAs (= the cluster) are the two channel groups 2g, 2g+1 of one tile span
+  const int bspan = PAIR ? (int) blockIdx.x / p.groups : (int) blockIdx.x, bgroup = PAIR ? (int) blockIdx.x % p.groups : (int) blockIdx.y;
+  const int ts = bspan * p.span, te = min(ts + p.span, p.ntiles), T = te - ts;
+  const int c0 = bgroup * CH;
   const int K = p.K;
 
   if(tid == 0)
   {
-    for(int i = 0; i < NSTAGE; i++) { mbar_init(full + i, 4); mbar_init(empty + i, 1); }
-    for(int i = 0; i < 3; i++) { mbar_init(tfull + i, 1); mbar_init(tempty + i, 4); }
+    // pair: the barriers the MMA issuer waits on collect the arrivals of both CTAs (in the leader's shared memory)
+    constexpr int NC = PAIR ? 2 : 1;
+    for(int i = 0; i < NSTAGE; i++) { mbar_init(full + i, 4 * NC); mbar_init(empty + i, 1); }
+    for(int i = 0; i < 3; i++) { mbar_init(tfull + i, 1); mbar_init(tempty + i, 4 * NC); }
     for(int i = 0; i < NRAW; i++) { mbar_init(rfull + i, 32); mbar_init(rempty + i, 4); }
-    for(int i = 0; i < NT; i++) { mbar_init(bfull + i, NGEN); mbar_init(bempty + i, 1); }
+    for(int i = 0; i < NT; i++) { mbar_init(bfull + i, NGEN * NC); mbar_init(bempty + i, 1); }
     mbar_fence_init();
   }
   if(warp == MMA_WARP)
   {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if(PAIR)
+    {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    else
+    {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   if(warp == 0 && lane < T)
   {
@@ -112,7 +190,8 @@ template<bool LUTS> __global__ void __launch_bounds__(NTHREADS, 1) resamp_tc_ker
   if(LUTS)
     for(int i = tid; i < p.lut_elems; i += NTHREADS) lut_s[i] = __ldg(p.lut + i);
   fence_before();
-  __syncthreads();
+  if(PAIR) cluster_sync_all();   // the peer's barriers are initialised before anyone arrives on them
+  else __syncthreads();
   fence_after();
   const uint32_t tmem = *tmem_slot;
   const int c_begin = cA[0], nchunks = cB[T - 1] - c_begin + 1;
@@ -209,7 +288,7 @@ template<bool LUTS> __global__ void __launch_bounds__(NTHREADS, 1) resamp_tc_ker
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       fence_before();
       __syncwarp();
-      if(lane == 0) mbar_arrive(full + stage);
+      if(lane == 0) arrive_to_mma<PAIR>(full + stage);
       PROF_ADD(2, t_c)
     }
     PROF_END
@@ -247,17 +326,23 @@ template<bool LUTS> __global__ void __launch_bounds__(NTHREADS, 1) resamp_tc_ker
           jlo += __popc(__ballot_sync(0xffffffffu, e.y >= 0 && c * CHUNK + e.x > K - 1));     // window entirely after the chunk
           jend += __popc(__ballot_sync(0xffffffffu, e.y >= 0 && c * CHUNK + 31 + e.x >= 0));  // valid and not entirely before it
         }
-        const int j0 = p.band ? (min(jlo, TILE - 16) & ~15) : 0;
-        const int nn = p.band ? max(16, ((jend + 15) & ~15) - j0) : TILE;
+        // band [j0, j0 + nn): multiple of 16 columns (32 for a pair: each CTA supplies nn / 2 rows of the block)
+        constexpr int GRAN = PAIR ? 32 : 16;
+        int j0 = p.band ? (min(jlo, TILE - GRAN) & ~15) : 0;
+        const int nn = p.band ? max(GRAN, (jend - j0 + GRAN - 1) & ~(GRAN - 1)) : TILE;
+        if(j0 + nn > TILE) j0 = TILE - nn;
         if(gw == 0 && lane == 0) bmeta[slot] = make_int2(j0, nn);
-        // GROWS independent, branch-free rows per warp: clamped LUT index, value masked afterwards; lane = column kk
-        const int2 *srow = sched_s + tt[w] * TILE + gw;
+        // this CTA's rows of the block: nh rows from jb on, stored band-relative (row l at 128 l, swizzled); warp gw
+        // builds rows l = gw + NGEN r.  Branch-free rows: clamped LUT index, value masked afterwards; lane = column kk.
+        const int nh = PAIR ? nn >> 1 : nn, jb = j0 + (PAIR ? (int) rank * nh : 0);
+        constexpr int GR = PAIR ? GROWS / 2 : GROWS;
+        const int2 *srow = sched_s + tt[w] * TILE;
         const int tcol = c * CHUNK + lane;
-        float v[GROWS];
+        float v[GR];
 #pragma unroll
-        for(int r = 0; r < GROWS; r++)
+        for(int r = 0; r < GR; r++)
         {
-          const int2 e = srow[min(NGEN * r, TILE - 1 - gw)];           // broadcast read
+          const int2 e = srow[min(jb + gw + NGEN * r, TILE - 1)];      // broadcast read
           const int tap = tcol + e.x;
           const bool ok = (e.y >= 0) & ((unsigned) tap < (unsigned) K);
           const int idx = ok ? e.y + tap : 0;
@@ -265,14 +350,13 @@ template<bool LUTS> __global__ void __launch_bounds__(NTHREADS, 1) resamp_tc_ker
           v[r] = ok ? val : 0.f;
         }
 #pragma unroll
-        for(int r = 0; r < GROWS; r++)
+        for(int r = 0; r < GR; r++)
         {
-          // rows outside the band are never read by the MMAs: skip their stores (warp-uniform predicate, no branch)
-          const int j = gw + NGEN * r;
+          const int l = gw + NGEN * r;
           const float hi = to_tf32(v[r]), lo = to_tf32(v[r] - hi);
-          if(j < TILE && (unsigned) (j - j0) < (unsigned) nn)
+          if(l < nh)                                                    // warp-uniform predicate, no branch
           {
-            const uint32_t off = swz((uint32_t) (j * 128 + lane * 4));
+            const uint32_t off = swz((uint32_t) (l * 128 + lane * 4));
             *reinterpret_cast<float *>(thi + off) = hi;
             *reinterpret_cast<float *>(tlo_ + off) = lo;
           }
@@ -287,7 +371,7 @@ template<bool LUTS> __global__ void __launch_bounds__(NTHREADS, 1) resamp_tc_ker
       if(lane == 0)
       {
         const int nb = (tt[0] >= 0) + (tt[1] >= 0);
-        for(int k = nb; k > 0; k--) mbar_arrive(bfull + (bseq - k) % NT);
+        for(int k = nb; k > 0; k--) arrive_to_mma<PAIR>(bfull + (bseq - k) % NT);
       }
       PROF_ADD(1, t_f)
     }
@@ -295,7 +379,8 @@ template<bool LUTS> __global__ void __launch_bounds__(NTHREADS, 1) resamp_tc_ker
   }
   else if(warp == MMA_WARP)
   {
-    // ===== MMA issuer
+    // ===== MMA issuer (pair: the leader CTA only)
+    if(PAIR && rank != 0) goto done;
     const uint64_t dbase = smem_desc(0);
     Walk wk{cA, cB, T, 0};
     int bseq = 0;
@@ -306,7 +391,7 @@ template<bool LUTS> __global__ void __launch_bounds__(NTHREADS, 1) resamp_tc_ker
       int tt[2];
       wk.feeds(c, tt[0], tt[1]);
       PROF_BEGIN(t_w)
-      mbar_wait(full + stage, (unsigned) ((it >> 1) & 1));
+      wait_in_mma<PAIR>(full + stage, (unsigned) ((it >> 1) & 1));
       PROF_ADD(0, t_w)
       const uint32_t xh0 = tmem + (uint32_t) (ACOL + 64 * stage), xl0 = xh0 + 32;
 #pragma unroll
@@ -315,33 +400,42 @@ template<bool LUTS> __global__ void __launch_bounds__(NTHREADS, 1) resamp_tc_ker
         if(tt[w] < 0) continue;
         const int tl = tt[w], region = tl % 3, slot = bseq % NT;
         PROF_BEGIN(t_w2)
-        mbar_wait(bfull + slot, (unsigned) ((bseq / NT) & 1));
+        wait_in_mma<PAIR>(bfull + slot, (unsigned) ((bseq / NT) & 1));
         PROF_ADD(1, t_w2)
         PROF_BEGIN(t_c)
-        if(c == cA[tl]) mbar_wait(tempty + region, (unsigned) ((tl / 3) & 1));   // first block of the tile: region drained and zeroed
+        if(c == cA[tl]) wait_in_mma<PAIR>(tempty + region, (unsigned) ((tl / 3) & 1));   // first block of the tile: region drained and zeroed
         fence_after();
         const int2 meta = bmeta[slot];                    // {first output column, columns} of the block's band
-        const uint32_t thi = base + slot * TB_BYTES + (uint32_t) meta.x * 128;
+        const uint32_t thi = base + slot * TB_BYTES;      // rows are stored band-relative
         const uint64_t bh0 = dbase + (thi >> 4), bl0 = bh0 + (TB_PART >> 4);
         const uint32_t dcol = tmem + (uint32_t) (region * NCOL + meta.x);
-        const uint32_t idesc = IDESC_M128 | ((uint32_t) (meta.y >> 3) << 17);
+        const uint32_t idesc = (PAIR ? IDESC_M256 : IDESC_M128) | ((uint32_t) (meta.y >> 3) << 17);
         if(elect_one())
         {
 #pragma unroll
           for(int ks = 0; ks < 4; ks++)
           {
-            mma_tf32(dcol, xh0 + 8 * ks, bl0 + 2 * ks, idesc);
-            mma_tf32(dcol, xl0 + 8 * ks, bh0 + 2 * ks, idesc);
-            mma_tf32(dcol, xh0 + 8 * ks, bh0 + 2 * ks, idesc);
+            if(PAIR)
+            {
+              mma_tf32_pair(dcol, xh0 + 8 * ks, bl0 + 2 * ks, idesc);
+              mma_tf32_pair(dcol, xl0 + 8 * ks, bh0 + 2 * ks, idesc);
+              mma_tf32_pair(dcol, xh0 + 8 * ks, bh0 + 2 * ks, idesc);
+            }
+            else
+            {
+              mma_tf32(dcol, xh0 + 8 * ks, bl0 + 2 * ks, idesc);
+              mma_tf32(dcol, xl0 + 8 * ks, bh0 + 2 * ks, idesc);
+              mma_tf32(dcol, xh0 + 8 * ks, bh0 + 2 * ks, idesc);
+            }
           }
-          mma_commit(bempty + slot);
-          if(c == cB[tl]) mma_commit(tfull + region);     // last block of the tile: accumulator complete
+          commit_from_mma<PAIR>(bempty + slot);
+          if(c == cB[tl]) commit_from_mma<PAIR>(tfull + region);     // last block of the tile: accumulator complete
         }
         __syncwarp();
         PROF_ADD(2, t_c)
         bseq++;
       }
-      if(elect_one()) mma_commit(empty + stage);
+      if(elect_one()) commit_from_mma<PAIR>(empty + stage);
       __syncwarp();
     }
     PROF_END
@@ -365,7 +459,7 @@ template<bool LUTS> __global__ void __launch_bounds__(NTHREADS, 1) resamp_tc_ker
       zero_region(region);
       fence_before();
       __syncwarp();
-      if(lane == 0) mbar_arrive(tempty + region);
+      if(lane == 0) arrive_to_mma<PAIR>(tempty + region);
     }
     for(int tl = 0; tl < T; tl++)
     {
@@ -411,15 +505,18 @@ template<bool LUTS> __global__ void __launch_bounds__(NTHREADS, 1) resamp_tc_ker
       zero_region(region);
       fence_before();
       __syncwarp();
-      if(lane == 0) mbar_arrive(tempty + region);
+      if(lane == 0) arrive_to_mma<PAIR>(tempty + region);
     }
   }
+done:
   fence_before();
-  __syncthreads();
+  if(PAIR) cluster_sync_all();   // nobody leaves (or frees tensor memory) while the pair's MMAs and remote arrivals are in flight
+  else __syncthreads();
   if(warp == MMA_WARP)
   {
     fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS) : "memory");
+    if(PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS) : "memory");
   }
 }
 
@@ -431,7 +528,7 @@ template<bool LUTS> __global__ void __launch_bounds__(NTHREADS, 1) resamp_tc_ker
 extern "C" int tsdgpu_debug_rtcprof_dump(const char *path)
 {
   cudaDeviceSynchronize();
-  static long long h[1024][24][4];
+  static long long h[1024][32][4];
   if(cudaMemcpyFromSymbol(h, rtc::g_rtcprof, sizeof(h)) != cudaSuccess) return 1;
   FILE *fp = fopen(path, "wb");
   if(!fp) return 1;
@@ -462,8 +559,10 @@ int resamp_tc_launch(const ResampTcParams &p0)
   static bool attr_set = false;
   if(!attr_set)
   {
-    TSD_CUDA(cudaFuncSetAttribute(rtc::resamp_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rtc::SMEM_BYTES));
-    TSD_CUDA(cudaFuncSetAttribute(rtc::resamp_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, rtc::SMEM_BYTES));
+    TSD_CUDA(cudaFuncSetAttribute(rtc::resamp_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, rtc::SMEM_BYTES));
+    TSD_CUDA(cudaFuncSetAttribute(rtc::resamp_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, rtc::SMEM_BYTES));
+    TSD_CUDA(cudaFuncSetAttribute(rtc::resamp_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rtc::SMEM_BYTES));
+    TSD_CUDA(cudaFuncSetAttribute(rtc::resamp_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rtc::SMEM_BYTES));
     attr_set = true;
   }
   p.ntiles = (int) ((p.n_out + rtc::TILE - 1) / rtc::TILE);
@@ -479,10 +578,42 @@ int resamp_tc_launch(const ResampTcParams &p0)
     if(best < 0 || cost < best) { best = cost; span = s; }
   }
   p.span = span;
+  p.groups = groups;
   p.vec_store = ((((uintptr_t) (p.y + p.out0)) & 15) == 0 && (p.y_stride % 2) == 0) ? 1 : 0;
   dim3 grid((p.ntiles + span - 1) / span, groups);
-  if(p.lut_elems * 4 <= rtc::LUT_SMEM_MAX) rtc::resamp_tc_kernel<true><<<grid, rtc::NTHREADS, rtc::SMEM_BYTES, r.stream>>>(p);
-  else rtc::resamp_tc_kernel<false><<<grid, rtc::NTHREADS, rtc::SMEM_BYTES, r.stream>>>(p);
+  const bool luts = p.lut_elems * 4 <= rtc::LUT_SMEM_MAX;
+  // CTA pairs (cta_group::2, clusters of 2 along the channel groups) whenever the groups pair up
+  const bool pair = (groups % 2 == 0) && !(getenv("TSDGPU_RESAMP_TC_PAIR") && atoi(getenv("TSDGPU_RESAMP_TC_PAIR")) == 0);
+  if(pair)
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid.x * grid.y);
+    cfg.blockDim = dim3(rtc::NTHREADS);
+    cfg.dynamicSmemBytes = rtc::SMEM_BYTES;
+    cfg.stream = r.stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    if(getenv("TSDGPU_DEBUG_CLUSTER"))
+    {
+      int nc = -1;
+      cudaError_t e = cudaOccupancyMaxActiveClusters(&nc, rtc::resamp_tc_kernel<true, true>, &cfg);
+      fprintf(stderr, "[resamp_tc] grid %u x %u, block %d, smem %d: max active clusters %d (%s)\n", grid.x, grid.y, rtc::NTHREADS,
+              rtc::SMEM_BYTES, nc, cudaGetErrorString(e));
+      cudaFuncAttributes fa;
+      cudaFuncGetAttributes(&fa, rtc::resamp_tc_kernel<true, true>);
+      fprintf(stderr, "[resamp_tc] regs %d, static smem %zu, max dyn %d, clusterDimMustBeSet %d\n", fa.numRegs, fa.sharedSizeBytes,
+              fa.maxDynamicSharedSizeBytes, fa.clusterDimMustBeSet);
+    }
+    if(luts) TSD_CUDA(cudaLaunchKernelEx(&cfg, rtc::resamp_tc_kernel<true, true>, p));
+    else TSD_CUDA(cudaLaunchKernelEx(&cfg, rtc::resamp_tc_kernel<false, true>, p));
+  }
+  else if(luts) rtc::resamp_tc_kernel<true, false><<<grid, rtc::NTHREADS, rtc::SMEM_BYTES, r.stream>>>(p);
+  else rtc::resamp_tc_kernel<false, false><<<grid, rtc::NTHREADS, rtc::SMEM_BYTES, r.stream>>>(p);
   TSD_LAUNCH_CHECK();
   return 0;
 }

@@ -17,7 +17,7 @@ struct ResampTcParams
   int n;                  // input samples of the call (positions >= n read as zero)
   int K, hist_len, nchan;
   int lut_elems;          // K * (nphases + 1)
-  int ntiles, span, vec_store, band;   // filled by resamp_tc_launch
+  int ntiles, span, vec_store, band, groups;   // filled by resamp_tc_launch
 };
 
 bool resamp_tc_eligible(const int2 *sched_host, long long n_out, int K, const void *x, long long x_stride);
