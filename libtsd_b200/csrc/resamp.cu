@@ -222,6 +222,8 @@ struct tsdgpu_resamp_s
   int2 *h_sched[NBUF] = {nullptr, nullptr, nullptr};
   int2 *d_sched[NBUF] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev[NBUF] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_sched[NBUF] = {nullptr, nullptr, nullptr};
+  cudaStream_t sched_stream = nullptr;   // schedule uploads overlap the previous chunk's kernel
   size_t sched_cap = 0;
   int next_buf = 0;
   size_t smem_set = 0;
@@ -312,6 +314,7 @@ static int resamp_run_device(tsdgpu_resamp_s *f, const float2 *x, long long xs, 
       TSD_CUDA(cudaMallocHost(&f->h_sched[b], cap * sizeof(int2)));
       TSD_CUDA(cudaMalloc(&f->d_sched[b], cap * sizeof(int2)));
       if(!f->ev[b]) TSD_CUDA(cudaEventCreateWithFlags(&f->ev[b], cudaEventDisableTiming));
+      if(!f->ev_sched[b]) TSD_CUDA(cudaEventCreateWithFlags(&f->ev_sched[b], cudaEventDisableTiming));
     }
     f->sched_cap = cap;
   }
@@ -329,7 +332,11 @@ static int resamp_run_device(tsdgpu_resamp_s *f, const float2 *x, long long xs, 
     if(ovf) return fail("tsdgpu_resamp_step: schedule overflow");
     if(cnt == 0) continue;
     if(produced + (long long) cnt > ycap) return fail("tsdgpu_resamp_step: output capacity too small");
-    TSD_CUDA(cudaMemcpyAsync(f->d_sched[b], f->h_sched[b], cnt * sizeof(int2), cudaMemcpyHostToDevice, r.stream));
+    // the schedule travels on its own stream so that it overlaps the previous chunk's kernel
+    if(!f->sched_stream) TSD_CUDA(cudaStreamCreateWithFlags(&f->sched_stream, cudaStreamNonBlocking));
+    TSD_CUDA(cudaMemcpyAsync(f->d_sched[b], f->h_sched[b], cnt * sizeof(int2), cudaMemcpyHostToDevice, f->sched_stream));
+    TSD_CUDA(cudaEventRecord(f->ev_sched[b], f->sched_stream));
+    TSD_CUDA(cudaStreamWaitEvent(r.stream, f->ev_sched[b], 0));
     ResampParams p;
     p.x = x;
     p.y = y;
@@ -362,9 +369,11 @@ static int resamp_run_device(tsdgpu_resamp_s *f, const float2 *x, long long xs, 
     // banded filter-bank GEMM on the tensor cores (3xTF32, resamp_tc.cu); TSDGPU_RESAMP_TC=0 keeps the FP32 FMA kernels
     const char *tc_env = getenv("TSDGPU_RESAMP_TC");
     const bool tc_on = !(tc_env && atoi(tc_env) == 0);
-    if(tc_on && resamp_tc_eligible(f->h_sched[b], (long long) cnt, f->K, x, xs))
+    int max_tile_chunks = 0;
+    if(tc_on && resamp_tc_eligible(f->h_sched[b], (long long) cnt, f->K, x, xs, &max_tile_chunks))
     {
       ResampTcParams t;
+      t.max_tile_chunks = max_tile_chunks;
       t.x = x;
       t.y = y;
       t.hist = hist_old;
@@ -505,6 +514,19 @@ int tsdgpu_resamp_schedule(float *phase, float ratio, int nphases, int n, int32_
   const float inc = 1 / ratio;
   float ph = *phase;
   long long j = 0;
+  if(in_idx && lut_idx && (double) n / (double) inc + 16.0 <= (double) capacity)
+  {
+    // same code path as step(): interleaved pairs, then split
+    std::vector<int2> tmp((size_t) capacity);
+    size_t cnt = 0;
+    bool ovf = false;
+    ph = resamp_schedule(ph, inc, nphases, 0, n, tmp.data(), (size_t) capacity, &cnt, &ovf);
+    if(ovf) return fail("tsdgpu_resamp_schedule: capacity too small");
+    for(size_t k = 0; k < cnt; k++) { in_idx[k] = tmp[k].x; lut_idx[k] = tmp[k].y; }
+    *phase = ph;
+    *n_out = (long long) cnt;
+    return 0;
+  }
   for(int i = 0; i < n; i++)
   {
     while(ph < 1)
@@ -537,7 +559,9 @@ int tsdgpu_resamp_destroy(tsdgpu_resamp_t f)
     if(f->h_sched[b]) cudaFreeHost(f->h_sched[b]);
     if(f->d_sched[b]) cudaFree(f->d_sched[b]);
     if(f->ev[b]) cudaEventDestroy(f->ev[b]);
+    if(f->ev_sched[b]) cudaEventDestroy(f->ev_sched[b]);
   }
+  if(f->sched_stream) cudaStreamDestroy(f->sched_stream);
   delete f;
   return 0;
 }

@@ -33,7 +33,8 @@ constexpr int RAW_PITCH = 272, RAW_BYTES = CH * RAW_PITCH;
 constexpr int TB_PART = TILE * 128, TB_BYTES = 2 * TB_PART;     // 128 rows x 32 tf32, hi + lo
 constexpr int MAXSPAN = 16;                      // tiles per CTA: its slice of the schedule (16 KiB) sits in shared memory
 constexpr int LUT_SMEM_MAX = 66 * 1024;          // the LUT too when it fits (64 taps x 257 phases = 64.25 KiB)
-constexpr int SMEM_BYTES = NT * TB_BYTES + NRAW * RAW_BYTES + MAXSPAN * TILE * 8 + LUT_SMEM_MAX + 1024 + 512 + 2 * MAXSPAN * 4 + 64;
+constexpr int NB_MAX = 512;                       // (chunk, tile) blocks per CTA: their bands are tabulated in the prologue
+constexpr int SMEM_BYTES = NT * TB_BYTES + NRAW * RAW_BYTES + MAXSPAN * TILE * 8 + LUT_SMEM_MAX + 1024 + 512 + 2 * MAXSPAN * 4 + 64 + NB_MAX * 8;
 constexpr int ACOL = 3 * NCOL;
 constexpr int CONV_WARP0 = 4, GEN_WARP0 = 8, NGEN = 16, MMA_WARP = GEN_WARP0 + NGEN, LOAD_WARP = MMA_WARP + 1;
 constexpr int NTHREADS = 32 * (LOAD_WARP + 1);
@@ -140,7 +141,7 @@ template<bool LUTS, bool PAIR> __global__ void __launch_bounds__(NTHREADS, 1) re
   uint64_t *rfull = tempty + 3, *rempty = rfull + NRAW, *bfull = rempty + NRAW, *bempty = bfull + NT;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bempty + NT);
   int *cA = reinterpret_cast<int *>(tmem_slot + 2), *cB = cA + MAXSPAN;
-  int2 *bmeta = reinterpret_cast<int2 *>(cB + MAXSPAN);      // per coefficient-block slot: {first output column, columns}
+  int2 *bandtab = reinterpret_cast<int2 *>(cB + MAXSPAN);    // per block of the walk: {first output column, columns} of its band
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // pair: 1-D grid, consecutive CTAs (= the cluster) are the two channel groups 2g, 2g+1 of one tile span
@@ -189,6 +190,34 @@ template<bool LUTS, bool PAIR> __global__ void __launch_bounds__(NTHREADS, 1) re
   }
   if(LUTS)
     for(int i = tid; i < p.lut_elems; i += NTHREADS) lut_s[i] = __ldg(p.lut + i);
+  __syncthreads();
+  if(warp < T)
+  {
+    // bands of the blocks of tile `warp`, one lane per chunk.  A block (c, tl) keeps the rows whose K taps overlap the
+    // chunk: e.x = K-1 - in_j is non-increasing in j and the rows past the end (e.y < 0) come last, so "window entirely
+    // after the chunk" and "valid and not entirely before it" are prefix properties -> two binary searches.
+    // Position in the walk (chunks ascending, then tiles): blocks of earlier chunks + the other tile of this chunk.
+    const int tl = warp;
+    const int2 *srow = sched_s + tl * TILE;
+    for(int c = cA[tl] + lane; c <= cB[tl]; c += 32)
+    {
+      int lo = 0, hi = TILE;
+      while(lo < hi) { const int m = (lo + hi) >> 1; const int2 e = srow[m]; if(e.y >= 0 && c * CHUNK + e.x > K - 1) lo = m + 1; else hi = m; }
+      const int jlo = lo;
+      hi = TILE;
+      while(lo < hi) { const int m = (lo + hi) >> 1; const int2 e = srow[m]; if(e.y >= 0 && c * CHUNK + 31 + e.x >= 0) lo = m + 1; else hi = m; }
+      const int jend = lo;
+      // band [j0, j0 + nn): multiple of 16 columns (32 for a pair: each CTA supplies nn / 2 rows of the block)
+      constexpr int GRAN = PAIR ? 32 : 16;
+      int j0 = p.band ? (min(jlo, TILE - GRAN) & ~15) : 0;
+      const int nn = p.band ? max(GRAN, (jend - j0 + GRAN - 1) & ~(GRAN - 1)) : TILE;
+      if(j0 + nn > TILE) j0 = TILE - nn;
+      int seq = 0;
+      for(int t = 0; t < T; t++) seq += min(max(c - cA[t], 0), cB[t] - cA[t] + 1);
+      if(tl > 0 && cA[tl - 1] <= c && c <= cB[tl - 1]) seq++;
+      bandtab[seq] = make_int2(j0, nn);
+    }
+  }
   fence_before();
   if(PAIR) cluster_sync_all();   // the peer's barriers are initialised before anyone arrives on them
   else __syncthreads();
@@ -277,8 +306,8 @@ template<bool LUTS, bool PAIR> __global__ void __launch_bounds__(NTHREADS, 1) re
           const float a0 = my_ri ? x.y : x.x, a1 = my_ri ? x.w : x.z;
           hi[2 * m] = to_tf32(a0);
           hi[2 * m + 1] = to_tf32(a1);
-          lo[2 * m] = to_tf32(a0 - hi[2 * m]);
-          lo[2 * m + 1] = to_tf32(a1 - hi[2 * m + 1]);
+          lo[2 * m] = a0 - hi[2 * m];             // exact; the tensor core truncates it to tf32 (error <= 2^-21 |x|)
+          lo[2 * m + 1] = a1 - hi[2 * m + 1];
         }
         tmem_st16(my_a + hq * 16, hi);
         tmem_st16(my_a + 32 + hq * 16, lo);
@@ -315,23 +344,8 @@ template<bool LUTS, bool PAIR> __global__ void __launch_bounds__(NTHREADS, 1) re
         PROF_ADD(0, t_w)
         PROF_BEGIN(t_c)
         unsigned char *thi = tring + slot * TB_BYTES, *tlo_ = thi + TB_PART;
-        // this warp's rows j = gw + 8 r: lane r < 16 fetches the schedule entry, broadcast row by row
-        // band of this block: rows whose K taps overlap the chunk.  e.x = K-1 - in_j is non-increasing in j and the rows
-        // past the end (e.y < 0) come last, so both conditions are prefix properties: count them with ballots.
-        int jlo = 0, jend = 0;
-#pragma unroll
-        for(int q = 0; q < 4; q++)
-        {
-          const int2 e = sched_s[tt[w] * TILE + 32 * q + lane];
-          jlo += __popc(__ballot_sync(0xffffffffu, e.y >= 0 && c * CHUNK + e.x > K - 1));     // window entirely after the chunk
-          jend += __popc(__ballot_sync(0xffffffffu, e.y >= 0 && c * CHUNK + 31 + e.x >= 0));  // valid and not entirely before it
-        }
-        // band [j0, j0 + nn): multiple of 16 columns (32 for a pair: each CTA supplies nn / 2 rows of the block)
-        constexpr int GRAN = PAIR ? 32 : 16;
-        int j0 = p.band ? (min(jlo, TILE - GRAN) & ~15) : 0;
-        const int nn = p.band ? max(GRAN, (jend - j0 + GRAN - 1) & ~(GRAN - 1)) : TILE;
-        if(j0 + nn > TILE) j0 = TILE - nn;
-        if(gw == 0 && lane == 0) bmeta[slot] = make_int2(j0, nn);
+        const int2 meta = bandtab[bseq];                 // {first output column, columns}, tabulated in the prologue
+        const int j0 = meta.x, nn = meta.y;
         // this CTA's rows of the block: nh rows from jb on, stored band-relative (row l at 128 l, swizzled); warp gw
         // builds rows l = gw + NGEN r.  Branch-free rows: clamped LUT index, value masked afterwards; lane = column kk.
         const int nh = PAIR ? nn >> 1 : nn, jb = j0 + (PAIR ? (int) rank * nh : 0);
@@ -353,7 +367,7 @@ template<bool LUTS, bool PAIR> __global__ void __launch_bounds__(NTHREADS, 1) re
         for(int r = 0; r < GR; r++)
         {
           const int l = gw + NGEN * r;
-          const float hi = to_tf32(v[r]), lo = to_tf32(v[r] - hi);
+          const float hi = to_tf32(v[r]), lo = v[r] - hi;
           if(l < nh)                                                    // warp-uniform predicate, no branch
           {
             const uint32_t off = swz((uint32_t) (l * 128 + lane * 4));
@@ -405,7 +419,7 @@ template<bool LUTS, bool PAIR> __global__ void __launch_bounds__(NTHREADS, 1) re
         PROF_BEGIN(t_c)
         if(c == cA[tl]) wait_in_mma<PAIR>(tempty + region, (unsigned) ((tl / 3) & 1));   // first block of the tile: region drained and zeroed
         fence_after();
-        const int2 meta = bmeta[slot];                    // {first output column, columns} of the block's band
+        const int2 meta = bandtab[bseq];                  // {first output column, columns} of the block's band
         const uint32_t thi = base + slot * TB_BYTES;      // rows are stored band-relative
         const uint64_t bh0 = dbase + (thi >> 4), bl0 = bh0 + (TB_PART >> 4);
         const uint32_t dcol = tmem + (uint32_t) (region * NCOL + meta.x);
@@ -538,11 +552,21 @@ extern "C" int tsdgpu_debug_rtcprof_dump(const char *path)
 }
 #endif
 
-bool resamp_tc_eligible(const int2 *sched_host, long long n_out, int K, const void *x, long long x_stride)
+bool resamp_tc_eligible(const int2 *sched_host, long long n_out, int K, const void *x, long long x_stride, int *max_tile_chunks)
 {
   if(K < 1 || K > 4096 || n_out < 1) return false;
   if(((uintptr_t) x & 15) != 0 || (x_stride % 2) != 0) return false;
   const long long ntiles = (n_out + rtc::TILE - 1) / rtc::TILE;
+  // chunks per tile: the CTA tabulates the bands of its (chunk, tile) blocks, at most NB_MAX of them
+  int mc = 1;
+  for(long long t = 0; t < ntiles; t++)
+  {
+    const int endc = sched_host[std::min<long long>(t * rtc::TILE + rtc::TILE, n_out) - 1].x >> 5;
+    const int begc = (sched_host[t * rtc::TILE].x - (K - 1)) >> 5;
+    mc = std::max(mc, endc - begc + 1);
+  }
+  if(mc > rtc::NB_MAX) return false;
+  *max_tile_chunks = mc;
   for(long long t = 0; t + 2 < ntiles; t++)
   {
     const int endc = sched_host[std::min<long long>(t * rtc::TILE + rtc::TILE, n_out) - 1].x >> 5;
@@ -570,9 +594,10 @@ int resamp_tc_launch(const ResampTcParams &p0)
   const int groups = (p.nchan + rtc::CH - 1) / rtc::CH;
   int span = 1;
   long long best = -1;
-  for(int s = 1; s <= rtc::MAXSPAN; s++)
+  const int smax = std::max(1, std::min(rtc::MAXSPAN, rtc::NB_MAX / std::max(1, p.max_tile_chunks)));
+  for(int s = 1; s <= smax; s++)
   {
-    if(s < 4 && p.ntiles > 4) continue;
+    if(s < std::min(4, smax) && p.ntiles > 4) continue;
     const long long ctas = (long long) groups * ((p.ntiles + s - 1) / s);
     const long long cost = ((ctas + r.num_sms - 1) / r.num_sms) * (s + 1);
     if(best < 0 || cost < best) { best = cost; span = s; }

@@ -17,10 +17,11 @@ struct ResampTcParams
   int n;                  // input samples of the call (positions >= n read as zero)
   int K, hist_len, nchan;
   int lut_elems;          // K * (nphases + 1)
+  int max_tile_chunks;    // from resamp_tc_eligible: most 32-input chunks feeding one tile of 128 outputs
   int ntiles, span, vec_store, band, groups;   // filled by resamp_tc_launch
 };
 
-bool resamp_tc_eligible(const int2 *sched_host, long long n_out, int K, const void *x, long long x_stride);
+bool resamp_tc_eligible(const int2 *sched_host, long long n_out, int K, const void *x, long long x_stride, int *max_tile_chunks);
 int resamp_tc_launch(const ResampTcParams &p);
 
 }

@@ -37,9 +37,9 @@ def test_host_only_entries(port):
         assert Fo.ola_complexite_optimise(M) == port.ola_complexite_optimise(M)
     assert Fo.ola_complexite_optimise(4095)[1:] == (65536, 4094, 61442)
     # resampler schedule == the oracle's recurrence, for several ratios and block partitions
-    for ratio in (147 / 160, 1.5, 0.5, 1.9999, 3.7, 0.3):
+    for ratio in (147 / 160, 1.5, 0.5, 1.9999, 3.7, 0.3, 1.0, 0.999999, 0.50001, 0.75, 2 / 3, 0.6180339, 0.97, 0.51, 44100 / 48000):
         phase_g, phase_o = ctypes.c_float(0), 0.0
-        for n in (1, 10, 1000, 65536, 777):
+        for n in (1, 10, 1000, 65536, 777, 300001):
             cap = int(np.ceil(np.float32(ratio) * n) + 10)
             a, b = np.zeros(cap, np.int32), np.zeros(cap, np.int32)
             no = ctypes.c_longlong()
