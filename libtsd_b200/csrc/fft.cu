@@ -14,6 +14,7 @@
 //    tuned; the reference's own structure, fourier.cc:86-117).
 #include "fft_tiles.cuh"
 #include "fft_plan.h"
+#include "host_pipe.cuh"
 #include "tsdgpu.h"
 
 #include <algorithm>
@@ -682,17 +683,37 @@ int tsdgpu_fft_exec(tsdgpu_fft_t p, const void *x, long long xs, void *y, long l
   if(!p || !x || !y) return fail("tsdgpu_fft_exec: null argument");
   if(xs < p->n || ys < p->n) return fail("tsdgpu_fft_exec: stride smaller than n");
   if(mem == TSDGPU_DEVICE) return fft_exec_device(p, (const float2 *) x, xs, (float2 *) y, ys, forward != 0);
-  float2 *d = nullptr;
+  // host memory: groups of transforms pipelined through the persistent device staging buffers (H2D of group k+1,
+  // transforms of group k and D2H of group k-1 overlap on three streams)
   const size_t row = (size_t) p->n * sizeof(float2);
-  TSD_CUDA(cudaMalloc(&d, row * p->batch));
-  int rc = 0;
-  cudaError_t e = cudaMemcpy2DAsync(d, row, x, (size_t) xs * 8, row, p->batch, cudaMemcpyHostToDevice, rt().stream);
-  if(e == cudaSuccess) rc = fft_exec_device(p, d, p->n, d, p->n, forward != 0);
-  if(e == cudaSuccess && !rc)
-    e = cudaMemcpy2DAsync(y, (size_t) ys * 8, d, row, row, p->batch, cudaMemcpyDeviceToHost, rt().stream);
-  if(e == cudaSuccess) e = cudaStreamSynchronize(rt().stream);
-  cudaFree(d);
-  if(e != cudaSuccess) return fail(std::string("tsdgpu_fft_exec: ") + cudaGetErrorString(e));
+  // plans with sub-plans (n not a power of two) are sized for the whole batch: one group
+  long long group = p->sub ? p->batch : std::max<long long>(1, std::min<long long>(p->batch, (long long) ((32ull << 20) / row)));
+  if(host_stage_reserve(row * group, row * group)) return 1;
+  HostStage &hs = host_stage();
+  const float2 *xh = (const float2 *) x;
+  float2 *yh = (float2 *) y;
+  const int full_batch = p->batch;
+  long long done = 0;
+  const int rc = host_pipeline(
+    full_batch, group,
+    [&](int slot, long long first, long long count) -> int {
+      TSD_CUDA(cudaMemcpy2DAsync(hs.in[slot], row, xh + first * xs, (size_t) xs * 8, row, (size_t) count, cudaMemcpyHostToDevice, rt().copy_in));
+      return 0;
+    },
+    [&](long long count) { return count; },
+    [&](int slot, long long count, long long *got) -> int {
+      p->batch = (int) count;   // the kernels take the number of transforms from the plan
+      const int r2 = fft_exec_device(p, (const float2 *) hs.in[slot], p->n, (float2 *) hs.out[slot], p->n, forward != 0);
+      p->batch = full_batch;
+      *got = count;
+      return r2;
+    },
+    [&](int slot, long long out_first, long long count) -> int {
+      TSD_CUDA(cudaMemcpy2DAsync(yh + out_first * ys, (size_t) ys * 8, hs.out[slot], row, row, (size_t) count, cudaMemcpyDeviceToHost, rt().copy_out));
+      return 0;
+    },
+    &done);
+  p->batch = full_batch;
   return rc;
 }
 

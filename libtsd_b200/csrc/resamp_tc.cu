@@ -28,7 +28,8 @@ using namespace tc;
 constexpr int TILE = 128, CH = 64, NCOL = 128, CHUNK = 32;
 constexpr int NRAW = 4;                          // raw staging ring
 constexpr int NSTAGE = 2;                        // A-operand stages in tensor memory
-constexpr int NT = 2;                            // coefficient-block ring
+constexpr int NT = 2;                            // coefficient-block ring (pair: 4 slots of half the rows, same 64 KiB)
+constexpr int NT_MAX = 4;
 constexpr int RAW_PITCH = 272, RAW_BYTES = CH * RAW_PITCH;
 constexpr int TB_PART = TILE * 128, TB_BYTES = 2 * TB_PART;     // 128 rows x 32 tf32, hi + lo
 constexpr int MAXSPAN = 16;                      // tiles per CTA: its slice of the schedule (16 KiB) sits in shared memory
@@ -129,6 +130,8 @@ struct Walk
 template<bool LUTS, bool PAIR> __global__ void __launch_bounds__(NTHREADS, 1) resamp_tc_kernel(ResampTcParams p)
 {
   const uint32_t rank = PAIR ? cluster_rank() : 0u;
+  constexpr int NTR = PAIR ? 2 * NT : NT;                       // ring slots
+  constexpr int TBP = PAIR ? TB_PART / 2 : TB_PART, TBB = 2 * TBP;   // bytes of the hi (= lo) part of a slot, of a slot
   extern __shared__ unsigned char raw[];
   const uint32_t base = (smem_u32(raw) + 1023u) & ~1023u;
   unsigned char *sm = raw + (base - smem_u32(raw));
@@ -138,8 +141,8 @@ template<bool LUTS, bool PAIR> __global__ void __launch_bounds__(NTHREADS, 1) re
   float *lut_s = reinterpret_cast<float *>(sched_s + MAXSPAN * TILE);
   uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(lut_s) + LUT_SMEM_MAX);
   uint64_t *full = bars, *empty = full + NSTAGE, *tfull = empty + NSTAGE, *tempty = tfull + 3;
-  uint64_t *rfull = tempty + 3, *rempty = rfull + NRAW, *bfull = rempty + NRAW, *bempty = bfull + NT;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bempty + NT);
+  uint64_t *rfull = tempty + 3, *rempty = rfull + NRAW, *bfull = rempty + NRAW, *bempty = bfull + NT_MAX;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bempty + NT_MAX);
   int *cA = reinterpret_cast<int *>(tmem_slot + 2), *cB = cA + MAXSPAN;
   int2 *bandtab = reinterpret_cast<int2 *>(cB + MAXSPAN);    // per block of the walk: {first output column, columns} of its band
 
@@ -157,7 +160,7 @@ template<bool LUTS, bool PAIR> __global__ void __launch_bounds__(NTHREADS, 1) re
     for(int i = 0; i < NSTAGE; i++) { mbar_init(full + i, 4 * NC); mbar_init(empty + i, 1); }
     for(int i = 0; i < 3; i++) { mbar_init(tfull + i, 1); mbar_init(tempty + i, 4 * NC); }
     for(int i = 0; i < NRAW; i++) { mbar_init(rfull + i, 32); mbar_init(rempty + i, 4); }
-    for(int i = 0; i < NT; i++) { mbar_init(bfull + i, NGEN * NC); mbar_init(bempty + i, 1); }
+    for(int i = 0; i < NTR; i++) { mbar_init(bfull + i, NGEN * NC); mbar_init(bempty + i, 1); }
     mbar_fence_init();
   }
   if(warp == MMA_WARP)
@@ -338,12 +341,12 @@ template<bool LUTS, bool PAIR> __global__ void __launch_bounds__(NTHREADS, 1) re
       for(int w = 0; w < 2; w++)
       {
         if(tt[w] < 0) continue;
-        const int slot = bseq % NT;
+        const int slot = bseq % NTR;
         PROF_BEGIN(t_w)
-        mbar_wait(bempty + slot, (unsigned) (((bseq / NT) & 1) ^ 1));
+        mbar_wait(bempty + slot, (unsigned) (((bseq / NTR) & 1) ^ 1));
         PROF_ADD(0, t_w)
         PROF_BEGIN(t_c)
-        unsigned char *thi = tring + slot * TB_BYTES, *tlo_ = thi + TB_PART;
+        unsigned char *thi = tring + slot * TBB, *tlo_ = thi + TBP;
         const int2 meta = bandtab[bseq];                 // {first output column, columns}, tabulated in the prologue
         const int j0 = meta.x, nn = meta.y;
         // this CTA's rows of the block: nh rows from jb on, stored band-relative (row l at 128 l, swizzled); warp gw
@@ -385,7 +388,7 @@ template<bool LUTS, bool PAIR> __global__ void __launch_bounds__(NTHREADS, 1) re
       if(lane == 0)
       {
         const int nb = (tt[0] >= 0) + (tt[1] >= 0);
-        for(int k = nb; k > 0; k--) arrive_to_mma<PAIR>(bfull + (bseq - k) % NT);
+        for(int k = nb; k > 0; k--) arrive_to_mma<PAIR>(bfull + (bseq - k) % NTR);
       }
       PROF_ADD(1, t_f)
     }
@@ -412,16 +415,16 @@ template<bool LUTS, bool PAIR> __global__ void __launch_bounds__(NTHREADS, 1) re
       for(int w = 0; w < 2; w++)
       {
         if(tt[w] < 0) continue;
-        const int tl = tt[w], region = tl % 3, slot = bseq % NT;
+        const int tl = tt[w], region = tl % 3, slot = bseq % NTR;
         PROF_BEGIN(t_w2)
-        wait_in_mma<PAIR>(bfull + slot, (unsigned) ((bseq / NT) & 1));
+        wait_in_mma<PAIR>(bfull + slot, (unsigned) ((bseq / NTR) & 1));
         PROF_ADD(1, t_w2)
         PROF_BEGIN(t_c)
         if(c == cA[tl]) wait_in_mma<PAIR>(tempty + region, (unsigned) ((tl / 3) & 1));   // first block of the tile: region drained and zeroed
         fence_after();
         const int2 meta = bandtab[bseq];                  // {first output column, columns} of the block's band
-        const uint32_t thi = base + slot * TB_BYTES;      // rows are stored band-relative
-        const uint64_t bh0 = dbase + (thi >> 4), bl0 = bh0 + (TB_PART >> 4);
+        const uint32_t thi = base + slot * TBB;           // rows are stored band-relative
+        const uint64_t bh0 = dbase + (thi >> 4), bl0 = bh0 + (TBP >> 4);
         const uint32_t dcol = tmem + (uint32_t) (region * NCOL + meta.x);
         const uint32_t idesc = (PAIR ? IDESC_M256 : IDESC_M128) | ((uint32_t) (meta.y >> 3) << 17);
         if(elect_one())
