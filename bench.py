@@ -39,6 +39,8 @@ WORKLOADS = {
     "fft": ("batched fft/ifft: 4096 ch x 65536-pt cf32, forward+inverse round trip", 32.0),
     "fir": ("direct FIR: 1024 ch x 1Mi cf32, 127-tap low-pass, filtre_rif step() in 64Ki blocks", 16.0),
     "resample": ("polyphase/LUT resampler 147/160 on 512 ch x 8Mi cf32, sinc LUT 64 taps x 257 phases", 8.0 + 8.0 * 147 / 160),
+    # secondary line of SURVEY 8(d) config 5: the stock resample() chain (15-tap interpolator only at this ratio)
+    "reechan": ("stock resample() / filtre_reechan 147/160 on 512 ch x 8Mi cf32 (15-tap sinc interpolator x 257 phases)", 8.0 + 8.0 * 147 / 160),
 }
 
 
@@ -159,6 +161,20 @@ def cpu_workload_setup(workload):
                 f = O.itrp(147.0 / 160.0, lut, 256)
                 return lambda: f.step(x)
         return make_job, n, kind, f"1 channel x {n} cf32 samples per host thread, filtre_itrp 147/160, sinc 64x257"
+    if workload == "reechan":
+        n = 1 << 20
+        x = cn(n)
+        if have_ref:
+            def make_job():
+                f = O.reechan(147.0 / 160.0)
+                return lambda: f.step(x)
+        else:
+            lut = O.itrp_sinc_lut(15, 256, 0.4)
+
+            def make_job():
+                f = O.itrp(147.0 / 160.0, lut, 256)
+                return lambda: f.step(x)
+        return make_job, n, kind, f"1 channel x {n} cf32 samples per host thread, filtre_reechan 147/160"
     raise SystemExit(f"unknown workload {workload}")
 
 
@@ -202,12 +218,17 @@ class GpuWorkload:
         self.torch = torch
         O = oracle.ref() if oracle.have_ref() else oracle.port()   # set-up data (taps, H, LUT) only
         g = torch.Generator(device="cuda")
-        g.manual_seed({"ola": 0x7D5D0004, "fft": 0x7D5D0002, "fir": 0x7D5D0003, "resample": 0x7D5D0005}[name])
+        g.manual_seed({"ola": 0x7D5D0004, "fft": 0x7D5D0002, "fir": 0x7D5D0003, "resample": 0x7D5D0005, "reechan": 0x7D5D0005}[name])
+
+        pad = int(os.environ.get("TSDGPU_BENCH_PAD", "0"))   # experiment: channel stride n + pad instead of n
 
         def randc(nchan, n):
-            x = torch.empty((nchan, n), dtype=torch.complex64, device="cuda")
+            x = torch.empty((nchan, n + pad), dtype=torch.complex64, device="cuda")
             torch.view_as_real(x).normal_(generator=g)
-            return x
+            return x[:, :n]
+
+        def emptyc(nchan, n):
+            return torch.empty((nchan, n + pad), dtype=torch.complex64, device="cuda")[:, :n]
 
         if name == "ola":
             self.nchan, self.n = max(1, int(256 * scale)), 1 << 24
@@ -216,15 +237,15 @@ class GpuWorkload:
             self.flt, N = Fo.filtre_fft(Fo.FiltreFFTConfig(61441, 4095, H=self.H, fir_len=4095), self.nchan)
             assert N == 65536
             self.x = randc(self.nchan, self.n)
-            self.y = torch.empty((self.nchan, self.flt.Ne * ((self.n + self.flt.Ne - 1) // self.flt.Ne)), dtype=torch.complex64, device="cuda")
+            self.y = emptyc(self.nchan, self.flt.Ne * ((self.n + self.flt.Ne - 1) // self.flt.Ne))
             self.samples_per_step = self.nchan * self.n
             self.step = lambda: self.flt.step(self.x, out=self.y)
         elif name == "fft":
             self.nchan, self.n = max(1, int(4096 * scale)), 65536
             self.plan = Fo.tfrplan_creation(65536, batch=self.nchan)
             self.x = randc(self.nchan, self.n)
-            self.X = torch.empty_like(self.x)
-            self.y = torch.empty_like(self.x)
+            self.X = emptyc(self.nchan, self.n)
+            self.y = emptyc(self.nchan, self.n)
             self.samples_per_step = self.nchan * self.n
 
             def step():
@@ -236,7 +257,7 @@ class GpuWorkload:
             h = O.design_rif_fen(127, "lp", 0.1)
             self.flt = F.filtre_rif(h, np.complex64, self.nchan)
             self.x = randc(self.nchan, self.n)
-            self.y = torch.empty_like(self.x)
+            self.y = emptyc(self.nchan, self.n)
             self.samples_per_step = self.nchan * self.n
 
             def step():
@@ -248,6 +269,12 @@ class GpuWorkload:
             self.nchan, self.n = max(1, int(512 * scale)), 1 << 23
             lut = O.itrp_sinc_lut(64, 256, 0.4)
             self.flt = F.filtre_itrp(147.0 / 160.0, F.InterpolateurLUT(lut), self.nchan)
+            self.x = randc(self.nchan, self.n)
+            self.samples_per_step = self.nchan * self.n
+            self.step = lambda: self.flt.step(self.x)
+        elif name == "reechan":
+            self.nchan, self.n = max(1, int(512 * scale)), 1 << 23
+            self.flt = F.filtre_reechan(147.0 / 160.0, self.nchan)
             self.x = randc(self.nchan, self.n)
             self.samples_per_step = self.nchan * self.n
             self.step = lambda: self.flt.step(self.x)
@@ -296,6 +323,13 @@ def e2e_measure(name, steps, warmup, barrier=None):
         ty, y = pinned(nchan, n)
         step = lambda: flt.step(x, out=y)   # noqa: E731
         out_per_step = n
+    elif name == "reechan":
+        nchan, n = 128, 1 << 20
+        flt = F.filtre_reechan(147.0 / 160.0, nchan)
+        tx, x = pinned(nchan, n)
+        ty, y = pinned(nchan, int(n * 147 / 160) + 32)
+        step = lambda: flt.step(x, out=y)   # noqa: E731
+        out_per_step = int(n * 147 / 160)
     else:
         nchan, n = 128, 1 << 20
         flt = F.filtre_itrp(147.0 / 160.0, F.InterpolateurLUT(O.itrp_sinc_lut(64, 256, 0.4)), nchan)
@@ -425,7 +459,8 @@ def main():
         # ola: the block filter runs as three stage kernels per chunk of 32 blocks, overlapped on four streams; the timed
         # unit is the whole pipeline of one step() (events around its first and last launch on the launching stream)
         kernel_name = {"ola": "ola64k_stage<0|1|2> (stage kernels of one step(), overlapped)", "fft": "fft64k_kernel", "fir": "fir_tc_kernel (tcgen05 3xTF32 Toeplitz GEMM)",
-                       "resample": "resamp_tc_kernel (tcgen05 3xTF32 banded filter-bank GEMM)"}[args.workload]
+                       "resample": "resamp_tc_kernel (tcgen05 3xTF32 banded filter-bank GEMM, CTA pairs)",
+                       "reechan": "resamp_tc_kernel (tcgen05 3xTF32 banded filter-bank GEMM, CTA pairs)"}[args.workload]
         roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_kind,
                     "algorithmic_bytes_per_sample": bytes_per_sample, "kernel_ms_per_step": kern_ms / args.steps,

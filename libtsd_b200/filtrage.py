@@ -396,7 +396,9 @@ class AdaptationRythmeArbitraire(FiltreGen):
         fcut = min(np.float32(0.4), np.float32(f / 2))
         self.interpolateur = filtre_itrp(float(f), itrp_sinc(InterpolateurSincConfig(15, 256, float(fcut), "hn")), nchan)
 
-    def step(self, x):
+    def step(self, x, out=None):
+        """``out`` (optional) is handed to the final interpolator (see AdaptationRythmeSimple.step); it is ignored when
+        the chain ends with a polyphase stage."""
         if self.ratio == 1:                        # ra.cc:162-163
             return x.clone() if hasattr(x, "clone") else np.array(x, np.complex64)
         y = x
@@ -408,7 +410,7 @@ class AdaptationRythmeArbitraire(FiltreGen):
             if y is x:
                 return x.clone() if hasattr(x, "clone") else np.array(x, np.complex64)
             return y
-        return self.interpolateur.step(y)
+        return self.interpolateur.step(y, out=out)
 
 
 def filtre_reechan(ratio: float, nchan: int = 1) -> AdaptationRythmeArbitraire:

@@ -148,6 +148,30 @@ def rfft(x):
     return y
 
 
+def reechan_freq(x, lom: float):
+    """rééchan_freq<T>(x, lom) (fourier.hpp:143, fourier.cc:1391-1419): delay-free resampling of a whole signal by
+    zero-padding (lom > 1) or truncating (lom < 1) its spectrum.  n2 = round(n * lom); the two transforms run on GPU
+    plans of n and n2 points (any size).  Like the reference, the result is the REAL part of the inverse transform,
+    also for complex input (``return real(x)``, :1408,1416)."""
+    x = np.asarray(x)
+    cplx = np.iscomplexobj(x)
+    x = np.ascontiguousarray(x, np.complex64 if cplx else np.float32)
+    if lom == 1:
+        return x.copy()
+    n = x.shape[0]
+    n2 = int(np.floor(np.float32(n) * np.float32(lom) + np.float32(0.5)))      # (entier) round(n * lom), float32 product
+    X = fft(x) if cplx else rfft(x)
+    X2 = np.zeros(n2, np.complex64)
+    h = n // 2 if lom > 1 else n2 // 2
+    X2[:h] = X[:h]
+    X2[n2 - h:] = X[n - h:]
+    y = ifft(X2) * np.float32(np.sqrt(np.float32(lom)))
+    return y.real.astype(np.complex64) if cplx else np.ascontiguousarray(y.real)
+
+
+resample_freq = reechan_freq
+
+
 @dataclass
 class FiltreFFTConfig:
     """fourier.hpp:305-320.  The reference's ``traitement_freq`` callback is a host std::function; the

@@ -368,6 +368,17 @@ class _Ref:
         f.N = no.value
         return f
 
+    def reechan_freq(self, x, lom):
+        """rééchan_freq<T>(x, lom) (fourier.cc:1391-1419), T = float or cfloat after the dtype of x."""
+        cplx = np.iscomplexobj(x)
+        xx = _c64(x) if cplx else _f32(x)
+        cap = int(len(xx) * max(lom, 1.0)) + 8
+        y = np.empty(cap, xx.dtype)
+        no = _i()
+        if self.L.tsdref_reechan_freq(_i(1 if cplx else 0), _ptr(xx), _i(len(xx)), _f(lom), _ptr(y), _i(cap), C.byref(no)):
+            raise RuntimeError(self._err())
+        return y[: no.value].copy()
+
     def ola_make_H(self, h, N):
         h = _f32(h)
         H = np.zeros(N, np.complex64)

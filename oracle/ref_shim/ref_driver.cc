@@ -151,6 +151,27 @@ int tsdref_fenetre(const char *nom, int n, int sym, float *w)
   });
 }
 
+// rééchan_freq<T>(x, lom) (fourier.cc:1391-1419); kind 0 = float, 1 = cfloat.  y needs round(n * lom) elements.
+int tsdref_reechan_freq(int kind, const void *x, int n, float lom, void *y, int cap, int *n_out)
+{
+  return guarded([&] {
+    if(kind == 0)
+    {
+      Vecf r = rééchan_freq<float>(Vecf::map((const float *) x, n).clone(), lom);
+      *n_out = r.rows();
+      if(r.rows() > cap) échec("tsdref_reechan_freq: capacity");
+      memcpy(y, r.data(), sizeof(float) * r.rows());
+    }
+    else
+    {
+      Veccf r = rééchan_freq<cfloat>(Veccf::map((const cfloat *) x, n).clone(), lom);
+      *n_out = r.rows();
+      if(r.rows() > cap) échec("tsdref_reechan_freq: capacity");
+      memcpy(y, r.data(), sizeof(cfloat) * r.rows());
+    }
+  });
+}
+
 // H of the FiltreFFTRIF convention (fourier.cc:962-965): h2.tail(K) = h ; H = fft(h2) * sqrt(N)
 int tsdref_ola_make_H(const float *h, int K, int N, float *H)
 {

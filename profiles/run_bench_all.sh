@@ -1,7 +1,7 @@
 #!/bin/bash
 # All four workloads at BASELINE size on one GPU + the CPU reference arm of the headline workload.
 mkdir -p gpurun_out
-for w in ola fft fir resample; do
+for w in ola fft fir resample reechan; do
   timeout 500 python bench.py --workload $w --steps 10 --warmup 3 > gpurun_out/r01_bench_$w.json 2> gpurun_out/r01_bench_$w.err
   tail -c 400 gpurun_out/r01_bench_$w.err
 done

@@ -87,6 +87,17 @@ def main():
     out["ola_small_lens"] = np.array(lens, np.int32)
     out["ola_small_y"] = np.concatenate(ys)
 
+    # rééchan_freq (fourier.cc:1391-1419): real and complex input, up and down
+    rng = np.random.default_rng(79)
+    xr = rng.standard_normal(1000).astype(np.float32)
+    xc = cn(rng, 777)
+    out["rfq_xr"] = xr
+    out["rfq_xc"] = xc
+    out["rfq_loms"] = np.array([1.5, 0.7, 2.0, 0.37], np.float32)
+    for i, lom in enumerate(out["rfq_loms"]):
+        out[f"rfq_yr{i}"] = R.reechan_freq(xr, float(lom))
+        out[f"rfq_yc{i}"] = R.reechan_freq(xc, float(lom))
+
     # OLA, Hann-window 50 % overlap mode (fourier.cc:884-930): Ne = 512, N = 1024, random spectral gain
     rng = np.random.default_rng(78)
     x = cn(rng, 6000)

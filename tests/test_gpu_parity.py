@@ -339,6 +339,22 @@ def test_ola_fenetre(tsd, cpu_oracle, Ne, nz, useH):
     assert np.max(np.abs(fenetre("hn", Ne, False) - w)) <= 2e-7
 
 
+def test_reechan_freq_golden(tsd):
+    """rééchan_freq (fourier.cc:1391-1419) through GPU plans of n and round(n * lom) points vs the reference build's
+    vectors: lengths exact, samples within the bar; complex input keeps only the real part, like the reference."""
+    import os
+    from libtsd_b200 import fourier as Fo
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_vectors.npz"))
+    for i, lom in enumerate(G["rfq_loms"]):
+        for x, yref in ((G["rfq_xr"], G[f"rfq_yr{i}"]), (G["rfq_xc"], G[f"rfq_yc{i}"])):
+            y = Fo.reechan_freq(x, float(lom))
+            assert y.shape == yref.shape and y.dtype == yref.dtype
+            assert rel_err(y, yref, rms(x)) <= TOL
+            if np.iscomplexobj(y):
+                assert np.all(y.imag == 0)
+    assert np.array_equal(Fo.reechan_freq(G["rfq_xr"], 1.0), G["rfq_xr"])
+
+
 def test_ola_fenetre_golden(tsd):
     import os
     from libtsd_b200 import fourier as Fo
