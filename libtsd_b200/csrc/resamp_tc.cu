@@ -626,17 +626,6 @@ int resamp_tc_launch(const ResampTcParams &p0)
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    if(getenv("TSDGPU_DEBUG_CLUSTER"))
-    {
-      int nc = -1;
-      cudaError_t e = cudaOccupancyMaxActiveClusters(&nc, rtc::resamp_tc_kernel<true, true>, &cfg);
-      fprintf(stderr, "[resamp_tc] grid %u x %u, block %d, smem %d: max active clusters %d (%s)\n", grid.x, grid.y, rtc::NTHREADS,
-              rtc::SMEM_BYTES, nc, cudaGetErrorString(e));
-      cudaFuncAttributes fa;
-      cudaFuncGetAttributes(&fa, rtc::resamp_tc_kernel<true, true>);
-      fprintf(stderr, "[resamp_tc] regs %d, static smem %zu, max dyn %d, clusterDimMustBeSet %d\n", fa.numRegs, fa.sharedSizeBytes,
-              fa.maxDynamicSharedSizeBytes, fa.clusterDimMustBeSet);
-    }
     if(luts) TSD_CUDA(cudaLaunchKernelEx(&cfg, rtc::resamp_tc_kernel<true, true>, p));
     else TSD_CUDA(cudaLaunchKernelEx(&cfg, rtc::resamp_tc_kernel<false, true>, p));
   }
