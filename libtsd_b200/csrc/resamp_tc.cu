@@ -35,7 +35,7 @@ constexpr int TB_PART = TILE * 128, TB_BYTES = 2 * TB_PART;     // 128 rows x 32
 constexpr int MAXSPAN = 16;                      // tiles per CTA: its slice of the schedule (16 KiB) sits in shared memory
 constexpr int LUT_SMEM_MAX = 66 * 1024;          // the LUT too when it fits (64 taps x 257 phases = 64.25 KiB)
 constexpr int NB_MAX = 512;                       // (chunk, tile) blocks per CTA: their bands are tabulated in the prologue
-constexpr int SMEM_BYTES = NT * TB_BYTES + NRAW * RAW_BYTES + MAXSPAN * TILE * 8 + LUT_SMEM_MAX + 1024 + 512 + 2 * MAXSPAN * 4 + 64 + NB_MAX * 8;
+constexpr int SMEM_BYTES = NT * TB_BYTES + NRAW * RAW_BYTES + MAXSPAN * TILE * 8 + LUT_SMEM_MAX + 1024 + 512 + 2 * MAXSPAN * 4 + 64 + NB_MAX * 8 + NB_MAX * 2;
 constexpr int ACOL = 3 * NCOL;
 constexpr int CONV_WARP0 = 4, GEN_WARP0 = 8, NGEN = 16, MMA_WARP = GEN_WARP0 + NGEN, LOAD_WARP = MMA_WARP + 1;
 constexpr int NTHREADS = 32 * (LOAD_WARP + 1);
@@ -145,6 +145,7 @@ template<bool LUTS, bool PAIR> __global__ void __launch_bounds__(NTHREADS, 1) re
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bempty + NT_MAX);
   int *cA = reinterpret_cast<int *>(tmem_slot + 2), *cB = cA + MAXSPAN;
   int2 *bandtab = reinterpret_cast<int2 *>(cB + MAXSPAN);    // per block of the walk: {first output column, columns} of its band
+  unsigned short *ftab = reinterpret_cast<unsigned short *>(bandtab + NB_MAX);   // per chunk: tiles it feeds, t0 | t1 << 8 (0xff = none)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // pair: 1-D grid, consecutive CTAs (= the cluster) are the two channel groups 2g, 2g+1 of one tile span
@@ -194,6 +195,20 @@ template<bool LUTS, bool PAIR> __global__ void __launch_bounds__(NTHREADS, 1) re
   if(LUTS)
     for(int i = tid; i < p.lut_elems; i += NTHREADS) lut_s[i] = __ldg(p.lut + i);
   __syncthreads();
+  {
+    // tiles fed by every chunk of this CTA (at most two, consecutive): the first tile whose last chunk is >= c, and
+    // its successor, when they have started
+    const int cb0 = cA[0], nch = cB[T - 1] - cb0 + 1;
+    for(int it = tid; it < nch; it += NTHREADS)
+    {
+      const int c = cb0 + it;
+      int tlo = 0;
+      while(tlo < T && cB[tlo] < c) tlo++;
+      const int t0 = (tlo < T && cA[tlo] <= c) ? tlo : 0xff;
+      const int t1 = (t0 != 0xff && tlo + 1 < T && cA[tlo + 1] <= c) ? tlo + 1 : 0xff;
+      ftab[it] = (unsigned short) (t0 | (t1 << 8));
+    }
+  }
   if(warp < T)
   {
     // bands of the blocks of tile `warp`, one lane per chunk.  A block (c, tl) keeps the rows whose K taps overlap the
@@ -329,67 +344,78 @@ template<bool LUTS, bool PAIR> __global__ void __launch_bounds__(NTHREADS, 1) re
   {
     // ===== coefficient-block generators: block (c, tile) row j = lut row p_j shifted to the chunk, lane = column kk
     const int gw = warp - GEN_WARP0;
-    Walk wk{cA, cB, T, 0};
     int bseq = 0;
+    constexpr int GR = PAIR ? (TILE / 2 + NGEN - 1) / NGEN : GROWS;
+    // pair: the two blocks of a chunk are built together (their loads interleave); single CTA: one after the other
+    constexpr int NBK = PAIR ? 2 : 1;
     PROF_DECL
     for(int it = 0; it < nchunks; it++)
     {
       const int c = c_begin + it;
-      int tt[2];
-      wk.feeds(c, tt[0], tt[1]);
-#pragma unroll
-      for(int w = 0; w < 2; w++)
+      const int f = ftab[it];
+      const int tf[2] = {f & 0xff, (f >> 8) & 0xff};
+      const int nb = (tf[0] != 0xff) + (tf[1] != 0xff);
+      const int tcol = c * CHUNK + lane;
+      for(int b0 = 0; b0 < nb; b0 += NBK)
       {
-        if(tt[w] < 0) continue;
-        const int slot = bseq % NTR;
-        PROF_BEGIN(t_w)
-        mbar_wait(bempty + slot, (unsigned) (((bseq / NTR) & 1) ^ 1));
-        PROF_ADD(0, t_w)
+        unsigned char *thi[NBK];
+        const int2 *srow[NBK];
+        int nh[NBK], jb[NBK];
+#pragma unroll
+        for(int k = 0; k < NBK; k++)
+        {
+          const bool on = b0 + k < nb;                       // second block of the group absent: built nowhere (nh = 0)
+          const int bs = bseq + b0 + (on ? k : 0), slot = bs % NTR;
+          PROF_BEGIN(t_w)
+          if(on) mbar_wait(bempty + slot, (unsigned) (((bs / NTR) & 1) ^ 1));
+          PROF_ADD(0, t_w)
+          const int2 meta = bandtab[bs];                     // {first output column, columns}, tabulated in the prologue
+          // this CTA's rows of the block: nh rows from jb on, stored band-relative (row l at 128 l, swizzled); warp gw
+          // builds rows l = gw + NGEN r
+          const int nhk = PAIR ? meta.y >> 1 : meta.y;
+          nh[k] = on ? nhk : 0;
+          jb[k] = meta.x + (PAIR ? (int) rank * nhk : 0);
+          thi[k] = tring + slot * TBB;
+          srow[k] = sched_s + tf[on ? b0 + k : b0] * TILE;
+        }
         PROF_BEGIN(t_c)
-        unsigned char *thi = tring + slot * TBB, *tlo_ = thi + TBP;
-        const int2 meta = bandtab[bseq];                 // {first output column, columns}, tabulated in the prologue
-        const int j0 = meta.x, nn = meta.y;
-        // this CTA's rows of the block: nh rows from jb on, stored band-relative (row l at 128 l, swizzled); warp gw
-        // builds rows l = gw + NGEN r.  Branch-free rows: clamped LUT index, value masked afterwards; lane = column kk.
-        const int nh = PAIR ? nn >> 1 : nn, jb = j0 + (PAIR ? (int) rank * nh : 0);
-        constexpr int GR = PAIR ? GROWS / 2 : GROWS;
-        const int2 *srow = sched_s + tt[w] * TILE;
-        const int tcol = c * CHUNK + lane;
-        float v[GR];
+        // branch-free rows: clamped LUT index, value masked afterwards; lane = column kk
+        float v[NBK][GR];
 #pragma unroll
-        for(int r = 0; r < GR; r++)
-        {
-          const int2 e = srow[min(jb + gw + NGEN * r, TILE - 1)];      // broadcast read
-          const int tap = tcol + e.x;
-          const bool ok = (e.y >= 0) & ((unsigned) tap < (unsigned) K);
-          const int idx = ok ? e.y + tap : 0;
-          const float val = LUTS ? lut_s[idx] : __ldg(p.lut + idx);
-          v[r] = ok ? val : 0.f;
-        }
+        for(int k = 0; k < NBK; k++)
 #pragma unroll
-        for(int r = 0; r < GR; r++)
-        {
-          const int l = gw + NGEN * r;
-          const float hi = to_tf32(v[r]), lo = v[r] - hi;
-          if(l < nh)                                                    // warp-uniform predicate, no branch
+          for(int r = 0; r < GR; r++)
           {
-            const uint32_t off = swz((uint32_t) (l * 128 + lane * 4));
-            *reinterpret_cast<float *>(thi + off) = hi;
-            *reinterpret_cast<float *>(tlo_ + off) = lo;
+            const int2 e = srow[k][min(jb[k] + gw + NGEN * r, TILE - 1)];      // broadcast read
+            const int tap = tcol + e.x;
+            const bool ok = (e.y >= 0) & ((unsigned) tap < (unsigned) K);
+            const int idx = ok ? e.y + tap : 0;
+            const float val = LUTS ? lut_s[idx] : __ldg(p.lut + idx);
+            v[k][r] = ok ? val : 0.f;
           }
-        }
+#pragma unroll
+        for(int k = 0; k < NBK; k++)
+#pragma unroll
+          for(int r = 0; r < GR; r++)
+          {
+            const int l = gw + NGEN * r;
+            const float hi = to_tf32(v[k][r]), lo = v[k][r] - hi;
+            if(l < nh[k])                                                    // warp-uniform predicate, no branch
+            {
+              const uint32_t off = swz((uint32_t) (l * 128 + lane * 4));
+              *reinterpret_cast<float *>(thi[k] + off) = hi;
+              *reinterpret_cast<float *>(thi[k] + TBP + off) = lo;
+            }
+          }
         PROF_ADD(2, t_c)
-        bseq++;
       }
+      bseq += nb;
       // one generic -> async proxy fence per chunk (it is the expensive part), then publish the chunk's blocks
       PROF_BEGIN(t_f)
       fence_proxy_async();
       __syncwarp();
       if(lane == 0)
-      {
-        const int nb = (tt[0] >= 0) + (tt[1] >= 0);
         for(int k = nb; k > 0; k--) arrive_to_mma<PAIR>(bfull + (bseq - k) % NTR);
-      }
       PROF_ADD(1, t_f)
     }
     PROF_END
@@ -399,14 +425,13 @@ template<bool LUTS, bool PAIR> __global__ void __launch_bounds__(NTHREADS, 1) re
     // ===== MMA issuer (pair: the leader CTA only)
     if(PAIR && rank != 0) goto done;
     const uint64_t dbase = smem_desc(0);
-    Walk wk{cA, cB, T, 0};
     int bseq = 0;
     PROF_DECL
     for(int it = 0; it < nchunks; it++)
     {
       const int c = c_begin + it, stage = it & 1;
-      int tt[2];
-      wk.feeds(c, tt[0], tt[1]);
+      const int f = ftab[it];
+      const int tt[2] = {(f & 0xff) == 0xff ? -1 : (f & 0xff), ((f >> 8) & 0xff) == 0xff ? -1 : ((f >> 8) & 0xff)};
       PROF_BEGIN(t_w)
       wait_in_mma<PAIR>(full + stage, (unsigned) ((it >> 1) & 1));
       PROF_ADD(0, t_w)
@@ -416,17 +441,19 @@ template<bool LUTS, bool PAIR> __global__ void __launch_bounds__(NTHREADS, 1) re
       {
         if(tt[w] < 0) continue;
         const int tl = tt[w], region = tl % 3, slot = bseq % NTR;
-        PROF_BEGIN(t_w2)
-        wait_in_mma<PAIR>(bfull + slot, (unsigned) ((bseq / NTR) & 1));
-        PROF_ADD(1, t_w2)
-        PROF_BEGIN(t_c)
-        if(c == cA[tl]) wait_in_mma<PAIR>(tempty + region, (unsigned) ((tl / 3) & 1));   // first block of the tile: region drained and zeroed
-        fence_after();
+        // descriptors first (shared-memory reads, uniform arithmetic), then the waits
         const int2 meta = bandtab[bseq];                  // {first output column, columns} of the block's band
+        const bool first = c == cA[tl], last = c == cB[tl];
         const uint32_t thi = base + slot * TBB;           // rows are stored band-relative
         const uint64_t bh0 = dbase + (thi >> 4), bl0 = bh0 + (TBP >> 4);
         const uint32_t dcol = tmem + (uint32_t) (region * NCOL + meta.x);
         const uint32_t idesc = (PAIR ? IDESC_M256 : IDESC_M128) | ((uint32_t) (meta.y >> 3) << 17);
+        PROF_BEGIN(t_w2)
+        wait_in_mma<PAIR>(bfull + slot, (unsigned) ((bseq / NTR) & 1));
+        PROF_ADD(1, t_w2)
+        PROF_BEGIN(t_c)
+        if(first) wait_in_mma<PAIR>(tempty + region, (unsigned) ((tl / 3) & 1));   // first block of the tile: region drained and zeroed
+        fence_after();
         if(elect_one())
         {
 #pragma unroll
@@ -446,7 +473,7 @@ template<bool LUTS, bool PAIR> __global__ void __launch_bounds__(NTHREADS, 1) re
             }
           }
           commit_from_mma<PAIR>(bempty + slot);
-          if(c == cB[tl]) commit_from_mma<PAIR>(tfull + region);     // last block of the tile: accumulator complete
+          if(last) commit_from_mma<PAIR>(tfull + region);     // last block of the tile: accumulator complete
         }
         __syncwarp();
         PROF_ADD(2, t_c)
