@@ -120,6 +120,15 @@ int tsdgpu_ola_step(tsdgpu_ola_t f, const void *x, long long x_stride, int n,
                     void *y, long long y_stride, long long *n_out, int mem);
 int tsdgpu_ola_destroy(tsdgpu_ola_t f);
 
+/* periodogramme_tfd(x, N) (fourier.hpp:967, fourier.cc:1451-1481): short-time spectra of the frames of the windowed
+ * filter_fft object (dim_blocs_temporel = N, nb_zeros_min = 0, avec_fenetrage, callback recording
+ * 10 log10(|X|^2 + 1e-20) of the first N2/2 bins, N2 = p2(N)).  Every full block of N samples gives two frames: the
+ * window [previous half, new half] and the block itself, both times `fenetre` (N floats; the reference uses
+ * fenêtre("hn", N, non)).  out: per channel [2 * (n / N)][N2 / 2] floats (dB), frames in time order, channels
+ * out_stride floats apart.  Even N only (see tsdgpu_ola_create_fen).  *n_frames, *n_bins receive the matrix shape. */
+int tsdgpu_periodogramme_tfd(const void *x, long long x_stride, int n, int nchan, int N, const float *fenetre,
+                             float *out, long long out_stride, int *n_frames, int *n_bins, int mem);
+
 /* ---- arbitrary-ratio resampler: replaces filtre_itrp<cfloat>(ratio, itrp) ------------------- */
 /* (filtrage.hpp:2039; ra.cc:13-79; InterpolateurRIF::step filtrage.hpp:1873-1881; LUT of
  * InterpolateurSinc itrp.cc:16-54).  lut[p*K + i], p in [0,nphases], is the interpolator's

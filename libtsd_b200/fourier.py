@@ -148,6 +148,34 @@ def rfft(x):
     return y
 
 
+def periodogramme_tfd(x, N: int, fenetre=None):
+    """Tabf periodogramme_tfd(x, N) (fourier.hpp:967, fourier.cc:1451-1481): 10 log10(|X|^2 + 1e-20) of the first N2/2
+    bins of every frame of the windowed filtre_fft object (two frames per block of N samples, Hann window, N2 = p2(N)).
+    x: [n] -> [frames, N2/2]; [nchan, n] -> [nchan, frames, N2/2] (numpy = host, torch.cuda = device)."""
+    nchan = 1 if x.ndim == 1 else int(x.shape[0])
+    b = Batch(x, np.complex64, nchan)
+    N = int(N)
+    if fenetre is None:
+        from .filtrage import fenetre as _fen
+        fenetre = _fen("hn", N, False)                       # fourier.cc:796
+    w = np.ascontiguousarray(fenetre, np.float32)
+    if w.shape != (N,):
+        raise TsdGpuError(f"periodogramme_tfd: la fenêtre doit comporter N = {N} points")
+    frames, bins = 2 * (b.n // N), prochaine_puissance_de_2(N) // 2
+    if b.torch:
+        import torch
+        out = torch.empty((nchan, frames, bins), dtype=torch.float32, device=b.arr.device)
+        optr = out.data_ptr()
+    else:
+        out = np.empty((nchan, frames, bins), np.float32)
+        optr = out.ctypes.data
+    nf, nb = C.c_int(), C.c_int()
+    check(lib().tsdgpu_periodogramme_tfd(b.ptr, b.stride, b.n, nchan, N, w.ctypes.data_as(_vp), _vp(optr),
+                                         max(frames * bins, 1), C.byref(nf), C.byref(nb), b.mem))
+    assert (nf.value, nb.value) == (frames, bins)
+    return out[0] if b.ndim == 1 else out
+
+
 def reechan_freq(x, lom: float):
     """rééchan_freq<T>(x, lom) (fourier.hpp:143, fourier.cc:1391-1419): delay-free resampling of a whole signal by
     zero-padding (lom > 1) or truncating (lom < 1) its spectrum.  n2 = round(n * lom); the two transforms run on GPU

@@ -368,6 +368,16 @@ class _Ref:
         f.N = no.value
         return f
 
+    def periodogramme_tfd(self, x, N):
+        """periodogramme_tfd(x, N) (fourier.cc:1451-1481) -> [frames, N2/2] float32 (dB)."""
+        xx = _c64(x)
+        cap = 4 * len(xx) + 4 * N + 64
+        out = np.empty(cap, np.float32)
+        r, c = _i(), _i()
+        if self.L.tsdref_periodogramme_tfd(_ptr(xx), _i(len(xx)), _i(N), _ptr(out), _i(cap), C.byref(r), C.byref(c)):
+            raise RuntimeError(self._err())
+        return out[: r.value * c.value].reshape(r.value, c.value).copy()
+
     def reechan_freq(self, x, lom):
         """rééchan_freq<T>(x, lom) (fourier.cc:1391-1419), T = float or cfloat after the dtype of x."""
         cplx = np.iscomplexobj(x)

@@ -151,6 +151,19 @@ int tsdref_fenetre(const char *nom, int n, int sym, float *w)
   });
 }
 
+// periodogramme_tfd(x, N) (fourier.cc:1451-1481): out[rows][cols] row-major (rows = frames, cols = N2 / 2)
+int tsdref_periodogramme_tfd(const float *x, int n, int N, float *out, int cap, int *rows, int *cols)
+{
+  return guarded([&] {
+    Tabf M = tsd::tf::periodogramme_tfd(Veccf::map((const cfloat *) x, n).clone(), N);
+    *rows = M.rows();
+    *cols = M.cols();
+    if((long long) M.rows() * M.cols() > cap) échec("tsdref_periodogramme_tfd: capacity");
+    for(int i = 0; i < M.rows(); i++)
+      for(int j = 0; j < M.cols(); j++) out[(size_t) i * M.cols() + j] = M(i, j);
+  });
+}
+
 // rééchan_freq<T>(x, lom) (fourier.cc:1391-1419); kind 0 = float, 1 = cfloat.  y needs round(n * lom) elements.
 int tsdref_reechan_freq(int kind, const void *x, int n, float lom, void *y, int cap, int *n_out)
 {

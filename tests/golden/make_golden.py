@@ -87,6 +87,15 @@ def main():
     out["ola_small_lens"] = np.array(lens, np.int32)
     out["ola_small_y"] = np.concatenate(ys)
 
+    # periodogramme_tfd (fourier.cc:1451-1481): N = 64 (N2 = 64) and N = 100 (N2 = 128, zero-padded frames)
+    rng = np.random.default_rng(80)
+    xp = cn(rng, 1000)
+    out["pg_x"] = xp
+    out["pg_w64"] = R.fenetre("hn", 64, False)
+    out["pg_w100"] = R.fenetre("hn", 100, False)
+    out["pg_M64"] = R.periodogramme_tfd(xp, 64)
+    out["pg_M100"] = R.periodogramme_tfd(xp, 100)
+
     # rééchan_freq (fourier.cc:1391-1419): real and complex input, up and down
     rng = np.random.default_rng(79)
     xr = rng.standard_normal(1000).astype(np.float32)

@@ -339,6 +339,27 @@ def test_ola_fenetre(tsd, cpu_oracle, Ne, nz, useH):
     assert np.max(np.abs(fenetre("hn", Ne, False) - w)) <= 2e-7
 
 
+def test_periodogramme_tfd_golden(tsd):
+    """periodogramme_tfd (fourier.cc:1451-1481) = log-magnitudes of the frames of the windowed filtre_fft object, vs
+    the reference build's matrices: shape exact, values within 1e-3 dB (power well above the 1e-20 floor)."""
+    import os
+    import torch
+    from libtsd_b200 import fourier as Fo
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_vectors.npz"))
+    x = G["pg_x"]
+    for N, key in ((64, "64"), (100, "100")):
+        Mref = G["pg_M" + key]
+        M = Fo.periodogramme_tfd(x, N, fenetre=G["pg_w" + key])
+        assert M.shape == Mref.shape == (2 * (len(x) // N), tsd.fourier.prochaine_puissance_de_2(N) // 2)
+        assert np.max(np.abs(M - Mref)) <= 1e-3
+        # default window of the mirror, several channels, device-resident input
+        xs = torch.from_numpy(np.stack([x, x[::-1].copy(), 2 * x])).cuda()
+        Md = Fo.periodogramme_tfd(xs, N).cpu().numpy()
+        assert Md.shape == (3,) + Mref.shape
+        assert np.max(np.abs(Md[0] - Mref)) <= 1e-3
+        assert np.max(np.abs(Md[2] - (Mref + 20 * np.log10(2.0)))) <= 1e-3
+
+
 def test_reechan_freq_golden(tsd):
     """rééchan_freq (fourier.cc:1391-1419) through GPU plans of n and round(n * lom) points vs the reference build's
     vectors: lengths exact, samples within the bar; complex input keeps only the real part, like the reference."""
