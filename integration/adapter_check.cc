@@ -89,6 +89,17 @@ int main()
       printf("filtre_fft   fenetre N %d/%d, %d/%d echantillons : ecart %.2e\n", Nwc, Nwg, ywc.rows(), ywg.rows(), e3b);
       bad += (e3b > 1e-5) + (Nwc != Nwg);
     }
+    {
+      // periodogramme_tfd: same matrix (dB) from the reference and from the GPU frames
+      soit xs = bruit(20000, 9);
+      Tabf Mc = tsd::tf::periodogramme_tfd(xs, 512), Mg = tsd::gpu::periodogramme_tfd_gpu(xs, 512);
+      double e = (Mc.rows() == Mg.rows() && Mc.cols() == Mg.cols()) ? 0.0 : 1e9;
+      pour(auto i = 0; i < Mc.rows() && e < 1e9; i++)
+        pour(auto j = 0; j < Mc.cols(); j++)
+          e = std::max(e, (double) std::abs(Mc(i, j) - Mg(i, j)));
+      printf("periodogramme_tfd %d x %d : ecart max %.2e dB\n", Mg.rows(), Mg.cols(), e);
+      bad += e > 1e-3;
+    }
     // filtre_itrp 147/160, sinc 64 x 257
     soit it = itrp_sinc<cfloat>({64, 256, 0.4f, "hn"});
     soit rc = filtre_itrp<cfloat>(147.0f / 160.0f, it);

@@ -3,7 +3,9 @@
 // forwards to the C ABI of include/tsdgpu.h; no arithmetic lives here.
 //
 //   #include "tsd/tsd.hpp" / "tsd/filtrage.hpp" / "tsd/fourier.hpp"   (reference)
-//   #include "tsdgpu.h"                                               (this repo)
+//   #include "tsdgpu.h"
+
+#include <vector>                                               (this repo)
 //   link: -ltsdgpu
 //
 // Drop-in points (reference file:line):
@@ -220,6 +222,23 @@ struct AdaptationRythmeArbitraireGpu: Filtre<cfloat, cfloat, float>
 inline sptr<Filtre<cfloat, cfloat, float>> filtre_reechan_gpu(float ratio)
 {
   retourne std::make_shared<AdaptationRythmeArbitraireGpu>(ratio);
+}
+
+// periodogramme_tfd(x, N) (fourier.hpp:967, fourier.cc:1451-1481): frames x N2/2 matrix of 10 log10(|X|^2 + 1e-20)
+inline Tabf periodogramme_tfd_gpu(const Veccf &x, entier N)
+{
+  Vecf fen = tsd::filtrage::fenêtre("hn", N, non);                 // fourier.cc:796
+  soit N2 = prochaine_puissance_de_2(N);
+  std::vector<float> buf((size_t) 2 * (x.rows() / N) * (N2 / 2) + 1);
+  int nf = 0, nb = 0;
+  verifie(tsdgpu_periodogramme_tfd(x.data(), x.rows(), x.rows(), 1, N, fen.data(), buf.data(), (long long) buf.size(), &nf, &nb,
+                                   TSDGPU_HOST),
+          "periodogramme_tfd (gpu)");
+  Tabf M(nf, nb);
+  pour(auto i = 0; i < nf; i++)
+    pour(auto j = 0; j < nb; j++)
+      M(i, j) = buf[(size_t) i * nb + j];
+  retourne M;
 }
 
 } // namespace tsd::gpu
