@@ -827,6 +827,8 @@ static int ola_create(int dim_blocs_temporel, int nb_zeros_min, const float *H, 
     if(f->ring <= 2 * f->lag) f->ring = 2 * f->lag + 16;
     // TSDGPU_OLA_MODE=persistent selects the single persistent kernel; default = staged kernels
     if(const char *v = getenv("TSDGPU_OLA_MODE")) f->staged = v[0] == 'p' ? 0 : 1;
+    // blocks per stage kernel: one full wave of the 4-CTA/SM stages (16 tiles per block): 37 on 148 SMs, +3.5 % over 32
+    f->chunk = std::max(8, rt().num_sms * 4 / 16);
     if(const char *v = getenv("TSDGPU_OLA_CHUNK")) f->chunk = std::max(1, atoi(v));
     if(const char *v = getenv("TSDGPU_OLA_STREAMS")) f->nslots = std::min((int) Runtime::MAX_AUX, std::max(1, atoi(v)));
     if(aux_init()) e = cudaErrorUnknown;   // twiddle tables (and the auxiliary streams of the staged form)

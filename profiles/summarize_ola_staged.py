@@ -17,7 +17,7 @@ for r in rows:
 agg = collections.OrderedDict()
 with open(os.path.join(ROOT, "profiles", "r01_ola_launches.csv"), "w") as f:
     f.write("# ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --cache-control none\n")
-    f.write("# one step() of filtre_fft (K=4095, Ne=61441, N=65536) on 4 channels x 16 Mi samples: 35 chunks x 3 stage kernels + carry update\n")
+    f.write("# one step() of filtre_fft (K=4095, Ne=61441, N=65536) on 4 channels x 16 Mi samples: 30 chunks x 3 stage kernels + carry update\n")
     f.write("id,kernel,grid,block,duration_ns,dram_read_bytes,dram_write_bytes\n")
     for i, d in L.items():
         t, rd, wr = d.get("gpu__time_duration.sum", 0), d.get("dram__bytes_read.sum", 0), d.get("dram__bytes_write.sum", 0)
@@ -31,7 +31,7 @@ with open(os.path.join(ROOT, "profiles", "r01_ola_launches.csv"), "w") as f:
 rd = sum(a[2] for a in agg.values()); wr = sum(a[3] for a in agg.values())
 json.dump({"kernel": "ola64k_stage<0|1|2> (all launches of one step)", "dram_bytes_per_launch": rd + wr, "dram_read": rd, "dram_write": wr,
            "samples_in_profiled_launch": SAMPLES, "dram_bytes_per_sample": (rd + wr) / SAMPLES,
-           "note": "sum over the 105 stage launches + carry update of one step() at 4 channels x 16 Mi (profiles/run_profiles_ola_staged.sh), "
+           "note": "sum over the 90 stage launches + carry update of one step() at 4 channels x 16 Mi (profiles/run_profiles_ola_staged.sh), "
                    "caches not flushed between launches; the last chunks' output can still sit dirty in L2, so dram_write can undercount"},
           open(os.path.join(ROOT, "profiles", "traffic_ola.json"), "w"))
 print("DRAM bytes/sample", (rd + wr) / SAMPLES, {k: round(100 * a[1] / tot, 1) for k, a in agg.items()})
@@ -47,7 +47,7 @@ rr = list(csv.reader(io.StringIO(out)))
 hdr, units = rr[0], rr[1]
 with open(os.path.join(ROOT, "profiles", "r01_ola_ncu.txt"), "w") as f:
     f.write("# ncu --set full --clock-control none --cache-control none, one launch of each stage kernel of the staged filtre_fft\n")
-    f.write("# (32 blocks x 16 tiles = 512 CTAs per launch, profiled alone: in a real step four such launches overlap); see run_profiles_ola_staged.sh\n")
+    f.write("# (37 blocks x 16 tiles = 592 CTAs per launch, profiled alone: in a real step four such launches overlap); see run_profiles_ola_staged.sh\n")
     for vals in rr[2:]:
         d = dict(zip(hdr, vals)); u = dict(zip(hdr, units))
         f.write(f"== {d.get('Kernel Name', '?')[:90]}\n")
