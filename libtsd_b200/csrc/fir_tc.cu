@@ -49,12 +49,13 @@ constexpr int GROWS = 352;           // generator rows r in [-96, 256)
 constexpr int G_BYTES = GROWS * 128; // per split part (multiple of 1024)
 constexpr int RAW_PITCH = 272;                  // bytes per channel row of the raw staging (256 + 16: conflict-free LDS.128 down a column)
 constexpr int RAW_BYTES = CH * RAW_PITCH;       // one group's staging buffer: 64 channels x 32 cf32 samples
-constexpr int SMEM_BYTES = 2 * G_BYTES + NRAW * RAW_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
+constexpr int SMEM_BYTES = 2 * G_BYTES + NRAW * RAW_BYTES + 1024 /* alignment slack */ + 512 /* barriers */;
 constexpr int ACOL = 3 * NCOL;                  // TMEM columns [ACOL + 64 s, +32) = x_hi, [+32, +64) = x_lo of stage s
 constexpr int NGROUP = 2;              // converter groups (4 warps each, one warp per TMEM lane quadrant)
 constexpr int MMA_WARP = 4 + 4 * NGROUP;
 constexpr int LOAD_WARP = MMA_WARP + 1;
-constexpr int NTHREADS = 32 * (LOAD_WARP + 1);
+constexpr int NLOAD = 2;                         // loader warps: each takes half of the 64 channel rows of a chunk
+constexpr int NTHREADS = 32 * (LOAD_WARP + NLOAD);
 constexpr int TMEM_COLS = 512;
 
 constexpr uint32_t IDESC = IDESC_M128;
@@ -97,7 +98,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc_kernel(FirTcParams p)
   {
     for(int i = 0; i < NSTAGE; i++) { mbar_init(full + i, 4); mbar_init(empty + i, 1); }
     for(int i = 0; i < 3; i++) { mbar_init(tfull + i, 1); mbar_init(tempty + i, 4); }
-    for(int i = 0; i < NRAW; i++) { mbar_init(rfull + i, 32); mbar_init(rempty + i, 4); }
+    for(int i = 0; i < NRAW; i++) { mbar_init(rfull + i, 32 * NLOAD); mbar_init(rempty + i, 4); }
     mbar_fence_init();
   }
   if(warp == MMA_WARP)
@@ -123,8 +124,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc_kernel(FirTcParams p)
   const long long pf_setup = clock64();
 #endif
 
-  if(warp == LOAD_WARP)
+  if(warp >= LOAD_WARP)
   {
+    const int j_lo = (warp - LOAD_WARP) * (32 / NLOAD), j_hi = j_lo + 32 / NLOAD;
     // ===== loader: raw chunk it (inputs [32 c, 32 c + 32), c = 4 ts - 4 + it, of 64 channels) -> staging slot it % NRAW,
     // one 256-byte row per channel, with 16-byte asynchronous copies (LDGSTS): no registers, NRAW chunks in flight,
     // completion counted on the slot's mbarrier (cp.async.mbarrier.arrive.noinc, one arrival per lane).  Lane l copies
@@ -136,7 +138,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc_kernel(FirTcParams p)
       const int slot = it % NRAW;
       const uint32_t dst0 = smem_u32(stages + slot * RAW_BYTES + clb * RAW_PITCH + sp * 16);
       const long long pos = (long long) (4 * ts - 4 + it) * CHUNK + 2 * sp;
-      for(int j = 0; j < 32; j++)
+      for(int j = j_lo; j < j_hi; j++)
       {
         const int chan = c0 + clb + 2 * j;
         const float2 *src = p.x;   // any valid address when nothing is read
@@ -172,7 +174,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc_kernel(FirTcParams p)
       for(int g = 0; g < LGRP; g++) dst[g] = smem_u32(stages + ((it + g) % NRAW) * RAW_BYTES + clb * RAW_PITCH + sp * 16);
       const float2 *src = p.x + (long long) (c0 + clb) * p.x_stride + pos0 + 2 * sp;
 #pragma unroll 4
-      for(int j = 0; j < 32; j++)
+      for(int j = j_lo; j < j_hi; j++)
       {
         const float2 *sj = src + (long long) j * 2 * p.x_stride;
 #pragma unroll
