@@ -3,6 +3,7 @@
 // pieces of the call; the per-object state is carried from chunk to chunk exactly as it is from call
 // to call (every path is block-partition independent), so the result is the one-shot one.
 #pragma once
+#include <cstdlib>
 #include "common.cuh"
 
 #include <algorithm>
@@ -62,7 +63,11 @@ int host_pipeline(long long total, long long chunk, CopyIn copy_in, OutCount out
 // chunk length (in samples) for a batch of nchan channels: ~48 MiB of input per chunk
 inline long long host_chunk_len(int nchan, size_t elem_bytes, long long n, long long align = 1)
 {
-  long long c = (long long) ((48ull << 20) / ((size_t) nchan * elem_bytes));
+  static const unsigned long long mb = [] {
+    const char *v = getenv("TSDGPU_HOST_CHUNK_MB");   // tuning knob: input bytes per pipeline chunk
+    return (unsigned long long) std::max(1, v ? atoi(v) : 48);
+  }();
+  long long c = (long long) ((mb << 20) / ((size_t) nchan * elem_bytes));
   c = std::max<long long>(c, 4096);
   c = std::max<long long>(align, (c / align) * align);
   return std::min(c, std::max<long long>(n, 1));
