@@ -489,20 +489,25 @@ def test_itrp_vs_oracle(tsd, port, cpu_oracle, ratio, K, fcut):
 
 
 @pytest.mark.parametrize("tc", ["0", "1"])
-@pytest.mark.parametrize("ratio,K,nchan,n", [(147 / 160, 64, 70, 20000), (1.3, 15, 3, 5000), (0.6, 31, 64, 70001), (147 / 160, 64, 130, 4097)])
+@pytest.mark.parametrize("ratio,K,nchan,n", [(147 / 160, 64, 70, 20000), (1.3, 15, 3, 5000), (0.6, 31, 64, 70001), (147 / 160, 64, 130, 4097),
+                                             (1.9, 64, 128, 9000), (0.5001, 64, 256, 30000), (1.0, 16, 128, 5000),
+                                             (147 / 160, 128, 128, 12000), (147 / 160, 64, 192, 6000)])
 def test_itrp_tensor_core_and_fma_paths(tsd, port, cpu_oracle, monkeypatch, tc, ratio, K, nchan, n):
-    """The tcgen05 banded filter-bank GEMM (resamp_tc.cu) and the FP32 FMA kernel (resamp.cu) on the same ragged input:
-    per-call output counts and final phase bit-exact, samples within tolerance, state carried over ragged calls."""
+    """The tcgen05 banded filter-bank GEMM (resamp_tc.cu; CTA pairs when the 64-channel groups pair up, single CTAs
+    otherwise; LUT in shared memory or, for 128 taps x 257 phases, read from global memory) and the FP32 FMA kernel
+    (resamp.cu) on the same ragged input: per-call output counts and final phase bit-exact, samples within tolerance,
+    state carried over ragged calls.  Checked channels include both CTAs of a pair and the last (ragged) group."""
     from libtsd_b200 import filtrage as F
     monkeypatch.setenv("TSDGPU_RESAMP_TC", tc)
     rng = np.random.default_rng(int(ratio * 100) + K + nchan)
     lut = cpu_oracle.itrp_sinc_lut(K, 256, 0.4)
     g = F.filtre_itrp(ratio, F.InterpolateurLUT(lut), nchan)
-    refs = [port.itrp(ratio, lut, 256) for _ in range(min(nchan, 3))]
+    chans = sorted({0, 1, min(63, nchan - 1), min(64, nchan - 1), nchan // 2, nchan - 1})
+    refs = {c: port.itrp(ratio, lut, 256) for c in chans}
     for blk in (n, 131, 1, 4096):
         x = cn(rng, nchan, blk)
         y = g.step(x)
-        for c, r in enumerate(refs):
+        for c, r in refs.items():
             yr = r.step(x[c])
             assert y[c].shape == yr.shape
             if yr.size:
