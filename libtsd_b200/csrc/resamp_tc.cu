@@ -39,10 +39,12 @@ constexpr int SMEM_BYTES = NT * TB_BYTES + NRAW * RAW_BYTES + MAXSPAN * TILE * 8
 constexpr int ACOL = 3 * NCOL;
 constexpr int CONV_WARP0 = 4, GEN_WARP0 = 8, NGEN = 16, MMA_WARP = GEN_WARP0 + NGEN, LOAD_WARP = MMA_WARP + 1;
 constexpr int NTHREADS = 32 * (LOAD_WARP + 1);
+constexpr int NPRO = NTHREADS - 32;             // threads of the prologue: the loader (last warp) starts copying at once
 constexpr int GROWS = (TILE + NGEN - 1) / NGEN;   // rows per generator warp and block: j = gw + NGEN * r
 constexpr int TMEM_COLS = 512;
 
 #ifdef TSD_TC_PROF
+__device__ long long g_rtclife[8192][4];   // per CTA: start ns, end ns, SM id, cluster rank
 __device__ long long g_rtcprof[1024][32][4];
 #define PROF_ARRAY g_rtcprof
 #endif
@@ -130,6 +132,11 @@ struct Walk
 template<bool LUTS, bool PAIR> __global__ void __launch_bounds__(NTHREADS, 1) resamp_tc_kernel(ResampTcParams p)
 {
   const uint32_t rank = PAIR ? cluster_rank() : 0u;
+#ifdef TSD_TC_PROF
+  const long long t_entry = clock64();
+  unsigned long long gt_entry;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_entry));
+#endif
   constexpr int NTR = PAIR ? 2 * NT : NT;                       // ring slots
   constexpr int TBP = PAIR ? TB_PART / 2 : TB_PART, TBB = 2 * TBP;   // bytes of the hi (= lo) part of a slot, of a slot
   extern __shared__ unsigned char raw[];
@@ -164,87 +171,23 @@ template<bool LUTS, bool PAIR> __global__ void __launch_bounds__(NTHREADS, 1) re
     for(int i = 0; i < NTR; i++) { mbar_init(bfull + i, NGEN * NC); mbar_init(bempty + i, 1); }
     mbar_fence_init();
   }
-  if(warp == MMA_WARP)
-  {
-    if(PAIR)
-    {
-      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
-      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-    }
-    else
-    {
-      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
-      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-  }
-  if(warp == 0 && lane < T)
-  {
-    // chunk range of tile ts + lane: first window sample ... newest input of its last output
-    const int jf = (ts + lane) * TILE, jl = (int) min((long long) (jf + TILE), p.n_out) - 1;
-    cA[lane] = floor_div32(p.sched[jf].x - (K - 1));
-    cB[lane] = floor_div32(p.sched[jl].x);
-  }
-  for(int i = tid; i < T * TILE; i += NTHREADS)
-  {
-    const long long j = (long long) ts * TILE + i;
-    // per output: {K-1 - in_j, p_j * K} (second word < 0 marks rows past the end): all the generators need per row
-    int2 e = make_int2(0, -1);
-    if(j < p.n_out) { const int2 q = __ldg(p.sched + j); e = make_int2(K - 1 - q.x, q.y * K); }
-    sched_s[i] = e;
-  }
-  if(LUTS)
-    for(int i = tid; i < p.lut_elems; i += NTHREADS) lut_s[i] = __ldg(p.lut + i);
-  __syncthreads();
-  {
-    // tiles fed by every chunk of this CTA (at most two, consecutive): the first tile whose last chunk is >= c, and
-    // its successor, when they have started
-    const int cb0 = cA[0], nch = cB[T - 1] - cb0 + 1;
-    for(int it = tid; it < nch; it += NTHREADS)
-    {
-      const int c = cb0 + it;
-      int tlo = 0;
-      while(tlo < T && cB[tlo] < c) tlo++;
-      const int t0 = (tlo < T && cA[tlo] <= c) ? tlo : 0xff;
-      const int t1 = (t0 != 0xff && tlo + 1 < T && cA[tlo + 1] <= c) ? tlo + 1 : 0xff;
-      ftab[it] = (unsigned short) (t0 | (t1 << 8));
-    }
-  }
-  if(warp < T)
-  {
-    // bands of the blocks of tile `warp`, one lane per chunk.  A block (c, tl) keeps the rows whose K taps overlap the
-    // chunk: e.x = K-1 - in_j is non-increasing in j and the rows past the end (e.y < 0) come last, so "window entirely
-    // after the chunk" and "valid and not entirely before it" are prefix properties -> two binary searches.
-    // Position in the walk (chunks ascending, then tiles): blocks of earlier chunks + the other tile of this chunk.
-    const int tl = warp;
-    const int2 *srow = sched_s + tl * TILE;
-    for(int c = cA[tl] + lane; c <= cB[tl]; c += 32)
-    {
-      int lo = 0, hi = TILE;
-      while(lo < hi) { const int m = (lo + hi) >> 1; const int2 e = srow[m]; if(e.y >= 0 && c * CHUNK + e.x > K - 1) lo = m + 1; else hi = m; }
-      const int jlo = lo;
-      hi = TILE;
-      while(lo < hi) { const int m = (lo + hi) >> 1; const int2 e = srow[m]; if(e.y >= 0 && c * CHUNK + 31 + e.x >= 0) lo = m + 1; else hi = m; }
-      const int jend = lo;
-      // band [j0, j0 + nn): multiple of 16 columns (32 for a pair: each CTA supplies nn / 2 rows of the block)
-      constexpr int GRAN = PAIR ? 32 : 16;
-      int j0 = p.band ? (min(jlo, TILE - GRAN) & ~15) : 0;
-      const int nn = p.band ? max(GRAN, (jend - j0 + GRAN - 1) & ~(GRAN - 1)) : TILE;
-      if(j0 + nn > TILE) j0 = TILE - nn;
-      int seq = 0;
-      for(int t = 0; t < T; t++) seq += min(max(c - cA[t], 0), cB[t] - cA[t] + 1);
-      if(tl > 0 && cA[tl - 1] <= c && c <= cB[tl - 1]) seq++;
-      bandtab[seq] = make_int2(j0, nn);
-    }
-  }
-  fence_before();
-  if(PAIR) cluster_sync_all();   // the peer's barriers are initialised before anyone arrives on them
-  else __syncthreads();
-  fence_after();
-  const uint32_t tmem = *tmem_slot;
-  const int c_begin = cA[0], nchunks = cB[T - 1] - c_begin + 1;
-
+  __syncthreads();   // barriers initialised (everybody is still at the top of the kernel)
+  uint32_t tmem = 0;
+  int c_begin = 0, nchunks = 0;
+#ifdef TSD_TC_PROF
+  long long t_pro = 0;
+#endif
   if(warp == LOAD_WARP)
   {
+    // The loader starts at once: its first chunks cross HBM while the other warps fill the tables, so every CTA begins
+    // with a full staging ring.  It takes part in neither prologue barrier (named barrier 1 is for the other warps);
+    // in a pair it arrives on the cluster barrier now and waits for it after its last copy.
+    int v = 0;
+    if(lane == 0) v = floor_div32(__ldg(&p.sched[(long long) ts * TILE].x) - (K - 1));
+    if(lane == 1) v = floor_div32(__ldg(&p.sched[min((long long) te * TILE, p.n_out) - 1].x));
+    c_begin = __shfl_sync(0xffffffffu, v, 0);
+    nchunks = __shfl_sync(0xffffffffu, v, 1) - c_begin + 1;
+    if(PAIR) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     // ===== loader: raw chunk (inputs [32 c, 32 c + 32) of 64 channels) -> staging slot, one 256-byte row per channel
     const int sp = lane & 15, clb = lane >> 4;
     for(int it = 0; it < nchunks;)
@@ -293,8 +236,98 @@ template<bool LUTS, bool PAIR> __global__ void __launch_bounds__(NTHREADS, 1) re
       asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(rfull + it % NRAW)) : "memory");
       it += 1;
     }
+    if(PAIR) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    goto done;
   }
-  else if(warp >= CONV_WARP0 && warp < CONV_WARP0 + 4)
+  if(warp == MMA_WARP)
+  {
+    if(PAIR)
+    {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    else
+    {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+  }
+  if(warp == 0 && lane < T)
+  {
+    // chunk range of tile ts + lane: first window sample ... newest input of its last output
+    const int jf = (ts + lane) * TILE, jl = (int) min((long long) (jf + TILE), p.n_out) - 1;
+    cA[lane] = floor_div32(p.sched[jf].x - (K - 1));
+    cB[lane] = floor_div32(p.sched[jl].x);
+  }
+  for(int i = tid; i < T * TILE; i += NPRO)
+  {
+    const long long j = (long long) ts * TILE + i;
+    // per output: {K-1 - in_j, p_j * K} (second word < 0 marks rows past the end): all the generators need per row
+    int2 e = make_int2(0, -1);
+    if(j < p.n_out) { const int2 q = __ldg(p.sched + j); e = make_int2(K - 1 - q.x, q.y * K); }
+    sched_s[i] = e;
+  }
+  if(LUTS)
+  {
+    // the LUT comes in with 16-byte loads when its size allows (cudaMalloc'ed: 256-byte aligned)
+    const int n4 = (p.lut_elems % 4 == 0) ? p.lut_elems / 4 : 0;
+    for(int i = tid; i < n4; i += NPRO) reinterpret_cast<float4 *>(lut_s)[i] = __ldg(reinterpret_cast<const float4 *>(p.lut) + i);
+    for(int i = 4 * n4 + tid; i < p.lut_elems; i += NPRO) lut_s[i] = __ldg(p.lut + i);
+  }
+  named_bar(1, NPRO);
+  {
+    // tiles fed by every chunk of this CTA (at most two, consecutive): the first tile whose last chunk is >= c, and
+    // its successor, when they have started
+    const int cb0 = cA[0], nch = cB[T - 1] - cb0 + 1;
+    for(int it = tid; it < nch; it += NPRO)
+    {
+      const int c = cb0 + it;
+      int tlo = 0;
+      while(tlo < T && cB[tlo] < c) tlo++;
+      const int t0 = (tlo < T && cA[tlo] <= c) ? tlo : 0xff;
+      const int t1 = (t0 != 0xff && tlo + 1 < T && cA[tlo + 1] <= c) ? tlo + 1 : 0xff;
+      ftab[it] = (unsigned short) (t0 | (t1 << 8));
+    }
+  }
+  if(warp < T)
+  {
+    // bands of the blocks of tile `warp`, one lane per chunk.  A block (c, tl) keeps the rows whose K taps overlap the
+    // chunk: e.x = K-1 - in_j is non-increasing in j and the rows past the end (e.y < 0) come last, so "window entirely
+    // after the chunk" and "valid and not entirely before it" are prefix properties -> two binary searches.
+    // Position in the walk (chunks ascending, then tiles): blocks of earlier chunks + the other tile of this chunk.
+    const int tl = warp;
+    const int2 *srow = sched_s + tl * TILE;
+    for(int c = cA[tl] + lane; c <= cB[tl]; c += 32)
+    {
+      int lo = 0, hi = TILE;
+      while(lo < hi) { const int m = (lo + hi) >> 1; const int2 e = srow[m]; if(e.y >= 0 && c * CHUNK + e.x > K - 1) lo = m + 1; else hi = m; }
+      const int jlo = lo;
+      hi = TILE;
+      while(lo < hi) { const int m = (lo + hi) >> 1; const int2 e = srow[m]; if(e.y >= 0 && c * CHUNK + 31 + e.x >= 0) lo = m + 1; else hi = m; }
+      const int jend = lo;
+      // band [j0, j0 + nn): multiple of 16 columns (32 for a pair: each CTA supplies nn / 2 rows of the block)
+      constexpr int GRAN = PAIR ? 32 : 16;
+      int j0 = p.band ? (min(jlo, TILE - GRAN) & ~15) : 0;
+      const int nn = p.band ? max(GRAN, (jend - j0 + GRAN - 1) & ~(GRAN - 1)) : TILE;
+      if(j0 + nn > TILE) j0 = TILE - nn;
+      int seq = 0;
+      for(int t = 0; t < T; t++) seq += min(max(c - cA[t], 0), cB[t] - cA[t] + 1);
+      if(tl > 0 && cA[tl - 1] <= c && c <= cB[tl - 1]) seq++;
+      bandtab[seq] = make_int2(j0, nn);
+    }
+  }
+  fence_before();
+  if(PAIR) cluster_sync_all();   // the peer's barriers are initialised before anyone arrives on them
+  else named_bar(1, NPRO);
+  fence_after();
+  tmem = *tmem_slot;
+  c_begin = cA[0];
+  nchunks = cB[T - 1] - c_begin + 1;
+#ifdef TSD_TC_PROF
+  t_pro = clock64();
+#endif
+
+  if(warp >= CONV_WARP0 && warp < CONV_WARP0 + 4)
   {
     // ===== converters (one warp per TMEM lane quadrant): raw row (channel, re|im) -> tf32 hi / lo -> tensor memory
     const int pw = warp - CONV_WARP0;
@@ -553,6 +586,9 @@ template<bool LUTS, bool PAIR> __global__ void __launch_bounds__(NTHREADS, 1) re
     }
   }
 done:
+#ifdef TSD_TC_PROF
+  const long long t_fin = clock64();
+#endif
   fence_before();
   if(PAIR) cluster_sync_all();   // nobody leaves (or frees tensor memory) while the pair's MMAs and remote arrivals are in flight
   else __syncthreads();
@@ -562,6 +598,28 @@ done:
     if(PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS) : "memory");
     else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS) : "memory");
   }
+#ifdef TSD_TC_PROF
+  if(tid == 0 && blockIdx.y == 0 && blockIdx.x < 8192)
+  {
+    unsigned long long gt_end;
+    unsigned smid;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_end));
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    g_rtclife[blockIdx.x][0] = (long long) gt_entry;
+    g_rtclife[blockIdx.x][1] = (long long) gt_end;
+    g_rtclife[blockIdx.x][2] = smid;
+    g_rtclife[blockIdx.x][3] = rank;
+  }
+  if(tid == 0 && blockIdx.y == 0 && blockIdx.x < 1024)
+  {
+    g_rtcprof[blockIdx.x][31][0] = t_pro - t_entry;     // prologue
+    g_rtcprof[blockIdx.x][31][1] = t_fin - t_pro;       // epilogue warp 0: its whole role
+    g_rtcprof[blockIdx.x][31][2] = clock64() - t_fin;   // final sync
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    g_rtcprof[blockIdx.x][31][3] = (long long) gt;      // end time (ns)
+  }
+#endif
 }
 
 } // namespace rtc
@@ -577,6 +635,9 @@ extern "C" int tsdgpu_debug_rtcprof_dump(const char *path)
   FILE *fp = fopen(path, "wb");
   if(!fp) return 1;
   fwrite(h, 1, sizeof(h), fp);
+  static long long l[8192][4];
+  if(cudaMemcpyFromSymbol(l, rtc::g_rtclife, sizeof(l)) != cudaSuccess) return 1;
+  fwrite(l, 1, sizeof(l), fp);
   fclose(fp);
   return 0;
 }
