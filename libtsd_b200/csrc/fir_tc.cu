@@ -101,25 +101,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc_kernel(FirTcParams p)
     for(int i = 0; i < NRAW; i++) { mbar_init(rfull + i, 32 * NLOAD); mbar_init(rempty + i, 4); }
     mbar_fence_init();
   }
-  if(warp == MMA_WARP)
+  __syncthreads();   // barriers initialised
+  // The loader warps (the last NLOAD) go straight to their role: the first chunks cross HBM while the others build the
+  // generator matrix, so the CTA starts with a full staging ring.  Named barrier 1 closes the set-up of the others.
+  constexpr int NPRO = NTHREADS - 32 * NLOAD;
+  if(warp < LOAD_WARP)
   {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if(warp == MMA_WARP)
+    {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for(int idx = tid; idx < GROWS * 32; idx += NPRO)
+    {
+      const int row = idx >> 5, kk = idx & 31, tap = (row - 96) - kk;
+      const float v = (tap >= 0 && tap < p.K) ? __ldg(p.taps_rev + (p.K - 1 - tap)) : 0.f;
+      const float hi = to_tf32(v), lo = to_tf32(v - hi);
+      const uint32_t off = swz((uint32_t) (row * 128 + kk * 4));
+      *reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(Ghi) + off) = hi;
+      *reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(Glo) + off) = lo;
+    }
+    fence_proxy_async();   // generic-proxy writes of G -> visible to the tensor core (async proxy)
+    fence_before();
+    named_bar(1, NPRO);
+    fence_after();
   }
-  for(int idx = tid; idx < GROWS * 32; idx += NTHREADS)
-  {
-    const int row = idx >> 5, kk = idx & 31, tap = (row - 96) - kk;
-    const float v = (tap >= 0 && tap < p.K) ? __ldg(p.taps_rev + (p.K - 1 - tap)) : 0.f;
-    const float hi = to_tf32(v), lo = to_tf32(v - hi);
-    const uint32_t off = swz((uint32_t) (row * 128 + kk * 4));
-    *reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(Ghi) + off) = hi;
-    *reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(Glo) + off) = lo;
-  }
-  fence_proxy_async();   // generic-proxy writes of G -> visible to the tensor core (async proxy)
-  fence_before();
-  __syncthreads();
-  fence_after();
-  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem = warp < LOAD_WARP ? *tmem_slot : 0u;
 #ifdef TSD_TC_PROF
   const long long pf_setup = clock64();
 #endif
