@@ -515,6 +515,34 @@ def test_itrp_tensor_core_and_fma_paths(tsd, port, cpu_oracle, monkeypatch, tc, 
         assert np.float32(g.phase) == np.float32(refs[0].phase)
 
 
+def test_tensor_kernels_do_not_depend_on_stale_shared_memory(tsd, cpu_oracle):
+    """Bit-identical results when another kernel has scribbled over the SMs' shared memory in between: the tolerance
+    tests above can pass on left-overs of the previous launch (a prologue loop that skips a few table entries did,
+    once); equality across interleaved launches of different kernels cannot."""
+    import torch
+    from libtsd_b200 import filtrage as F
+    g = torch.Generator(device="cuda")
+    g.manual_seed(7)
+    lut64, lut15 = cpu_oracle.itrp_sinc_lut(64, 256, 0.4), cpu_oracle.itrp_sinc_lut(15, 256, 0.3)
+    h = cpu_oracle.design_rif_fen(127, "lp", 0.1)
+    nchan, n = 256, 1 << 18
+    x = torch.empty((nchan, n), dtype=torch.complex64, device="cuda")
+    torch.view_as_real(x).normal_(generator=g)
+
+    def rs(lut, ratio):
+        return F.filtre_itrp(ratio, F.InterpolateurLUT(lut), nchan).step(x).clone()
+
+    def fir():
+        return F.filtre_rif(h, np.complex64, nchan).step(x).clone()
+
+    a0, f0 = rs(lut64, 147 / 160), fir()
+    b0 = rs(lut15, 0.7)          # other LUT, other schedule: different tables in shared memory
+    f1, a1 = fir(), rs(lut64, 147 / 160)
+    b1, a2 = rs(lut15, 0.7), rs(lut64, 147 / 160)
+    tsd.synchronize()
+    assert torch.equal(a0, a1) and torch.equal(a0, a2) and torch.equal(b0, b1) and torch.equal(f0, f1)
+
+
 def test_itrp_vs_reference_object(tsd, ref):
     """Same comparison against the reference's own filtre_itrp + itrp_sinc objects (config 5 parameters)."""
     from libtsd_b200 import filtrage as F
