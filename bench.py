@@ -207,16 +207,35 @@ def cpu_run(workload, steps, warmup, threads=None):
 
 
 # --------------------------------------------------------------------------------------- GPU arm
+class _Setup:
+    """Set-up tables (taps, H, LUT) of the GPU arms, from the package's own host-side mirror of the reference's design
+    functions — oracle/ is touched by the cpu_baseline / --impl reference legs only."""
+
+    @staticmethod
+    def design_rif_fen(n, type_, fc):
+        from libtsd_b200 import filtrage as F
+        return F.design_rif_fen(n, type_, fc)
+
+    @staticmethod
+    def ola_make_H(h, N):
+        from libtsd_b200 import fourier as Fo
+        return Fo.ola_make_H(h, N)
+
+    @staticmethod
+    def itrp_sinc_lut(K, nphases, fcut):
+        from libtsd_b200 import filtrage as F
+        return F.itrp_sinc(F.InterpolateurSincConfig(K, nphases, fcut, "hn")).lut
+
+
 class GpuWorkload:
     """Builds the device-resident synthetic batch and the filter objects of one workload."""
 
     def __init__(self, name, scale=1.0):
         import torch
-        import oracle
         from libtsd_b200 import filtrage as F, fourier as Fo
         self.name = name
         self.torch = torch
-        O = oracle.ref() if oracle.have_ref() else oracle.port()   # set-up data (taps, H, LUT) only
+        O = _Setup
         g = torch.Generator(device="cuda")
         g.manual_seed({"ola": 0x7D5D0004, "fft": 0x7D5D0002, "fir": 0x7D5D0003, "resample": 0x7D5D0005, "reechan": 0x7D5D0005}[name])
 
@@ -285,9 +304,8 @@ class GpuWorkload:
 def e2e_measure(name, steps, warmup, barrier=None):
     """Same metric through the C ABI with pinned HOST buffers (H2D + D2H inside the timed region)."""
     import torch
-    import oracle
     from libtsd_b200 import filtrage as F, fourier as Fo
-    O = oracle.ref() if oracle.have_ref() else oracle.port()
+    O = _Setup
     rng = np.random.default_rng(1)
 
     def pinned(nchan, n):
