@@ -52,7 +52,7 @@ int tsdgpu_synchronize(void);
 const char *tsdgpu_last_error(void);
 /* Number of kernels launched by this library since the last call with reset != 0. */
 long long tsdgpu_launch_count(int reset);
-/* Device-side timing of the dominant kernel of each path (fir_direct, fft64k, ola64k, resamp_lut):
+/* Device-side timing of the dominant kernel of each path (fir_tc / fir_direct, fft64k, ola64k stages, resamp_tc / resamp_banded):
  * when enabled, every such launch is bracketed by a CUDA event pair on the launch stream;
  * tsdgpu_timing_read synchronises, returns the summed duration and the number of launches, and
  * clears the list.  Used by bench.py for the roofline figure. */

@@ -9,6 +9,9 @@
 // The device then evaluates out[c][j] = sum_{i<K} lut[lut_idx[j]][i] * x[c][in_idx[j]-(K-1)+i]
 // with i ascending, as InterpolateurRIF::step does.  State across calls: phase (host) and the
 // last K-1 inputs of every channel (device).
+// Kernels: resamp_tc.cu (tcgen05 3xTF32 banded filter-bank GEMM, default whenever resamp_tc_eligible() accepts the
+// chunk's schedule and alignment), resamp_banded_kernel (FP32 FMA, 8 outputs x 64 channels per warp) and
+// resamp_lut_kernel (one thread per output, any window) below.
 #include "common.cuh"
 #include "host_pipe.cuh"
 #include "resamp_tc.h"
