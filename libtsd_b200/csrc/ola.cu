@@ -522,7 +522,7 @@ struct tsdgpu_ola_s
   int ring = 80, lag = 24, ctas = 0;
   // staged form (default): blocks per stage kernel, number of auxiliary streams
   // 1 = staged kernels over auxiliary streams (default), 0 = single persistent kernel
-  int staged = 1, chunk = 32, nslots = 4;
+  int staged = 1, chunk = 32, nslots = 8;   // 8 streams: 112 vs 108 Gsamples/s with 4 (profiles/sweep_ola_streams.sh)
   // windowed mode (always unfused): window [Ne], `last` of the reference [nchan][Ne]
   bool fen = false;
   float *d_fen = nullptr;
