@@ -7,12 +7,14 @@
 //   D[n][j] += X[n][kk] * T[j][kk],   T[j][kk] = lut[p_j][32 c + kk - (in_j - (K-1))]  (0 outside the K taps)
 // with D in tensor memory (lane n = one of the 128 real rows {re, im} x 64 channels, column j = output), X the
 // de-interleaved input chunk (A operand, in tensor memory) and T the block of the banded coefficient matrix that
-// eight generator warps build from the LUT and the schedule (B operand, shared memory, K-major, 128-byte swizzle).
+// sixteen generator warps build from the LUT and the schedule (B operand, shared memory, K-major, 128-byte swizzle).
 // Same machine as fir_tc.cu (loader warp with LDGSTS staging ring, converter warps -> tcgen05.st, one elected MMA
 // issuer, 16x256b epilogue, 3 accumulator regions); what differs is the B operand (generated per block instead of a
 // view of one Toeplitz generator) and the irregular chunk <-> tile incidence: tile t is fed by the chunks
 // floor((in_first - (K-1)) / 32) ... floor(in_last / 32), a chunk feeds one or two consecutive tiles (checked on the
-// host: tile t+2 must start after tile t ends), every role walks the same (chunk, tile) block sequence.
+// host: tile t+2 must start after tile t ends), every role walks the same (chunk, tile) block sequence, tabulated with
+// the band of every block in the prologue.  Two CTAs of a cluster (adjacent 64-channel groups) run as a CTA pair
+// (cta_group::2, M = 256): each builds half of the rows of every coefficient block.
 // fp32 accuracy: x = x_hi + x_lo, T = T_hi + T_lo (tf32 parts), three MMAs per K-step, fp32 accumulation.
 #include "tc_common.cuh"
 #include "resamp_tc.h"
@@ -116,19 +118,6 @@ template<bool PAIR> __device__ __forceinline__ void wait_in_mma(uint64_t *bar, u
   if(PAIR) mbar_wait_cluster(bar, parity);
   else mbar_wait(bar, parity);
 }   // arithmetic shift: floor for negatives too
-
-// the (chunk, tile) block sequence: for chunk c, the tiles it feeds (at most two, consecutive)
-struct Walk
-{
-  const int *cA, *cB;
-  int T, tlo;
-  __device__ __forceinline__ void feeds(int c, int &t0, int &t1)
-  {
-    while(tlo < T && cB[tlo] < c) tlo++;
-    t0 = (tlo < T && cA[tlo] <= c) ? tlo : -1;
-    t1 = (tlo + 1 < T && cA[tlo + 1] <= c) ? tlo + 1 : -1;
-  }
-};
 
 template<bool LUTS, bool PAIR> __global__ void __launch_bounds__(NTHREADS, 1) resamp_tc_kernel(ResampTcParams p)
 {
