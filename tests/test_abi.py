@@ -52,6 +52,30 @@ def test_host_only_entries(port):
             assert np.float32(phase_g.value) == np.float32(phase_o)
 
 
+def test_resampler_schedule_integer_runs(port):
+    """Ratios in [8/9, 1) take the integer-exact run form of the phase recurrence inside the library
+    (resamp.cu:resamp_schedule_runs): it must reproduce the reference's float32 loop bit for bit, for any chunking of
+    the stream (carried phase) and any number of phases."""
+    from libtsd_b200 import _lib
+    L = _lib.lib()
+    rng = np.random.default_rng(0)
+    ratios = [147 / 160, 0.999999, 0.97, 44100 / 48000, 8 / 9, 0.8889, 0.9000001, 0.99999994] + list(rng.uniform(0.8889, 0.99999, 12))
+    for nph in (256, 100, 7):
+        for ratio in ratios:
+            phase_g, phase_o = ctypes.c_float(0), 0.0
+            for n in [1, 7, 1000, 65536, 777, 300001, 12, 13, 11, 5] + [int(v) for v in rng.integers(1, 5000, 6)]:
+                cap = int(np.ceil(np.float32(ratio) * n) + 32)
+                a, b = np.zeros(cap, np.int32), np.zeros(cap, np.int32)
+                no = ctypes.c_longlong()
+                rc = L.tsdgpu_resamp_schedule(ctypes.byref(phase_g), ctypes.c_float(ratio), nph, n,
+                                              a.ctypes.data_as(ctypes.c_void_p), b.ctypes.data_as(ctypes.c_void_p), cap, ctypes.byref(no))
+                assert rc == 0
+                ia, ib, phase_o = port.itrp_schedule(phase_o, ratio, nph, n)
+                assert no.value == len(ia)
+                assert np.array_equal(a[: no.value], ia) and np.array_equal(b[: no.value], ib)
+                assert np.float32(phase_g.value) == np.float32(phase_o)
+
+
 def test_no_cpu_fallback():
     import torch
     if torch.cuda.is_available():
