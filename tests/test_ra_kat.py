@@ -1,0 +1,51 @@
+"""Known-answer test of the reference for its rate adapters (tests/test-ra.cc): sine purity after filtre_itrp (127-tap
+sinc), filtre_reechan, the half-band, xR and /R polyphase stages.  CPU: the reference build itself through the restated
+checker (tests/ra_kat.py) - pins the checker.  GPU: the CUDA path through the same checker."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import ra_kat  # noqa: E402
+
+RATIOS = (1.0, 1.5, 0.5, 2.0, 1.2, float(np.float32(np.pi)))   # test-ra.cc:215
+
+
+@pytest.fixture(scope="module")
+def ref():
+    import oracle
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built (reference tree absent)")
+    return oracle.ref()
+
+
+def _cstep(f, **kw):
+    return lambda x: np.real(f.step(x.astype(np.complex64), **kw))
+
+
+def test_reference_passes_its_own_kat(ref):
+    for ratio in RATIOS:
+        ra_kat.check_adapter(_cstep(ref.reechan(ratio), cap=9000), ratio)
+        ra_kat.check_adapter(_cstep(ref.itrp(ratio, 127, 256, 0.5), cap=9000), ratio)
+    h = ref.design_rif_fen(15, "lp", 0.25)
+    ra_kat.check_adapter(_cstep(ref.polyphase(0, h), cap=9000), 0.5)          # ref driver kinds: 0 half-band, 1 xR, 2 /R
+    ra_kat.check_adapter(_cstep(ref.polyphase(1, h, 2), cap=9000), 2.0)
+    for R in (2, 3, 4, 5, 8):
+        ra_kat.check_adapter(_cstep(ref.polyphase(2, ref.design_rif_fen(15, "lp", 0.5 / R), R), cap=9000), 1.0 / R)
+
+
+@pytest.mark.gpu
+def test_gpu_rate_adapters_sine_purity():
+    import libtsd_b200
+    from libtsd_b200 import filtrage as F
+    libtsd_b200.init(0)
+    for ratio in RATIOS:
+        ra_kat.check_adapter(_cstep(F.filtre_reechan(ratio)), ratio)
+        ra_kat.check_adapter(_cstep(F.filtre_itrp(ratio, F.itrp_sinc(F.InterpolateurSincConfig(127, 256, 0.5, "hn")))), ratio)
+    h = F.design_rif_fen(15, "lp", 0.25)
+    ra_kat.check_adapter(_cstep(F.filtre_rif_demi_bande(h)), 0.5)
+    ra_kat.check_adapter(_cstep(F.filtre_rif_ups(h, 2)), 2.0)
+    for R in (2, 3, 4, 5, 8):
+        ra_kat.check_adapter(_cstep(F.filtre_rif_decim(F.design_rif_fen(15, "lp", 0.5 / R), R)), 1.0 / R)
