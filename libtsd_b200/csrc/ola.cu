@@ -23,6 +23,7 @@
 #include "fft_tiles.cuh"
 #include "fft_plan.h"
 #include "host_pipe.cuh"
+#include "ols16k.h"
 #include "tsdgpu.h"
 
 #include <algorithm>
@@ -511,6 +512,8 @@ struct tsdgpu_ola_s
   int residual = 0;            // TamponNv2 windex (tsd.cc:310)
   long long blocks_done = 0;
   bool fused = false;
+  // FIR-derived gains (fir_len > 0): single-SM overlap-save kernel with its own transform size (ols16k.cu)
+  Ols16k *ols = nullptr;
   float2 *d_H = nullptr;       // fused: H/N ; unfused: raw H (nullptr = identity)
   float2 *d_carry[2] = {nullptr, nullptr};
   int cur = 0, carry_len = 0;
@@ -733,7 +736,10 @@ static int ola_run_device(tsdgpu_ola_s *f, const float2 *x, long long xs, int n,
   if(B > 0)
   {
     if(ys < *n_out) return fail("tsdgpu_ola_step: output stride smaller than the emitted count");
-    int rc = f->fen ? ola_run_fen(f, x, xs, y, ys, B) : f->fused ? ola_run_fused(f, x, xs, n, y, ys, B) : ola_run_unfused(f, x, xs, y, ys, B);
+    int rc = f->fen   ? ola_run_fen(f, x, xs, y, ys, B)
+             : f->ols ? ols16k_run(f->ols, x, xs, n, f->d_carry[f->cur], f->carry_len, y, ys, *n_out, f->Ne - f->K, f->residual, f->nchan)
+             : f->fused ? ola_run_fused(f, x, xs, n, y, ys, B)
+                        : ola_run_unfused(f, x, xs, y, ys, B);
     if(rc) return rc;
   }
   dim3 grid((f->carry_len + 255) / 256, f->nchan);
@@ -795,6 +801,25 @@ static int ola_create(int dim_blocs_temporel, int nb_zeros_min, const float *H, 
   f->fused = (N == 65536) && !f->fen;
   f->K = f->fused ? fir_len : 0;   // the unfused path always runs the overlap-add form
   f->carry_len = N + Ne;
+  // gains that are the transform of K taps: the samples do not depend on the block structure, the single-SM
+  // overlap-save kernel produces them with its own 16384-point transforms (TSDGPU_OLA_OLS=0 keeps the N-point paths)
+  {
+    const char *v = getenv("TSDGPU_OLA_OLS");
+    if(fir_len > 0 && !f->fen && !(v && v[0] == '0'))
+    {
+      if(ols16k_create(H, N, fir_len, &f->ols))
+      {
+        delete f;
+        return 1;
+      }
+      if(f->ols)
+      {
+        f->K = fir_len;
+        f->fused = false;
+        f->carry_len = std::max(N + Ne, 2 * Ne + f->ols->O + 2);   // look-back of a window: delay + overlap + residual
+      }
+    }
+  }
   cudaError_t e = cudaSuccess;
   for(int i = 0; i < 2 && e == cudaSuccess; i++)
   {
@@ -1012,6 +1037,7 @@ int tsdgpu_ola_destroy(tsdgpu_ola_t f)
   if(f->flags) cudaFree(f->flags);
   if(f->plan) fft_plan_destroy(f->plan);
   if(f->work) cudaFree(f->work);
+  ols16k_destroy(f->ols);
   delete f;
   return 0;
 }

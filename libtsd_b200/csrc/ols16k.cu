@@ -1,0 +1,628 @@
+// Overlap-save block filter with the whole transform resident on ONE SM (sm_100a).
+//
+// Serves every filtre_fft / filtre_rif_fft object whose spectral gains are the transform of K taps
+// (FiltreFFTRIF convention, reference fourier.cc:946-990; C ABI: fir_len = K > 0).  For such an H the samples the
+// reference's overlap-add emits (fourier.cc:837-882) are y_out[t] = sum_m h[m] x[t - (Ne-K) - m] whatever its block
+// length Ne and transform size N are, so the device is free to pick the transform size that fits the
+// machine: M = 16384 points = 128 KiB of cf32, the largest block that stays inside one SM's shared memory.  The
+// reference's bookkeeping (Ne, N, N_zeros, re-blocking residual, Ne samples per completed block, delay Ne-K) is kept
+// on the host (ola.cu); this file only produces the samples.
+//
+// One persistent CTA per SM walks consecutive internal blocks of L = M - O outputs (O = 4096 or 8192 >= K-1 samples of
+// overlap).  Per block, with n = 512 n1 + 32 n2 + n3 and k = k1 + 32 k2 + 512 k3 (radices 32 x 16 x 32):
+//   P1  window (shared memory, filled by the TMA unit)  -> radix-32 over n1 -> exchange buffer E          [warp = n2, lane = n3]
+//   P2  E -> W512 twiddle -> radix-16 over n2 -> W_M twiddle -> warp-local transpose -> radix-32 over n3 -> x H/M ->
+//       inverse radix-32 -> warp-local transpose -> conj W_M twiddle -> inverse radix-16 -> conj W512 twiddle -> E
+//       (a warp owns k1 = 2w, 2w+1: everything between the two CTA barriers happens in the warp's own 8 KiB of E)
+//   P3  E -> inverse radix-32 over k1 -> the L valid outputs, plain coalesced stores                        [warp = n2, lane = n3]
+// A sample crosses HBM once in and once out (16 B per sample; the O overlap samples are re-read from L2), nothing
+// else leaves the SM: no scratch in L2, no inter-CTA hand-over.
+//
+// What is Blackwell-specific here:
+//   * the 256 KiB of tensor memory hold the per-thread constants — the 32 gains H[k]/M and the 32 W_M twiddles each
+//     thread needs in every block (tcgen05.st once per launch, tcgen05.ld in the loop): 16 B per point that neither
+//     shared memory (full: 128 KiB exchange + 96 KiB staging) nor L2 has to deliver;
+//   * the next block's input is prefetched by 1-D bulk copies (cp.async.bulk, SASS UBLKCP) issued by a producer warp:
+//     the L new samples as soon as every math warp has consumed the current window, the O overlap samples (an L2
+//     hit) into the exchange buffer as soon as the current block has left it; completion on mbarriers, the math
+//     warps never wait on a global load in steady state.
+#include "common.cuh"
+#include "tc_common.cuh"
+#include "ols16k.h"
+
+#include <algorithm>
+#include <cmath>
+#include <complex>
+#include <vector>
+
+namespace tsdgpu {
+
+constexpr int OLS_M = 16384;
+constexpr int OLS_MATH_WARPS = 16;
+constexpr int OLS_MATH_THREADS = OLS_MATH_WARPS * 32;
+constexpr int OLS_THREADS = OLS_MATH_THREADS + 128;    // + producer warpgroup (one lane works; a whole group so that setmaxnreg applies)
+constexpr int OLS_MATH_REGS = 112, OLS_PROD_REGS = 24;  // 512 * 112 + 128 * 24 <= 640 * 96, the CTA's register allocation at launch
+constexpr int OLS_E_BYTES = OLS_M * 8;                 // exchange buffer
+constexpr int OLS_PIECE = 16384;                       // bytes per bulk copy
+
+// W512^(n2*k1) at [k1*16 + n2], k1 < 32, n2 < 16 (host-built in double)
+__constant__ float2 c_ols_tw1[512];
+
+struct OlsParams
+{
+  const float2 *x;
+  float2 *y;
+  const float2 *carry;        // [nchan][carry_len], samples preceding x[0]
+  const float4 *tmem_init;    // [512 threads][32 float4]: 16 float4 of gains, 16 of twiddles
+  long long x_stride, y_stride, out_count, total;
+  int carry_len, n, base, jblocks, aligned;
+};
+
+// ---- radix-4 / 16 / 32 butterflies on registers: v[i*S], all indices static ---------------------------------
+#define OLS_C1 0.92387953251128674f   // cos(pi/8)
+#define OLS_S1 0.38268343236508977f   // sin(pi/8)
+#define OLS_R2 0.70710678118654752f   // sqrt(1/2)
+
+template<bool INV> __device__ __forceinline__ void bf4(float2 &a0, float2 &a1, float2 &a2, float2 &a3)
+{
+  const float2 s0 = add2(a0, a2), s1 = sub2(a0, a2), s2 = add2(a1, a3), d = sub2(a1, a3);
+  const float2 ds = make_float2(d.y, d.x);
+  const float2 j = INV ? make_float2(-1.f, 1.f) : make_float2(1.f, -1.f);
+  const float2 nj = INV ? make_float2(1.f, -1.f) : make_float2(-1.f, 1.f);
+  a0 = add2(s0, s2);
+  a2 = sub2(s0, s2);
+  a1 = fma2(ds, j, s1);
+  a3 = fma2(ds, nj, s1);
+}
+// cos / sin of 2 pi k / 32 as compile-time constants
+__host__ __device__ constexpr float ols_cos32(int k)
+{
+  k &= 31;
+  if(k > 16) k = 32 - k;
+  return k == 0 ? 1.f : k == 1 ? 0.98078528040323044913f : k == 2 ? 0.92387953251128675613f : k == 3 ? 0.83146961230254523708f
+       : k == 4 ? 0.70710678118654752440f : k == 5 ? 0.55557023301960222474f : k == 6 ? 0.38268343236508977173f
+       : k == 7 ? 0.19509032201612826785f : k == 8 ? 0.f : k == 9 ? -0.19509032201612826785f : k == 10 ? -0.38268343236508977173f
+       : k == 11 ? -0.55557023301960222474f : k == 12 ? -0.70710678118654752440f : k == 13 ? -0.83146961230254523708f
+       : k == 14 ? -0.92387953251128675613f : k == 15 ? -0.98078528040323044913f : -1.f;
+}
+__host__ __device__ constexpr float ols_sin32(int k) { return ols_cos32(k - 8); }
+// v * W32^K (forward, W = exp(-2 pi i / 32)) or its conjugate (inverse): the twiddle and its rotation are constants
+template<bool INV, int K> __device__ __forceinline__ float2 mul_w32(float2 v)
+{
+  if(K == 0) return v;
+  if(K == 8) return mul2(make_float2(v.y, v.x), INV ? make_float2(-1.f, 1.f) : make_float2(1.f, -1.f));   // -+ i
+  constexpr float wr = ols_cos32(K), wi = INV ? ols_sin32(K) : -ols_sin32(K);
+  return cmul_rot(v, make_float2(wr, wi), make_float2(-wi, wr));
+}
+// 16-point DFT of v[0], v[S], ..., v[15 S]; natural order in and out
+template<bool INV, int S> __device__ __forceinline__ void fft16s(float2 *v)
+{
+#pragma unroll
+  for(int b = 0; b < 4; b++) bf4<INV>(v[b * S], v[(4 + b) * S], v[(8 + b) * S], v[(12 + b) * S]);
+  v[5 * S] = mul_w32<INV, 2>(v[5 * S]);
+  v[6 * S] = mul_w32<INV, 4>(v[6 * S]);
+  v[7 * S] = mul_w32<INV, 6>(v[7 * S]);
+  v[9 * S] = mul_w32<INV, 4>(v[9 * S]);
+  v[10 * S] = mul_w32<INV, 8>(v[10 * S]);
+  v[11 * S] = mul_w32<INV, 12>(v[11 * S]);
+  v[13 * S] = mul_w32<INV, 6>(v[13 * S]);
+  v[14 * S] = mul_w32<INV, 12>(v[14 * S]);
+  v[15 * S] = mul_w32<INV, 18>(v[15 * S]);
+#pragma unroll
+  for(int k0 = 0; k0 < 4; k0++) bf4<INV>(v[(4 * k0) * S], v[(4 * k0 + 1) * S], v[(4 * k0 + 2) * S], v[(4 * k0 + 3) * S]);
+  float2 t;
+#define OLS_SWAP(i, j) t = v[(i) * S]; v[(i) * S] = v[(j) * S]; v[(j) * S] = t;
+  OLS_SWAP(1, 4) OLS_SWAP(2, 8) OLS_SWAP(3, 12) OLS_SWAP(6, 9) OLS_SWAP(7, 13) OLS_SWAP(11, 14)
+#undef OLS_SWAP
+}
+// X[k] = E[k] + W32^k O[k], X[k+16] = E[k] - W32^k O[k] as four packed FMAs
+template<bool INV, int K> __device__ __forceinline__ void comb32(float2 e, float2 o, float2 &lo, float2 &hi)
+{
+  if(K == 0)
+  {
+    lo = add2(e, o);
+    hi = sub2(e, o);
+    return;
+  }
+  if(K == 8)
+  {
+    const float2 os = make_float2(o.y, o.x);
+    lo = fma2(os, INV ? make_float2(-1.f, 1.f) : make_float2(1.f, -1.f), e);
+    hi = fma2(os, INV ? make_float2(1.f, -1.f) : make_float2(-1.f, 1.f), e);
+    return;
+  }
+  constexpr float wr = ols_cos32(K), wi = INV ? ols_sin32(K) : -ols_sin32(K);
+  const float2 ox = bcast2(o.x), oy = bcast2(o.y);
+  lo = fma2(oy, make_float2(-wi, wr), fma2(ox, make_float2(wr, wi), e));
+  hi = fma2(oy, make_float2(wi, -wr), fma2(ox, make_float2(-wr, -wi), e));
+}
+// 32-point DFT of v[0..32), natural order in and out
+template<bool INV> __device__ __forceinline__ void fft32(float2 (&v)[32])
+{
+  fft16s<INV, 2>(&v[0]);   // E[k] at v[2k]
+  fft16s<INV, 2>(&v[1]);   // O[k] at v[2k+1]
+  float2 r[32];
+#define OLS_CB(K) comb32<INV, K>(v[2 * K], v[2 * K + 1], r[K], r[K + 16]);
+  OLS_CB(0) OLS_CB(1) OLS_CB(2) OLS_CB(3) OLS_CB(4) OLS_CB(5) OLS_CB(6) OLS_CB(7)
+  OLS_CB(8) OLS_CB(9) OLS_CB(10) OLS_CB(11) OLS_CB(12) OLS_CB(13) OLS_CB(14) OLS_CB(15)
+#undef OLS_CB
+#pragma unroll
+  for(int i = 0; i < 32; i++) v[i] = r[i];
+}
+
+// ---- complex products with run-time twiddles held as plain (re, im): four scalar FMA-pipe instructions ----------
+__device__ __forceinline__ float2 cmul_s(float2 a, float wr, float wi)
+{
+  return make_float2(fmaf(-a.y, wi, a.x * wr), fmaf(a.y, wr, a.x * wi));
+}
+__device__ __forceinline__ float2 cmulc_s(float2 a, float wr, float wi)
+{
+  return make_float2(fmaf(a.y, wi, a.x * wr), fmaf(-a.x, wi, a.y * wr));
+}
+
+// 16 consecutive TMEM columns of this thread's lane -> 16 registers
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&r)[16])
+{
+  uint32_t u[16];
+  asm volatile(
+    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+    : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]), "=r"(u[9]),
+      "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+    : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for(int i = 0; i < 16; i++) r[i] = __uint_as_float(u[i]);
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// v[i] = v[i] (*) w[i] for the 32 constants of this thread at TMEM columns [col, col + 64)
+template<bool CONJ> __device__ __forceinline__ void mul_tmem32(float2 (&v)[32], uint32_t taddr)
+{
+#pragma unroll
+  for(int q = 0; q < 4; q++)
+  {
+    float w[16];
+    tmem_ld16(taddr + 16 * q, w);
+#pragma unroll
+    for(int i = 0; i < 8; i++)
+      v[8 * q + i] = CONJ ? cmulc_s(v[8 * q + i], w[2 * i], w[2 * i + 1]) : cmul_s(v[8 * q + i], w[2 * i], w[2 * i + 1]);
+  }
+}
+
+// constant-bank load kept in program order (a plain read would be hoisted to the top of the phase: 60 live registers)
+__device__ __forceinline__ float2 ldc64(const float2 *p)
+{
+  float2 v;
+  asm volatile("ld.const.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float2 lds64(uint32_t addr)
+{
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts64(uint32_t addr, float2 v)
+{
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
+}
+// swizzled accesses of the warp-local transposes: address = (base ^ X) + OFF with compile-time X, OFF.  The XOR sits
+// inside the asm so that the compiler recomputes it (one ALU-pipe LOP3) instead of keeping 64 addresses alive.
+template<int X, int OFF> __device__ __forceinline__ float2 lds64x(uint32_t base)
+{
+  float2 v;
+  asm volatile("{\n\t.reg .u32 t;\n\txor.b32 t, %2, %3;\n\tld.shared.v2.f32 {%0, %1}, [t+%4];\n\t}"
+               : "=f"(v.x), "=f"(v.y) : "r"(base), "n"(X), "n"(OFF));
+  return v;
+}
+template<int X, int OFF> __device__ __forceinline__ void sts64x(uint32_t base, float2 v)
+{
+  asm volatile("{\n\t.reg .u32 t;\n\txor.b32 t, %0, %1;\n\tst.shared.v2.f32 [t+%2], {%3, %4};\n\t}"
+               ::"r"(base), "n"(X), "n"(OFF), "f"(v.x), "f"(v.y) : "memory");
+}
+template<int R> struct OlsX
+{
+  // rows R..31 of the row-static pattern (row r at r*256, column lane ^ r) and of the lane = row pattern
+  static __device__ __forceinline__ void st_rows(uint32_t bl, const float2 (&v)[32])
+  {
+    sts64x<R * 8, R * 256>(bl, v[R]);
+    OlsX<R + 1>::st_rows(bl, v);
+  }
+  static __device__ __forceinline__ void ld_rows(uint32_t bl, float2 (&v)[32])
+  {
+    v[R] = lds64x<R * 8, R * 256>(bl);
+    OlsX<R + 1>::ld_rows(bl, v);
+  }
+  static __device__ __forceinline__ void st_cols(uint32_t al, const float2 (&v)[32])
+  {
+    sts64x<R * 8, 0>(al, v[R]);
+    OlsX<R + 1>::st_cols(al, v);
+  }
+  static __device__ __forceinline__ void ld_cols(uint32_t al, float2 (&v)[32])
+  {
+    v[R] = lds64x<R * 8, 0>(al);
+    OlsX<R + 1>::ld_cols(al, v);
+  }
+};
+template<> struct OlsX<32>
+{
+  static __device__ __forceinline__ void st_rows(uint32_t, const float2 (&)[32]) {}
+  static __device__ __forceinline__ void ld_rows(uint32_t, float2 (&)[32]) {}
+  static __device__ __forceinline__ void st_cols(uint32_t, const float2 (&)[32]) {}
+  static __device__ __forceinline__ void ld_cols(uint32_t, float2 (&)[32]) {}
+};
+__device__ __forceinline__ void mbar_arrive_cta(uint64_t *bar)
+{
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Shared-memory map (dynamic): [E : 128 KiB][S : L*8 + 16][barriers]
+//   E  exchange buffer, element (k1, n2, n3) at sample index (k1*16 + n2)*32 + n3; its first O*8 + 16 bytes double as
+//      the landing zone X of the next window's overlap samples while the block is not in E
+//   S  the L new samples of the next window (+ 2 samples of alignment slack)
+template<int OQ>   // overlap in quarters of M: O = 4096 * OQ
+__global__ void __launch_bounds__(OLS_THREADS, 1) ols16k_kernel(OlsParams p)
+{
+  constexpr int O = 4096 * OQ, L = OLS_M - O, NX = 8 * OQ;   // window samples n1 < NX live in X
+  constexpr uint32_t S_BYTES = L * 8 + 16, X_BYTES = O * 8 + 16;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const uint32_t sE = smem_u32(smem), sS = sE + OLS_E_BYTES;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + OLS_E_BYTES + S_BYTES);
+  uint64_t *s_full = bars, *x_full = bars + 1, *w_free = bars + 2, *e_free = bars + 3;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4);
+  const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
+
+  if(tid == 0)
+  {
+    mbar_init(s_full, 1);
+    mbar_init(x_full, 1);
+    mbar_init(w_free, OLS_MATH_WARPS);
+    mbar_init(e_free, OLS_MATH_WARPS);
+    mbar_fence_init();
+  }
+  if(w == 0)
+  {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc::fence_before();
+  __syncthreads();
+  tc::fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if((sE & 255u) != 0) __trap();   // the swizzled addressing relies on a 256-byte aligned base
+
+  // contiguous share of the (channel-major) internal blocks
+  const long long first = p.total * blockIdx.x / gridDim.x, last = p.total * (blockIdx.x + 1) / gridDim.x;
+
+  if(w >= OLS_MATH_WARPS)
+  {
+    // ===== producer: one lane feeds the window of every block through the TMA unit =====
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(OLS_PROD_REGS));
+    if(tid == OLS_MATH_THREADS)
+    {
+      for(long long b = first; b < last; b++)
+      {
+        const unsigned it = (unsigned) (b - first);
+        const int chan = (int) (b / p.jblocks), j = (int) (b - (long long) chan * p.jblocks);
+        const long long pos0 = (long long) j * L + p.base;
+        const long long a0 = pos0 & ~1LL;                          // 16-byte aligned start
+        const bool fast = p.aligned && a0 >= 0 && a0 + OLS_M + 2 <= p.n;
+        const float2 *src = p.x + (long long) chan * p.x_stride + a0;
+        if(it > 0) mbar_wait(w_free, (it - 1) & 1);                // S consumed by every math warp
+        if(fast)
+        {
+          mbar_expect_tx(s_full, S_BYTES);
+#pragma unroll 1
+          for(uint32_t off = 0; off < S_BYTES; off += OLS_PIECE)
+          {
+            const uint32_t nb = (S_BYTES - off < OLS_PIECE + 4096) ? S_BYTES - off : OLS_PIECE;
+            bulk_g2s(smem + OLS_E_BYTES + off, reinterpret_cast<const unsigned char *>(src + O) + off, nb, s_full);
+            if(nb != OLS_PIECE) break;
+          }
+        }
+        else mbar_arrive_cta(s_full);
+        if(it > 0) mbar_wait(e_free, (it - 1) & 1);                // previous block has left E
+        if(fast)
+        {
+          mbar_expect_tx(x_full, X_BYTES);
+#pragma unroll 1
+          for(uint32_t off = 0; off < X_BYTES; off += OLS_PIECE)
+          {
+            const uint32_t nb = (X_BYTES - off < OLS_PIECE + 4096) ? X_BYTES - off : OLS_PIECE;
+            bulk_g2s(smem + off, reinterpret_cast<const unsigned char *>(src) + off, nb, x_full);
+            if(nb != OLS_PIECE) break;
+          }
+        }
+        else mbar_arrive_cta(x_full);
+      }
+    }
+  }
+  else
+  {
+    // ===== math warps =====
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(OLS_MATH_REGS));
+    // per-thread constants -> tensor memory: columns [128 (w>>2), +64) gains, [+64, +128) W_M twiddles
+    const uint32_t tm = tmem_base + ((uint32_t) (32 * (w & 3)) << 16) + 128u * (uint32_t) (w >> 2);
+    {
+      const float4 *src = p.tmem_init + (size_t) tid * 32;
+#pragma unroll
+      for(int q = 0; q < 8; q++)
+      {
+        float r[16];
+#pragma unroll
+        for(int i = 0; i < 4; i++)
+        {
+          const float4 t = __ldg(src + 4 * q + i);
+          r[4 * i] = t.x;
+          r[4 * i + 1] = t.y;
+          r[4 * i + 2] = t.z;
+          r[4 * i + 3] = t.w;
+        }
+        tc::tmem_st16(tm + 16 * q, r);
+      }
+      tmem_wait_st();
+    }
+    const uint32_t sEw = sE + (uint32_t) w * 8192u;   // this warp's rows of E (k1 = 2w, 2w+1)
+    const uint32_t lx = (uint32_t) l * 8u;
+
+    for(long long b = first; b < last; b++)
+    {
+      const unsigned it = (unsigned) (b - first);
+      const int chan = (int) (b / p.jblocks), j = (int) (b - (long long) chan * p.jblocks);
+      const long long pos0 = (long long) j * L + p.base;
+      const long long a0 = pos0 & ~1LL;
+      const bool fast = p.aligned && a0 >= 0 && a0 + OLS_M + 2 <= p.n;
+      float2 v[32];
+
+      // ---- P1: window -> radix-32 over n1 -> E ----
+      mbar_wait(s_full, it & 1);
+      if(fast)
+      {
+        const uint32_t sh = (uint32_t) (pos0 & 1) * 8u + (uint32_t) (32 * w) * 8u + lx;
+#pragma unroll
+        for(int n1 = NX; n1 < 32; n1++) v[n1] = lds64(sS + sh + (uint32_t) (512 * (n1 - NX)) * 8u);
+        mbar_wait(x_full, it & 1);
+#pragma unroll
+        for(int n1 = 0; n1 < NX; n1++) v[n1] = lds64(sE + sh + (uint32_t) (512 * n1) * 8u);
+      }
+      else
+      {
+        mbar_wait(x_full, it & 1);
+        // edge block (start / end of the call, or unaligned rows): bounds-checked loads straight into registers
+        const float2 *xc = p.x + (long long) chan * p.x_stride;
+        const float2 *cr = p.carry + (long long) chan * p.carry_len + p.carry_len;
+#pragma unroll
+        for(int n1 = 0; n1 < 32; n1++)
+        {
+          const long long pos = pos0 + 512 * n1 + 32 * w + l;
+          float2 val = make_float2(0.f, 0.f);
+          if(pos >= 0) { if(pos < p.n) val = ldg_stream(xc + pos); }
+          else if(pos >= -(long long) p.carry_len) val = __ldg(cr + pos);
+          v[n1] = val;
+        }
+      }
+      __syncwarp();
+      if(l == 0) mbar_arrive_cta(w_free);
+      fft32<false>(v);
+      mbar_wait(w_free, it & 1);   // every warp has read its part of X (inside E) before anyone overwrites it
+      {
+        const uint32_t a = sE + (uint32_t) (32 * w) * 8u + lx;
+#pragma unroll
+        for(int k1 = 0; k1 < 32; k1++) sts64(a + (uint32_t) (k1 * 512) * 8u, v[k1]);
+      }
+      tc::named_bar(1, OLS_MATH_THREADS);
+
+      // ---- P2: everything between the two exchanges, inside the warp's own 8 KiB ----
+#pragma unroll
+      for(int r = 0; r < 32; r++) v[r] = lds64(sEw + (uint32_t) (r * 32) * 8u + lx);
+      {
+        // W512^(n2 * k1), k1 = 2w + c
+        const float2 *t1 = c_ols_tw1 + (2 * w) * 16;
+#pragma unroll
+        for(int r = 1; r < 32; r++)
+          if(r != 16)
+          {
+            const float2 t = ldc64(t1 + r);
+            v[r] = cmul_s(v[r], t.x, t.y);
+          }
+      }
+      fft16s<false, 1>(&v[0]);
+      fft16s<false, 1>(&v[16]);
+      mul_tmem32<false>(v, tm + 64);
+      __syncwarp();
+      OlsX<0>::st_rows(sEw + lx, v);          // row r (= c*16 + k2), column n3 = lane, at r*32 + (lane ^ r)
+      __syncwarp();
+      {
+        const uint32_t al = sEw + (uint32_t) l * 256u + lx;
+        OlsX<0>::ld_cols(al, v);              // row = lane, columns n3 = 0..31
+        fft32<false>(v);
+        mul_tmem32<false>(v, tm);
+        fft32<true>(v);
+        OlsX<0>::st_cols(al, v);
+      }
+      __syncwarp();
+      OlsX<0>::ld_rows(sEw + lx, v);
+      mul_tmem32<true>(v, tm + 64);
+      fft16s<true, 1>(&v[0]);
+      fft16s<true, 1>(&v[16]);
+      {
+        const float2 *t1 = c_ols_tw1 + (2 * w) * 16;
+#pragma unroll
+        for(int r = 1; r < 32; r++)
+          if(r != 16)
+          {
+            const float2 t = ldc64(t1 + r);
+            v[r] = cmulc_s(v[r], t.x, t.y);
+          }
+      }
+      __syncwarp();
+#pragma unroll
+      for(int r = 0; r < 32; r++) sts64(sEw + (uint32_t) (r * 32) * 8u + lx, v[r]);
+      tc::named_bar(2, OLS_MATH_THREADS);
+
+      // ---- P3: E -> inverse radix-32 over k1 -> outputs ----
+      {
+        const uint32_t a = sE + (uint32_t) (32 * w) * 8u + lx;
+#pragma unroll
+        for(int k1 = 0; k1 < 32; k1++) v[k1] = lds64(a + (uint32_t) (k1 * 512) * 8u);
+      }
+      __syncwarp();
+      if(l == 0) mbar_arrive_cta(e_free);
+      fft32<true>(v);
+      {
+        const long long i0 = (long long) j * L + 32 * w + l;   // output index of window sample n = O + 32 w + l
+        float2 *yc = p.y + (long long) chan * p.y_stride + i0;
+        const int rem = (int) min(p.out_count - i0, (long long) L);   // outputs of this lane's column still inside the call
+#pragma unroll
+        for(int n1 = NX; n1 < 32; n1++)
+          if(512 * (n1 - NX) < rem) stg_stream(yc + 512 * (n1 - NX), v[n1]);
+      }
+    }
+  }
+
+  tc::fence_before();
+  __syncthreads();
+  if(w == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+}
+
+// ---- host side ------------------------------------------------------------------------------------------------
+static void fft_double(std::vector<std::complex<double>> &a, bool inverse)
+{
+  const size_t n = a.size();
+  for(size_t i = 1, j = 0; i < n; i++)
+  {
+    size_t bit = n >> 1;
+    for(; j & bit; bit >>= 1) j ^= bit;
+    j ^= bit;
+    if(i < j) std::swap(a[i], a[j]);
+  }
+  for(size_t len = 2; len <= n; len <<= 1)
+  {
+    const double ang = 2.0 * M_PI / (double) len * (inverse ? 1.0 : -1.0);
+    std::vector<std::complex<double>> w(len / 2);
+    for(size_t k = 0; k < len / 2; k++) w[k] = std::polar(1.0, ang * (double) k);
+    for(size_t i = 0; i < n; i += len)
+      for(size_t k = 0; k < len / 2; k++)
+      {
+        const std::complex<double> u = a[i + k], t = a[i + k + len / 2] * w[k];
+        a[i + k] = u + t;
+        a[i + k + len / 2] = u - t;
+      }
+  }
+}
+
+static bool g_tw1_ready = false;
+static int g_tw1_device = -1;
+
+int ols16k_create(const float *H, int N, int K, Ols16k **out)
+{
+  *out = nullptr;
+  if(K < 1 || K - 1 > 8192 || N < K) return 0;   // not served here: the caller keeps its N-point path
+  // taps back from the gains: H = DFT(h2), h2 = [0^(N-K), h]  (fourier.cc:962-965)
+  std::vector<std::complex<double>> a((size_t) N);
+  for(int i = 0; i < N; i++) a[i] = std::complex<double>(H[2 * i], H[2 * i + 1]);
+  fft_double(a, true);
+  double e_in = 0, e_out = 0;
+  for(int i = 0; i < N; i++)
+  {
+    a[i] /= (double) N;
+    (i >= N - K ? e_in : e_out) += std::norm(a[i]);
+  }
+  // the caller's promise (fir_len) is checked: energy outside the K-tap support must be rounding noise
+  if(!(e_out <= 1e-9 * e_in)) return 0;
+  const int O = (K - 1 <= 4096) ? 4096 : 8192;
+  std::vector<std::complex<double>> hm((size_t) OLS_M);
+  for(int m = 0; m < K; m++) hm[m] = a[(size_t) (N - K + m)];
+  fft_double(hm, false);
+  // thread-major constants: thread t = 32 w + l owns gains k = (2w + (l>>4)) + 32 (l&15) + 512 k3 and the twiddles
+  // W_M^(l * ((2w + c) + 32 k2)) at [c*16 + k2]
+  std::vector<float> init((size_t) 512 * 128);
+  for(int t = 0; t < 512; t++)
+  {
+    const int w = t >> 5, l = t & 31;
+    float *dst = init.data() + (size_t) t * 128;
+    for(int k3 = 0; k3 < 32; k3++)
+    {
+      const std::complex<double> g = hm[(size_t) ((2 * w + (l >> 4)) + 32 * (l & 15) + 512 * k3)] / (double) OLS_M;
+      dst[2 * k3] = (float) g.real();
+      dst[2 * k3 + 1] = (float) g.imag();
+    }
+    for(int c = 0; c < 2; c++)
+      for(int k2 = 0; k2 < 16; k2++)
+      {
+        const long long e = ((long long) l * ((2 * w + c) + 32 * k2)) % OLS_M;
+        const double ang = -2.0 * M_PI * (double) e / (double) OLS_M;
+        dst[64 + 2 * (c * 16 + k2)] = (float) cos(ang);
+        dst[64 + 2 * (c * 16 + k2) + 1] = (float) sin(ang);
+      }
+  }
+  if(!g_tw1_ready || g_tw1_device != rt().device)
+  {
+    std::vector<float2> t1(512);
+    for(int k1 = 0; k1 < 32; k1++)
+      for(int n2 = 0; n2 < 16; n2++)
+      {
+        const double ang = -2.0 * M_PI * (double) (k1 * n2) / 512.0;
+        t1[k1 * 16 + n2] = make_float2((float) cos(ang), (float) sin(ang));
+      }
+    TSD_CUDA(cudaMemcpyToSymbol(c_ols_tw1, t1.data(), 512 * sizeof(float2)));
+    TSD_CUDA(cudaFuncSetAttribute(ols16k_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ols16k_smem_bytes(4096)));
+    TSD_CUDA(cudaFuncSetAttribute(ols16k_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ols16k_smem_bytes(8192)));
+    g_tw1_ready = true;
+    g_tw1_device = rt().device;
+  }
+  auto *o = new Ols16k;
+  o->O = O;
+  o->L = OLS_M - O;
+  o->K = K;
+  cudaError_t e = cudaMalloc(&o->d_init, init.size() * sizeof(float));
+  if(e == cudaSuccess) e = cudaMemcpy(o->d_init, init.data(), init.size() * sizeof(float), cudaMemcpyHostToDevice);
+  if(e != cudaSuccess)
+  {
+    ols16k_destroy(o);
+    return fail(std::string("ols16k_create: ") + cudaGetErrorString(e));
+  }
+  *out = o;
+  return 0;
+}
+
+void ols16k_destroy(Ols16k *o)
+{
+  if(!o) return;
+  if(o->d_init) cudaFree(o->d_init);
+  delete o;
+}
+
+int ols16k_smem_bytes(int O) { return OLS_E_BYTES + (OLS_M - O) * 8 + 16 + 64; }
+
+// y[c][i] = y_fir[t0 + i - delay], i in [0, out_count): window positions are relative to x[0] of this call, whose
+// stream index is t0 + residual
+int ols16k_run(Ols16k *o, const float2 *x, long long xs, int n, const float2 *carry, int carry_len, float2 *y, long long ys,
+               long long out_count, int delay, int residual, int nchan)
+{
+  if(out_count <= 0) return 0;
+  Runtime &r = rt();
+  OlsParams p;
+  p.x = x;
+  p.y = y;
+  p.carry = carry;
+  p.tmem_init = reinterpret_cast<const float4 *>(o->d_init);
+  p.x_stride = xs;
+  p.y_stride = ys;
+  p.out_count = out_count;
+  p.carry_len = carry_len;
+  p.n = n;
+  p.base = -(delay + o->O + residual);
+  p.jblocks = (int) ((out_count + o->L - 1) / o->L);
+  p.total = (long long) nchan * p.jblocks;
+  p.aligned = ((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (xs & 1) == 0) ? 1 : 0;
+  const int grid = (int) std::min<long long>(r.num_sms, p.total);
+  const int smem = ols16k_smem_bytes(o->O);
+  KernelTimer timer;
+  if(o->O == 4096) ols16k_kernel<1><<<grid, OLS_THREADS, smem, r.stream>>>(p);
+  else ols16k_kernel<2><<<grid, OLS_THREADS, smem, r.stream>>>(p);
+  TSD_LAUNCH_CHECK();
+  return 0;
+}
+
+} // namespace tsdgpu
