@@ -190,10 +190,10 @@ template<bool CONJ> __device__ __forceinline__ void mul_tmem32(float2 (&v)[32], 
 }
 
 // constant-bank load kept in program order (a plain read would be hoisted to the top of the phase: 60 live registers)
-__device__ __forceinline__ float2 ldc64(const float2 *p)
+__device__ __forceinline__ float2 ldc64(uint64_t const_addr)
 {
   float2 v;
-  asm volatile("ld.const.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+  asm volatile("ld.const.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(const_addr));
   return v;
 }
 __device__ __forceinline__ float2 lds64(uint32_t addr)
@@ -364,6 +364,7 @@ __global__ void __launch_bounds__(OLS_THREADS, 1) ols16k_kernel(OlsParams p)
     }
     const uint32_t sEw = sE + (uint32_t) w * 8192u;   // this warp's rows of E (k1 = 2w, 2w+1)
     const uint32_t lx = (uint32_t) l * 8u;
+    const uint64_t t1c = (uint64_t) __cvta_generic_to_constant(c_ols_tw1 + (2 * w) * 16);   // W512^(n2 * k1), k1 = 2w + c
 
     for(long long b = first; b < last; b++)
     {
@@ -417,12 +418,11 @@ __global__ void __launch_bounds__(OLS_THREADS, 1) ols16k_kernel(OlsParams p)
       for(int r = 0; r < 32; r++) v[r] = lds64(sEw + (uint32_t) (r * 32) * 8u + lx);
       {
         // W512^(n2 * k1), k1 = 2w + c
-        const float2 *t1 = c_ols_tw1 + (2 * w) * 16;
 #pragma unroll
         for(int r = 1; r < 32; r++)
           if(r != 16)
           {
-            const float2 t = ldc64(t1 + r);
+            const float2 t = ldc64(t1c + 8 * r);
             v[r] = cmul_s(v[r], t.x, t.y);
           }
       }
@@ -446,12 +446,11 @@ __global__ void __launch_bounds__(OLS_THREADS, 1) ols16k_kernel(OlsParams p)
       fft16s<true, 1>(&v[0]);
       fft16s<true, 1>(&v[16]);
       {
-        const float2 *t1 = c_ols_tw1 + (2 * w) * 16;
 #pragma unroll
         for(int r = 1; r < 32; r++)
           if(r != 16)
           {
-            const float2 t = ldc64(t1 + r);
+            const float2 t = ldc64(t1c + 8 * r);
             v[r] = cmulc_s(v[r], t.x, t.y);
           }
       }

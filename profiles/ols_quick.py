@@ -38,7 +38,7 @@ if len(sys.argv) <= 1 or sys.argv[1] != "time":
     check(4095, 61441, 2, 400000)
     check(4095, 61441, 3, 400001, chunks=[65536, 65537, 100000, 3, 169325])
     check(8000, 123072, 2, 600000)
-    check(31, 1000, 150, 50000)
+    check(31, 2000, 150, 50000)
 else:
     nchan = int(sys.argv[2]) if len(sys.argv) > 2 else 64
     n = 1 << (int(sys.argv[3]) if len(sys.argv) > 3 else 22)
