@@ -10,7 +10,8 @@ import os
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "libtsdgpu.so")
+# TSDGPU_LIB selects another build of the same library (kernel A/B experiments under profiles/); default = the in-tree build
+SO_PATH = os.environ.get("TSDGPU_LIB") or os.path.join(HERE, "libtsdgpu.so")
 HOST, DEVICE = 0, 1
 
 _vp, _i, _ll, _f = C.c_void_p, C.c_int, C.c_longlong, C.c_float

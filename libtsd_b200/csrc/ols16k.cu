@@ -33,6 +33,8 @@
 #include <algorithm>
 #include <cmath>
 #include <complex>
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 namespace tsdgpu {
@@ -56,6 +58,7 @@ struct OlsParams
   const float4 *tmem_init;    // [512 threads][32 float4]: 16 float4 of gains, 16 of twiddles
   long long x_stride, y_stride, out_count, total;
   int carry_len, n, base, jblocks, aligned;
+  unsigned *prof;             // optional per-phase clock trace of CTA 0 (TSDGPU_OLS_PROF), else null
 };
 
 // ---- radix-4 / 16 / 32 butterflies on registers: v[i*S], all indices static ---------------------------------
@@ -189,17 +192,29 @@ template<bool CONJ> __device__ __forceinline__ void mul_tmem32(float2 (&v)[32], 
   }
 }
 
-// constant-bank load kept in program order (a plain read would be hoisted to the top of the phase: 60 live registers)
-__device__ __forceinline__ float2 ldc64(uint64_t const_addr)
+// the same for 16 values at 32 consecutive TMEM columns
+template<bool CONJ> __device__ __forceinline__ void mul_tmem16(float2 *v, uint32_t taddr)
 {
-  float2 v;
-  asm volatile("ld.const.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(const_addr));
-  return v;
+#pragma unroll
+  for(int q = 0; q < 2; q++)
+  {
+    float w[16];
+    tmem_ld16(taddr + 16 * q, w);
+#pragma unroll
+    for(int i = 0; i < 8; i++)
+      v[8 * q + i] = CONJ ? cmulc_s(v[8 * q + i], w[2 * i], w[2 * i + 1]) : cmul_s(v[8 * q + i], w[2 * i], w[2 * i + 1]);
+  }
 }
 __device__ __forceinline__ float2 lds64(uint32_t addr)
 {
   float2 v;
   asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr)
+{
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
   return v;
 }
 __device__ __forceinline__ void sts64(uint32_t addr, float2 v)
@@ -220,40 +235,67 @@ template<int X, int OFF> __device__ __forceinline__ void sts64x(uint32_t base, f
   asm volatile("{\n\t.reg .u32 t;\n\txor.b32 t, %0, %1;\n\tst.shared.v2.f32 [t+%2], {%3, %4};\n\t}"
                ::"r"(base), "n"(X), "n"(OFF), "f"(v.x), "f"(v.y) : "memory");
 }
-template<int R> struct OlsX
+template<int R, int END> struct OlsX
 {
-  // rows R..31 of the row-static pattern (row r at r*256, column lane ^ r) and of the lane = row pattern
+  // rows R..END-1 of the row-static pattern (row r at r*256, column lane ^ r) and of the lane = row pattern
   static __device__ __forceinline__ void st_rows(uint32_t bl, const float2 (&v)[32])
   {
     sts64x<R * 8, R * 256>(bl, v[R]);
-    OlsX<R + 1>::st_rows(bl, v);
+    OlsX<R + 1, END>::st_rows(bl, v);
   }
   static __device__ __forceinline__ void ld_rows(uint32_t bl, float2 (&v)[32])
   {
     v[R] = lds64x<R * 8, R * 256>(bl);
-    OlsX<R + 1>::ld_rows(bl, v);
+    OlsX<R + 1, END>::ld_rows(bl, v);
   }
-  static __device__ __forceinline__ void st_cols(uint32_t al, const float2 (&v)[32])
+  static __device__ __forceinline__ void ld_cols_even(uint32_t al, float2 (&v)[32])
   {
-    sts64x<R * 8, 0>(al, v[R]);
-    OlsX<R + 1>::st_cols(al, v);
+    if((R & 1) == 0) v[R] = lds64x<R * 8, 0>(al);
+    OlsX<R + 1, END>::ld_cols_even(al, v);
   }
-  static __device__ __forceinline__ void ld_cols(uint32_t al, float2 (&v)[32])
+  static __device__ __forceinline__ void ld_cols_odd(uint32_t al, float2 (&v)[32])
   {
-    v[R] = lds64x<R * 8, 0>(al);
-    OlsX<R + 1>::ld_cols(al, v);
+    if(R & 1) v[R] = lds64x<R * 8, 0>(al);
+    OlsX<R + 1, END>::ld_cols_odd(al, v);
   }
 };
-template<> struct OlsX<32>
+template<int END> struct OlsX<END, END>
 {
   static __device__ __forceinline__ void st_rows(uint32_t, const float2 (&)[32]) {}
   static __device__ __forceinline__ void ld_rows(uint32_t, float2 (&)[32]) {}
-  static __device__ __forceinline__ void st_cols(uint32_t, const float2 (&)[32]) {}
-  static __device__ __forceinline__ void ld_cols(uint32_t, float2 (&)[32]) {}
+  static __device__ __forceinline__ void ld_cols_even(uint32_t, float2 (&)[32]) {}
+  static __device__ __forceinline__ void ld_cols_odd(uint32_t, float2 (&)[32]) {}
 };
 __device__ __forceinline__ void mbar_arrive_cta(uint64_t *bar)
 {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// profiling aid: lane 0 of every math warp of CTA 0 records the SM clock at phase boundaries of a few blocks
+constexpr int OLS_PROF_IT0 = 8, OLS_PROF_NIT = 6, OLS_PROF_PTS = 14;
+__device__ __forceinline__ void ols_stamp(const OlsParams &p, unsigned it, int w, int l, int pt)
+{
+  if(p.prof && blockIdx.x == 0 && l == 0 && it - OLS_PROF_IT0 < (unsigned) OLS_PROF_NIT)
+  {
+    unsigned c;
+    asm volatile("mov.u32 %0, %%clock;" : "=r"(c));
+    p.prof[((it - OLS_PROF_IT0) * OLS_MATH_WARPS + w) * OLS_PROF_PTS + pt] = c;
+  }
+}
+
+// output stores: streaming (L1 no-allocate) by default; OLS_STG = 1 plain, 2 evict-first (.cs) for A/B runs
+#ifndef OLS_STG
+#define OLS_STG 0
+#endif
+__device__ __forceinline__ void ols_stg(float2 *p, float2 v)
+{
+#if OLS_STG == 0
+  stg_stream(p, v);
+#elif OLS_STG == 1
+  *p = v;
+#else
+  __stcs(p, v);
+#endif
 }
 
 // Shared-memory map (dynamic): [E : 128 KiB][S : L*8 + 16][barriers]
@@ -269,7 +311,8 @@ __global__ void __launch_bounds__(OLS_THREADS, 1) ols16k_kernel(OlsParams p)
   const uint32_t sE = smem_u32(smem), sS = sE + OLS_E_BYTES;
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + OLS_E_BYTES + S_BYTES);
   uint64_t *s_full = bars, *x_full = bars + 1, *w_free = bars + 2, *e_free = bars + 3;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4);
+  uint64_t *row_full = bars + 4;   // [16]: rows 2w', 2w'+1 of E written by every warp -> their owner may start P2
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4 + OLS_MATH_WARPS);
   const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
 
   if(tid == 0)
@@ -278,6 +321,7 @@ __global__ void __launch_bounds__(OLS_THREADS, 1) ols16k_kernel(OlsParams p)
     mbar_init(x_full, 1);
     mbar_init(w_free, OLS_MATH_WARPS);
     mbar_init(e_free, OLS_MATH_WARPS);
+    for(int i = 0; i < OLS_MATH_WARPS; i++) mbar_init(row_full + i, OLS_MATH_WARPS);
     mbar_fence_init();
   }
   if(w == 0)
@@ -300,10 +344,11 @@ __global__ void __launch_bounds__(OLS_THREADS, 1) ols16k_kernel(OlsParams p)
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(OLS_PROD_REGS));
     if(tid == OLS_MATH_THREADS)
     {
+      int chan = (int) (first / p.jblocks), j = (int) (first - (long long) chan * p.jblocks) - 1;
       for(long long b = first; b < last; b++)
       {
         const unsigned it = (unsigned) (b - first);
-        const int chan = (int) (b / p.jblocks), j = (int) (b - (long long) chan * p.jblocks);
+        if(++j == p.jblocks) { j = 0; chan++; }
         const long long pos0 = (long long) j * L + p.base;
         const long long a0 = pos0 & ~1LL;                          // 16-byte aligned start
         const bool fast = p.aligned && a0 >= 0 && a0 + OLS_M + 2 <= p.n;
@@ -364,16 +409,26 @@ __global__ void __launch_bounds__(OLS_THREADS, 1) ols16k_kernel(OlsParams p)
     }
     const uint32_t sEw = sE + (uint32_t) w * 8192u;   // this warp's rows of E (k1 = 2w, 2w+1)
     const uint32_t lx = (uint32_t) l * 8u;
-    const uint64_t t1c = (uint64_t) __cvta_generic_to_constant(c_ols_tw1 + (2 * w) * 16);   // W512^(n2 * k1), k1 = 2w + c
+    // W512^(n2 * k1), k1 = 2w + c, is the same for every lane: lane r = c*16 + n2 keeps entry r in two registers and the
+    // warp spreads the 32 entries through the first 256 bytes of its own rows of E (free while the data sits in
+    // registers) right before each use: 1 STS + 16 broadcast LDS.128 instead of 30 constant-bank loads
+    const float2 tw1c = c_ols_tw1[(2 * w) * 16 + l];
 
+    int chan = (int) (first / p.jblocks), j = (int) (first - (long long) chan * p.jblocks) - 1;
     for(long long b = first; b < last; b++)
     {
       const unsigned it = (unsigned) (b - first);
-      const int chan = (int) (b / p.jblocks), j = (int) (b - (long long) chan * p.jblocks);
+      if(++j == p.jblocks) { j = 0; chan++; }
       const long long pos0 = (long long) j * L + p.base;
       const long long a0 = pos0 & ~1LL;
       const bool fast = p.aligned && a0 >= 0 && a0 + OLS_M + 2 <= p.n;
       float2 v[32];
+      ols_stamp(p, it, w, l, 0);
+
+      // Every phase is written as a software pipeline inside the thread: loads of the second half are in flight while the
+      // first half is transformed, and every result leaves for shared / global memory as soon as its butterfly is done.
+      // The sixteen warps run the same code almost in lock-step, so this is what lets the shared-memory pipe and the
+      // FMA pipe work at the same time.
 
       // ---- P1: window -> radix-32 over n1 -> E ----
       mbar_wait(s_full, it & 1);
@@ -381,10 +436,14 @@ __global__ void __launch_bounds__(OLS_THREADS, 1) ols16k_kernel(OlsParams p)
       {
         const uint32_t sh = (uint32_t) (pos0 & 1) * 8u + (uint32_t) (32 * w) * 8u + lx;
 #pragma unroll
-        for(int n1 = NX; n1 < 32; n1++) v[n1] = lds64(sS + sh + (uint32_t) (512 * (n1 - NX)) * 8u);
+        for(int h = 0; h < 2; h++)      // even n1 first: the first radix-16 starts while the odd half is still arriving
+#pragma unroll
+          for(int n1 = NX + h; n1 < 32; n1 += 2) v[n1] = lds64(sS + sh + (uint32_t) (512 * (n1 - NX)) * 8u);
         mbar_wait(x_full, it & 1);
 #pragma unroll
-        for(int n1 = 0; n1 < NX; n1++) v[n1] = lds64(sE + sh + (uint32_t) (512 * n1) * 8u);
+        for(int h = 0; h < 2; h++)
+#pragma unroll
+          for(int n1 = h; n1 < NX; n1 += 2) v[n1] = lds64(sE + sh + (uint32_t) (512 * n1) * 8u);
       }
       else
       {
@@ -404,78 +463,140 @@ __global__ void __launch_bounds__(OLS_THREADS, 1) ols16k_kernel(OlsParams p)
       }
       __syncwarp();
       if(l == 0) mbar_arrive_cta(w_free);
-      fft32<false>(v);
+      ols_stamp(p, it, w, l, 1);
+      fft16s<false, 2>(&v[0]);
+      fft16s<false, 2>(&v[1]);
+      ols_stamp(p, it, w, l, 2);
       mbar_wait(w_free, it & 1);   // every warp has read its part of X (inside E) before anyone overwrites it
       {
+        // last radix-2 stage: rows k1 = K and K + 16 are stored as soon as they exist.  One arrival per row pair: the
+        // owner of rows (2w', 2w'+1) starts P2 when all sixteen warps have written them.
         const uint32_t a = sE + (uint32_t) (32 * w) * 8u + lx;
-#pragma unroll
-        for(int k1 = 0; k1 < 32; k1++) sts64(a + (uint32_t) (k1 * 512) * 8u, v[k1]);
+#define OLS_P1(K)                                                                              \
+        {                                                                                          \
+          float2 lo, hi;                                                                           \
+          comb32<false, K>(v[2 * K], v[2 * K + 1], lo, hi);                                        \
+          sts64(a + (uint32_t) (K * 512) * 8u, lo);                                                \
+          sts64(a + (uint32_t) ((K + 16) * 512) * 8u, hi);                                         \
+          if(K & 1)                                                                                \
+          {                                                                                        \
+            __syncwarp();                                                                          \
+            if(l == 0)                                                                             \
+            {                                                                                      \
+              mbar_arrive_cta(row_full + (K >> 1));                                                \
+              mbar_arrive_cta(row_full + 8 + (K >> 1));                                            \
+            }                                                                                      \
+          }                                                                                        \
+        }
+        OLS_P1(0) OLS_P1(1) OLS_P1(2) OLS_P1(3) OLS_P1(4) OLS_P1(5) OLS_P1(6) OLS_P1(7)
+        OLS_P1(8) OLS_P1(9) OLS_P1(10) OLS_P1(11) OLS_P1(12) OLS_P1(13) OLS_P1(14) OLS_P1(15)
+#undef OLS_P1
       }
-      tc::named_bar(1, OLS_MATH_THREADS);
+      ols_stamp(p, it, w, l, 3);
+      mbar_wait(row_full + w, it & 1);
+      ols_stamp(p, it, w, l, 4);
 
       // ---- P2: everything between the two exchanges, inside the warp's own 8 KiB ----
+      // W512 twiddle table of the warp: row 31 of its region, each lane overwrites the element it has just read; the
+      // row is rewritten last (by the final store of row 31), after the last table read
+      const uint32_t tab = sEw + 31u * 256u;
 #pragma unroll
       for(int r = 0; r < 32; r++) v[r] = lds64(sEw + (uint32_t) (r * 32) * 8u + lx);
-      {
-        // W512^(n2 * k1), k1 = 2w + c
-#pragma unroll
-        for(int r = 1; r < 32; r++)
-          if(r != 16)
-          {
-            const float2 t = ldc64(t1c + 8 * r);
-            v[r] = cmul_s(v[r], t.x, t.y);
-          }
-      }
-      fft16s<false, 1>(&v[0]);
-      fft16s<false, 1>(&v[16]);
-      mul_tmem32<false>(v, tm + 64);
+      sts64(tab + lx, tw1c);
       __syncwarp();
-      OlsX<0>::st_rows(sEw + lx, v);          // row r (= c*16 + k2), column n3 = lane, at r*32 + (lane ^ r)
+#pragma unroll
+      for(int c = 0; c < 2; c++)
+      {
+        // k1 = 2w + c: W512 twiddle, radix-16 over n2, W_M twiddle, rows c*16 + k2 into the transpose
+#pragma unroll
+        for(int i = 8 * c; i < 8 * c + 8; i++)
+        {
+          const float4 t = lds128(tab + 16u * i);
+          if(i != 8 * c) v[2 * i] = cmul_s(v[2 * i], t.x, t.y);
+          v[2 * i + 1] = cmul_s(v[2 * i + 1], t.z, t.w);
+        }
+        fft16s<false, 1>(&v[16 * c]);
+        mul_tmem16<false>(&v[16 * c], tm + 64 + 32 * c);
+        if(c == 0) OlsX<0, 16>::st_rows(sEw + lx, v);   // row r, column n3 = lane, at r*32 + (lane ^ r)
+        else OlsX<16, 32>::st_rows(sEw + lx, v);
+      }
+      ols_stamp(p, it, w, l, 5);
       __syncwarp();
       {
         const uint32_t al = sEw + (uint32_t) l * 256u + lx;
-        OlsX<0>::ld_cols(al, v);              // row = lane, columns n3 = 0..31
+        OlsX<0, 32>::ld_cols_even(al, v);      // row = lane, columns n3 = 0, 2, ..., 30
+        OlsX<0, 32>::ld_cols_odd(al, v);
+        ols_stamp(p, it, w, l, 6);
         fft32<false>(v);
         mul_tmem32<false>(v, tm);
-        fft32<true>(v);
-        OlsX<0>::st_cols(al, v);
+        fft16s<true, 2>(&v[0]);
+        fft16s<true, 2>(&v[1]);
+        ols_stamp(p, it, w, l, 7);
+#define OLS_T2(K)                                                                              \
+        {                                                                                          \
+          float2 lo, hi;                                                                           \
+          comb32<true, K>(v[2 * K], v[2 * K + 1], lo, hi);                                         \
+          sts64x<K * 8, 0>(al, lo);                                                                \
+          sts64x<(K + 16) * 8, 0>(al, hi);                                                         \
+        }
+        OLS_T2(0) OLS_T2(1) OLS_T2(2) OLS_T2(3) OLS_T2(4) OLS_T2(5) OLS_T2(6) OLS_T2(7)
+        OLS_T2(8) OLS_T2(9) OLS_T2(10) OLS_T2(11) OLS_T2(12) OLS_T2(13) OLS_T2(14) OLS_T2(15)
+#undef OLS_T2
       }
       __syncwarp();
-      OlsX<0>::ld_rows(sEw + lx, v);
-      mul_tmem32<true>(v, tm + 64);
-      fft16s<true, 1>(&v[0]);
-      fft16s<true, 1>(&v[16]);
+      OlsX<0, 32>::ld_rows(sEw + lx, v);
+      sts64(tab + lx, tw1c);
+      __syncwarp();
+      ols_stamp(p, it, w, l, 8);
+#pragma unroll
+      for(int c = 0; c < 2; c++)
       {
+        mul_tmem16<true>(&v[16 * c], tm + 64 + 32 * c);
+        fft16s<true, 1>(&v[16 * c]);
 #pragma unroll
-        for(int r = 1; r < 32; r++)
-          if(r != 16)
-          {
-            const float2 t = ldc64(t1c + 8 * r);
-            v[r] = cmulc_s(v[r], t.x, t.y);
-          }
+        for(int i = 8 * c; i < 8 * c + 8; i++)
+        {
+          const float4 t = lds128(tab + 16u * i);
+          if(i != 8 * c) v[2 * i] = cmulc_s(v[2 * i], t.x, t.y);
+          v[2 * i + 1] = cmulc_s(v[2 * i + 1], t.z, t.w);
+        }
+#pragma unroll
+        for(int r = 16 * c; r < 16 * c + 16; r++) sts64(sEw + (uint32_t) (r * 32) * 8u + lx, v[r]);
       }
-      __syncwarp();
-#pragma unroll
-      for(int r = 0; r < 32; r++) sts64(sEw + (uint32_t) (r * 32) * 8u + lx, v[r]);
+      ols_stamp(p, it, w, l, 9);
       tc::named_bar(2, OLS_MATH_THREADS);
+      ols_stamp(p, it, w, l, 10);
 
       // ---- P3: E -> inverse radix-32 over k1 -> outputs ----
       {
         const uint32_t a = sE + (uint32_t) (32 * w) * 8u + lx;
 #pragma unroll
-        for(int k1 = 0; k1 < 32; k1++) v[k1] = lds64(a + (uint32_t) (k1 * 512) * 8u);
+        for(int h = 0; h < 2; h++)
+#pragma unroll
+          for(int k1 = h; k1 < 32; k1 += 2) v[k1] = lds64(a + (uint32_t) (k1 * 512) * 8u);
       }
       __syncwarp();
       if(l == 0) mbar_arrive_cta(e_free);
-      fft32<true>(v);
+      ols_stamp(p, it, w, l, 11);
       {
         const long long i0 = (long long) j * L + 32 * w + l;   // output index of window sample n = O + 32 w + l
         float2 *yc = p.y + (long long) chan * p.y_stride + i0;
         const int rem = (int) min(p.out_count - i0, (long long) L);   // outputs of this lane's column still inside the call
-#pragma unroll
-        for(int n1 = NX; n1 < 32; n1++)
-          if(512 * (n1 - NX) < rem) stg_stream(yc + 512 * (n1 - NX), v[n1]);
+        // inverse radix-32 whose last stage hands every output pair (n1 = K, K + 16) to the store as soon as it exists
+        fft16s<true, 2>(&v[0]);
+        fft16s<true, 2>(&v[1]);
+#define OLS_OUT(K)                                                                                   \
+        {                                                                                                \
+          float2 lo, hi;                                                                                 \
+          comb32<true, K>(v[2 * K], v[2 * K + 1], lo, hi);                                               \
+          if(K >= NX && 512 * (K - NX) < rem) ols_stg(yc + 512 * (K - NX), lo);                       \
+          if(K + 16 >= NX && 512 * (K + 16 - NX) < rem) ols_stg(yc + 512 * (K + 16 - NX), hi);        \
+        }
+        OLS_OUT(0) OLS_OUT(1) OLS_OUT(2) OLS_OUT(3) OLS_OUT(4) OLS_OUT(5) OLS_OUT(6) OLS_OUT(7)
+        OLS_OUT(8) OLS_OUT(9) OLS_OUT(10) OLS_OUT(11) OLS_OUT(12) OLS_OUT(13) OLS_OUT(14) OLS_OUT(15)
+#undef OLS_OUT
       }
+      ols_stamp(p, it, w, l, 12);
     }
   }
 
@@ -592,7 +713,7 @@ void ols16k_destroy(Ols16k *o)
   delete o;
 }
 
-int ols16k_smem_bytes(int O) { return OLS_E_BYTES + (OLS_M - O) * 8 + 16 + 64; }
+int ols16k_smem_bytes(int O) { return OLS_E_BYTES + (OLS_M - O) * 8 + 16 + 32 + 8 * OLS_MATH_WARPS + 16; }
 
 // y[c][i] = y_fir[t0 + i - delay], i in [0, out_count): window positions are relative to x[0] of this call, whose
 // stream index is t0 + residual
@@ -617,10 +738,32 @@ int ols16k_run(Ols16k *o, const float2 *x, long long xs, int n, const float2 *ca
   p.aligned = ((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (xs & 1) == 0) ? 1 : 0;
   const int grid = (int) std::min<long long>(r.num_sms, p.total);
   const int smem = ols16k_smem_bytes(o->O);
+  p.prof = nullptr;
+  const char *prof_path = getenv("TSDGPU_OLS_PROF");   // profiling aid: clock trace of CTA 0 written to this file
+  const size_t prof_words = (size_t) OLS_PROF_NIT * OLS_MATH_WARPS * OLS_PROF_PTS;
+  if(prof_path)
+  {
+    TSD_CUDA(cudaMalloc(&p.prof, prof_words * sizeof(unsigned)));
+    TSD_CUDA(cudaMemsetAsync(p.prof, 0, prof_words * sizeof(unsigned), r.stream));
+  }
+  {
   KernelTimer timer;
   if(o->O == 4096) ols16k_kernel<1><<<grid, OLS_THREADS, smem, r.stream>>>(p);
   else ols16k_kernel<2><<<grid, OLS_THREADS, smem, r.stream>>>(p);
+  }
   TSD_LAUNCH_CHECK();
+  if(prof_path)
+  {
+    std::vector<unsigned> h(prof_words);
+    TSD_CUDA(cudaStreamSynchronize(r.stream));
+    TSD_CUDA(cudaMemcpy(h.data(), p.prof, prof_words * sizeof(unsigned), cudaMemcpyDeviceToHost));
+    cudaFree(p.prof);
+    if(FILE *fp = fopen(prof_path, "wb"))
+    {
+      fwrite(h.data(), sizeof(unsigned), prof_words, fp);
+      fclose(fp);
+    }
+  }
   return 0;
 }
 
