@@ -42,8 +42,26 @@ typedef struct tsdgpu_resamp_s *tsdgpu_resamp_t;
 typedef struct tsdgpu_poly_s   *tsdgpu_poly_t;
 
 /* ---- runtime ------------------------------------------------------------------------------ */
-/* Selects the CUDA device for the calling thread and creates the library stream. */
+/* Selects the CUDA device for the calling thread and creates that device's runtime (library stream, copy streams).
+ * One runtime per device: a process may drive all the GPUs of a box; every object lives on the device that was current
+ * when it was created and its entry points switch the calling thread to it.  Calls that target the same device are
+ * serialised by a per-device lock (independent objects may be stepped from different threads, like the reference's —
+ * SURVEY 8b); calls on different devices run concurrently. */
 int tsdgpu_init(int device);
+/* Initialises several devices at once (channel-sharded batches); the calling thread ends up on devices[0]. */
+int tsdgpu_init_devices(const int *devices, int n);
+/* Switches the calling thread to `device` (initialising it if needed) / returns its current device (-1: none yet). */
+int tsdgpu_set_device(int device);
+int tsdgpu_current_device(void);
+/* Releases every runtime of the process (streams, events, staging buffers, tables) after synchronising the devices.
+ * Objects must have been destroyed before.  The library can be initialised again afterwards. */
+int tsdgpu_shutdown(void);
+/* Final gather of per-device result shards (the only cross-GPU step of the hot path): shard i
+ * (bytes[i] bytes at srcs[i] on src_devices[i]) is copied to dst + dst_offsets[i] on dst_device by peer copies over
+ * NVLink, each on its source device's library stream — i.e. behind the kernels that produce the shard.  Returns when
+ * all shards have arrived. */
+int tsdgpu_gather(void *dst, int dst_device, const long long *dst_offsets, const void *const *srcs, const int *src_devices,
+                  const long long *bytes, int n);
 /* Use an existing cudaStream_t (e.g. torch's current stream) for all subsequent launches;
  * NULL restores the library's own stream. */
 int tsdgpu_set_stream(void *cuda_stream);

@@ -3,9 +3,7 @@
 // forwards to the C ABI of include/tsdgpu.h; no arithmetic lives here.
 //
 //   #include "tsd/tsd.hpp" / "tsd/filtrage.hpp" / "tsd/fourier.hpp"   (reference)
-//   #include "tsdgpu.h"
-
-#include <vector>                                               (this repo)
+//   #include "tsdgpu.h"                                               (this repo)
 //   link: -ltsdgpu
 //
 // Drop-in points (reference file:line):
@@ -20,6 +18,8 @@
 #include "tsd/filtrage.hpp"
 #include "tsd/fourier.hpp"
 #include "tsdgpu.h"
+
+#include <vector>
 
 namespace tsd::gpu {
 

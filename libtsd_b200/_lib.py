@@ -30,6 +30,11 @@ def build(verbose: bool = False) -> str:
 
 _SIGS = {
     "tsdgpu_init": (_i, [_i]),
+    "tsdgpu_init_devices": (_i, [C.POINTER(_i), _i]),
+    "tsdgpu_set_device": (_i, [_i]),
+    "tsdgpu_current_device": (_i, []),
+    "tsdgpu_shutdown": (_i, []),
+    "tsdgpu_gather": (_i, [_vp, _i, C.POINTER(_ll), C.POINTER(_vp), C.POINTER(_i), C.POINTER(_ll), _i]),
     "tsdgpu_set_stream": (_i, [_vp]),
     "tsdgpu_synchronize": (_i, []),
     "tsdgpu_last_error": (C.c_char_p, []),

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
+#include <mutex>
 #include <string>
 #include <utility>
 #include <vector>
@@ -10,8 +11,21 @@
 namespace tsdgpu {
 
 // ---------------------------------------------------------------- host runtime state
+// staging of the host-memory entry points (host_pipe.cuh): two device slots each way + their events
+struct HostStage
+{
+  void *in[2] = {nullptr, nullptr}, *out[2] = {nullptr, nullptr};
+  size_t in_bytes = 0, out_bytes = 0;
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+};
+// One Runtime per CUDA device (runtime.cu keeps a table).  A host thread works on one device at a time
+// (tsdgpu_init / tsdgpu_set_device; every object remembers the device it was created on and its entry points switch
+// to it); calls that target the same device are serialised by `mu`, calls on different devices run concurrently.
 struct Runtime
 {
+  std::recursive_mutex mu;
+  HostStage hs;
+  bool ols_ready = false;            // ols16k.cu: constant table + shared-memory opt-in done on this device
   int device = -1;
   int num_sms = 0;
   cudaStream_t own_stream = nullptr;
@@ -38,8 +52,13 @@ struct KernelTimer
   KernelTimer();
   ~KernelTimer();
 };
-Runtime &rt();
-int ensure_init();
+Runtime &rt();               // runtime of the calling thread's current device
+int ensure_init();           // makes sure the calling thread has a usable device (default: the first one initialised, else 0)
+int enter_device(int device);   // switches the calling thread to `device` (< 0: keep / default) and initialises it if needed
+// first statement of every C-ABI entry that touches a device: select it, then hold its lock for the whole call
+#define TSD_ENTER(dev)                                                                  \
+  if(::tsdgpu::enter_device(dev)) return 1;                                             \
+  std::lock_guard<std::recursive_mutex> tsd_guard__(::tsdgpu::rt().mu)
 int aux_init();          // creates the auxiliary streams, their events and the twiddle table (idempotent)
 int aux_fork(int n);     // aux[0..n) wait for everything enqueued so far on rt().stream
 int aux_join(int n);     // rt().stream waits for everything enqueued on aux[0..n)

@@ -391,8 +391,10 @@ int fft_plan_create(int n, int batch, tsdgpu_fft_s **out)
   if(batch <= 0) return fail("tsdgpu_fft_plan: batch must be > 0");
   if(n > (1 << 24)) return fail("tsdgpu_fft_plan: n > 2^24 not supported");
   auto *p = new tsdgpu_fft_s;
+  p->device = rt().device;
   p->n = n;
   p->batch = batch;
+  p->batch_created = batch;
   if(n & (n - 1))
   {
     cudaError_t e = cudaSuccess;
@@ -498,10 +500,22 @@ void fft_plan_destroy(tsdgpu_fft_s *p)
   delete p;
 }
 
+// work buffers of the radix-2 path: sized for the live batch (the host entry temporarily runs the plan with a
+// smaller batch, fft_exec below), regrown when a later call needs more
 static int ensure_work(tsdgpu_fft_s *p, int which)
 {
-  if(p->work[which]) return 0;
-  TSD_CUDA(cudaMalloc(&p->work[which], (size_t) p->n * p->batch * sizeof(float2)));
+  const size_t need = (size_t) p->n * p->batch;
+  if(p->work[which] && p->work_cap[which] >= need) return 0;
+  if(p->work[which])
+  {
+    TSD_CUDA(cudaStreamSynchronize(rt().stream));
+    cudaFree(p->work[which]);
+    p->work[which] = nullptr;
+    p->work_cap[which] = 0;
+  }
+  const size_t cap = std::max(need, (size_t) p->n * p->batch_created);
+  TSD_CUDA(cudaMalloc(&p->work[which], cap * sizeof(float2)));
+  p->work_cap[which] = cap;
   return 0;
 }
 
@@ -672,14 +686,14 @@ extern "C" {
 
 int tsdgpu_fft_plan(int n, int batch, tsdgpu_fft_t *out)
 {
-  if(ensure_init()) return 1;
+  TSD_ENTER(-1);
   if(!out) return fail("tsdgpu_fft_plan: null argument");
   return fft_plan_create(n, batch, out);
 }
 
 int tsdgpu_fft_exec(tsdgpu_fft_t p, const void *x, long long xs, void *y, long long ys, int forward, int mem)
 {
-  if(ensure_init()) return 1;
+  TSD_ENTER(p ? p->device : -1);
   if(!p || !x || !y) return fail("tsdgpu_fft_exec: null argument");
   if(xs < p->n || ys < p->n) return fail("tsdgpu_fft_exec: stride smaller than n");
   if(mem == TSDGPU_DEVICE) return fft_exec_device(p, (const float2 *) x, xs, (float2 *) y, ys, forward != 0);
@@ -719,7 +733,9 @@ int tsdgpu_fft_exec(tsdgpu_fft_t p, const void *x, long long xs, void *y, long l
 
 int tsdgpu_fft_destroy(tsdgpu_fft_t p)
 {
-  if(p) cudaStreamSynchronize(rt().stream);
+  if(!p) return 0;
+  TSD_ENTER(p->device);
+  cudaStreamSynchronize(rt().stream);
   fft_plan_destroy(p);
   return 0;
 }

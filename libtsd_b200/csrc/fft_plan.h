@@ -4,6 +4,7 @@
 
 struct tsdgpu_fft_s
 {
+  int device = 0;              // CUDA device the plan lives on
   int n = 0, batch = 0;
   // N = 65536 pipeline
   float2 *scratch = nullptr;   // ring of L2-resident intermediates
@@ -13,6 +14,8 @@ struct tsdgpu_fft_s
   bool smem_optin = false;     // shared-memory kernel: > 48 KiB of dynamic shared memory enabled
   // generic radix-2 path
   float2 *work[2] = {nullptr, nullptr};
+  size_t work_cap[2] = {0, 0};   // elements allocated
+  int batch_created = 0;          // batch the plan was created with
   // n not a power of two (TFRPlanDefaut::configure, fourier.cc:372-405): even n -> two transforms of n/2 + one
   // radix-2 combine (fourier.cc:438-462); odd n -> chirp-z through a power-of-two plan of n2 = p2(2n-1) (fourier.cc:237-255)
   tsdgpu_fft_s *sub = nullptr;

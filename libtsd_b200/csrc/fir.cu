@@ -184,6 +184,7 @@ using namespace tsdgpu;
 
 struct tsdgpu_fir_s
 {
+  int device = 0;              // CUDA device the object lives on
   int kind = 0, K = 0, nchan = 0, halo = 0, DC = 1, TC = 1;
   long long total = 0;        // samples consumed per channel so far
   void *d_taps = nullptr;
@@ -291,13 +292,14 @@ extern "C" {
 
 int tsdgpu_fir_create(int kind, const float *taps, int K, int nchan, tsdgpu_fir_t *out)
 {
-  if(ensure_init()) return 1;
+  TSD_ENTER(-1);
   if(!out || !taps) return fail("tsdgpu_fir_create: null argument");
   if(K <= 0) return fail("tsdgpu_fir_create: K must be > 0 (assertion K > 0, filtre-rt.cc:69)");
   if(nchan <= 0 || nchan > 65535) return fail("tsdgpu_fir_create: nchan must be in [1, 65535]");
   if(kind < 0 || kind > 2) return fail("tsdgpu_fir_create: unknown kind");
   if(K > 8192) return fail("tsdgpu_fir_create: K > 8192 is not supported by the direct form (use tsdgpu_ola_create)");
   auto *f = new tsdgpu_fir_s;
+  f->device = rt().device;
   f->kind = kind;
   f->K = K;
   f->nchan = nchan;
@@ -324,7 +326,7 @@ int tsdgpu_fir_create(int kind, const float *taps, int K, int nchan, tsdgpu_fir_
 
 int tsdgpu_fir_step(tsdgpu_fir_t f, const void *x, long long xs, int n, void *y, long long ys, int mem)
 {
-  if(ensure_init()) return 1;
+  TSD_ENTER(f ? f->device : -1);
   if(!f) return fail("tsdgpu_fir_step: null handle");
   if(n < 0) return fail("tsdgpu_fir_step: n < 0");
   if(n == 0) return 0;
@@ -359,7 +361,7 @@ int tsdgpu_fir_step(tsdgpu_fir_t f, const void *x, long long xs, int n, void *y,
 
 int tsdgpu_fir_get_state(tsdgpu_fir_t f, void *fen_host, int *index)
 {
-  if(ensure_init()) return 1;
+  TSD_ENTER(f ? f->device : -1);
   if(!f) return fail("tsdgpu_fir_get_state: null handle");
   const size_t ssz = (f->DC == 1) ? 4 : 8;
   const int K = f->K, idx = (int) (f->total % K);
@@ -386,7 +388,7 @@ int tsdgpu_fir_get_state(tsdgpu_fir_t f, void *fen_host, int *index)
 
 int tsdgpu_fir_set_state(tsdgpu_fir_t f, const void *fen_host, int index)
 {
-  if(ensure_init()) return 1;
+  TSD_ENTER(f ? f->device : -1);
   if(!f || !fen_host) return fail("tsdgpu_fir_set_state: null argument");
   if(index < 0 || index >= f->K) return fail("tsdgpu_fir_set_state: index out of range");
   const size_t ssz = (f->DC == 1) ? 4 : 8;
@@ -410,6 +412,7 @@ int tsdgpu_fir_set_state(tsdgpu_fir_t f, const void *fen_host, int index)
 int tsdgpu_fir_destroy(tsdgpu_fir_t f)
 {
   if(!f) return 0;
+  TSD_ENTER(f->device);
   cudaFree(f->d_taps);
   cudaFree(f->d_hist[0]);
   cudaFree(f->d_hist[1]);

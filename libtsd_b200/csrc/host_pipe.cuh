@@ -10,12 +10,6 @@
 
 namespace tsdgpu {
 
-struct HostStage
-{
-  void *in[2] = {nullptr, nullptr}, *out[2] = {nullptr, nullptr};
-  size_t in_bytes = 0, out_bytes = 0;
-  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
-};
 HostStage &host_stage();
 int host_stage_reserve(size_t in_bytes, size_t out_bytes);
 

@@ -508,6 +508,7 @@ using namespace tsdgpu;
 
 struct tsdgpu_ola_s
 {
+  int device = 0;              // CUDA device the object lives on
   int Ne = 0, N = 0, Nz = 0, K = 0, nchan = 0;
   int residual = 0;            // TamponNv2 windex (tsd.cc:310)
   long long blocks_done = 0;
@@ -635,28 +636,44 @@ static int ola_run_fused(tsdgpu_ola_s *f, const float2 *x, long long xs, int n, 
   return 0;
 }
 
+// The unfused / windowed paths keep ONE plan and work buffer sized for the largest batch seen; smaller chunks (the
+// ragged last chunk, or calls that alternate between B and B+1 blocks) run the same plan with the live batch, so no
+// allocation or device synchronisation happens on the data path after the first call of that size.
+static int ola_reserve_plan(tsdgpu_ola_s *f, int batch)
+{
+  if(f->plan && f->plan_batch >= batch)
+  {
+    f->plan->batch = batch;
+    return 0;
+  }
+  if(f->plan)
+  {
+    TSD_CUDA(cudaStreamSynchronize(rt().stream));
+    fft_plan_destroy(f->plan);
+  }
+  f->plan = nullptr;
+  if(f->work) cudaFree(f->work);
+  f->work = nullptr;
+  if(fft_plan_create(f->N, batch, &f->plan)) return 1;
+  f->plan_batch = batch;
+  TSD_CUDA(cudaMalloc(&f->work, (size_t) batch * f->N * sizeof(float2)));
+  return 0;
+}
+
 static int ola_run_unfused(tsdgpu_ola_s *f, const float2 *x, long long xs, float2 *y, long long ys, int B)
 {
   Runtime &r = rt();
   const int N = f->N, Ne = f->Ne, Nz = f->Nz;
   // blocks per chunk: bounded work buffer (<= 256 MiB)
+  // blocks per chunk: bounded work buffer (<= 256 MiB) and grid (<= 65535 rows per launch)
+  if(f->nchan > 65535) return fail("tsdgpu_ola_step: more than 65535 channels on the unfused path");
   long long per_block = (long long) f->nchan * N * (long long) sizeof(float2);
-  int nb_max = (int) std::max(1LL, (256LL << 20) / per_block);
+  const int nb_max = (int) std::max(1LL, std::min((256LL << 20) / per_block, 65535LL / f->nchan));
   for(int b0 = 0; b0 < B; b0 += nb_max)
   {
     const int nb = std::min(nb_max, B - b0);
     const int batch = f->nchan * nb;
-    if(batch > 65535) return fail("tsdgpu_ola_step: nchan * blocks per chunk > 65535 on the unfused path");
-    if(!f->plan || f->plan_batch != batch)
-    {
-      if(f->plan) fft_plan_destroy(f->plan);
-      f->plan = nullptr;
-      if(f->work) cudaFree(f->work);
-      f->work = nullptr;
-      if(fft_plan_create(N, batch, &f->plan)) return 1;
-      f->plan_batch = batch;
-      TSD_CUDA(cudaMalloc(&f->work, (size_t) batch * N * sizeof(float2)));
-    }
+    if(ola_reserve_plan(f, batch)) return 1;
     dim3 gg((N + 255) / 256, batch);
     ola_gather_kernel<<<gg, 256, 0, r.stream>>>(x, xs, f->d_carry[f->cur], f->carry_len, f->work, N, Ne, Nz, nb, b0,
                                                f->residual);
@@ -684,24 +701,15 @@ static int ola_run_fen(tsdgpu_ola_s *f, const float2 *x, long long xs, float2 *y
 {
   Runtime &r = rt();
   const int N = f->N, Ne = f->Ne, Nz = f->Nz;
+  if(2LL * f->nchan > 65535) return fail("tsdgpu_ola_step: more than 32767 channels in the windowed mode");
   const long long per_block = 2LL * f->nchan * N * (long long) sizeof(float2);
-  const int nb_max = (int) std::max(1LL, (256LL << 20) / per_block);
+  const int nb_max = (int) std::max(1LL, std::min((256LL << 20) / per_block, 65535LL / (2LL * f->nchan)));
   const long long g0 = f->blocks_done, e_first = std::max(g0, 1LL);
   for(int b0 = 0; b0 < B; b0 += nb_max)
   {
     const int nb = std::min(nb_max, B - b0);
     const int batch = f->nchan * nb * 2;
-    if(batch > 65535) return fail("tsdgpu_ola_step: 2 * nchan * blocks per chunk > 65535 in the windowed mode");
-    if(!f->plan || f->plan_batch != batch)
-    {
-      if(f->plan) fft_plan_destroy(f->plan);
-      f->plan = nullptr;
-      if(f->work) cudaFree(f->work);
-      f->work = nullptr;
-      if(fft_plan_create(N, batch, &f->plan)) return 1;
-      f->plan_batch = batch;
-      TSD_CUDA(cudaMalloc(&f->work, (size_t) batch * N * sizeof(float2)));
-    }
+    if(ola_reserve_plan(f, batch)) return 1;
     dim3 gg((N + 255) / 256, batch);
     ola_gather_fen_kernel<<<gg, 256, 0, r.stream>>>(x, xs, f->d_carry[f->cur], f->carry_len, f->work, f->d_fen, N, Ne, Nz, nb,
                                                    b0, f->residual);
@@ -773,7 +781,7 @@ int tsdgpu_ola_create_fen(int dim_blocs_temporel, int nb_zeros_min, const float 
 static int ola_create(int dim_blocs_temporel, int nb_zeros_min, const float *H, int fir_len, const float *fenetre, int nchan,
                       tsdgpu_ola_t *out)
 {
-  if(ensure_init()) return 1;
+  TSD_ENTER(-1);
   if(!out) return fail("tsdgpu_ola_create: null argument");
   if(nchan <= 0) return fail("tsdgpu_ola_create: nchan must be > 0");
   if(nb_zeros_min < 0) return fail("tsdgpu_ola_create: nb_zeros_min < 0");
@@ -793,6 +801,7 @@ static int ola_create(int dim_blocs_temporel, int nb_zeros_min, const float *H, 
     return fail("tsdgpu_ola_create_fen: odd dim_blocs_temporel is not supported in the windowed mode (the reference never "
                 "resets the centre sample of its `last` buffer there, fourier.cc:899-906)");
   auto *f = new tsdgpu_ola_s;
+  f->device = rt().device;
   f->Ne = Ne;
   f->N = N;
   f->Nz = Nz;
@@ -894,7 +903,7 @@ long long tsdgpu_ola_out_count(tsdgpu_ola_t f, int n)
 
 int tsdgpu_ola_step(tsdgpu_ola_t f, const void *x, long long xs, int n, void *y, long long ys, long long *n_out, int mem)
 {
-  if(ensure_init()) return 1;
+  TSD_ENTER(f ? f->device : -1);
   if(!f || !n_out) return fail("tsdgpu_ola_step: null argument");
   *n_out = 0;
   if(n < 0) return fail("tsdgpu_ola_step: n < 0");
@@ -938,7 +947,7 @@ int tsdgpu_ola_step(tsdgpu_ola_t f, const void *x, long long xs, int n, void *y,
 int tsdgpu_periodogramme_tfd(const void *x, long long x_stride, int n, int nchan, int N, const float *fenetre, float *out,
                              long long out_stride, int *n_frames, int *n_bins, int mem)
 {
-  if(ensure_init()) return 1;
+  TSD_ENTER(-1);
   if(!x || !fenetre || !out || !n_frames || !n_bins) return fail("tsdgpu_periodogramme_tfd: null argument");
   if(n < 0 || nchan <= 0 || N < 2 || N > (1 << 24)) return fail("tsdgpu_periodogramme_tfd: invalid size");
   if(N & 1) return fail("tsdgpu_periodogramme_tfd: odd N is not supported (see tsdgpu_ola_create_fen)");
@@ -1026,6 +1035,7 @@ int tsdgpu_periodogramme_tfd(const void *x, long long x_stride, int n, int nchan
 int tsdgpu_ola_destroy(tsdgpu_ola_t f)
 {
   if(!f) return 0;
+  TSD_ENTER(f->device);
   cudaStreamSynchronize(rt().stream);
   cudaFree(f->d_H);
   cudaFree(f->d_carry[0]);

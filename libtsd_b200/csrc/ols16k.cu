@@ -631,8 +631,6 @@ static void fft_double(std::vector<std::complex<double>> &a, bool inverse)
   }
 }
 
-static bool g_tw1_ready = false;
-static int g_tw1_device = -1;
 
 int ols16k_create(const float *H, int N, int K, Ols16k **out)
 {
@@ -676,7 +674,7 @@ int ols16k_create(const float *H, int N, int K, Ols16k **out)
         dst[64 + 2 * (c * 16 + k2) + 1] = (float) sin(ang);
       }
   }
-  if(!g_tw1_ready || g_tw1_device != rt().device)
+  if(!rt().ols_ready)
   {
     std::vector<float2> t1(512);
     for(int k1 = 0; k1 < 32; k1++)
@@ -688,8 +686,7 @@ int ols16k_create(const float *H, int N, int K, Ols16k **out)
     TSD_CUDA(cudaMemcpyToSymbol(c_ols_tw1, t1.data(), 512 * sizeof(float2)));
     TSD_CUDA(cudaFuncSetAttribute(ols16k_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ols16k_smem_bytes(4096)));
     TSD_CUDA(cudaFuncSetAttribute(ols16k_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ols16k_smem_bytes(8192)));
-    g_tw1_ready = true;
-    g_tw1_device = rt().device;
+    rt().ols_ready = true;
   }
   auto *o = new Ols16k;
   o->O = O;

@@ -105,6 +105,7 @@ using namespace tsdgpu;
 
 struct tsdgpu_poly_s
 {
+  int device = 0;              // CUDA device the object lives on
   int kind = 0, K = 0, R = 1, L = 0, nrows = 1, DC = 2, nchan = 1;
   int cnt = 0;               // decimation counter of the reference object (`cnt` / `odd`)
   long long total = 0;       // samples fed so far (ring index = total mod L)
@@ -167,7 +168,7 @@ extern "C" {
 
 int tsdgpu_poly_create(int kind, const float *coefs, int K, int R, int data_complex, int nchan, tsdgpu_poly_t *out)
 {
-  if(ensure_init()) return 1;
+  TSD_ENTER(-1);
   if(!out || !coefs) return fail("tsdgpu_poly_create: null argument");
   if(K <= 0) return fail("tsdgpu_poly_create: K must be > 0 (assertion K > 0, polyphase.cc:69,172,283)");
   if(kind < 0 || kind > 2) return fail("tsdgpu_poly_create: unknown kind");
@@ -175,6 +176,7 @@ int tsdgpu_poly_create(int kind, const float *coefs, int K, int R, int data_comp
   if(R < 1) return fail("tsdgpu_poly_create: R must be >= 1");
   if(nchan <= 0 || nchan > 65535) return fail("tsdgpu_poly_create: nchan must be in [1, 65535]");
   auto *f = new tsdgpu_poly_s;
+  f->device = rt().device;
   f->kind = kind;
   f->K = K;
   f->R = R;
@@ -242,7 +244,7 @@ int tsdgpu_poly_state(tsdgpu_poly_t f, int *index, int *cnt)
 
 int tsdgpu_poly_step(tsdgpu_poly_t f, const void *x, long long xs, int n, void *y, long long ys, long long *n_out, int mem)
 {
-  if(ensure_init()) return 1;
+  TSD_ENTER(f ? f->device : -1);
   if(!f || !n_out) return fail("tsdgpu_poly_step: null argument");
   *n_out = 0;
   if(n < 0) return fail("tsdgpu_poly_step: n < 0");
@@ -281,6 +283,7 @@ int tsdgpu_poly_step(tsdgpu_poly_t f, const void *x, long long xs, int n, void *
 int tsdgpu_poly_destroy(tsdgpu_poly_t f)
 {
   if(!f) return 0;
+  TSD_ENTER(f->device);
   cudaStreamSynchronize(rt().stream);
   cudaFree(f->d_rows);
   cudaFree(f->d_hist[0]);

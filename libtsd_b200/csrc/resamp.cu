@@ -215,6 +215,7 @@ using namespace tsdgpu;
 
 struct tsdgpu_resamp_s
 {
+  int device = 0;              // CUDA device the object lives on
   float ratio = 1, increment = 1, phase = 0;
   int K = 0, nphases = 0, nchan = 0, hist_len = 0;
   float *d_lut = nullptr;
@@ -485,12 +486,13 @@ extern "C" {
 
 int tsdgpu_resamp_create(float ratio, const float *lut, int K, int nphases, int nchan, tsdgpu_resamp_t *out)
 {
-  if(ensure_init()) return 1;
+  TSD_ENTER(-1);
   if(!out || !lut) return fail("tsdgpu_resamp_create: null argument");
   if(K <= 0 || nphases <= 0) return fail("tsdgpu_resamp_create: K and nphases must be > 0");
   if(nchan <= 0 || nchan > 65535) return fail("tsdgpu_resamp_create: nchan must be in [1, 65535]");
   if(!(ratio > 0) || std::isinf(ratio)) return fail("tsdgpu_resamp_create: invalid ratio");
   auto *f = new tsdgpu_resamp_s;
+  f->device = rt().device;
   f->ratio = ratio;
   f->increment = 1 / ratio;     // ra.cc:28
   f->phase = 0;
@@ -526,12 +528,15 @@ float tsdgpu_resamp_phase(tsdgpu_resamp_t f) { return f ? f->phase : 0.f; }
 int tsdgpu_resamp_step(tsdgpu_resamp_t f, const void *x, long long xs, int n, void *y, long long ys, long long ycap,
                        long long *n_out, int mem)
 {
-  if(ensure_init()) return 1;
+  TSD_ENTER(f ? f->device : -1);
   if(!f || !n_out) return fail("tsdgpu_resamp_step: null argument");
   *n_out = 0;
   if(n < 0) return fail("tsdgpu_resamp_step: n < 0");
   if(n == 0) return 0;            // ra.cc:45-49
-  if(!x || !y) return fail("tsdgpu_resamp_step: null buffer");
+  if(!x) return fail("tsdgpu_resamp_step: null input");
+  // a short call may emit nothing (n = 1 with a carried phase >= 1 at ratio < 1): the reference then returns an empty
+  // vector (ra.cc:39-77) and the caller's y may be null; phase and history still advance
+  if(!y && tsdgpu_resamp_out_count(f, n) > 0) return fail("tsdgpu_resamp_step: null output");
   if(xs < n) return fail("tsdgpu_resamp_step: channel stride smaller than n");
   if(mem == TSDGPU_DEVICE) return resamp_run_device(f, (const float2 *) x, xs, n, (float2 *) y, ys, ycap, n_out);
   const long long cnt = tsdgpu_resamp_out_count(f, n);
@@ -605,6 +610,7 @@ int tsdgpu_resamp_schedule(float *phase, float ratio, int nphases, int n, int32_
 int tsdgpu_resamp_destroy(tsdgpu_resamp_t f)
 {
   if(!f) return 0;
+  TSD_ENTER(f->device);
   cudaStreamSynchronize(rt().stream);
   cudaFree(f->d_lut);
   cudaFree(f->d_hist[0]);

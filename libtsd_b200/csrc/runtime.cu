@@ -11,11 +11,13 @@ namespace tsdgpu {
 
 static thread_local std::string g_error;
 
-Runtime &rt()
-{
-  static Runtime r;
-  return r;
-}
+constexpr int MAX_DEVICES = 64;
+static Runtime g_rt[MAX_DEVICES];
+static std::mutex g_table_mu;          // guards creation / destruction of the per-device runtimes
+static int g_default_device = -1;      // first device initialised in this process
+static thread_local int t_device = -1; // device the calling thread works on
+
+Runtime &rt() { return g_rt[t_device < 0 ? (g_default_device < 0 ? 0 : g_default_device) : t_device]; }
 void set_error(const std::string &s) { g_error = s; }
 int fail(const std::string &s)
 {
@@ -29,9 +31,12 @@ static int init_device(int device)
   cudaError_t e = cudaGetDeviceCount(&count);
   if(e != cudaSuccess || count == 0)
     return fail(std::string("libtsdgpu: no CUDA device (") + cudaGetErrorString(e) + "); there is no CPU fallback");
-  if(device < 0 || device >= count) return fail("libtsdgpu: device index out of range");
+  if(device < 0 || device >= count || device >= MAX_DEVICES) return fail("libtsdgpu: device index out of range");
   TSD_CUDA(cudaSetDevice(device));
-  Runtime &r = rt();
+  t_device = device;
+  std::lock_guard<std::mutex> table_guard(g_table_mu);
+  if(g_default_device < 0) g_default_device = device;
+  Runtime &r = g_rt[device];
   if(r.device == device && r.own_stream) return 0;
   cudaDeviceProp prop;
   TSD_CUDA(cudaGetDeviceProperties(&prop, device));
@@ -48,15 +53,65 @@ static int init_device(int device)
   return 0;
 }
 
-int ensure_init()
+int ensure_init() { return enter_device(-1); }
+
+int enter_device(int device)
 {
-  if(rt().device >= 0)
+  if(device < 0) device = t_device >= 0 ? t_device : (g_default_device >= 0 ? g_default_device : 0);
+  if(device < MAX_DEVICES && g_rt[device].device == device && g_rt[device].own_stream)
   {
-    // CUDA's current device is per host thread
-    cudaSetDevice(rt().device);
+    t_device = device;
+    cudaSetDevice(device);   // CUDA's current device is per host thread
     return 0;
   }
-  return init_device(0);
+  return init_device(device);
+}
+
+// releases everything the runtime of one device owns (objects must have been destroyed by their owners)
+static void shutdown_device(Runtime &r)
+{
+  if(r.device < 0) return;
+  cudaSetDevice(r.device);
+  cudaDeviceSynchronize();
+  for(int i = 0; i < Runtime::MAX_AUX; i++)
+  {
+    if(r.aux[i]) cudaStreamDestroy(r.aux[i]);
+    if(r.ev_join[i]) cudaEventDestroy(r.ev_join[i]);
+    r.aux[i] = nullptr;
+    r.ev_join[i] = nullptr;
+  }
+  if(r.ev_fork) cudaEventDestroy(r.ev_fork);
+  r.ev_fork = nullptr;
+  if(r.tw256) cudaFree(r.tw256);
+  if(r.tw4) cudaFree(r.tw4);
+  r.tw256 = nullptr;
+  r.tw4 = nullptr;
+  HostStage &hs = r.hs;
+  for(int i = 0; i < 2; i++)
+  {
+    if(hs.in[i]) cudaFree(hs.in[i]);
+    if(hs.out[i]) cudaFree(hs.out[i]);
+    if(hs.ev_in[i]) cudaEventDestroy(hs.ev_in[i]);
+    if(hs.ev_done[i]) cudaEventDestroy(hs.ev_done[i]);
+    if(hs.ev_out[i]) cudaEventDestroy(hs.ev_out[i]);
+    hs.in[i] = hs.out[i] = nullptr;
+    hs.ev_in[i] = hs.ev_done[i] = hs.ev_out[i] = nullptr;
+  }
+  hs.in_bytes = hs.out_bytes = 0;
+  for(auto &pr : r.timed)
+  {
+    cudaEventDestroy(pr.first);
+    cudaEventDestroy(pr.second);
+  }
+  r.timed.clear();
+  if(r.own_stream) cudaStreamDestroy(r.own_stream);
+  if(r.copy_in) cudaStreamDestroy(r.copy_in);
+  if(r.copy_out) cudaStreamDestroy(r.copy_out);
+  r.own_stream = r.stream = r.copy_in = r.copy_out = nullptr;
+  r.ols_ready = false;
+  r.timing = false;
+  r.launches = 0;
+  r.device = -1;
 }
 
 int aux_init()
@@ -123,11 +178,7 @@ int aux_join(int n)
   return 0;
 }
 
-HostStage &host_stage()
-{
-  static HostStage hs;
-  return hs;
-}
+HostStage &host_stage() { return rt().hs; }
 int host_stage_reserve(size_t in_bytes, size_t out_bytes)
 {
   HostStage &hs = host_stage();
@@ -191,17 +242,78 @@ extern "C" {
 
 int tsdgpu_init(int device) { return init_device(device); }
 
+int tsdgpu_init_devices(const int *devices, int n)
+{
+  if(!devices || n <= 0) return fail("tsdgpu_init_devices: empty device list");
+  for(int i = n - 1; i >= 0; i--)
+    if(init_device(devices[i])) return 1;   // the calling thread ends up on devices[0]
+  return 0;
+}
+
+int tsdgpu_set_device(int device) { return enter_device(device); }
+
+int tsdgpu_current_device(void) { return rt().device; }
+
+int tsdgpu_shutdown(void)
+{
+  std::lock_guard<std::mutex> table_guard(g_table_mu);
+  for(int d = 0; d < MAX_DEVICES; d++)
+  {
+    std::lock_guard<std::recursive_mutex> g(g_rt[d].mu);
+    shutdown_device(g_rt[d]);
+  }
+  g_default_device = -1;
+  t_device = -1;
+  return 0;
+}
+
 int tsdgpu_set_stream(void *s)
 {
-  if(ensure_init()) return 1;
+  TSD_ENTER(-1);
   rt().stream = s ? (cudaStream_t) s : rt().own_stream;
   return 0;
 }
 
 int tsdgpu_synchronize(void)
 {
-  if(ensure_init()) return 1;
+  TSD_ENTER(-1);
   TSD_CUDA(cudaStreamSynchronize(rt().stream));
+  return 0;
+}
+
+// Final gather of per-device result shards: shard i, `bytes[i]` bytes on device src_devices[i], lands at
+// dst + dst_offsets[i] on dst_device.  Peer copies over NVLink on the source devices' library streams, so each shard leaves
+// as soon as the kernels that produce it have finished; returns when every shard has arrived.
+int tsdgpu_gather(void *dst, int dst_device, const long long *dst_offsets, const void *const *srcs, const int *src_devices,
+                  const long long *bytes, int n)
+{
+  if(!dst || !dst_offsets || !srcs || !src_devices || !bytes || n <= 0) return fail("tsdgpu_gather: null argument");
+  const int back = rt().device;
+  for(int i = 0; i < n; i++)
+  {
+    if(bytes[i] <= 0) continue;
+    if(enter_device(src_devices[i])) return 1;
+    std::lock_guard<std::recursive_mutex> g(rt().mu);
+    if(src_devices[i] != dst_device)
+    {
+      int can = 0;
+      cudaDeviceCanAccessPeer(&can, src_devices[i], dst_device);
+      if(can)
+      {
+        cudaError_t e = cudaDeviceEnablePeerAccess(dst_device, 0);
+        if(e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(std::string("tsdgpu_gather: ") + cudaGetErrorString(e));
+        cudaGetLastError();
+      }
+    }
+    TSD_CUDA(cudaMemcpyPeerAsync((char *) dst + dst_offsets[i], dst_device, srcs[i], src_devices[i], (size_t) bytes[i], rt().stream));
+  }
+  for(int i = 0; i < n; i++)
+  {
+    if(bytes[i] <= 0) continue;
+    if(enter_device(src_devices[i])) return 1;
+    TSD_CUDA(cudaStreamSynchronize(rt().stream));
+  }
+  if(back >= 0) enter_device(back);
   return 0;
 }
 
@@ -216,14 +328,14 @@ long long tsdgpu_launch_count(int reset)
 
 int tsdgpu_timing_enable(int on)
 {
-  if(ensure_init()) return 1;
+  TSD_ENTER(-1);
   rt().timing = on != 0;
   return 0;
 }
 
 int tsdgpu_timing_read(double *total_ms, long long *launches)
 {
-  if(ensure_init()) return 1;
+  TSD_ENTER(-1);
   Runtime &r = rt();
   TSD_CUDA(cudaStreamSynchronize(r.stream));
   double tot = 0;
