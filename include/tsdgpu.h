@@ -129,6 +129,16 @@ int tsdgpu_ola_create(int dim_blocs_temporel, int nb_zeros_min, const float *H, 
  * inverse-transform output from the second block on (:923).  Even Ne only. */
 int tsdgpu_ola_create_fen(int dim_blocs_temporel, int nb_zeros_min, const float *H, const float *fenetre,
                           int nchan, tsdgpu_ola_t *out);
+/* Generic spectral callback: FiltreFFTConfig::traitement_freq is an arbitrary host std::function<void(Veccf&)>
+ * (fourier.hpp:319) that the reference calls once per transformed block (fourier.cc:863; twice per block in the windowed
+ * mode, :895,915).  cb(user, chan, X, N) receives the N unitary-scaled bins of one block of channel `chan` in host memory
+ * (interleaved cfloat) and may modify them in place; calls arrive in the reference's order for every channel.  The path
+ * is FFT -> D2H -> callback -> H2D -> IFFT -> overlap-add, so it is bounded by the host link, not by the GPU; callers
+ * whose callback is "X *= H" should hand H over as data (tsdgpu_ola_create).  fenetre: NULL = plain mode, else the Ne
+ * window values of the windowed mode (see tsdgpu_ola_create_fen). */
+typedef void (*tsdgpu_spectral_cb)(void *user, int chan, float *X, int N);
+int tsdgpu_ola_create_cb(int dim_blocs_temporel, int nb_zeros_min, tsdgpu_spectral_cb cb, void *user, const float *fenetre,
+                         int nchan, tsdgpu_ola_t *out);
 int tsdgpu_ola_dims(tsdgpu_ola_t f, int *Ne, int *N, int *N_zeros, int *residual);
 /* Number of samples the next step(n) will emit: Ne * ((residual + n) / Ne), one block less for the
  * first block of a windowed filter (TamponNv2 re-blocking, tsd.cc:332-370; fourier.cc:813-833). */
@@ -154,6 +164,17 @@ int tsdgpu_periodogramme_tfd(const void *x, long long x_stride, int n, int nchan
  * on the host, once for all channels. */
 int tsdgpu_resamp_create(float ratio, const float *lut, int K, int nphases, int nchan,
                          tsdgpu_resamp_t *out);
+/* Same with the sample type chosen: data_complex = 0 is filtre_itrp<float> / filtre_reechan<float> (ra.cc:190-195, the
+ * instantiation the reference's own acceptance test drives, tests/test-ra.cc:148-165), 1 is cfloat. */
+int tsdgpu_resamp_create_ex(float ratio, const float *lut, int K, int nphases, int data_complex, int nchan,
+                            tsdgpu_resamp_t *out);
+/* Interpolators that evaluate their coefficients at the EXACT fractional delay instead of reading a LUT column:
+ * itrp_lineaire (itrp.cc:82-95, K = 2, {1 - tau, tau}) and itrp_lagrange(d) (itrp.cc:97-127, K = d + 1).  The host
+ * schedule ships the float32 phase of every output; the device evaluates the coefficients with the reference's float
+ * operations. */
+#define TSDGPU_ITRP_LINEAIRE 1
+#define TSDGPU_ITRP_LAGRANGE 2
+int tsdgpu_resamp_create_exact(float ratio, int kind, int degree, int data_complex, int nchan, tsdgpu_resamp_t *out);
 /* Output count of the next step(n) (identical for every channel) and the current phase. */
 long long tsdgpu_resamp_out_count(tsdgpu_resamp_t f, int n);
 float tsdgpu_resamp_phase(tsdgpu_resamp_t f);

@@ -5,6 +5,7 @@
 #include "tsd_gpu_adapters.hpp"
 #include <cstdio>
 #include <random>
+#include <thread>
 
 using namespace tsd;
 using namespace tsd::filtrage;
@@ -17,6 +18,21 @@ static Veccf bruit(entier n, unsigned seed)
   Veccf x(n);
   pour(auto i = 0; i < n; i++) x(i) = cfloat(d(g), d(g));
   retourne x;
+}
+static Vecf bruit_reel(entier n, unsigned seed)
+{
+  std::mt19937 g(seed);
+  std::normal_distribution<float> d(0, 1);
+  Vecf x(n);
+  pour(auto i = 0; i < n; i++) x(i) = d(g);
+  retourne x;
+}
+static double ecart_reel(const Vecf &a, const Vecf &b)
+{
+  si(a.rows() != b.rows()) retourne 1e9;
+  double m = 0;
+  pour(auto i = 0; i < a.rows(); i++) m = std::max(m, (double) std::abs(a(i) - b(i)));
+  retourne m;
 }
 static double ecart(const Veccf &a, const Veccf &b, const Veccf &x)
 {
@@ -123,6 +139,67 @@ int main()
       soit e8 = ecart(tsd::gpu::filtre_reechan_gpu(ratio)->step(xp), filtre_reechan<cfloat>(ratio)->step(xp), xp);
       printf("filtre_reechan %.4f : ecart %.2e\n", ratio, e8);
       bad += e8 > 1e-5;
+    }
+    {
+      // every interpolator of itrp.cc:130-157, T = float (the instantiation tests/test-ra.cc drives) and cfloat
+      soit xf = bruit_reel(20000, 11);
+      soit xc = bruit(20000, 12);
+      pour(float ratio: {1.2f, 0.73f})
+      {
+        double er = 0, ec = 0;
+        er = std::max(er, ecart_reel(tsd::gpu::filtre_itrp_gpu<float>(ratio, itrp_cspline<float>())->step(xf), filtre_itrp<float>(ratio, itrp_cspline<float>())->step(xf)));
+        er = std::max(er, ecart_reel(tsd::gpu::filtre_itrp_gpu<float>(ratio, itrp_lineaire<float>())->step(xf), filtre_itrp<float>(ratio, itrp_lineaire<float>())->step(xf)));
+        er = std::max(er, ecart_reel(tsd::gpu::filtre_itrp_gpu<float>(ratio, itrp_lagrange<float>(3))->step(xf), filtre_itrp<float>(ratio, itrp_lagrange<float>(3))->step(xf)));
+        er = std::max(er, ecart_reel(tsd::gpu::filtre_itrp_gpu<float>(ratio, itrp_sinc<float>({31, 100, 0.4f, "hn"}))->step(xf), filtre_itrp<float>(ratio, itrp_sinc<float>({31, 100, 0.4f, "hn"}))->step(xf)));
+        er = std::max(er, ecart_reel(tsd::gpu::filtre_reechan_gpu<float>(ratio)->step(xf), filtre_reechan<float>(ratio)->step(xf)));
+        ec = std::max(ec, ecart(tsd::gpu::filtre_itrp_gpu<cfloat>(ratio, itrp_lineaire<cfloat>())->step(xc), filtre_itrp<cfloat>(ratio, itrp_lineaire<cfloat>())->step(xc), xc));
+        ec = std::max(ec, ecart(tsd::gpu::filtre_itrp_gpu<cfloat>(ratio, itrp_lagrange<cfloat>(5))->step(xc), filtre_itrp<cfloat>(ratio, itrp_lagrange<cfloat>(5))->step(xc), xc));
+        ec = std::max(ec, ecart(tsd::gpu::filtre_itrp_gpu<cfloat>(ratio, itrp_cspline<cfloat>())->step(xc), filtre_itrp<cfloat>(ratio, itrp_cspline<cfloat>())->step(xc), xc));
+        printf("interpolateurs %.2f : float (cspline, lineaire, lagrange, sinc/100 phases, reechan) %.2e, cfloat %.2e\n", ratio, er, ec);
+        bad += (er > 1e-5) + (ec > 1e-5);
+      }
+    }
+    {
+      // filtre_rif_fft<T>(h) with the reference's real() quirk (fourier.cc:976), both instantiations
+      soit h127 = design_rif_fen(127, "lp", 0.2);
+      soit xq = bruit(9000, 13);
+      soit eq = ecart(tsd::gpu::filtre_rif_fft_gpu<cfloat>(h127)->step(xq), filtre_rif_fft<cfloat>(h127)->step(xq), xq);
+      soit xqr = bruit_reel(9000, 14);
+      soit eqr = ecart_reel(tsd::gpu::filtre_rif_fft_gpu<float>(h127)->step(xqr), filtre_rif_fft<float>(h127)->step(xqr));
+      printf("filtre_rif_fft<cfloat> %.2e, <float> %.2e\n", eq, eqr);
+      bad += (eq > 1e-5) + (eqr > 1e-5);
+    }
+    {
+      // filtre_fft(config) with an ARBITRARY host callback (not a multiplication by a fixed vector): the callback is
+      // called once per block on the host, like the reference does
+      FiltreFFTConfig cg;
+      cg.dim_blocs_temporel = 1000;
+      cg.nb_zeros_min = 24;
+      int appels_c = 0, appels_g = 0;
+      cg.traitement_freq = [&](Veccf &X) { appels_c++; pour(auto i = 0; i < X.rows(); i++) X(i) = (i % 7 == 0) ? cfloat(0, 0) : X(i) * cfloat(0.5f, (float) (appels_c % 3)); };
+      soit [gc, Ngc] = filtre_fft(cg);
+      soit cg2 = cg;
+      cg2.traitement_freq = [&](Veccf &X) { appels_g++; pour(auto i = 0; i < X.rows(); i++) X(i) = (i % 7 == 0) ? cfloat(0, 0) : X(i) * cfloat(0.5f, (float) (appels_g % 3)); };
+      soit [gg, Ngg] = tsd::gpu::filtre_fft_gpu(cg2);
+      soit xg = bruit(7777, 15);
+      soit eg = ecart(gg->step(xg), gc->step(xg), xg);
+      printf("filtre_fft rappel generique : %d/%d appels, ecart %.2e\n", appels_c, appels_g, eg);
+      bad += (eg > 1e-5) + (appels_c != appels_g) + (Ngc != Ngg);
+    }
+    {
+      // independent objects stepped from different threads (reference semantics): same results as sequentially
+      soit xa = bruit(40000, 16), xb = bruit(40000, 17);
+      soit ya_ref = filtre_rif<float, cfloat>(h)->step(xa);
+      soit yb_ref = filtre_reechan<cfloat>(1.3f)->step(xb);
+      Veccf ya, yb;
+      std::string err;
+      std::thread ta([&] { try { soit f = tsd::gpu::filtre_rif_gpu<float, cfloat>(h); pour(auto r = 0; r < 8; r++) { f = tsd::gpu::filtre_rif_gpu<float, cfloat>(h); ya = f->step(xa); } } catch(...) { err = "thread a"; } });
+      std::thread tb([&] { try { pour(auto r = 0; r < 8; r++) yb = tsd::gpu::filtre_reechan_gpu(1.3f)->step(xb); } catch(...) { err = "thread b"; } });
+      ta.join();
+      tb.join();
+      soit e_fils = std::max(ecart(ya, ya_ref, xa), ecart(yb, yb_ref, xb));
+      printf("deux fils d'execution : ecart %.2e %s\n", e_fils, err.c_str());
+      bad += (e_fils > 1e-5) + !err.empty();
     }
   }
   catch(const std::exception &e) { printf("exception: %s\n", e.what()); retourne 2; }

@@ -9,16 +9,24 @@
 // Drop-in points (reference file:line):
 //   filtre_rif<Tc,T>(h)            core/src/filtrage/filtre-rt.cc:171-175   -> tsd::gpu::filtre_rif_gpu<Tc,T>(h)
 //   filtre_fft(config)             core/src/fourier/fourier.cc:935-940      -> tsd::gpu::filtre_fft_gpu(config, H, K)
-//   filtre_itrp<cfloat>(r, itrp)   core/src/reechan/ra.cc:185-188           -> tsd::gpu::filtre_itrp_gpu(r, itrp)
+//   filtre_itrp<T>(r, itrp)        core/src/reechan/ra.cc:185-195           -> tsd::gpu::filtre_itrp_gpu<T>(r, itrp)
+//   filtre_rif_fft<T>(h)           core/src/fourier/fourier.cc:946-990      -> tsd::gpu::filtre_rif_fft_gpu<T>(h)
 //   fftplan_defaut (global hook)   core/src/fourier/fourier.cc:469-472      -> tsd::gpu::installe_fftplan_gpu()
 //   filtre_rif_ups / _demi_bande / _decim   core/src/reechan/polyphase.cc:344-360 -> tsd::gpu::filtre_rif_*_gpu<T>(c[, R])
-//   filtre_reechan<cfloat>(ratio)  core/src/reechan/ra.cc:180-183           -> tsd::gpu::filtre_reechan_gpu(ratio)
+//   filtre_reechan<T>(ratio)       core/src/reechan/ra.cc:180-183,190-191   -> tsd::gpu::filtre_reechan_gpu<T>(ratio)
+// integration/tsd_gpu_dropin.cc DEFINES the reference's own factory symbols on top of these classes, so that linking it
+// in front of the library routes filtre_rif / filtrer / filter_fir / filtre_reechan / resample / filtre_itrp /
+// filtre_rif_fft / filtre_fft to the GPU with no source change in the callers.
 #pragma once
 #include "tsd/tsd.hpp"
 #include "tsd/filtrage.hpp"
 #include "tsd/fourier.hpp"
 #include "tsdgpu.h"
 
+#include <cstdlib>
+#include <exception>
+#include <string>
+#include <tuple>
 #include <vector>
 
 namespace tsd::gpu {
@@ -84,27 +92,50 @@ inline void installe_fftplan_gpu()
   tsd::fourier::fftplan_defaut = []() -> sptr<tsd::fourier::FFTPlan> { retourne std::make_shared<FFTPlanGpu>(); };
 }
 
-// filtre_fft(config) with the callback of FiltreFFTRIF, "X *= H", passed as data (fourier.cc:956-959).
-// K > 0 declares H = fft([0^(N-K), h]) * sqrt(N) (fourier.cc:962-965): overlap-save form.
+// filtre_fft(config).  Two modes:
+//  * gains as data: the callback of FiltreFFTRIF, "X *= H" (fourier.cc:956-959), is replaced by the vector H itself; K > 0
+//    declares H = fft([0^(N-K), h]) * sqrt(N) (fourier.cc:962-965) and selects the single-SM overlap-save kernel;
+//  * generic: no H given -> config.traitement_freq, an arbitrary host std::function (fourier.hpp:319), is called once per
+//    transformed block exactly like the reference does (fourier.cc:863,895,915); the spectra travel device -> host ->
+//    callback -> device.  An exception thrown by the callback is re-thrown from step().
 struct OLAGpu: Filtre<cfloat, cfloat, tsd::fourier::FiltreFFTConfig>
 {
   tsdgpu_ola_t h = nullptr;
   Veccf H;
   entier K = 0, N = 0;
+  bouléen generique = non;
+  std::exception_ptr erreur_rappel;
   OLAGpu(const Veccf &H_, entier K_): H(H_), K(K_) {}
+  OLAGpu(): generique(oui) {}
   ~OLAGpu() { tsdgpu_ola_destroy(h); }
+  static void rappel(void *user, int, float *X, int n)
+  {
+    soit moi = (OLAGpu *) user;
+    si(moi->erreur_rappel) retourne;
+    try
+    {
+      Veccf Xv = Veccf::map((cfloat *) X, n);     // non-owning view: the callback works in place
+      moi->lis_config().traitement_freq(Xv);
+    }
+    catch(...) { moi->erreur_rappel = std::current_exception(); }
+  }
   void configure_impl(const tsd::fourier::FiltreFFTConfig &c) override
   {
     tsdgpu_ola_destroy(h);
     h = nullptr;
     const float *Hp = H.rows() ? (const float *) H.data() : nullptr;
+    Vecf fen;
     si(c.avec_fenetrage)
     {
       // Hann-window 50 % overlap mode (fourier.cc:794-798,884-930): same window as the reference object
       soit Ne = c.dim_blocs_temporel > 0 ? c.dim_blocs_temporel : 512;
-      Vecf fen = tsd::filtrage::fenêtre("hn", Ne, non);
-      verifie(tsdgpu_ola_create_fen(c.dim_blocs_temporel, c.nb_zeros_min, Hp, fen.data(), 1, &h), "filtre_fft (gpu)");
+      fen = tsd::filtrage::fenêtre("hn", Ne, non);
     }
+    si(generique && c.traitement_freq)
+      verifie(tsdgpu_ola_create_cb(c.dim_blocs_temporel, c.nb_zeros_min, &OLAGpu::rappel, this,
+                                   c.avec_fenetrage ? fen.data() : nullptr, 1, &h), "filtre_fft (gpu)");
+    sinon si(c.avec_fenetrage)
+      verifie(tsdgpu_ola_create_fen(c.dim_blocs_temporel, c.nb_zeros_min, Hp, fen.data(), 1, &h), "filtre_fft (gpu)");
     sinon
       verifie(tsdgpu_ola_create(c.dim_blocs_temporel, c.nb_zeros_min, Hp, K, 1, &h), "filtre_fft (gpu)");
     tsdgpu_ola_dims(h, nullptr, &N, nullptr, nullptr);
@@ -113,8 +144,14 @@ struct OLAGpu: Filtre<cfloat, cfloat, tsd::fourier::FiltreFFTConfig>
   {
     y.resize((entier) tsdgpu_ola_out_count(h, x.rows()));
     long long n_out = 0;
-    verifie(tsdgpu_ola_step(h, x.data(), x.rows(), x.rows(), y.data(), std::max(1, y.rows()), &n_out, TSDGPU_HOST),
-            "filtre_fft::step (gpu)");
+    soit rc = tsdgpu_ola_step(h, x.data(), x.rows(), x.rows(), y.data(), std::max(1, y.rows()), &n_out, TSDGPU_HOST);
+    si(erreur_rappel)
+    {
+      soit e = erreur_rappel;
+      erreur_rappel = nullptr;
+      std::rethrow_exception(e);
+    }
+    verifie(rc, "filtre_fft::step (gpu)");
   }
 };
 inline std::tuple<sptr<Filtre<cfloat, cfloat, tsd::fourier::FiltreFFTConfig>>, entier>
@@ -124,14 +161,80 @@ filtre_fft_gpu(const tsd::fourier::FiltreFFTConfig &config, const Veccf &H, enti
   res->configure(config);
   retourne {res, res->N};
 }
+// exact signature of the reference factory (fourier.hpp:370): the callback stays a callback
+inline std::tuple<sptr<Filtre<cfloat, cfloat, tsd::fourier::FiltreFFTConfig>>, entier>
+filtre_fft_gpu(const tsd::fourier::FiltreFFTConfig &config)
+{
+  soit res = std::make_shared<OLAGpu>();
+  res->configure(config);
+  retourne {res, res->N};
+}
 
-// filtre_itrp<cfloat>(ratio, itrp): the interpolator's LUT is read through its public coefs(tau)
-struct AdaptationRythmeGpu: FiltreGen<cfloat>
+// filtre_rif_fft<T>(h) (fourier.cc:946-990): Ne = 512, nb_zeros_min = K, H = rfft(h2) * sqrt(N) with h2.tail(K) = h, and the
+// reference's output convention y = real(ola.step(x.as_complex())) (fourier.cc:976) for BOTH instantiations.
+template<typename T> struct FiltreFFTRIFGpu: FiltreGen<T>
+{
+  sptr<Filtre<cfloat, cfloat, tsd::fourier::FiltreFFTConfig>> ola;
+  FiltreFFTRIFGpu(const Vecf &h)
+  {
+    tsd::fourier::FiltreFFTConfig c;
+    c.nb_zeros_min = h.rows();
+    c.dim_blocs_temporel = 512;                                   // fourier.cc:954-960 builds the object with the default
+    soit N = prochaine_puissance_de_2(512 + h.rows());
+    Vecf h2 = Vecf::zeros(N);
+    h2.tail(h.rows()) = h;
+    Veccf H = tsd::fourier::rfft(h2);                             // fourier.cc:962-965 (plan from fftplan_defaut)
+    H *= std::sqrt((float) N);
+    ola = std::get<0>(filtre_fft_gpu(c, H, h.rows()));
+  }
+  void step(const Vecteur<T> &x, Vecteur<T> &y) override
+  {
+    Veccf yc;
+    si constexpr(std::is_same<T, cfloat>::value) ola->step(x, yc);
+    sinon ola->step(x.as_complex(), yc);
+    y = real(yc);                                                 // converts back to T (fourier.cc:976)
+  }
+};
+template<typename T> sptr<FiltreGen<T>> filtre_rif_fft_gpu(const Vecf &h) { retourne std::make_shared<FiltreFFTRIFGpu<T>>(h); }
+
+// filtre_itrp<T>(ratio, itrp), T = float or cfloat (ra.cc:185-195).  The interpolator classes are private to itrp.cc; what
+// is public is coefs(tau), K and the description `nom` they all set in their constructor:
+//   "sinc - ncoefs=.., nphases=P, .."  LUT of P + 1 columns, column (int)(tau * P)      (itrp.cc:16-22,43-44)
+//   "cspline"                          LUT of 257 columns, column (int)(tau * 256)      (itrp.cc:62-67,74)
+//   "linéaire", "Lagrange degré d"     coefficients evaluated at the EXACT tau          (itrp.cc:84-87,113-127)
+// LUT interpolators are handed over as their table (read through coefs() at a delay inside every cell), the exact ones as
+// (kind, degree): the device evaluates the same float32 expressions at the float32 phase of every output.  Anything else
+// is refused rather than sampled wrongly.
+template<typename T> struct AdaptationRythmeGpu: FiltreGen<T>
 {
   tsdgpu_resamp_t h = nullptr;
-  AdaptationRythmeGpu(float ratio, sptr<tsd::filtrage::InterpolateurRIF<cfloat>> itrp, entier nphases)
+  AdaptationRythmeGpu(float ratio, sptr<tsd::filtrage::InterpolateurRIF<T>> itrp, entier nphases_force = 0)
   {
+    constexpr int cplx = std::is_same<T, cfloat>::value ? 1 : 0;
+    const std::string &nom = itrp->nom;
     soit K = itrp->K;
+    si(nphases_force <= 0 && nom.rfind("lin", 0) == 0)
+    {
+      verifie(tsdgpu_resamp_create_exact(ratio, TSDGPU_ITRP_LINEAIRE, 1, cplx, 1, &h), "filtre_itrp (gpu)");
+      retourne;
+    }
+    si(nphases_force <= 0 && nom.rfind("Lagrange", 0) == 0)
+    {
+      verifie(tsdgpu_resamp_create_exact(ratio, TSDGPU_ITRP_LAGRANGE, K - 1, cplx, 1, &h), "filtre_itrp (gpu)");
+      retourne;
+    }
+    entier nphases = nphases_force;
+    si(nphases <= 0)
+    {
+      si(nom == "cspline") nphases = 256;
+      sinon si(nom.rfind("sinc", 0) == 0)
+      {
+        soit pos = nom.find("nphases=");
+        si(pos != std::string::npos) nphases = std::atoi(nom.c_str() + pos + 8);
+      }
+    }
+    si(nphases <= 0)
+      échec("filtre_itrp (gpu) : interpolateur \"{}\" inconnu du chemin GPU (ni LUT sinc / cspline, ni linéaire / Lagrange).", nom);
     Vecf lut(K * (nphases + 1));
     pour(auto p = 0; p <= nphases; p++)
     {
@@ -139,22 +242,23 @@ struct AdaptationRythmeGpu: FiltreGen<cfloat>
       soit c = itrp->coefs(p == nphases ? 1.0f : (p + 0.5f) / nphases);
       pour(auto i = 0; i < K; i++) lut(p * K + i) = c(i);
     }
-    verifie(tsdgpu_resamp_create(ratio, lut.data(), K, nphases, 1, &h), "filtre_itrp (gpu)");
+    verifie(tsdgpu_resamp_create_ex(ratio, lut.data(), K, nphases, cplx, 1, &h), "filtre_itrp (gpu)");
   }
   ~AdaptationRythmeGpu() { tsdgpu_resamp_destroy(h); }
-  void step(const Veccf &x, Veccf &y) override
+  void step(const Vecteur<T> &x, Vecteur<T> &y) override
   {
     soit n = x.rows();
     y.resize((entier) tsdgpu_resamp_out_count(h, n));
     si(n == 0) retourne;                                  // ra.cc:45-49
     long long n_out = 0;
-    verifie(tsdgpu_resamp_step(h, x.data(), n, n, y.data(), std::max(1, y.rows()), y.rows(), &n_out, TSDGPU_HOST),
+    verifie(tsdgpu_resamp_step(h, x.data(), n, n, y.rows() ? y.data() : nullptr, std::max(1, y.rows()), y.rows(), &n_out, TSDGPU_HOST),
             "filtre_itrp::step (gpu)");
   }
 };
-inline sptr<FiltreGen<cfloat>> filtre_itrp_gpu(float ratio, sptr<tsd::filtrage::InterpolateurRIF<cfloat>> itrp, entier nphases = 256)
+template<typename T = cfloat>
+sptr<FiltreGen<T>> filtre_itrp_gpu(float ratio, sptr<tsd::filtrage::InterpolateurRIF<T>> itrp, entier nphases = 0)
 {
-  retourne std::make_shared<AdaptationRythmeGpu>(ratio, itrp, nphases);
+  retourne std::make_shared<AdaptationRythmeGpu<T>>(ratio, itrp, nphases);
 }
 
 // polyphase.cc stages: filtre_rif_ups<float,T>(c, R), filtre_rif_demi_bande<float,T>(c), filtre_rif_decim<float,T>(c, R)
@@ -188,10 +292,11 @@ template<typename T> sptr<FiltreGen<T>> filtre_rif_decim_gpu(const Vecf &c, enti
   retourne std::make_shared<FiltrePolyphaseGpu<T>>(TSDGPU_POLY_DECIM, c, R);
 }
 
-// filtre_reechan<cfloat>(ratio): the reference's own planner (ra.cc:104-156) with every stage on the GPU
-struct AdaptationRythmeArbitraireGpu: Filtre<cfloat, cfloat, float>
+// filtre_reechan<T>(ratio), T = float or cfloat (ra.cc:180-183,190-191): the reference's own planner (ra.cc:104-156) with
+// every stage on the GPU
+template<typename T> struct AdaptationRythmeArbitraireGpu: Filtre<T, T, float>
 {
-  std::vector<sptr<FiltreGen<cfloat>>> etages;
+  std::vector<sptr<FiltreGen<T>>> etages;
   float ratio = 1;
   AdaptationRythmeArbitraireGpu(float r) { Configurable<float>::configure(r); }
   void configure_impl(const float &ratio_) override
@@ -205,23 +310,23 @@ struct AdaptationRythmeArbitraireGpu: Filtre<cfloat, cfloat, float>
     etages.clear();
     float f = ratio;
     soit coefs = tsd::filtrage::design_rif_fen(15, "lp", 0.25, "hn");
-    tantque(f < 0.5) { etages.push_back(filtre_rif_demi_bande_gpu<cfloat>(coefs)); f *= 2; }
-    std::vector<sptr<FiltreGen<cfloat>>> ups;
-    tantque(f >= 2) { ups.push_back(filtre_rif_ups_gpu<cfloat>(coefs, 2)); f /= 2; }
+    tantque(f < 0.5) { etages.push_back(filtre_rif_demi_bande_gpu<T>(coefs)); f *= 2; }
+    std::vector<sptr<FiltreGen<T>>> ups;
+    tantque(f >= 2) { ups.push_back(filtre_rif_ups_gpu<T>(coefs, 2)); f /= 2; }
     etages.insert(etages.end(), ups.begin(), ups.end());
     si(!(std::abs(f - 1) < 1e-6f))
-      etages.push_back(filtre_itrp_gpu(f, tsd::filtrage::itrp_sinc<cfloat>({15, 256, std::min(0.4f, f / 2), "hn"}), 256));
+      etages.push_back(filtre_itrp_gpu<T>(f, tsd::filtrage::itrp_sinc<T>({15, 256, std::min(0.4f, f / 2), "hn"})));
   }
-  void step(const Veccf &x, Veccf &y) override
+  void step(const Vecteur<T> &x, Vecteur<T> &y) override
   {
     y = x;
     si(ratio == 1) retourne;
     pour(auto &e: etages) y = e->step(y);
   }
 };
-inline sptr<Filtre<cfloat, cfloat, float>> filtre_reechan_gpu(float ratio)
+template<typename T = cfloat> sptr<Filtre<T, T, float>> filtre_reechan_gpu(float ratio)
 {
-  retourne std::make_shared<AdaptationRythmeArbitraireGpu>(ratio);
+  retourne std::make_shared<AdaptationRythmeArbitraireGpu<T>>(ratio);
 }
 
 // periodogramme_tfd(x, N) (fourier.hpp:967, fourier.cc:1451-1481): frames x N2/2 matrix of 10 log10(|X|^2 + 1e-20)

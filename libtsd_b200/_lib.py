@@ -54,12 +54,15 @@ _SIGS = {
     "tsdgpu_fft_destroy": (_i, [_vp]),
     "tsdgpu_ola_create": (_i, [_i, _i, _vp, _i, _i, C.POINTER(_vp)]),
     "tsdgpu_ola_create_fen": (_i, [_i, _i, _vp, _vp, _i, C.POINTER(_vp)]),
+    "tsdgpu_ola_create_cb": (_i, [_i, _i, _vp, _vp, _vp, _i, C.POINTER(_vp)]),
     "tsdgpu_periodogramme_tfd": (_i, [_vp, C.c_longlong, _i, _i, _i, _vp, _vp, C.c_longlong, C.POINTER(_i), C.POINTER(_i), _i]),
     "tsdgpu_ola_dims": (_i, [_vp, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "tsdgpu_ola_out_count": (_ll, [_vp, _i]),
     "tsdgpu_ola_step": (_i, [_vp, _vp, _ll, _i, _vp, _ll, C.POINTER(_ll), _i]),
     "tsdgpu_ola_destroy": (_i, [_vp]),
     "tsdgpu_resamp_create": (_i, [_f, _vp, _i, _i, _i, C.POINTER(_vp)]),
+    "tsdgpu_resamp_create_ex": (_i, [_f, _vp, _i, _i, _i, _i, C.POINTER(_vp)]),
+    "tsdgpu_resamp_create_exact": (_i, [_f, _i, _i, _i, _i, C.POINTER(_vp)]),
     "tsdgpu_resamp_out_count": (_ll, [_vp, _i]),
     "tsdgpu_resamp_phase": (_f, [_vp]),
     "tsdgpu_resamp_step": (_i, [_vp, _vp, _ll, _i, _vp, _ll, _ll, C.POINTER(_ll), _i]),

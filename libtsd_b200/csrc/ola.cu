@@ -531,6 +531,12 @@ struct tsdgpu_ola_s
   bool fen = false;
   float *d_fen = nullptr;
   float2 *d_last = nullptr;
+  // generic spectral callback (FiltreFFTConfig::traitement_freq, fourier.hpp:319): host function called once per
+  // transformed block, in stream order; the block spectra make a round trip through pinned host memory
+  tsdgpu_spectral_cb cb = nullptr;
+  void *cb_user = nullptr;
+  float2 *h_spec = nullptr;    // pinned, [batch][N]
+  size_t h_spec_cap = 0;
   // unfused
   tsdgpu_fft_s *plan = nullptr;
   float2 *work = nullptr;
@@ -660,6 +666,39 @@ static int ola_reserve_plan(tsdgpu_ola_s *f, int batch)
   return 0;
 }
 
+// The spectral step between the two transforms: multiply by H on the device, or hand every spectrum to the caller's
+// host callback (FFT -> D2H -> callback -> H2D -> IFFT, SURVEY 7 "generic callbacks").  Spectra are unitary-scaled like
+// the reference's X (fourier.cc:855-865); batch entries are in the reference's call order for every channel.
+static int ola_spectral_step(tsdgpu_ola_s *f, int batch, int per_chan)
+{
+  Runtime &r = rt();
+  const int N = f->N;
+  if(f->cb)
+  {
+    const size_t need = (size_t) batch * N;
+    if(need > f->h_spec_cap)
+    {
+      if(f->h_spec) cudaFreeHost(f->h_spec);
+      f->h_spec = nullptr;
+      f->h_spec_cap = 0;
+      TSD_CUDA(cudaMallocHost(&f->h_spec, need * sizeof(float2)));
+      f->h_spec_cap = need;
+    }
+    TSD_CUDA(cudaMemcpyAsync(f->h_spec, f->work, need * sizeof(float2), cudaMemcpyDeviceToHost, r.stream));
+    TSD_CUDA(cudaStreamSynchronize(r.stream));
+    for(int q = 0; q < batch; q++) f->cb(f->cb_user, q / per_chan, reinterpret_cast<float *>(f->h_spec + (size_t) q * N), N);
+    TSD_CUDA(cudaMemcpyAsync(f->work, f->h_spec, need * sizeof(float2), cudaMemcpyHostToDevice, r.stream));
+    return 0;
+  }
+  if(f->d_H)
+  {
+    const long long total = (long long) batch * N;
+    ola_mulH_kernel<<<(int) std::min<long long>((total + 255) / 256, r.num_sms * 16), 256, 0, r.stream>>>(f->work, f->d_H, N, total);
+    TSD_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
 static int ola_run_unfused(tsdgpu_ola_s *f, const float2 *x, long long xs, float2 *y, long long ys, int B)
 {
   Runtime &r = rt();
@@ -679,13 +718,7 @@ static int ola_run_unfused(tsdgpu_ola_s *f, const float2 *x, long long xs, float
                                                f->residual);
     TSD_LAUNCH_CHECK();
     if(fft_exec_device(f->plan, f->work, N, f->work, N, true)) return 1;
-    if(f->d_H)
-    {
-      const long long total = (long long) batch * N;
-      ola_mulH_kernel<<<(int) std::min<long long>((total + 255) / 256, rt().num_sms * 16), 256, 0, r.stream>>>(f->work, f->d_H,
-                                                                                                             N, total);
-      TSD_LAUNCH_CHECK();
-    }
+    if(ola_spectral_step(f, batch, nb)) return 1;
     if(fft_exec_device(f->plan, f->work, N, f->work, N, false)) return 1;
     dim3 gs((Ne + 255) / 256, batch);
     ola_scatter_kernel<<<gs, 256, 0, r.stream>>>(f->work, f->d_svg, y, ys, N, Ne, Nz, nb, b0);
@@ -715,13 +748,7 @@ static int ola_run_fen(tsdgpu_ola_s *f, const float2 *x, long long xs, float2 *y
                                                    b0, f->residual);
     TSD_LAUNCH_CHECK();
     if(fft_exec_device(f->plan, f->work, N, f->work, N, true)) return 1;
-    if(f->d_H)
-    {
-      const long long total = (long long) batch * N;
-      ola_mulH_kernel<<<(int) std::min<long long>((total + 255) / 256, rt().num_sms * 16), 256, 0, r.stream>>>(f->work, f->d_H,
-                                                                                                             N, total);
-      TSD_LAUNCH_CHECK();
-    }
+    if(ola_spectral_step(f, batch, 2 * nb)) return 1;
     if(fft_exec_device(f->plan, f->work, N, f->work, N, false)) return 1;
     dim3 gs((Ne + 255) / 256, f->nchan * nb);
     ola_scatter_fen_kernel<<<gs, 256, 0, r.stream>>>(f->work, f->d_last, y, ys, N, Ne, Nz, nb, g0 + b0, g0 + b0 - e_first);
@@ -762,7 +789,14 @@ static int ola_run_device(tsdgpu_ola_s *f, const float2 *x, long long xs, int n,
 extern "C" {
 
 static int ola_create(int dim_blocs_temporel, int nb_zeros_min, const float *H, int fir_len, const float *fenetre, int nchan,
-                      tsdgpu_ola_t *out);
+                      tsdgpu_ola_t *out, tsdgpu_spectral_cb cb = nullptr, void *cb_user = nullptr);
+
+int tsdgpu_ola_create_cb(int dim_blocs_temporel, int nb_zeros_min, tsdgpu_spectral_cb cb, void *user, const float *fenetre,
+                         int nchan, tsdgpu_ola_t *out)
+{
+  if(!cb) return fail("tsdgpu_ola_create_cb: null callback");
+  return ola_create(dim_blocs_temporel, nb_zeros_min, nullptr, 0, fenetre, nchan, out, cb, user);
+}
 
 int tsdgpu_ola_create(int dim_blocs_temporel, int nb_zeros_min, const float *H, int fir_len, int nchan, tsdgpu_ola_t *out)
 {
@@ -779,7 +813,7 @@ int tsdgpu_ola_create_fen(int dim_blocs_temporel, int nb_zeros_min, const float 
 } // extern "C"
 
 static int ola_create(int dim_blocs_temporel, int nb_zeros_min, const float *H, int fir_len, const float *fenetre, int nchan,
-                      tsdgpu_ola_t *out)
+                      tsdgpu_ola_t *out, tsdgpu_spectral_cb cb, void *cb_user)
 {
   TSD_ENTER(-1);
   if(!out) return fail("tsdgpu_ola_create: null argument");
@@ -807,7 +841,9 @@ static int ola_create(int dim_blocs_temporel, int nb_zeros_min, const float *H, 
   f->Nz = Nz;
   f->nchan = nchan;
   f->fen = fenetre != nullptr;
-  f->fused = (N == 65536) && !f->fen;
+  f->cb = cb;
+  f->cb_user = cb_user;
+  f->fused = (N == 65536) && !f->fen && !cb;   // a host callback needs the spectra on the host: N-point unfused path
   f->K = f->fused ? fir_len : 0;   // the unfused path always runs the overlap-add form
   f->carry_len = N + Ne;
   // gains that are the transform of K taps: the samples do not depend on the block structure, the single-SM
@@ -1048,6 +1084,7 @@ int tsdgpu_ola_destroy(tsdgpu_ola_t f)
   if(f->plan) fft_plan_destroy(f->plan);
   if(f->work) cudaFree(f->work);
   ols16k_destroy(f->ols);
+  if(f->h_spec) cudaFreeHost(f->h_spec);
   delete f;
   return 0;
 }

@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 namespace tsdgpu {
@@ -73,6 +74,61 @@ __global__ void __launch_bounds__(RS_NT) resamp_lut_kernel(ResampParams p)
     }
   }
   p.y[(long long) chan * p.y_stride + p.out0 + j] = make_float2(sr, si);
+}
+
+// ---- generic kernel for everything the fast kernels do not take: real-valued data (filtre_itrp<float>, ra.cc:190-195)
+// and the interpolators whose coefficients are evaluated at the exact delay instead of a LUT column (itrp.cc:82-127).
+// One thread per output; MODE 0: LUT column sched.y; MODE 1: InterpolateurLineaire {1 - tau, tau}; MODE 2:
+// InterpolateurLagrange of degree d = K - 1, t = (d - 1)/2 + tau, h_j = prod_{k != j} (t - k) / (j - k) with the reference's
+// float32 operations in the reference's order; tau = the float32 phase of the output (bits in sched.y).
+__device__ __forceinline__ float2 rs_load(const float2 *p) { return __ldg(p); }
+__device__ __forceinline__ float rs_load(const float *p) { return __ldg(p); }
+__device__ __forceinline__ void rs_acc(float2 &s, float2 v, float c) { s.x = fmaf(v.x, c, s.x); s.y = fmaf(v.y, c, s.y); }
+__device__ __forceinline__ void rs_acc(float &s, float v, float c) { s = fmaf(v, c, s); }
+__device__ __forceinline__ void rs_zero(float2 &s) { s = make_float2(0.f, 0.f); }
+__device__ __forceinline__ void rs_zero(float &s) { s = 0.f; }
+
+template<typename T> struct ResampGenParams
+{
+  const T *x;
+  T *y;
+  const T *hist;         // [nchan][K-1]
+  const float *lut;      // MODE 0
+  const int2 *sched;
+  long long x_stride, y_stride, out0;
+  int n_out_chunk, K, hist_len;
+};
+
+template<typename T, int MODE> __global__ void __launch_bounds__(RS_NT) resamp_gen_kernel(ResampGenParams<T> p)
+{
+  const int j = blockIdx.x * RS_NT + threadIdx.x;
+  if(j >= p.n_out_chunk) return;
+  const int chan = blockIdx.y;
+  const int2 sc = p.sched[j];
+  const T *x = p.x + (long long) chan * p.x_stride;
+  const T *hist = p.hist + (long long) chan * p.hist_len;
+  const int first = sc.x - (p.K - 1);   // call-relative index of the oldest sample in the window
+  const float tau = __int_as_float(sc.y);
+  const int d = p.K - 1;
+  const float t = ((float) d - 1.0f) / 2 + tau;   // itrp.cc:118
+  T acc;
+  rs_zero(acc);
+  for(int i = 0; i < p.K; i++)
+  {
+    float c;
+    if(MODE == 0) c = __ldg(p.lut + (size_t) sc.y * p.K + i);
+    else if(MODE == 1) c = (i == 0) ? 1 - tau : tau;            // itrp.cc:86
+    else
+    {
+      c = 1.0f;
+      for(int k = 0; k <= d; k++)
+        if(k != i) c *= (t - k) / (i - k);                       // itrp.cc:120-126
+    }
+    const int idx = first + i;
+    const T v = (idx >= 0) ? rs_load(x + idx) : hist[p.hist_len + idx];
+    rs_acc(acc, v, c);
+  }
+  p.y[(long long) chan * p.y_stride + p.out0 + j] = acc;
 }
 
 // ---- main kernel: channel-batched banded product ----------------------------------------------
@@ -199,7 +255,7 @@ __global__ void __launch_bounds__(RS2_WARPS * 32) resamp_banded_kernel(Resamp2Pa
 }
 
 // new_hist = last hist_len samples of (old_hist ++ x[0..n))
-__global__ void resamp_hist_kernel(const float2 *x, long long x_stride, int n, const float2 *o, float2 *d, int hl)
+template<typename T> __global__ void resamp_hist_kernel(const T *x, long long x_stride, int n, const T *o, T *d, int hl)
 {
   const int chan = blockIdx.y;
   for(int j = blockIdx.x * blockDim.x + threadIdx.x; j < hl; j += gridDim.x * blockDim.x)
@@ -218,6 +274,8 @@ struct tsdgpu_resamp_s
   int device = 0;              // CUDA device the object lives on
   float ratio = 1, increment = 1, phase = 0;
   int K = 0, nphases = 0, nchan = 0, hist_len = 0;
+  int dc = 2;                  // floats per sample: 1 = real data (filtre_itrp<float>), 2 = cfloat
+  int mode = 0;                // 0 LUT, 1 linear, 2 Lagrange (coefficients at the exact phase)
   float *d_lut = nullptr;
   float2 *d_hist[2] = {nullptr, nullptr};
   int cur = 0;
@@ -287,9 +345,28 @@ static bool resamp_schedule_runs(float *phase_io, float increment, int nphases, 
 // The reference recurrence (ra.cc:58-73), verbatim in float32.  Processes inputs [i0, i1) of the
 // call, appends (in_idx, lut_idx) pairs, returns the updated phase.
 static float resamp_schedule(float phase, float increment, int nphases, int i0, int i1, int2 *out, size_t cap,
-                             size_t *count, bool *overflow)
+                             size_t *count, bool *overflow, bool exact = false)
 {
   size_t j = 0;
+  if(exact && out)
+  {
+    // exact-delay interpolators: the second word carries the float32 phase itself
+    for(int i = i0; i < i1; i++)
+    {
+      while(phase < 1)
+      {
+        if(j >= cap) { *overflow = true; *count = j; return phase; }
+        int bits;
+        memcpy(&bits, &phase, sizeof bits);
+        out[j] = make_int2(i, bits);
+        j++;
+        phase += increment;
+      }
+      phase--;
+    }
+    *count = j;
+    return phase;
+  }
   // This loop is the host-side critical path of a step() (one float add + one float subtract of dependent latency per
   // input): keep it free of bounds checks (the caller sizes `out` for ceil((i1 - i0) * max(1, ratio)) + 16 entries,
   // checked once here) and, for increment >= 1 (at most one output per input), free of the inner loop.
@@ -345,6 +422,30 @@ static float resamp_schedule(float phase, float increment, int nphases, int i0, 
   return phase;
 }
 
+template<typename T> static int resamp_launch_gen(tsdgpu_resamp_s *f, const void *x, long long xs, void *y, long long ys,
+                                                  const void *hist, const int2 *sched, long long out0, size_t cnt)
+{
+  ResampGenParams<T> g;
+  g.x = (const T *) x;
+  g.y = (T *) y;
+  g.hist = (const T *) hist;
+  g.lut = f->d_lut;
+  g.sched = sched;
+  g.x_stride = xs;
+  g.y_stride = ys;
+  g.out0 = out0;
+  g.n_out_chunk = (int) cnt;
+  g.K = f->K;
+  g.hist_len = f->hist_len;
+  dim3 grid((unsigned) ((cnt + RS_NT - 1) / RS_NT), f->nchan);
+  KernelTimer timer;
+  if(f->mode == 0) resamp_gen_kernel<T, 0><<<grid, RS_NT, 0, rt().stream>>>(g);
+  else if(f->mode == 1) resamp_gen_kernel<T, 1><<<grid, RS_NT, 0, rt().stream>>>(g);
+  else resamp_gen_kernel<T, 2><<<grid, RS_NT, 0, rt().stream>>>(g);
+  TSD_LAUNCH_CHECK();
+  return 0;
+}
+
 static int resamp_run_device(tsdgpu_resamp_s *f, const float2 *x, long long xs, int n, float2 *y, long long ys,
                              long long ycap, long long *n_out)
 {
@@ -352,10 +453,13 @@ static int resamp_run_device(tsdgpu_resamp_s *f, const float2 *x, long long xs, 
   if(n <= 0) return 0;
   Runtime &r = rt();
   float2 *hist_old = f->d_hist[f->cur], *hist_new = f->d_hist[f->cur ^ 1];
+  const bool generic = f->dc == 1 || f->mode != 0;   // real data / exact-delay coefficients: one thread per output
   if(f->hist_len > 0)
   {
     dim3 grid((f->hist_len + 255) / 256, f->nchan);
-    resamp_hist_kernel<<<grid, 256, 0, r.stream>>>(x, xs, n, hist_old, hist_new, f->hist_len);
+    if(f->dc == 2) resamp_hist_kernel<float2><<<grid, 256, 0, r.stream>>>(x, xs, n, hist_old, hist_new, f->hist_len);
+    else
+      resamp_hist_kernel<float><<<grid, 256, 0, r.stream>>>((const float *) x, xs, n, (const float *) hist_old, (float *) hist_new, f->hist_len);
     TSD_LAUNCH_CHECK();
   }
   // chunks of inputs: the host computes chunk c+1 while the device works on chunk c
@@ -384,7 +488,7 @@ static int resamp_run_device(tsdgpu_resamp_s *f, const float2 *x, long long xs, 
     TSD_CUDA(cudaEventSynchronize(f->ev[b]));   // buffer b no longer in flight
     size_t cnt = 0;
     bool ovf = false;
-    phase = resamp_schedule(phase, f->increment, f->nphases, i0, i1, f->h_sched[b], f->sched_cap, &cnt, &ovf);
+    phase = resamp_schedule(phase, f->increment, f->nphases, i0, i1, f->h_sched[b], f->sched_cap, &cnt, &ovf, f->mode != 0);
     if(ovf) return fail("tsdgpu_resamp_step: schedule overflow");
     if(cnt == 0) continue;
     if(produced + (long long) cnt > ycap) return fail("tsdgpu_resamp_step: output capacity too small");
@@ -393,6 +497,15 @@ static int resamp_run_device(tsdgpu_resamp_s *f, const float2 *x, long long xs, 
     TSD_CUDA(cudaMemcpyAsync(f->d_sched[b], f->h_sched[b], cnt * sizeof(int2), cudaMemcpyHostToDevice, f->sched_stream));
     TSD_CUDA(cudaEventRecord(f->ev_sched[b], f->sched_stream));
     TSD_CUDA(cudaStreamWaitEvent(r.stream, f->ev_sched[b], 0));
+    if(generic)
+    {
+      const int rc = f->dc == 2 ? resamp_launch_gen<float2>(f, x, xs, y, ys, hist_old, f->d_sched[b], produced, cnt)
+                                : resamp_launch_gen<float>(f, x, xs, y, ys, hist_old, f->d_sched[b], produced, cnt);
+      if(rc) return rc;
+      TSD_CUDA(cudaEventRecord(f->ev[b], r.stream));
+      produced += (long long) cnt;
+      continue;
+    }
     ResampParams p;
     p.x = x;
     p.y = y;
@@ -484,10 +597,35 @@ static int resamp_run_device(tsdgpu_resamp_s *f, const float2 *x, long long xs, 
 
 extern "C" {
 
+static int resamp_create(float ratio, const float *lut, int K, int nphases, int mode, int data_complex, int nchan,
+                         tsdgpu_resamp_t *out);
+
 int tsdgpu_resamp_create(float ratio, const float *lut, int K, int nphases, int nchan, tsdgpu_resamp_t *out)
 {
+  return resamp_create(ratio, lut, K, nphases, 0, 1, nchan, out);
+}
+
+int tsdgpu_resamp_create_ex(float ratio, const float *lut, int K, int nphases, int data_complex, int nchan, tsdgpu_resamp_t *out)
+{
+  return resamp_create(ratio, lut, K, nphases, 0, data_complex, nchan, out);
+}
+
+int tsdgpu_resamp_create_exact(float ratio, int kind, int degree, int data_complex, int nchan, tsdgpu_resamp_t *out)
+{
+  if(kind == TSDGPU_ITRP_LINEAIRE) return resamp_create(ratio, nullptr, 2, 1, 1, data_complex, nchan, out);   // K = 2 (itrp.cc:92)
+  if(kind == TSDGPU_ITRP_LAGRANGE)
+  {
+    if(degree < 1 || degree > 31) return fail("tsdgpu_resamp_create_exact: Lagrange degree must be in [1, 31]");
+    return resamp_create(ratio, nullptr, degree + 1, 1, 2, data_complex, nchan, out);                          // K = d + 1 (itrp.cc:107)
+  }
+  return fail("tsdgpu_resamp_create_exact: unknown interpolator kind");
+}
+
+static int resamp_create(float ratio, const float *lut, int K, int nphases, int mode, int data_complex, int nchan,
+                         tsdgpu_resamp_t *out)
+{
   TSD_ENTER(-1);
-  if(!out || !lut) return fail("tsdgpu_resamp_create: null argument");
+  if(!out || (mode == 0 && !lut)) return fail("tsdgpu_resamp_create: null argument");
   if(K <= 0 || nphases <= 0) return fail("tsdgpu_resamp_create: K and nphases must be > 0");
   if(nchan <= 0 || nchan > 65535) return fail("tsdgpu_resamp_create: nchan must be in [1, 65535]");
   if(!(ratio > 0) || std::isinf(ratio)) return fail("tsdgpu_resamp_create: invalid ratio");
@@ -500,12 +638,17 @@ int tsdgpu_resamp_create(float ratio, const float *lut, int K, int nphases, int 
   f->nphases = nphases;
   f->nchan = nchan;
   f->hist_len = K - 1;
-  const size_t lut_n = (size_t) K * (nphases + 1);
-  TSD_CUDA(cudaMalloc(&f->d_lut, lut_n * sizeof(float)));
-  TSD_CUDA(cudaMemcpyAsync(f->d_lut, lut, lut_n * sizeof(float), cudaMemcpyHostToDevice, rt().stream));
+  f->mode = mode;
+  f->dc = data_complex ? 2 : 1;
+  if(mode == 0)
+  {
+    const size_t lut_n = (size_t) K * (nphases + 1);
+    TSD_CUDA(cudaMalloc(&f->d_lut, lut_n * sizeof(float)));
+    TSD_CUDA(cudaMemcpyAsync(f->d_lut, lut, lut_n * sizeof(float), cudaMemcpyHostToDevice, rt().stream));
+  }
   for(int i = 0; i < 2; i++)
   {
-    size_t bytes = std::max<size_t>(1, (size_t) nchan * f->hist_len) * sizeof(float2);
+    size_t bytes = std::max<size_t>(1, (size_t) nchan * f->hist_len) * sizeof(float) * f->dc;
     TSD_CUDA(cudaMalloc(&f->d_hist[i], bytes));
     TSD_CUDA(cudaMemsetAsync(f->d_hist[i], 0, bytes, rt().stream));
   }
@@ -541,16 +684,17 @@ int tsdgpu_resamp_step(tsdgpu_resamp_t f, const void *x, long long xs, int n, vo
   if(mem == TSDGPU_DEVICE) return resamp_run_device(f, (const float2 *) x, xs, n, (float2 *) y, ys, ycap, n_out);
   const long long cnt = tsdgpu_resamp_out_count(f, n);
   if(cnt > ycap) return fail("tsdgpu_resamp_step: output capacity too small");
-  const long long chunk = host_chunk_len(f->nchan, 8, n, 2);
-  const long long out_cap = (long long) std::ceil((double) chunk * std::max(1.0f, f->ratio)) + 16;
-  if(host_stage_reserve((size_t) f->nchan * chunk * 8, (size_t) f->nchan * out_cap * 8)) return 1;
+  const size_t es = sizeof(float) * f->dc;   // bytes per sample
+  const long long chunk = host_chunk_len(f->nchan, es, n, 4);
+  const long long out_cap = (((long long) std::ceil((double) chunk * std::max(1.0f, f->ratio)) + 16) + 3) & ~3LL;
+  if(host_stage_reserve((size_t) f->nchan * chunk * es, (size_t) f->nchan * out_cap * es)) return 1;
   HostStage &hs = host_stage();
-  const float2 *xh = (const float2 *) x;
-  float2 *yh = (float2 *) y;
+  const char *xh = (const char *) x;
+  char *yh = (char *) y;
   return host_pipeline(
     n, chunk,
     [&](int slot, long long first, long long count) -> int {
-      TSD_CUDA(cudaMemcpy2DAsync(hs.in[slot], (size_t) chunk * 8, xh + first, (size_t) xs * 8, (size_t) count * 8, f->nchan,
+      TSD_CUDA(cudaMemcpy2DAsync(hs.in[slot], (size_t) chunk * es, xh + first * es, (size_t) xs * es, (size_t) count * es, f->nchan,
                                  cudaMemcpyHostToDevice, rt().copy_in));
       return 0;
     },
@@ -559,7 +703,7 @@ int tsdgpu_resamp_step(tsdgpu_resamp_t f, const void *x, long long xs, int n, vo
       return resamp_run_device(f, (const float2 *) hs.in[slot], chunk, (int) count, (float2 *) hs.out[slot], out_cap, out_cap, got);
     },
     [&](int slot, long long out_first, long long count) -> int {
-      TSD_CUDA(cudaMemcpy2DAsync(yh + out_first, (size_t) ys * 8, hs.out[slot], (size_t) out_cap * 8, (size_t) count * 8, f->nchan,
+      TSD_CUDA(cudaMemcpy2DAsync(yh + out_first * es, (size_t) ys * es, hs.out[slot], (size_t) out_cap * es, (size_t) count * es, f->nchan,
                                  cudaMemcpyDeviceToHost, rt().copy_out));
       return 0;
     },

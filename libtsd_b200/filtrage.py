@@ -232,19 +232,77 @@ class InterpolateurLUT:
         self.K = int(self.lut.shape[1])
 
 
+class InterpolateurCSpline:
+    """itrp_cspline<T>() (itrp.cc:59-80): Catmull-Rom family, K = 4, LUT of n + 1 = 257 delays built by
+    cspline_calc_lut / cspline_filtre / cspline_calc (itrp.cc:292-320) with the reference's float32 operations."""
+
+    def __init__(self, n: int = 256, c: float = 0.0):
+        f = np.float32
+        self.K, self.delais, self.nom = 4, 1.5, "cspline"
+        lut = np.empty((n + 1, 4), np.float32)
+        one_c = f(1) - f(c)
+        for p in range(n + 1):
+            t = f(p) / f(n)
+            tm1 = t - f(1)
+            h0 = (f(1) + f(2) * t) * tm1 * tm1
+            h1 = t * tm1 * tm1
+            h2 = t * t * (f(3) - f(2) * t)
+            h3 = t * t * tm1
+            lut[p] = (-one_c * h1 / f(2), h0 - one_c * h3 / f(2), h2 + one_c * h1 / f(2), one_c * h3 / f(2))
+        self.lut = lut
+
+
+class InterpolateurLineaire:
+    """itrp_lineaire<T>() (itrp.cc:82-95): coefficients {1 - tau, tau} at the EXACT delay (no LUT)."""
+    K, delais, nom, exact_kind, degre = 2, 0.5, "linéaire", 1, 1
+
+
+class InterpolateurLagrange:
+    """itrp_lagrange<T>(d) (itrp.cc:97-127): Lagrange polynomial of degree d through d + 1 samples, evaluated at the
+    EXACT delay (no LUT)."""
+    exact_kind = 2
+
+    def __init__(self, degre: int):
+        self.degre = int(degre)
+        self.K, self.delais, self.nom = self.degre + 1, 0.5 * self.degre, f"Lagrange degré {self.degre}"
+
+
+def itrp_cspline() -> InterpolateurCSpline:
+    return InterpolateurCSpline()
+
+
+def itrp_lineaire() -> InterpolateurLineaire:
+    return InterpolateurLineaire()
+
+
+def itrp_lagrange(degre: int) -> InterpolateurLagrange:
+    return InterpolateurLagrange(degre)
+
+
 class AdaptationRythmeSimple(FiltreGen):
     """GPU counterpart of AdaptationRythmeSimple (ra.cc:13-79), created by :func:`filtre_itrp`."""
 
-    def __init__(self, ratio: float, itrp, nchan: int = 1):
+    def __init__(self, ratio: float, itrp, nchan: int = 1, T=np.complex64):
+        T = np.dtype(T).type
+        if T not in (np.float32, np.complex64):
+            raise TsdGpuError("filtre_itrp: T doit être float32 ou complex64")
         self.ratio = float(np.float32(ratio))
         self.itrp = itrp
         self.nchan = int(nchan)
-        lut = np.ascontiguousarray(itrp.lut, np.float32)
-        self.nphases = lut.shape[0] - 1
-        self.K = lut.shape[1]
+        self.dtype = T
+        cplx = 1 if T is np.complex64 else 0
         h = _vp()
-        check(lib().tsdgpu_resamp_create(C.c_float(self.ratio), lut.ctypes.data_as(_vp), self.K, self.nphases,
-                                         self.nchan, C.byref(h)))
+        if getattr(itrp, "exact_kind", 0):
+            # linear / Lagrange: coefficients evaluated at the exact float32 phase on the device
+            self.K, self.nphases = int(itrp.K), 0
+            check(lib().tsdgpu_resamp_create_exact(C.c_float(self.ratio), int(itrp.exact_kind), int(itrp.degre), cplx,
+                                                   self.nchan, C.byref(h)))
+        else:
+            lut = np.ascontiguousarray(itrp.lut, np.float32)
+            self.nphases = lut.shape[0] - 1
+            self.K = lut.shape[1]
+            check(lib().tsdgpu_resamp_create_ex(C.c_float(self.ratio), lut.ctypes.data_as(_vp), self.K, self.nphases, cplx,
+                                                self.nchan, C.byref(h)))
         self._h = h
 
     @property
@@ -257,18 +315,18 @@ class AdaptationRythmeSimple(FiltreGen):
     def step(self, x, out=None):
         """``out`` (optional, same memory space as ``x``) needs room for ceil(n * ratio) + 16 samples per channel; the
         result is the exact-length view of the buffer the samples were written to (no extra host copy)."""
-        b = Batch(x, np.complex64, self.nchan)
+        b = Batch(x, self.dtype, self.nchan)
         if b.n == 0:
-            return restore_shape(empty_like_batch(b, np.complex64, 0), b.ndim)
+            return restore_shape(empty_like_batch(b, self.dtype, 0), b.ndim)
         # the exact count comes out of the phase recurrence, which the library runs once inside the call: size the
         # buffer by the bound ceil(n * ratio) + 16 and return the exact-length view (a separate out_count() query would
         # run the whole recurrence a second time on the host)
         cap = int(np.ceil(b.n * max(self.ratio, 0.0))) + 16
         if out is None:
-            y = empty_like_batch(b, np.complex64, cap)
-            yb = Batch(y, np.complex64, self.nchan, "y")
+            y = empty_like_batch(b, self.dtype, cap)
+            yb = Batch(y, self.dtype, self.nchan, "y")
         else:
-            yb = Batch(out, np.complex64, self.nchan, "y")
+            yb = Batch(out, self.dtype, self.nchan, "y")
             y = yb.arr
             if yb.mem != b.mem:
                 raise TsdGpuError("filtre_itrp.step: tampon de sortie incompatible")
@@ -286,9 +344,10 @@ class AdaptationRythmeSimple(FiltreGen):
                 pass
 
 
-def filtre_itrp(ratio: float, itrp, nchan: int = 1) -> AdaptationRythmeSimple:
-    """sptr<FiltreGen<T>> filtre_itrp<T>(ratio, itrp) for T = cfloat (filtrage.hpp:2039, ra.cc:185-188)."""
-    return AdaptationRythmeSimple(ratio, itrp, nchan)
+def filtre_itrp(ratio: float, itrp, nchan: int = 1, T=np.complex64) -> AdaptationRythmeSimple:
+    """sptr<FiltreGen<T>> filtre_itrp<T>(ratio, itrp), T = cfloat or float (filtrage.hpp:2039, ra.cc:185-195); ``itrp`` from
+    itrp_sinc / itrp_cspline (LUT) or itrp_lineaire / itrp_lagrange (exact delay)."""
+    return AdaptationRythmeSimple(ratio, itrp, nchan, T)
 
 
 filter_itrp = filtre_itrp
@@ -374,7 +433,9 @@ class AdaptationRythmeArbitraire(FiltreGen):
     interpolators while it is >= 2 (both on design_rif_fen(15, "lp", 0.25, "hn")), then the arbitrary-ratio LUT
     interpolator itrp_sinc({15, 256, min(0.4, f/2), "hn"}) unless |f - 1| < 1e-6."""
 
-    def __init__(self, ratio: float, nchan: int = 1):
+    def __init__(self, ratio: float, nchan: int = 1, T=np.complex64):
+        T = np.dtype(T).type
+        self.dtype = T
         r = np.float32(ratio)
         if r <= 0 or np.isinf(r) or r >= 1e9:   # ra.cc:108-112: logged, ratio forced to 1
             r = np.float32(1)
@@ -391,16 +452,16 @@ class AdaptationRythmeArbitraire(FiltreGen):
             f = np.float32(f / 2)
         self.facteur_post_interpolation = float(f)
         coefs = design_rif_fen(15, "lp", 0.25, "hn")                      # ra.cc:135
-        self.decimateurs = [filtre_rif_demi_bande(coefs, np.complex64, nchan) for _ in range(self.nb_decimateurs)]
-        self.surechantillonneurs = [filtre_rif_ups(coefs, 2, np.complex64, nchan) for _ in range(self.nb_surechantillonneurs)]
+        self.decimateurs = [filtre_rif_demi_bande(coefs, T, nchan) for _ in range(self.nb_decimateurs)]
+        self.surechantillonneurs = [filtre_rif_ups(coefs, 2, T, nchan) for _ in range(self.nb_surechantillonneurs)]
         fcut = min(np.float32(0.4), np.float32(f / 2))
-        self.interpolateur = filtre_itrp(float(f), itrp_sinc(InterpolateurSincConfig(15, 256, float(fcut), "hn")), nchan)
+        self.interpolateur = filtre_itrp(float(f), itrp_sinc(InterpolateurSincConfig(15, 256, float(fcut), "hn")), nchan, T)
 
     def step(self, x, out=None):
         """``out`` (optional) is handed to the final interpolator (see AdaptationRythmeSimple.step); it is ignored when
         the chain ends with a polyphase stage."""
         if self.ratio == 1:                        # ra.cc:162-163
-            return x.clone() if hasattr(x, "clone") else np.array(x, np.complex64)
+            return x.clone() if hasattr(x, "clone") else np.array(x, self.dtype)
         y = x
         for d in self.decimateurs:                 # ra.cc:166-167
             y = d.step(y)
@@ -408,13 +469,14 @@ class AdaptationRythmeArbitraire(FiltreGen):
             y = s.step(y)
         if abs(np.float32(self.facteur_post_interpolation) - 1) < 1e-6:   # ra.cc:173-174
             if y is x:
-                return x.clone() if hasattr(x, "clone") else np.array(x, np.complex64)
+                return x.clone() if hasattr(x, "clone") else np.array(x, self.dtype)
             return y
         return self.interpolateur.step(y, out=out)
 
 
-def filtre_reechan(ratio: float, nchan: int = 1) -> AdaptationRythmeArbitraire:
-    return AdaptationRythmeArbitraire(ratio, nchan)
+def filtre_reechan(ratio: float, nchan: int = 1, T=np.complex64) -> AdaptationRythmeArbitraire:
+    """filtre_reechan<T>(ratio), T = cfloat or float (ra.cc:180-183,190-191)."""
+    return AdaptationRythmeArbitraire(ratio, nchan, T)
 
 
 filter_resample = filtre_reechan
@@ -423,7 +485,8 @@ filter_resample = filtre_reechan
 def reechan(x, r: float):
     """tsd::rééchan(x, r) (tsd.hpp:700-705) / dsp::resample (dsp/dsp.hpp:499-503)."""
     nchan = 1 if x.ndim == 1 else x.shape[0]
-    return filtre_reechan(r, nchan).step(x)
+    cplx = x.is_complex() if hasattr(x, "is_complex") else np.iscomplexobj(x)
+    return filtre_reechan(r, nchan, np.complex64 if cplx else np.float32).step(x)
 
 
 resample = reechan

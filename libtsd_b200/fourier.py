@@ -215,6 +215,9 @@ class FiltreFFTConfig:
     H: Optional[np.ndarray] = None
     fir_len: int = 0
     fenetre: Optional[np.ndarray] = None   # windowed mode: the Ne window values as data (default: Hann, periodic)
+    # the reference's own field: arbitrary host callback ``f(X)`` on the N bins of every block (numpy complex64 view,
+    # modified in place; ``f(X, chan)`` if it takes two arguments).  Runs FFT -> host -> callback -> device -> IFFT.
+    traitement_freq: Optional[object] = None
 
 
 FFTFilterConfig = FiltreFFTConfig
@@ -237,7 +240,30 @@ class OLA(FiltreGen):
             Hp = H.ctypes.data_as(_vp)
             self._H = H
         h = _vp()
-        if config.avec_fenetrage:
+        self._cb = None
+        if config.traitement_freq is not None:
+            if config.H is not None:
+                raise TsdGpuError("filtre_fft: H et traitement_freq sont exclusifs")
+            import inspect
+            fn = config.traitement_freq
+            two = len(inspect.signature(fn).parameters) >= 2
+
+            def _tramp(user, chan, X, n):
+                a = np.ctypeslib.as_array(C.cast(X, C.POINTER(C.c_float)), shape=(2 * n,)).view(np.complex64)
+                fn(a, chan) if two else fn(a)
+            self._cb = C.CFUNCTYPE(None, _vp, C.c_int, _vp, C.c_int)(_tramp)
+            wp = None
+            if config.avec_fenetrage:
+                w = config.fenetre
+                if w is None:
+                    from .filtrage import fenetre
+                    w = fenetre("hn", Ne, False)
+                w = np.ascontiguousarray(w, np.float32)
+                self._w = w
+                wp = w.ctypes.data_as(_vp)
+            check(lib().tsdgpu_ola_create_cb(int(config.dim_blocs_temporel), int(config.nb_zeros_min), self._cb, None, wp,
+                                             self.nchan, C.byref(h)))
+        elif config.avec_fenetrage:
             w = config.fenetre
             if w is None:
                 from .filtrage import fenetre

@@ -307,7 +307,8 @@ class _Ref:
         L = C.CDLL(REF_SO)
         L.tsdref_last_error.restype = C.c_char_p
         for name in ("tsdref_fir_new", "tsdref_rif_fft_new", "tsdref_ola_new", "tsdref_ola_new2", "tsdref_itrp_new",
-                     "tsdref_reechan_new", "tsdref_fftplan_new", "tsdref_polyphase_new"):
+                     "tsdref_reechan_new", "tsdref_fftplan_new", "tsdref_polyphase_new", "tsdref_itrp_new2",
+                     "tsdref_reechan_new_f32"):
             getattr(L, name).restype = _vp
         self.L = L
 
@@ -399,8 +400,22 @@ class _Ref:
     def itrp(self, ratio, K, nphases, fcut):
         return _RefFilter(self.L, self.L.tsdref_itrp_new(_f(ratio), _i(K), _i(nphases), _f(fcut)), self._err)
 
-    def reechan(self, ratio):
+    def reechan(self, ratio, cplx=True):
+        if not cplx:
+            return _RefFilter(self.L, self.L.tsdref_reechan_new_f32(_f(ratio)), self._err)
         return _RefFilter(self.L, self.L.tsdref_reechan_new(_f(ratio)), self._err)
+
+    def itrp2(self, ratio, kind, cplx=True, K=0, nphases=256, fcut=0.5, degree=0):
+        """filtre_itrp<T>(ratio, itrp): kind = "sinc" | "cspline" | "lineaire" | "lagrange"; T = cfloat or float."""
+        k = {"sinc": 0, "cspline": 1, "lineaire": 2, "lagrange": 3}[kind]
+        return _RefFilter(self.L, self.L.tsdref_itrp_new2(_f(ratio), _i(k), _i(1 if cplx else 0), _i(K), _i(nphases), _f(fcut),
+                                                          _i(degree)), self._err)
+
+    def cspline_lut(self, n=256, c=0.0):
+        lut = np.empty((n + 1, 4), np.float32)
+        if self.L.tsdref_cspline_lut(_i(n), _f(c), _ptr(lut)):
+            raise RuntimeError(self._err())
+        return lut
 
     def polyphase(self, kind, taps, R=2):
         t = _f32(taps)

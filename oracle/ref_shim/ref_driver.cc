@@ -9,6 +9,7 @@
 #include "tsd/tsd.hpp"
 #include "tsd/filtrage.hpp"
 #include "tsd/fourier.hpp"
+#include "tsd/filtrage/spline.hpp"
 
 #include <cstring>
 #include <stdexcept>
@@ -43,8 +44,17 @@ struct RefFilter
   sptr<FiltreGen<float>> fr;
   sptr<FiltreGen<cfloat>> fc;
   sptr<Interpolateur<cfloat>> keep_c;
+  sptr<Interpolateur<float>> keep_r;
   Veccf H;   // spectral gain captured by the OLA callback
 };
+
+template<typename T> static sptr<InterpolateurRIF<T>> make_itrp(int kind, int ncoefs, int nphases, float fcut, int degree)
+{
+  if(kind == 0) return itrp_sinc<T>({ncoefs, nphases, fcut, "hn"});
+  if(kind == 1) return itrp_cspline<T>();
+  if(kind == 2) return itrp_lineaire<T>();
+  return itrp_lagrange<T>(degree);
+}
 
 extern "C" {
 
@@ -207,6 +217,46 @@ void *tsdref_itrp_new(float ratio, int ncoefs, int nphases, float fcut)
   });
   if(rc) { delete f; return nullptr; }
   return f;
+}
+
+// filtre_itrp<T>(ratio, itrp) with any of the reference's interpolators (itrp.cc:130-157) and T = float (cplx = 0) or
+// cfloat: kind 0 = itrp_sinc({ncoefs, nphases, fcut, "hn"}), 1 = itrp_cspline, 2 = itrp_lineaire, 3 = itrp_lagrange(degree)
+void *tsdref_itrp_new2(float ratio, int kind, int cplx, int ncoefs, int nphases, float fcut, int degree)
+{
+  RefFilter *f = new RefFilter;
+  f->cplx = cplx != 0;
+  int rc = guarded([&] {
+    if(cplx)
+    {
+      f->keep_c = make_itrp<cfloat>(kind, ncoefs, nphases, fcut, degree);
+      f->fc = filtre_itrp<cfloat>(ratio, f->keep_c);
+    }
+    else
+    {
+      f->keep_r = make_itrp<float>(kind, ncoefs, nphases, fcut, degree);
+      f->fr = filtre_itrp<float>(ratio, f->keep_r);
+    }
+  });
+  if(rc) { delete f; return nullptr; }
+  return f;
+}
+// filtre_reechan<float>(ratio) (ra.cc:190-191), the instantiation tests/test-ra.cc:161-164 drives
+void *tsdref_reechan_new_f32(float ratio)
+{
+  RefFilter *f = new RefFilter;
+  f->cplx = false;
+  int rc = guarded([&] { f->fr = filtre_reechan<float>(ratio); });
+  if(rc) { delete f; return nullptr; }
+  return f;
+}
+// cspline_calc_lut(n, c) (itrp.cc:314-320): [4][n+1] column-major -> lut[p*4 + i]
+int tsdref_cspline_lut(int n, float c, float *lut)
+{
+  return guarded([&] {
+    Tabf L = cspline_calc_lut(n, c);
+    for(int p2 = 0; p2 <= n; p2++)
+      for(int i = 0; i < 4; i++) lut[p2 * 4 + i] = L(i, p2);
+  });
 }
 
 // filtre_reechan<cfloat>(ratio) (ra.cc:180-183) = what resample()/rééchan() builds (tsd.hpp:700-705)

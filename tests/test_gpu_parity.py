@@ -442,6 +442,78 @@ def test_64k_schedules(tsd, cpu_oracle, mode, monkeypatch):
         assert rel_err(Z, Zr, rms(z)) <= TOL
 
 
+@pytest.mark.parametrize("K,Ne", [(127, 0), (33, 0), (512, 0), (300, 3000)])
+def test_rif_fft_package_H_vs_reference(tsd, ref, cpu_oracle, K, Ne):
+    """filtre_rif_fft<cfloat>(h) end to end with the PACKAGE's own H (fourier.ola_make_H, float64 on the host) against the
+    reference object (fourier.cc:946-990, whose H is its float32 rfft * sqrt(N), :962-965), including the reference's
+    real(...) of the output (fourier.cc:976) behind compat_real_output; and the complex output against filtre_fft fed
+    with the reference's H."""
+    from libtsd_b200 import fourier as Fo
+    rng = np.random.default_rng(K)
+    h = cpu_oracle.design_rif_fen(K, "lp", 0.2)
+    x = cn(rng, 9000)
+    if Ne == 0:
+        r = ref.rif_fft(1, h)                                     # reference: Ne = 512 hard-wired (fourier.cc:954-960)
+        g = Fo.filtre_rif_fft(h, compat_real_output=True)
+        for i in range(0, 9000, 2500):
+            y, yr = g.step(x[i:i + 2500]), r.step(x[i:i + 2500])
+            assert y.shape == yr.shape
+            if y.size:
+                assert np.all(yr.imag == 0)                       # the quirk itself
+                assert rel_err(y, yr, max(1.0, rms(x))) <= TOL
+    ne = Ne if Ne > 0 else 512
+    N = cpu_oracle.p2(ne + K)
+    Href, Hpkg = cpu_oracle.ola_make_H(h, N), Fo.ola_make_H(h, N)
+    assert np.max(np.abs(Href - Hpkg)) <= 2e-6 * np.max(np.abs(Href))
+    g2 = Fo.filtre_rif_fft(h, Ne)                                 # package H, complex output kept
+    r2 = cpu_oracle.ola(ne, K, Href)
+    y2, yr2 = g2.step(x), r2.step(x)
+    assert y2.shape == yr2.shape and rel_err(y2, yr2, max(1.0, rms(x))) <= TOL
+
+
+@pytest.mark.parametrize("Ne,nz,fen", [(512, 512, False), (1000, 24, False), (61441, 4095, False), (512, 0, True), (1000, 24, True)])
+def test_ola_generic_callback(tsd, cpu_oracle, Ne, nz, fen):
+    """FiltreFFTConfig::traitement_freq as an arbitrary HOST callback (fourier.hpp:319, called at fourier.cc:863 and
+    :895/:915): the spectra go device -> host -> callback -> device.  Checked with a callback that multiplies by a gain
+    and zeroes a band (test-filtres.cc:428-432 style) against the reference object given the equivalent H, and the number
+    and order of calls."""
+    from libtsd_b200 import fourier as Fo
+    rng = np.random.default_rng(Ne + nz)
+    N = cpu_oracle.p2(Ne + nz)
+    Hm = cn(rng, N) * 0.7
+    Hm[N // 8: N // 4] = 0
+    calls = []
+
+    def traitement(X, chan):
+        assert X.shape == (N,) and X.dtype == np.complex64
+        calls.append(chan)
+        X *= Hm
+
+    nchan = 2
+    g, Ng = Fo.filtre_fft(Fo.FiltreFFTConfig(Ne, nz, avec_fenetrage=fen, traitement_freq=traitement), nchan)
+    refs = [cpu_oracle.ola(Ne, nz, Hm, avec_fenetrage=fen) for _ in range(nchan)]
+    assert Ng == N
+    blocks = 0
+    for n in (3 * Ne + 17, 100, Ne, 2 * Ne - 117):
+        x = cn(rng, nchan, n)
+        before = g.residual
+        y = g.step(x)
+        yref = np.stack([r.step(x[c]) for c, r in enumerate(refs)])
+        blocks += (before + n) // Ne
+        assert y.shape == yref.shape
+        if y.size:
+            assert rel_err(y, yref, rms(x)) <= TOL
+    assert len(calls) == nchan * blocks * (2 if fen else 1)     # one call per transformed block (two frames when windowed)
+
+
+def test_ola_fenetre_odd_Ne_is_refused(tsd):
+    """Windowed mode with odd dim_blocs_temporel: the reference never resets the centre sample of its `last` buffer there
+    (fourier.cc:899-906), the result depends on uninitialised history; the GPU path refuses the configuration loudly."""
+    from libtsd_b200 import fourier as Fo
+    with pytest.raises(tsd.TsdGpuError, match="odd dim_blocs_temporel"):
+        Fo.filtre_fft(Fo.FiltreFFTConfig(511, 1, avec_fenetrage=True))
+
+
 def test_ola_errors(tsd):
     from libtsd_b200 import fourier as Fo
     with pytest.raises(tsd.TsdGpuError):
@@ -486,6 +558,50 @@ def test_itrp_vs_oracle(tsd, port, cpu_oracle, ratio, K, fcut):
         if y.size:
             assert rel_err(y, yref, max(rms(x), 1e-3) * np.sqrt(K)) <= TOL
         assert np.float32(g.phase) == np.float32(refs[0].phase)
+
+
+@pytest.mark.parametrize("cplx", [True, False])
+@pytest.mark.parametrize("kind,kw", [("cspline", {}), ("lineaire", {}), ("lagrange", {"degree": 3}), ("lagrange", {"degree": 6}),
+                                     ("sinc", {"K": 15, "nphases": 256, "fcut": 0.4}), ("sinc", {"K": 32, "nphases": 100, "fcut": 0.3})])
+def test_itrp_every_interpolator_vs_reference(tsd, ref, kind, kw, cplx):
+    """filtre_itrp<T>(ratio, itrp) for every interpolator of itrp.cc:130-157 and both sample types (ra.cc:190-195)
+    against the reference objects: LUT-backed ones (sinc, cspline) and the exact-delay ones (lineaire, lagrange), whose
+    coefficients depend on the float32 phase itself (itrp.cc:82-127).  Chunked calls: counts bit-exact, samples 1e-5."""
+    from libtsd_b200 import filtrage as F
+    rng = np.random.default_rng(len(kind) * 7 + kw.get("degree", 0) + (3 if cplx else 0))
+    T = np.complex64 if cplx else np.float32
+    mk = {"cspline": lambda: F.itrp_cspline(), "lineaire": lambda: F.itrp_lineaire(),
+          "lagrange": lambda: F.itrp_lagrange(kw["degree"]),
+          "sinc": lambda: F.itrp_sinc(F.InterpolateurSincConfig(kw.get("K", 0), kw.get("nphases", 256), kw.get("fcut", 0.5), "hn"))}[kind]
+    for ratio in (1.2, 0.73, float(np.float32(np.pi)) / 2, 1.0):
+        nchan = 3
+        g = F.filtre_itrp(ratio, mk(), nchan, T)
+        refs = [ref.itrp2(ratio, kind, cplx=cplx, **kw) for _ in range(nchan)]
+        for n in (1000, 1, 2, 4097, 0, 333):
+            x = cn(rng, nchan, n) if cplx else rng.standard_normal((nchan, n)).astype(np.float32)
+            y = g.step(x)
+            yref = [r.step(x[c]) for c, r in enumerate(refs)]
+            assert y.shape == (nchan, len(yref[0]))            # per-call output count: bit-exact bookkeeping
+            if y.size:
+                assert rel_err(y, np.stack(yref), 1.0) <= TOL
+
+
+@pytest.mark.parametrize("ratio", [0.1, 0.3, 0.5, 147 / 160, 1.0, 1.5, 3.0, 7.3])
+def test_reechan_float(tsd, ref, ratio):
+    """filtre_reechan<float>(ratio) (ra.cc:190-191): real-valued chain (half-band / x2 stages + 15-tap sinc interpolator)
+    against the reference object, chunked."""
+    from libtsd_b200 import filtrage as F
+    rng = np.random.default_rng(int(ratio * 100))
+    nchan = 2
+    g = F.filtre_reechan(ratio, nchan, np.float32)
+    refs = [ref.reechan(ratio, cplx=False) for _ in range(nchan)]
+    for n in (3000, 1, 7, 2048, 0, 1001):
+        x = rng.standard_normal((nchan, n)).astype(np.float32)
+        y = g.step(x)
+        yref = [r.step(x[c], cap=8 * n + 64) for c, r in enumerate(refs)]
+        assert y.shape == (nchan, len(yref[0]))
+        if y.size:
+            assert rel_err(y, np.stack(yref), 1.0) <= TOL
 
 
 @pytest.mark.parametrize("tc", ["0", "1"])
@@ -690,3 +806,32 @@ def test_cpp_adapters_drop_in():
     print(r.stdout, r.stderr)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "ADAPTER CHECK OK" in r.stdout
+
+
+def test_cpp_dropin_tu():
+    """integration/tsd_gpu_dropin.cc defines the reference's own factory symbols (filtre_rif<..>, filtre_reechan<..>,
+    filtre_itrp<..>, filtre_rif_fft<..>, filtre_fft, + the fftplan_defaut hook).  integration/dropin_check.cc uses ONLY the
+    reference's public API; it is linked once against the reference objects alone and once with the drop-in TU in front
+    (oracle/Makefile target `dropin`).  Same source, same inputs: the outputs must agree and the second binary must have
+    launched GPU kernels."""
+    import os
+    import subprocess
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref")
+    cpu, gpu = os.path.join(d, "dropin_check_cpu"), os.path.join(d, "dropin_check_gpu")
+    if not (os.path.exists(cpu) and os.path.exists(gpu)):
+        pytest.skip("oracle/_ref/dropin_check_* not built (needs /root/reference)")
+    out = {}
+    for name, exe in (("cpu", cpu), ("gpu", gpu)):
+        r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout + r.stderr
+        out[name] = {ln.split()[0]: ln.split()[1:] for ln in r.stdout.strip().splitlines()}
+    assert int(out["cpu"]["noyaux_gpu"][0]) == 0 and int(out["gpu"]["noyaux_gpu"][0]) > 0
+    for key, vc in out["cpu"].items():
+        if key == "noyaux_gpu":
+            continue
+        vg = out["gpu"][key]
+        assert vc[0] == vg[0], (key, vc[0], vg[0])                       # output length: bit-exact bookkeeping
+        a = np.array([float(v) for v in vc[1:-2]]), np.array([float(v) for v in vg[1:-2]])
+        rms_c = float(vc[-1])
+        assert np.max(np.abs(a[0] - a[1])) <= 1.5 * TOL * max(rms_c, 1e-3), key
+        assert abs(float(vg[-1]) - rms_c) <= 1e-4 * rms_c, key
