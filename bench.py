@@ -21,6 +21,7 @@ workload definition with all host threads; under torchrun only rank 0 runs it.
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -301,33 +302,162 @@ class GpuWorkload:
             raise SystemExit(f"unknown workload {name}")
 
 
-def e2e_measure(name, steps, warmup, barrier=None):
-    """Same metric through the C ABI with pinned HOST buffers (H2D + D2H inside the timed region)."""
+KERNELS = {
+    "ola": "ols16k_kernel<1> (single-SM overlap-save, 16384-point transforms, TMEM constants, TMA bulk prefetch)",
+    "fft": "fft64k_kernel",
+    "fir": "fir_tc_kernel (tcgen05 3xTF32 Toeplitz GEMM)",
+    "resample": "resamp_tc_kernel (tcgen05 3xTF32 banded filter-bank GEMM, CTA pairs)",
+    "reechan": "resamp_tc_kernel (tcgen05 3xTF32 banded filter-bank GEMM, CTA pairs)",
+}
+
+
+def make_config(workload, world):
+    """The SAME dict in both arms (the driver compares them)."""
+    text, _ = WORKLOADS[workload]
+    return {"workload": text, "per_gpu_batch": "fixed (weak scaling)", "l2": "inputs larger than L2 (no flush needed)",
+            "parallelism": f"channel-sharded x{world}, no collective"}
+
+
+def pin_affinity(local_rank):
+    """Best effort: run this rank on the CPUs nvidia-smi lists as local to its GPU (NUMA), so that the pinned staging buffers
+    and the copy threads of different ranks do not share one socket's memory controllers."""
+    try:
+        out = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout
+        hdr = None
+        for ln in out.splitlines():
+            cols = [c.strip() for c in ln.split("\t") if c.strip()]
+            if hdr is None and any("CPU Affinity" in c for c in cols):
+                hdr = cols
+                continue
+            if hdr and cols and cols[0] == f"GPU{local_rank}":
+                idx = [i for i, c in enumerate(hdr) if "CPU Affinity" in c][0] + 1   # data rows carry the row label first
+                spec = cols[idx] if idx < len(cols) else ""
+                cpus = set()
+                for part in spec.split(","):
+                    if "-" in part:
+                        a, b = part.split("-")
+                        cpus.update(range(int(a), int(b) + 1))
+                    elif part.strip().isdigit():
+                        cpus.add(int(part))
+                cpus &= os.sched_getaffinity(0)
+                if cpus:
+                    os.sched_setaffinity(0, cpus)
+                    return sorted(cpus)
+    except Exception:
+        pass
+    return None
+
+
+def load_traffic(workload):
+    """DRAM bytes of ONE launch of the dominant kernel at the benched size, from the committed ncu capture of this same
+    command (profiles/r02_traffic_<workload>.json, written by profiles/tools/traffic_capture.sh)."""
+    f = os.path.join(ROOT, "profiles", f"r02_traffic_{workload}.json")
+    if os.path.exists(f):
+        with open(f) as fh:
+            return json.load(fh)
+    return None
+
+
+def measure_workload(name, steps, warmup, scale, stream, barrier, world, sample_clocks_on=None):
+    """Device-resident timing of one workload: returns (dict for the JSON line, samples per step)."""
+    import torch
+    import libtsd_b200
+    wl = GpuWorkload(name, scale)
+    torch.cuda.synchronize()
+    for _ in range(warmup):
+        wl.step()
+    barrier()
+    sampler = ClockSampler(sample_clocks_on) if sample_clocks_on is not None else None
+    if sampler:
+        sampler.start()
+    libtsd_b200.launch_count(reset=True)
+    libtsd_b200._lib.timing_enable(True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for _ in range(steps):
+        wl.step()
+    ev1.record(stream)
+    barrier()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    kern_ms, kern_launches = libtsd_b200._lib.timing_read()
+    libtsd_b200._lib.timing_enable(False)
+    launches = libtsd_b200.launch_count()
+    clocks = sampler.stop() if sampler else None
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([elapsed_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    samples_per_step = wl.samples_per_step
+    wl.step = None   # the step closure refers back to the workload: break the cycle so that the buffers go now
+    del wl
+    gc.collect()
+    torch.cuda.empty_cache()
+    _, bps = WORKLOADS[name]
+    peaks, peak_kind = load_peaks()
+    peak = float(peaks["hbm_gbs"])
+    achieved = bps * samples_per_step * steps / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else None
+    roofline = {"bound": "hbm", "kernel": KERNELS[name], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_kind,
+                "algorithmic_bytes_per_sample": bps, "kernel_ms_per_step": kern_ms / steps, "kernel_launches": kern_launches,
+                "algorithmic_bytes_per_launch": (bps * samples_per_step * steps / kern_launches) if kern_launches else None}
+    tr = load_traffic(name)
+    if tr and kern_launches:
+        roofline["traffic"] = tr.get("dram_bytes_per_launch")
+        roofline["traffic_source"] = tr.get("source")
+    res = {"value": float(samples_per_step) * world * steps / (elapsed_ms * 1e-3) / 1e9, "unit": "Gsamples/s",
+           "ms_per_step": elapsed_ms / steps, "steps": steps, "roofline": roofline, "gpu_launches": launches, "clocks": clocks,
+           "config": make_config(name, world)}
+    return res, samples_per_step
+
+
+def e2e_measure(name, steps, warmup, barrier=None, world=1, pageable=False):
+    """Same metric through the C ABI with HOST buffers (H2D + D2H inside the timed region).  pageable = False: pinned
+    buffers (cudaHostAlloc through torch); True: plain malloc'd numpy arrays, what a caller that owns ordinary Veccf
+    storage hands over (the library stages them itself)."""
     import torch
     from libtsd_b200 import filtrage as F, fourier as Fo
     O = _Setup
     rng = np.random.default_rng(1)
 
-    def pinned(nchan, n):
-        t = torch.empty((nchan, n), dtype=torch.complex64).pin_memory()
-        a = t.numpy()
-        a.real[...] = rng.standard_normal((1, n), dtype=np.float32)
-        a.imag[...] = rng.standard_normal((1, n), dtype=np.float32)
+    def hostbuf(nchan, n):
+        if pageable:
+            a = np.empty((nchan, n), np.complex64)
+            t = None
+        else:
+            t = torch.empty((nchan, n), dtype=torch.complex64).pin_memory()
+            a = t.numpy()
+        row_r = rng.standard_normal(n, dtype=np.float32)
+        row_i = rng.standard_normal(n, dtype=np.float32)
+        a.real[...] = row_r[None]
+        a.imag[...] = row_i[None]
         return t, a
 
     if name == "ola":
-        nchan, n = 8, 1 << 24
+        # the BASELINE batch itself at N = 1 (256 channels x 16 Mi); a share of it per rank when several GPUs pull from
+        # the same host memory; a bounded subset for the pageable variant
+        nchan = 32 if pageable else (256 if world == 1 else max(32, 256 // world))
+        n = 1 << 24
         H = O.ola_make_H(O.design_rif_fen(4095, "lp", 0.1), 65536)
         flt, _ = Fo.filtre_fft(Fo.FiltreFFTConfig(61441, 4095, H=H, fir_len=4095), nchan)
-        tx, x = pinned(nchan, n)
-        ty, y = pinned(nchan, 61441 * (n // 61441 + 1))
+        while True:
+            try:
+                tx, x = hostbuf(nchan, n)
+                ty, y = hostbuf(nchan, 61441 * (n // 61441 + 1))
+                break
+            except RuntimeError:
+                if nchan <= 8:
+                    raise
+                nchan //= 2
+                flt, _ = Fo.filtre_fft(Fo.FiltreFFTConfig(61441, 4095, H=H, fir_len=4095), nchan)
         step = lambda: flt.step(x, out=y)   # noqa: E731
         out_per_step = 61441 * (n // 61441)
     elif name == "fft":
         nchan, n = 256, 65536
         plan = Fo.tfrplan_creation(65536, batch=nchan)
-        tx, x = pinned(nchan, n)
-        ty, y = pinned(nchan, n)
+        tx, x = hostbuf(nchan, n)
+        ty, y = hostbuf(nchan, n)
 
         def step():
             plan.step(x, True, out=y)
@@ -337,22 +467,22 @@ def e2e_measure(name, steps, warmup, barrier=None):
     elif name == "fir":
         nchan, n = 64, 1 << 20
         flt = F.filtre_rif(O.design_rif_fen(127, "lp", 0.1), np.complex64, nchan)
-        tx, x = pinned(nchan, n)
-        ty, y = pinned(nchan, n)
+        tx, x = hostbuf(nchan, n)
+        ty, y = hostbuf(nchan, n)
         step = lambda: flt.step(x, out=y)   # noqa: E731
         out_per_step = n
     elif name == "reechan":
         nchan, n = 128, 1 << 20
         flt = F.filtre_reechan(147.0 / 160.0, nchan)
-        tx, x = pinned(nchan, n)
-        ty, y = pinned(nchan, int(n * 147 / 160) + 32)
+        tx, x = hostbuf(nchan, n)
+        ty, y = hostbuf(nchan, int(n * 147 / 160) + 32)
         step = lambda: flt.step(x, out=y)   # noqa: E731
         out_per_step = int(n * 147 / 160)
     else:
         nchan, n = 128, 1 << 20
         flt = F.filtre_itrp(147.0 / 160.0, F.InterpolateurLUT(O.itrp_sinc_lut(64, 256, 0.4)), nchan)
-        tx, x = pinned(nchan, n)
-        ty, y = pinned(nchan, int(n * 147 / 160) + 32)
+        tx, x = hostbuf(nchan, n)
+        ty, y = hostbuf(nchan, int(n * 147 / 160) + 32)
         step = lambda: flt.step(x, out=y)   # noqa: E731
         out_per_step = int(n * 147 / 160)
     for _ in range(warmup):
@@ -363,10 +493,93 @@ def e2e_measure(name, steps, warmup, barrier=None):
     for _ in range(steps):
         step()   # host-memory calls return when y is valid on the host
     dt = (time.perf_counter() - t0) / steps
+    # the link ceiling of the same buffers: H2D of x and D2H of y at the same time, no kernel (pinned buffers only)
+    ceiling = None
+    if not pageable:
+        dx = torch.empty((nchan, x.shape[1]), dtype=torch.complex64, device="cuda")
+        dy = torch.empty((nchan, out_per_step), dtype=torch.complex64, device="cuda")
+        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        torch.cuda.synchronize()
+        if barrier is not None:
+            barrier()
+        t1 = time.perf_counter()
+        with torch.cuda.stream(s_in):
+            dx.copy_(tx, non_blocking=True)
+        with torch.cuda.stream(s_out):
+            ty[:, :out_per_step].copy_(dy, non_blocking=True)
+        torch.cuda.synchronize()
+        ceiling = time.perf_counter() - t1
+        del dx, dy
     samples = nchan * (n if name != "fft" else n // 2)
-    return {"samples_per_step": samples, "seconds_per_step": dt, "unit": "Gsamples/s", "h2d_bytes_per_step": int(nchan * n * 8),
-            "d2h_bytes_per_step": int(nchan * out_per_step * 8),
-            "sample": f"{nchan} channels x {n if name != 'fft' else n // 2} cf32 in pinned host memory per step and per GPU"}
+    res = {"samples_per_step": samples, "seconds_per_step": dt, "unit": "Gsamples/s", "h2d_bytes_per_step": int(nchan * n * 8),
+           "d2h_bytes_per_step": int(nchan * out_per_step * 8), "host_memory": "pageable (malloc)" if pageable else "pinned",
+           "sample": f"{nchan} channels x {n if name != 'fft' else n // 2} cf32 in {'pageable' if pageable else 'pinned'} host memory per step and per GPU"}
+    if ceiling:
+        res["copy_only_seconds"] = ceiling
+    return res
+
+
+def strong_and_gathered(steps, warmup, stream, barrier, world, rank):
+    """BASELINE config 4 as north_star states it: 256 channels sharded over the N GPUs (256/N each), no collective during
+    the compute ("strong"), then the same with the final NCCL all-gather of the output shards, issued per channel group on
+    a side stream so that the transfer of group g overlaps the filtering of group g+1 ("gathered")."""
+    import torch
+    import torch.distributed as dist
+    from libtsd_b200 import fourier as Fo
+    total_ch, n, Ne = 256, 1 << 24, 61441
+    cpr = total_ch // world
+    H = _Setup.ola_make_H(_Setup.design_rif_fen(4095, "lp", 0.1), 65536)
+    G = 4 if cpr % 4 == 0 else 1
+    cg = cpr // G
+    n_out = Ne * (n // Ne)
+    g = torch.Generator(device="cuda")
+    g.manual_seed(0x7D5D0004 + rank)
+    x = torch.empty((cpr, n), dtype=torch.complex64, device="cuda")
+    torch.view_as_real(x).normal_(generator=g)
+    y = torch.empty((G, cg, n_out), dtype=torch.complex64, device="cuda")
+    flts = [Fo.filtre_fft(Fo.FiltreFFTConfig(Ne, 4095, H=H, fir_len=4095), cg)[0] for _ in range(G)]
+
+    def compute(gi):
+        flts[gi].step(x[gi * cg:(gi + 1) * cg], out=y[gi])
+
+    def timed(body):
+        for _ in range(warmup):
+            body()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            body()
+        e1.record(stream)
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / steps
+
+    ms_strong = timed(lambda: [compute(gi) for gi in range(G)])
+    full = torch.empty((G, world, cg, n_out), dtype=torch.complex64, device="cuda")   # gathered layout [group][rank][channel][sample]
+
+    def gathered():
+        works = []
+        for gi in range(G):
+            compute(gi)
+            works.append(dist.all_gather_into_tensor(full[gi], y[gi], async_op=True))   # NCCL's stream waits for the step
+        for w in works:
+            w.wait()
+    ms_gath = timed(gathered)
+    samples = float(total_ch) * n
+    recv = (world - 1) / world * total_ch * n_out * 8.0          # bytes every GPU receives per step
+    del x, y, full, flts
+    gc.collect()
+    torch.cuda.empty_cache()
+    return ({"value": samples / (ms_strong * 1e-3) / 1e9, "unit": "Gsamples/s", "ms_per_step": ms_strong, "channels_per_gpu": cpr,
+             "scaling": "strong", "collective": "none"},
+            {"value": samples / (ms_gath * 1e-3) / 1e9, "unit": "Gsamples/s", "ms_per_step": ms_gath, "channels_per_gpu": cpr,
+             "collective": f"ncclAllGather per group of {cg} channels, overlapped with the next group's filtering",
+             "link_gbs_per_gpu_received": recv / (ms_gath * 1e-3) / 1e9, "link_peak_gbs": 770.0,
+             "link_peak_source": "peer-copy figure of /opt/skills/guides/B200_PROFILING.md",
+             "link_frac": recv / (ms_gath * 1e-3) / 1e9 / 770.0,
+             "layout": "[group][rank][channel][sample]"})
 
 
 def main():
@@ -379,6 +592,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="channel-count multiplier (debug only; 1.0 = BASELINE size)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="headline workload only (no `workloads`, `strong`, `gathered` blocks)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -395,7 +609,7 @@ def main():
         line = {"impl": "reference", "metric": "Gsamples/s filtered (cf32)", "value": val, "unit": "Gsamples/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": text, "sample": sample},
+                "config": make_config(args.workload, args.gpus),
                 "cpu_baseline": {"value": val, "unit": "Gsamples/s", "cores": threads, "kind": kind, "sample": sample},
                 "e2e": {"value": val, "unit": "Gsamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
@@ -408,6 +622,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    affinity = pin_affinity(local_rank) if world > 1 else None
     if world > 1:
         # stdout carries exactly one JSON line: NCCL's version / debug banner goes to stderr
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
@@ -419,93 +634,97 @@ def main():
     torch.cuda.set_stream(stream)
     libtsd_b200.use_torch_stream()
 
-    wl = GpuWorkload(args.workload, args.scale)
-    torch.cuda.synchronize()
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        wl.step()
-    barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    libtsd_b200.launch_count(reset=True)
-    libtsd_b200._lib.timing_enable(True)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record(stream)
-    for _ in range(args.steps):
-        wl.step()
-    ev1.record(stream)
-    barrier()
-    elapsed_ms = ev0.elapsed_time(ev1)
-    kern_ms, kern_launches = libtsd_b200._lib.timing_read()
-    libtsd_b200._lib.timing_enable(False)
-    launches = libtsd_b200.launch_count()
-    clocks = sampler.stop() if rank == 0 else None
-    if world > 1:
-        t = torch.tensor([elapsed_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(t.item())
-    total_samples = float(wl.samples_per_step) * world * args.steps
-    value = total_samples / (elapsed_ms * 1e-3) / 1e9
-    samples_per_step = wl.samples_per_step
+    head, samples_per_step = measure_workload(args.workload, args.steps, args.warmup, args.scale, stream, barrier, world,
+                                              sample_clocks_on=local_rank if rank == 0 else None)
 
-    # end to end through the C ABI with pinned host buffers: every rank drives its own GPU, same metric
-    e2e = None
+    # the other BASELINE configs, same measurement, in the same run (fewer steps: they only need a stable mean)
+    extra = {}
+    if not args.no_extra:
+        for name in ("fft", "fir", "resample", "reechan", "ola"):
+            if name == args.workload:
+                continue
+            r, _ = measure_workload(name, min(args.steps, 6), 3, args.scale, stream, barrier, world,
+                                    sample_clocks_on=local_rank if rank == 0 else None)
+            r.pop("config")
+            extra[name] = r
+
+    strong = gath = None
+    if world > 1 and not args.no_extra and args.workload == "ola" and 256 % world == 0:
+        strong, gath = strong_and_gathered(min(args.steps, 6), 3, stream, barrier, world, rank)
+
+    # end to end through the C ABI with host buffers: every rank drives its own GPU, same metric
+    e2e = e2e_page = None
     if not args.no_e2e:
-        del wl
         torch.cuda.empty_cache()
-        m = e2e_measure(args.workload, 3, 1, barrier if world > 1 else None)
-        sec = m.pop("seconds_per_step")
-        smp = m.pop("samples_per_step")
-        if world > 1:
-            t = torch.tensor([sec], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            sec = float(t.item())
-        e2e = dict(value=smp * world / sec / 1e9, **m)
+
+        def run_e2e(pageable):
+            m = e2e_measure(args.workload, 2, 1, barrier if world > 1 else None, world, pageable)
+            sec = m.pop("seconds_per_step")
+            smp = m.pop("samples_per_step")
+            cop = m.pop("copy_only_seconds", None)
+            if world > 1:
+                t = torch.tensor([sec, cop or 0.0], device="cuda", dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                sec, cop = float(t[0].item()), (float(t[1].item()) or None)
+            d = dict(value=smp * world / sec / 1e9, **m)
+            if cop:
+                # what the host link alone allows for these buffers (both directions at once, all ranks at the same time)
+                d["link_ceiling"] = {"value": smp * world / cop / 1e9, "unit": "Gsamples/s",
+                                     "gbs_each_way_per_gpu": m["h2d_bytes_per_step"] / cop / 1e9,
+                                     "how": "H2D of the step's input and D2H of its output issued together, no kernel"}
+            return d
+        e2e = run_e2e(False)
+        if not args.no_extra:
+            e2e_page = run_e2e(True)
+            if rank == 0:
+                e2e["pageable"] = {k: e2e_page[k] for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step", "sample", "host_memory")}
 
     if rank == 0:
-        peaks, peak_kind = load_peaks()
-        peak = float(peaks["hbm_gbs"])
-        # dominant kernel: algorithmic bytes of one rank's launches / summed CUDA-event duration
-        achieved = bytes_per_sample * samples_per_step * args.steps / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else None
-        # ola: the block filter runs as three stage kernels per chunk of 32 blocks, overlapped on four streams; the timed
-        # unit is the whole pipeline of one step() (events around its first and last launch on the launching stream)
-        kernel_name = {"ola": "ola64k_stage<0|1|2> (stage kernels of one step(), overlapped)", "fft": "fft64k_kernel", "fir": "fir_tc_kernel (tcgen05 3xTF32 Toeplitz GEMM)",
-                       "resample": "resamp_tc_kernel (tcgen05 3xTF32 banded filter-bank GEMM, CTA pairs)",
-                       "reechan": "resamp_tc_kernel (tcgen05 3xTF32 banded filter-bank GEMM, CTA pairs)"}[args.workload]
-        roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_kind,
-                    "algorithmic_bytes_per_sample": bytes_per_sample, "kernel_ms_per_step": kern_ms / args.steps,
-                    "kernel_launches": kern_launches}
-        # DRAM bytes per launch from the committed ncu capture (measured at a reduced size, scaled per sample)
-        traffic_file = os.path.join(ROOT, "profiles", f"traffic_{args.workload}.json")
-        if os.path.exists(traffic_file) and kern_launches:
-            with open(traffic_file) as f:
-                per_sample = json.load(f).get("dram_bytes_per_sample")
-            if per_sample:
-                launches_per_sample_pass = 2 if args.workload == "fft" else 1   # fwd + inv are two launches over the same samples
-                roofline["traffic"] = per_sample * samples_per_step * args.steps * launches_per_sample_pass / kern_launches
-                roofline["algorithmic_bytes_per_launch"] = bytes_per_sample * samples_per_step * args.steps / kern_launches
         cpu = None
-        if not args.no_cpu_baseline and world == 1:
+        if not args.no_cpu_baseline:
             v, ms, threads, kind, sample = cpu_run(args.workload, 2, 1)
-            cpu = {"value": v, "unit": "Gsamples/s", "cores": threads, "kind": kind, "sample": sample}
-        line = {"metric": "Gsamples/s filtered (cf32)", "value": value, "unit": "Gsamples/s", "n_gpus": world,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+            cpu = {"value": v, "unit": "Gsamples/s", "cores": threads, "kind": kind, "sample": sample,
+                   "flags": "-O3 -march=x86-64 (the reference's release flags, core/std-makefile-defs:171)"}
+            nat = cpu_run_native(args.workload)
+            if nat:
+                cpu["value_avx2_build"] = nat
+        line = {"metric": "Gsamples/s filtered (cf32)", "value": head["value"], "unit": "Gsamples/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": text, "per_gpu_batch": "fixed (weak scaling)", "l2": "inputs larger than L2 (no flush needed)",
-                           "parallelism": f"channel-sharded x{world}, no collective"},
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
+                "config": head["config"], "roofline": head["roofline"], "cpu_baseline": cpu, "e2e": e2e,
+                "gpu_launches": head["gpu_launches"], "clocks": head["clocks"]}
+        if extra:
+            line["workloads"] = extra
+        if strong:
+            line["strong"] = strong
+            line["gathered"] = gath
+        if affinity:
+            line["cpu_affinity_rank0"] = f"{len(affinity)} CPUs local to GPU {local_rank}"
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def cpu_run_native(workload):
+    """SURVEY 8(d) also asks for the CPU figure of an -march=native-class build (timing only: FMA contraction makes it
+    differ from the parity build).  The GPU box's CPU is not the build container's, so the portable stand-in is
+    x86-64-v3 (AVX2 + FMA), built by `make -C oracle native` into oracle/_ref/libtsdref_v3.so."""
+    so = os.path.join(ROOT, "oracle", "_ref", "libtsdref_v3.so")
+    if not os.path.exists(so):
+        return None
+    try:
+        env = dict(os.environ, TSDREF_LIB=so)
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", workload, "--steps", "2",
+                              "--warmup", "1"], capture_output=True, text=True, timeout=300, env=env).stdout.strip().splitlines()
+        return {"value": json.loads(out[-1])["value"], "unit": "Gsamples/s", "flags": "-O3 -march=x86-64-v3 (AVX2 + FMA)"}
+    except Exception:
+        return None
 
 
 if __name__ == "__main__":

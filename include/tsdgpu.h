@@ -96,6 +96,10 @@ int tsdgpu_fir_step(tsdgpu_fir_t f, const void *x, long long x_stride, int n,
 /* Reference-layout state (filtre-rt.cc:56-58): fen[nchan][K] ring and the common ring index. */
 int tsdgpu_fir_get_state(tsdgpu_fir_t f, void *fen_host, int *index);
 int tsdgpu_fir_set_state(tsdgpu_fir_t f, const void *fen_host, int index);
+/* Same state as a time-ordered history: hist[nchan][K-1] = the last K-1 inputs of every channel, oldest first, and the
+ * number of samples the channel has consumed so far.  This is what a halo-split segment of a long stream starts from
+ * (the halo is read from the source buffer, nothing is exchanged). */
+int tsdgpu_fir_set_history(tsdgpu_fir_t f, const void *hist_host, long long samples_so_far);
 int tsdgpu_fir_destroy(tsdgpu_fir_t f);
 
 /* ---- FFT plan: replaces FFTPlan / tfrplan_création / fft() / ifft() ------------------------- */
@@ -146,6 +150,16 @@ long long tsdgpu_ola_out_count(tsdgpu_ola_t f, int n);
 /* Feeds n samples per channel; writes *n_out = tsdgpu_ola_out_count(f, n) samples per channel. */
 int tsdgpu_ola_step(tsdgpu_ola_t f, const void *x, long long x_stride, int n,
                     void *y, long long y_stride, long long *n_out, int mem);
+/* State hand-over (checkpoint / halo split of a long stream, SURVEY 5 + 8e): the re-blocking residual (TamponNv2 windex,
+ * tsd.cc:310), the number of Ne-blocks emitted so far, carry[nchan][carry_len] = the last carry_len input samples of every
+ * channel (oldest first; zeros before the stream start), and — only for the forms that have them — svg[nchan][Ne]
+ * (overlap-add partial sums, fourier.cc:870-872) and last[nchan][Ne] (windowed mode, fourier.cc:905-922).  A segment
+ * that starts at stream sample S is set up with residual = S mod Ne, blocks_done = S / Ne and the carry_len samples
+ * before S; its step() then emits exactly the samples the one-shot call emits for those blocks. */
+int tsdgpu_ola_state_dims(tsdgpu_ola_t f, int *carry_len, int *svg_len, int *last_len);
+int tsdgpu_ola_get_state(tsdgpu_ola_t f, int *residual, long long *blocks_done, void *carry_host, void *svg_host, void *last_host);
+int tsdgpu_ola_set_state(tsdgpu_ola_t f, int residual, long long blocks_done, const void *carry_host, const void *svg_host,
+                         const void *last_host);
 int tsdgpu_ola_destroy(tsdgpu_ola_t f);
 
 /* periodogramme_tfd(x, N) (fourier.hpp:967, fourier.cc:1451-1481): short-time spectra of the frames of the windowed
@@ -180,6 +194,11 @@ long long tsdgpu_resamp_out_count(tsdgpu_resamp_t f, int n);
 float tsdgpu_resamp_phase(tsdgpu_resamp_t f);
 int tsdgpu_resamp_step(tsdgpu_resamp_t f, const void *x, long long x_stride, int n,
                        void *y, long long y_stride, long long y_capacity, long long *n_out, int mem);
+/* State hand-over: the float32 phase (ra.cc:16-22) and hist[nchan][K-1] = the last K-1 inputs, oldest first.  The phase
+ * at any input index of a stream comes from tsdgpu_resamp_schedule (data-independent), which is how a halo-split segment
+ * gets its start state. */
+int tsdgpu_resamp_get_state(tsdgpu_resamp_t f, float *phase, void *hist_host);
+int tsdgpu_resamp_set_state(tsdgpu_resamp_t f, float phase, const void *hist_host);
 int tsdgpu_resamp_destroy(tsdgpu_resamp_t f);
 /* The host-side schedule on its own (no device needed): runs the reference's float32 phase
  * recurrence (ra.cc:58-73) over n inputs starting from *phase, writes for every output j the index
@@ -204,6 +223,10 @@ long long tsdgpu_poly_out_count(tsdgpu_poly_t f, int n);
 int tsdgpu_poly_state(tsdgpu_poly_t f, int *index, int *cnt);
 int tsdgpu_poly_step(tsdgpu_poly_t f, const void *x, long long x_stride, int n,
                      void *y, long long y_stride, long long *n_out, int mem);
+/* State hand-over: samples consumed so far (ring index = total mod L), the decimation counter, and hist[nchan][L-1] = the
+ * last L-1 inputs, oldest first. */
+int tsdgpu_poly_get_state(tsdgpu_poly_t f, long long *total, int *cnt, void *hist_host);
+int tsdgpu_poly_set_state(tsdgpu_poly_t f, long long total, int cnt, const void *hist_host);
 int tsdgpu_poly_destroy(tsdgpu_poly_t f);
 
 #ifdef __cplusplus

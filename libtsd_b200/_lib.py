@@ -48,6 +48,7 @@ _SIGS = {
     "tsdgpu_fir_step": (_i, [_vp, _vp, _ll, _i, _vp, _ll, _i]),
     "tsdgpu_fir_get_state": (_i, [_vp, _vp, C.POINTER(_i)]),
     "tsdgpu_fir_set_state": (_i, [_vp, _vp, _i]),
+    "tsdgpu_fir_set_history": (_i, [_vp, _vp, _ll]),
     "tsdgpu_fir_destroy": (_i, [_vp]),
     "tsdgpu_fft_plan": (_i, [_i, _i, C.POINTER(_vp)]),
     "tsdgpu_fft_exec": (_i, [_vp, _vp, _ll, _vp, _ll, _i, _i]),
@@ -59,6 +60,9 @@ _SIGS = {
     "tsdgpu_ola_dims": (_i, [_vp, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "tsdgpu_ola_out_count": (_ll, [_vp, _i]),
     "tsdgpu_ola_step": (_i, [_vp, _vp, _ll, _i, _vp, _ll, C.POINTER(_ll), _i]),
+    "tsdgpu_ola_state_dims": (_i, [_vp, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
+    "tsdgpu_ola_get_state": (_i, [_vp, C.POINTER(_i), C.POINTER(_ll), _vp, _vp, _vp]),
+    "tsdgpu_ola_set_state": (_i, [_vp, _i, _ll, _vp, _vp, _vp]),
     "tsdgpu_ola_destroy": (_i, [_vp]),
     "tsdgpu_resamp_create": (_i, [_f, _vp, _i, _i, _i, C.POINTER(_vp)]),
     "tsdgpu_resamp_create_ex": (_i, [_f, _vp, _i, _i, _i, _i, C.POINTER(_vp)]),
@@ -66,11 +70,15 @@ _SIGS = {
     "tsdgpu_resamp_out_count": (_ll, [_vp, _i]),
     "tsdgpu_resamp_phase": (_f, [_vp]),
     "tsdgpu_resamp_step": (_i, [_vp, _vp, _ll, _i, _vp, _ll, _ll, C.POINTER(_ll), _i]),
+    "tsdgpu_resamp_get_state": (_i, [_vp, C.POINTER(_f), _vp]),
+    "tsdgpu_resamp_set_state": (_i, [_vp, _f, _vp]),
     "tsdgpu_resamp_destroy": (_i, [_vp]),
     "tsdgpu_poly_create": (_i, [_i, _vp, _i, _i, _i, _i, C.POINTER(_vp)]),
     "tsdgpu_poly_out_count": (_ll, [_vp, _i]),
     "tsdgpu_poly_state": (_i, [_vp, C.POINTER(_i), C.POINTER(_i)]),
     "tsdgpu_poly_step": (_i, [_vp, _vp, _ll, _i, _vp, _ll, C.POINTER(_ll), _i]),
+    "tsdgpu_poly_get_state": (_i, [_vp, C.POINTER(_ll), C.POINTER(_i), _vp]),
+    "tsdgpu_poly_set_state": (_i, [_vp, _ll, _i, _vp]),
     "tsdgpu_poly_destroy": (_i, [_vp]),
     "tsdgpu_resamp_schedule": (_i, [C.POINTER(_f), _f, _i, _i, _vp, _vp, _ll, C.POINTER(_ll)]),
 }

@@ -409,6 +409,23 @@ int tsdgpu_fir_set_state(tsdgpu_fir_t f, const void *fen_host, int index)
   return 0;
 }
 
+// Time-ordered history (oldest first): what a halo-split segment needs to start in the middle of a stream
+int tsdgpu_fir_set_history(tsdgpu_fir_t f, const void *hist_host, long long samples_so_far)
+{
+  TSD_ENTER(f ? f->device : -1);
+  if(!f || (!hist_host && f->K > 1)) return fail("tsdgpu_fir_set_history: null argument");
+  if(samples_so_far < 0) return fail("tsdgpu_fir_set_history: negative sample count");
+  const size_t ssz = (f->DC == 1) ? 4 : 8;
+  const int L = f->K - 1;
+  std::vector<unsigned char> h((size_t) f->nchan * f->halo * ssz, 0);
+  for(int c = 0; c < f->nchan && L > 0; c++)
+    memcpy(h.data() + ((size_t) c * f->halo + (f->halo - L)) * ssz, (const unsigned char *) hist_host + (size_t) c * L * ssz, (size_t) L * ssz);
+  TSD_CUDA(cudaStreamSynchronize(rt().stream));
+  TSD_CUDA(cudaMemcpy(f->d_hist[f->cur], h.data(), h.size(), cudaMemcpyHostToDevice));
+  f->total = samples_so_far;
+  return 0;
+}
+
 int tsdgpu_fir_destroy(tsdgpu_fir_t f)
 {
   if(!f) return 0;

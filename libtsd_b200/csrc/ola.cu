@@ -1068,6 +1068,45 @@ int tsdgpu_periodogramme_tfd(const void *x, long long x_stride, int n, int nchan
   return rc;
 }
 
+int tsdgpu_ola_state_dims(tsdgpu_ola_t f, int *carry_len, int *svg_len, int *last_len)
+{
+  if(!f) return fail("tsdgpu_ola_state_dims: null handle");
+  if(carry_len) *carry_len = f->carry_len;
+  if(svg_len) *svg_len = (f->K > 0) ? 0 : f->Ne;      // overlap-save forms carry no partial sums
+  if(last_len) *last_len = f->fen ? f->Ne : 0;
+  return 0;
+}
+
+int tsdgpu_ola_get_state(tsdgpu_ola_t f, int *residual, long long *blocks_done, void *carry_host, void *svg_host, void *last_host)
+{
+  TSD_ENTER(f ? f->device : -1);
+  if(!f) return fail("tsdgpu_ola_get_state: null handle");
+  if(residual) *residual = f->residual;
+  if(blocks_done) *blocks_done = f->blocks_done;
+  TSD_CUDA(cudaStreamSynchronize(rt().stream));
+  if(carry_host) TSD_CUDA(cudaMemcpy(carry_host, f->d_carry[f->cur], (size_t) f->nchan * f->carry_len * sizeof(float2), cudaMemcpyDeviceToHost));
+  if(svg_host && f->K == 0) TSD_CUDA(cudaMemcpy(svg_host, f->d_svg, (size_t) f->nchan * f->Ne * sizeof(float2), cudaMemcpyDeviceToHost));
+  if(last_host && f->fen) TSD_CUDA(cudaMemcpy(last_host, f->d_last, (size_t) f->nchan * f->Ne * sizeof(float2), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int tsdgpu_ola_set_state(tsdgpu_ola_t f, int residual, long long blocks_done, const void *carry_host, const void *svg_host,
+                         const void *last_host)
+{
+  TSD_ENTER(f ? f->device : -1);
+  if(!f || !carry_host) return fail("tsdgpu_ola_set_state: null argument");
+  if(residual < 0 || residual >= f->Ne || blocks_done < 0) return fail("tsdgpu_ola_set_state: invalid counters");
+  if(f->K == 0 && !svg_host && blocks_done > 0) return fail("tsdgpu_ola_set_state: the overlap-add form needs the carried partial sums (svg)");
+  if(f->fen && !last_host && blocks_done > 0) return fail("tsdgpu_ola_set_state: the windowed mode needs its `last` buffer");
+  TSD_CUDA(cudaStreamSynchronize(rt().stream));
+  TSD_CUDA(cudaMemcpy(f->d_carry[f->cur], carry_host, (size_t) f->nchan * f->carry_len * sizeof(float2), cudaMemcpyHostToDevice));
+  if(svg_host && f->K == 0) TSD_CUDA(cudaMemcpy(f->d_svg, svg_host, (size_t) f->nchan * f->Ne * sizeof(float2), cudaMemcpyHostToDevice));
+  if(last_host && f->fen) TSD_CUDA(cudaMemcpy(f->d_last, last_host, (size_t) f->nchan * f->Ne * sizeof(float2), cudaMemcpyHostToDevice));
+  f->residual = residual;
+  f->blocks_done = blocks_done;
+  return 0;
+}
+
 int tsdgpu_ola_destroy(tsdgpu_ola_t f)
 {
   if(!f) return 0;

@@ -280,6 +280,36 @@ int tsdgpu_poly_step(tsdgpu_poly_t f, const void *x, long long xs, int n, void *
     n_out);
 }
 
+int tsdgpu_poly_get_state(tsdgpu_poly_t f, long long *total, int *cnt, void *hist_host)
+{
+  TSD_ENTER(f ? f->device : -1);
+  if(!f) return fail("tsdgpu_poly_get_state: null handle");
+  if(total) *total = f->total;
+  if(cnt) *cnt = f->cnt;
+  if(hist_host && f->L > 1)
+  {
+    TSD_CUDA(cudaStreamSynchronize(rt().stream));
+    TSD_CUDA(cudaMemcpy(hist_host, f->d_hist[f->cur], (size_t) f->nchan * (f->L - 1) * sizeof(float) * f->DC, cudaMemcpyDeviceToHost));
+  }
+  return 0;
+}
+
+int tsdgpu_poly_set_state(tsdgpu_poly_t f, long long total, int cnt, const void *hist_host)
+{
+  TSD_ENTER(f ? f->device : -1);
+  if(!f) return fail("tsdgpu_poly_set_state: null handle");
+  if(total < 0 || cnt < 0 || cnt >= std::max(1, f->R)) return fail("tsdgpu_poly_set_state: invalid counters");
+  TSD_CUDA(cudaStreamSynchronize(rt().stream));
+  if(f->L > 1)
+  {
+    if(!hist_host) return fail("tsdgpu_poly_set_state: null history");
+    TSD_CUDA(cudaMemcpy(f->d_hist[f->cur], hist_host, (size_t) f->nchan * (f->L - 1) * sizeof(float) * f->DC, cudaMemcpyHostToDevice));
+  }
+  f->total = total;
+  f->cnt = cnt;
+  return 0;
+}
+
 int tsdgpu_poly_destroy(tsdgpu_poly_t f)
 {
   if(!f) return 0;

@@ -751,6 +751,34 @@ int tsdgpu_resamp_schedule(float *phase, float ratio, int nphases, int n, int32_
   return 0;
 }
 
+int tsdgpu_resamp_get_state(tsdgpu_resamp_t f, float *phase, void *hist_host)
+{
+  TSD_ENTER(f ? f->device : -1);
+  if(!f) return fail("tsdgpu_resamp_get_state: null handle");
+  if(phase) *phase = f->phase;
+  if(hist_host && f->hist_len > 0)
+  {
+    TSD_CUDA(cudaStreamSynchronize(rt().stream));
+    TSD_CUDA(cudaMemcpy(hist_host, f->d_hist[f->cur], (size_t) f->nchan * f->hist_len * sizeof(float) * f->dc, cudaMemcpyDeviceToHost));
+  }
+  return 0;
+}
+
+int tsdgpu_resamp_set_state(tsdgpu_resamp_t f, float phase, const void *hist_host)
+{
+  TSD_ENTER(f ? f->device : -1);
+  if(!f) return fail("tsdgpu_resamp_set_state: null handle");
+  if(!(phase >= 0.0f) || !(phase < 1e9f)) return fail("tsdgpu_resamp_set_state: invalid phase");
+  TSD_CUDA(cudaStreamSynchronize(rt().stream));
+  if(f->hist_len > 0)
+  {
+    if(!hist_host) return fail("tsdgpu_resamp_set_state: null history");
+    TSD_CUDA(cudaMemcpy(f->d_hist[f->cur], hist_host, (size_t) f->nchan * f->hist_len * sizeof(float) * f->dc, cudaMemcpyHostToDevice));
+  }
+  f->phase = phase;
+  return 0;
+}
+
 int tsdgpu_resamp_destroy(tsdgpu_resamp_t f)
 {
   if(!f) return 0;

@@ -142,6 +142,12 @@ class FiltreRIF(FiltreGen):
         fen = np.ascontiguousarray(fen, self.dtype).reshape(self.nchan, self.K)
         check(lib().tsdgpu_fir_set_state(self._h, fen.ctypes.data_as(_vp), int(index)))
 
+    def set_history(self, hist, samples_so_far: int):
+        """Start in the middle of a stream: ``hist[nchan, K-1]`` = the K-1 samples before the first one to come (oldest
+        first), ``samples_so_far`` = their position in the stream (halo split, libtsd_b200.segments)."""
+        hist = np.ascontiguousarray(hist, self.dtype).reshape(self.nchan, max(self.K - 1, 0))
+        check(lib().tsdgpu_fir_set_history(self._h, hist.ctypes.data_as(_vp) if hist.size else None, int(samples_so_far)))
+
     def __del__(self):
         h = getattr(self, "_h", None)
         if h:
@@ -312,6 +318,17 @@ class AdaptationRythmeSimple(FiltreGen):
     def out_count(self, n: int) -> int:
         return int(lib().tsdgpu_resamp_out_count(self._h, int(n)))
 
+    def get_state(self):
+        """(phase, hist[nchan, K-1]) — ra.cc:16-22."""
+        ph = C.c_float()
+        hist = np.zeros((self.nchan, max(self.K - 1, 0)), self.dtype)
+        check(lib().tsdgpu_resamp_get_state(self._h, C.byref(ph), hist.ctypes.data_as(_vp) if hist.size else None))
+        return float(ph.value), hist
+
+    def set_state(self, phase: float, hist):
+        hist = np.ascontiguousarray(hist, self.dtype).reshape(self.nchan, max(self.K - 1, 0))
+        check(lib().tsdgpu_resamp_set_state(self._h, C.c_float(phase), hist.ctypes.data_as(_vp) if hist.size else None))
+
     def step(self, x, out=None):
         """``out`` (optional, same memory space as ``x``) needs room for ceil(n * ratio) + 16 samples per channel; the
         result is the exact-length view of the buffer the samples were written to (no extra host copy)."""
@@ -381,6 +398,26 @@ class FiltrePolyphase(FiltreGen):
         i, c = C.c_int(), C.c_int()
         check(lib().tsdgpu_poly_state(self._h, C.byref(i), C.byref(c)))
         return i.value, c.value
+
+    def get_state(self):
+        """(samples so far, decimation counter, hist[nchan, L-1])."""
+        tot, cnt = C.c_longlong(), C.c_int()
+        check(lib().tsdgpu_poly_get_state(self._h, C.byref(tot), C.byref(cnt), None))
+        L = self.hist_len
+        hist = np.zeros((self.nchan, L), self.dtype)
+        check(lib().tsdgpu_poly_get_state(self._h, None, None, hist.ctypes.data_as(_vp) if hist.size else None))
+        return tot.value, cnt.value, hist
+
+    def set_state(self, total: int, cnt: int, hist):
+        hist = np.ascontiguousarray(hist, self.dtype).reshape(self.nchan, self.hist_len)
+        check(lib().tsdgpu_poly_set_state(self._h, int(total), int(cnt), hist.ctypes.data_as(_vp) if hist.size else None))
+
+    @property
+    def hist_len(self) -> int:
+        """Delay line of the reference object minus one: K (half-band, decimator) or ceil(K / R) (interpolator)."""
+        K = int(self.coefs.shape[0])
+        L = (K + self.R - 1) // self.R if self.kind == POLY_UPS else K
+        return max(L - 1, 0)
 
     def step(self, x):
         b = Batch(x, self.dtype, self.nchan)

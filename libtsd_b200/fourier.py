@@ -290,6 +290,31 @@ class OLA(FiltreGen):
     def out_count(self, n: int) -> int:
         return int(lib().tsdgpu_ola_out_count(self._h, int(n)))
 
+    def state_dims(self):
+        a, b, c = C.c_int(), C.c_int(), C.c_int()
+        check(lib().tsdgpu_ola_state_dims(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def get_state(self):
+        """dict(residual, blocks_done, carry[nchan, carry_len], svg, last) — see tsdgpu_ola_get_state."""
+        cl, sl, ll = self.state_dims()
+        carry = np.zeros((self.nchan, cl), np.complex64)
+        svg = np.zeros((self.nchan, sl), np.complex64) if sl else None
+        last = np.zeros((self.nchan, ll), np.complex64) if ll else None
+        r, bd = C.c_int(), C.c_longlong()
+        check(lib().tsdgpu_ola_get_state(self._h, C.byref(r), C.byref(bd), carry.ctypes.data_as(_vp),
+                                         svg.ctypes.data_as(_vp) if sl else None, last.ctypes.data_as(_vp) if ll else None))
+        return dict(residual=r.value, blocks_done=bd.value, carry=carry, svg=svg, last=last)
+
+    def set_state(self, residual: int, blocks_done: int, carry, svg=None, last=None):
+        cl, sl, ll = self.state_dims()
+        carry = np.ascontiguousarray(carry, np.complex64).reshape(self.nchan, cl)
+        svg = np.ascontiguousarray(svg, np.complex64).reshape(self.nchan, sl) if (svg is not None and sl) else None
+        last = np.ascontiguousarray(last, np.complex64).reshape(self.nchan, ll) if (last is not None and ll) else None
+        check(lib().tsdgpu_ola_set_state(self._h, int(residual), int(blocks_done), carry.ctypes.data_as(_vp),
+                                         svg.ctypes.data_as(_vp) if svg is not None else None,
+                                         last.ctypes.data_as(_vp) if last is not None else None))
+
     def step(self, x, out=None):
         b = Batch(x, np.complex64, self.nchan)
         cnt = self.out_count(b.n)

@@ -18,7 +18,8 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 PORT_SO = os.path.join(HERE, "libtsd_oracle.so")
-REF_SO = os.path.join(HERE, "_ref", "libtsdref.so")
+# TSDREF_LIB selects another build of the same reference sources (bench.py: the AVX2 timing build, oracle/Makefile `native`)
+REF_SO = os.environ.get("TSDREF_LIB") or os.path.join(HERE, "_ref", "libtsdref.so")
 
 _vp = C.c_void_p
 _f = C.c_float
