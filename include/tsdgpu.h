@@ -171,6 +171,23 @@ int tsdgpu_ola_destroy(tsdgpu_ola_t f);
 int tsdgpu_periodogramme_tfd(const void *x, long long x_stride, int n, int nchan, int N, const float *fenetre,
                              float *out, long long out_stride, int *n_frames, int *n_bins, int mem);
 
+/* ---- normalised-correlation detector: the hot part of détecteur_création(config) / Detecteur::step -------------------- */
+/* (fourier.hpp:577-679; src/fourier/detection.cc:120-260, MODE_OLA).  The reference correlates the stream with a fixed
+ * motif through its block filter (traitement_freq = "X *= conj(fft(motif))", nb_zeros_min = M - 1, :146-170), tracks the
+ * energy of the same M samples with a moving average and a delay line (:132,165,209-217) and normalises
+ * (:231,246): score[i] = sqrt(N/M) |corr[i]| / sqrt(en[i] + 1e-20) in [0, 1], corr and score delayed by Ne samples.  Those
+ * three steps run on the device (single-SM overlap-save correlator for motifs up to 8193 samples, N-point path beyond);
+ * the peak logic that follows (:262-500: erosion over M samples, quadratic interpolation, gain / phase / SNR of every
+ * detection) is sparse serial host work on `score` and `corr` and stays with the caller (libtsd_b200/detection.py).
+ *   motif : M cfloat; Ne <= 0 -> ola_complexite_optimise(M) like the reference; n must be a multiple of Ne.
+ *   corr  : the correlation signal (cfloat), with the reference's clean-up of |corr| <= 1e-6 applied in place. */
+typedef struct tsdgpu_detect_s *tsdgpu_detect_t;
+int tsdgpu_detect_create(const float *motif, int M, int Ne, int nchan, tsdgpu_detect_t *out);
+int tsdgpu_detect_dims(tsdgpu_detect_t d, int *Ne, int *N, int *M, int *delais_corr, float *norme_motif);
+int tsdgpu_detect_step(tsdgpu_detect_t d, const void *x, long long x_stride, int n, float *score, long long score_stride,
+                       void *corr, long long corr_stride, int mem);
+int tsdgpu_detect_destroy(tsdgpu_detect_t d);
+
 /* ---- arbitrary-ratio resampler: replaces filtre_itrp<cfloat>(ratio, itrp) ------------------- */
 /* (filtrage.hpp:2039; ra.cc:13-79; InterpolateurRIF::step filtrage.hpp:1873-1881; LUT of
  * InterpolateurSinc itrp.cc:16-54).  lut[p*K + i], p in [0,nphases], is the interpolator's

@@ -5,7 +5,7 @@ FFT-domain block filtering (`filtre_fft` / OLA) and the LUT resampler (`filtre_i
 reference's own step() interface.  The compute lives in libtsdgpu.so (C ABI: include/tsdgpu.h);
 this package is the thin host-side mirror of the reference's names.  No CPU fallback.
 """
-from . import _lib, filtrage, fourier  # noqa: F401
+from . import _lib, detection, filtrage, fourier, segments  # noqa: F401
 from ._lib import TsdGpuError, init, launch_count, synchronize, use_torch_stream  # noqa: F401
 
-__all__ = ["filtrage", "fourier", "TsdGpuError", "init", "synchronize", "launch_count", "use_torch_stream"]
+__all__ = ["filtrage", "fourier", "detection", "segments", "TsdGpuError", "init", "synchronize", "launch_count", "use_torch_stream"]

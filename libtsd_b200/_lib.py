@@ -64,6 +64,10 @@ _SIGS = {
     "tsdgpu_ola_get_state": (_i, [_vp, C.POINTER(_i), C.POINTER(_ll), _vp, _vp, _vp]),
     "tsdgpu_ola_set_state": (_i, [_vp, _i, _ll, _vp, _vp, _vp]),
     "tsdgpu_ola_destroy": (_i, [_vp]),
+    "tsdgpu_detect_create": (_i, [_vp, _i, _i, _i, C.POINTER(_vp)]),
+    "tsdgpu_detect_dims": (_i, [_vp, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_f)]),
+    "tsdgpu_detect_step": (_i, [_vp, _vp, _ll, _i, _vp, _ll, _vp, _ll, _i]),
+    "tsdgpu_detect_destroy": (_i, [_vp]),
     "tsdgpu_resamp_create": (_i, [_f, _vp, _i, _i, _i, C.POINTER(_vp)]),
     "tsdgpu_resamp_create_ex": (_i, [_f, _vp, _i, _i, _i, _i, C.POINTER(_vp)]),
     "tsdgpu_resamp_create_exact": (_i, [_f, _i, _i, _i, _i, C.POINTER(_vp)]),

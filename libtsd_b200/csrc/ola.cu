@@ -502,6 +502,73 @@ __global__ void ola_last_fen_kernel(const float2 *work, float2 *last, int N, int
   }
 }
 
+
+// ---- normalised-correlation detector (reference src/fourier/detection.cc:204-260) ---------------------------------------
+// score[i] = ratio * sqrt(|corr[i]|^2 / (en[i] + 1e-20)), en[i] = mean of |stream|^2 over the M samples the correlation
+// at output i covers, i.e. stream positions [i - Ne, i - Ne + M) (filtre_mg<float,double>(M) followed by the delay line
+// of Ne - M + 1 samples, detection.cc:132,165,213-217).  The moving sum is a difference of a double-precision running sum,
+// like the reference's double accumulator (filtre-rt.cc:633-667).
+// Pass 1: P[c][j] = sum of |s|^2 over stream positions [-Ne - 1, -Ne - 1 + j), j in [0, Ne + n + 1], one CTA per channel.
+__global__ void __launch_bounds__(1024) detect_energy_scan_kernel(const float2 *x, long long x_stride, const float2 *carry, int carry_len,
+                                                                  int Ne, int n, double *P)
+{
+  __shared__ double part[1024];
+  const int chan = blockIdx.x, tid = threadIdx.x;
+  const long long L = (long long) Ne + 1 + n;                 // elements, positions -Ne-1 .. n-1
+  const long long per = (L + 1023) / 1024;
+  const float2 *xc = x + (long long) chan * x_stride;
+  const float2 *cr = carry + (long long) chan * carry_len + carry_len;
+  double *Pc = P + (long long) chan * (L + 1);
+  const long long j0 = tid * per, j1 = min(L, j0 + per);
+  double s = 0;
+  for(long long j = j0; j < j1; j++)
+  {
+    const long long pos = j - Ne - 1;
+    const float2 v = pos >= 0 ? xc[pos] : cr[pos];
+    s += (double) (v.x * v.x + v.y * v.y);                   // abs2 in float like the reference, accumulated in double
+  }
+  part[tid] = s;
+  __syncthreads();
+  for(int d = 1; d < 1024; d <<= 1)
+  {
+    const double t = tid >= d ? part[tid - d] : 0.0;
+    __syncthreads();
+    part[tid] += t;
+    __syncthreads();
+  }
+  double run = tid ? part[tid - 1] : 0.0;
+  if(tid == 0) Pc[0] = 0.0;
+  for(long long j = j0; j < j1; j++)
+  {
+    const long long pos = j - Ne - 1;
+    const float2 v = pos >= 0 ? xc[pos] : cr[pos];
+    run += (double) (v.x * v.x + v.y * v.y);
+    Pc[j + 1] = run;
+  }
+}
+// Pass 2: the score, and the reference's clean-up of tiny correlations (detection.cc:240-244) applied to corr in place
+__global__ void detect_score_kernel(float2 *corr, long long corr_stride, const double *P, float *score, long long score_stride,
+                                    int Ne, int M, int n, float ratio, float K_inv)
+{
+  const int chan = blockIdx.y;
+  const long long L1 = (long long) Ne + 2 + n;
+  const double *Pc = P + (long long) chan * L1;
+  for(int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+  {
+    // positions [i - Ne, i - Ne + M): prefix indices (pos + Ne + 1) .. (+ M)
+    const double acc = Pc[i + 1 + M] - Pc[i + 1];
+    const float en = ((float) acc) * K_inv;
+    float2 c = corr[(long long) chan * corr_stride + i];
+    if(hypotf(c.x, c.y) <= 1e-6f)                       // abs(corr) <= sqrt(1e-12f)
+    {
+      c = make_float2(0.f, 0.f);
+      corr[(long long) chan * corr_stride + i] = c;
+    }
+    const float a2 = c.x * c.x + c.y * c.y;
+    score[(long long) chan * score_stride + i] = ratio * sqrtf(a2 / (en + 1e-20f));
+  }
+}
+
 } // namespace tsdgpu
 
 using namespace tsdgpu;
@@ -515,6 +582,7 @@ struct tsdgpu_ola_s
   bool fused = false;
   // FIR-derived gains (fir_len > 0): single-SM overlap-save kernel with its own transform size (ols16k.cu)
   Ols16k *ols = nullptr;
+  int delay = 0;               // output t = FIR output t - delay: Ne - K (FiltreFFTRIF convention), Ne - M + 1 for the detector's correlator
   float2 *d_H = nullptr;       // fused: H/N ; unfused: raw H (nullptr = identity)
   float2 *d_carry[2] = {nullptr, nullptr};
   int cur = 0, carry_len = 0;
@@ -772,7 +840,7 @@ static int ola_run_device(tsdgpu_ola_s *f, const float2 *x, long long xs, int n,
   {
     if(ys < *n_out) return fail("tsdgpu_ola_step: output stride smaller than the emitted count");
     int rc = f->fen   ? ola_run_fen(f, x, xs, y, ys, B)
-             : f->ols ? ols16k_run(f->ols, x, xs, n, f->d_carry[f->cur], f->carry_len, y, ys, *n_out, f->Ne - f->K, f->residual, f->nchan)
+             : f->ols ? ols16k_run(f->ols, x, xs, n, f->d_carry[f->cur], f->carry_len, y, ys, *n_out, f->delay, f->residual, f->nchan)
              : f->fused ? ola_run_fused(f, x, xs, n, y, ys, B)
                         : ola_run_unfused(f, x, xs, y, ys, B);
     if(rc) return rc;
@@ -859,6 +927,7 @@ static int ola_create(int dim_blocs_temporel, int nb_zeros_min, const float *H, 
       }
       if(f->ols)
       {
+        f->delay = Ne - fir_len;
         f->K = fir_len;
         f->fused = false;
         f->carry_len = std::max(N + Ne, 2 * Ne + f->ols->O + 2);   // look-back of a window: delay + overlap + residual
@@ -1125,6 +1194,201 @@ int tsdgpu_ola_destroy(tsdgpu_ola_t f)
   ols16k_destroy(f->ols);
   if(f->h_spec) cudaFreeHost(f->h_spec);
   delete f;
+  return 0;
+}
+
+} // extern "C"
+
+// ---- detector object ---------------------------------------------------------------------------------------------------------
+struct tsdgpu_detect_s
+{
+  int device = 0;
+  tsdgpu_ola_s *ola = nullptr;   // correlator: block filter whose taps are the reversed, conjugated, normalised motif / sqrt(N)
+  int M = 0, Ne = 0, N = 0, nchan = 0;
+  float ratio = 1, K_inv = 1, norme_motif = 1;
+  double *P = nullptr;           // [nchan][Ne + n + 2] running sums
+  size_t P_cap = 0;
+  float2 *d_x = nullptr, *d_corr = nullptr;   // staging of the host-memory entry
+  float *d_score = nullptr;
+  size_t stage_cap = 0;          // samples per channel
+};
+
+extern "C" {
+
+int tsdgpu_detect_create(const float *motif, int M, int Ne, int nchan, tsdgpu_detect_t *out)
+{
+  TSD_ENTER(-1);
+  if(!motif || !out) return fail("tsdgpu_detect_create: null argument");
+  if(M < 2 || nchan <= 0) return fail("tsdgpu_detect_create: M must be >= 2 and nchan > 0");
+  if(Ne <= 0 && tsdgpu_ola_complexite_optimise(M, nullptr, nullptr, nullptr, &Ne)) return 1;   // detection.cc:136-144
+  // norme_motif = ||motif||_2 in float like Tab::norme; motif normalised (detection.cc:124-127)
+  double e = 0;
+  for(int i = 0; i < M; i++) e += (double) motif[2 * i] * motif[2 * i] + (double) motif[2 * i + 1] * motif[2 * i + 1];
+  if(!(e > 0)) return fail("tsdgpu_detect_create: null motif");
+  const double nrm = std::sqrt(e);
+  const int N = tsdgpu_p2(Ne + M - 1);                   // nb_zeros_min = M - 1 (detection.cc:149-150, fourier.cc:775)
+  if(N - Ne > Ne) return fail("tsdgpu_detect_create: N_zeros > Ne (choose a larger Ne)");
+  if(2 * M > N) return fail("tsdgpu_detect_create: the motif must fit twice in the transform (detection.cc:166)");
+  auto *d = new tsdgpu_detect_s;
+  d->device = rt().device;
+  d->M = M;
+  d->Ne = Ne;
+  d->N = N;
+  d->nchan = nchan;
+  d->norme_motif = (float) nrm;
+  d->ratio = std::sqrt(1.0f * N) / std::sqrt(1.0f * M);   // detection.cc:231
+  d->K_inv = (float) (1.0 / (double) M);                  // filtre-rt.cc:646
+  // corr_ref[t] = (1/sqrt N) sum_q conj(m[q]) stream[t - Ne + q]  (unitary transforms both ways, X *= conj(fft(motif))):
+  // as a causal filter, taps h[k] = conj(m[M-1-k]) / sqrt(N) and delay Ne - M + 1
+  std::vector<std::complex<double>> taps((size_t) M);
+  const double sc = 1.0 / (nrm * std::sqrt((double) N));
+  for(int k = 0; k < M; k++)
+    taps[k] = std::complex<double>(motif[2 * (M - 1 - k)] * sc, -motif[2 * (M - 1 - k) + 1] * sc);
+  // the block-filter object carries the re-blocking state and the input history; gains as data for the N-point path
+  std::vector<float> H((size_t) 2 * N);
+  {
+    std::vector<std::complex<double>> g((size_t) N);
+    for(int q = 0; q < M; q++) g[(size_t) ((N - q) % N)] = std::conj(std::complex<double>(motif[2 * q], motif[2 * q + 1])) / (nrm * std::sqrt((double) N));
+    // plain DFT by the definition is O(N^2): use the radix-2 recursion on the host (N is a power of two)
+    std::vector<std::complex<double>> a = g;
+    for(size_t i2 = 1, j = 0; i2 < a.size(); i2++)
+    {
+      size_t bit = a.size() >> 1;
+      for(; j & bit; bit >>= 1) j ^= bit;
+      j ^= bit;
+      if(i2 < j) std::swap(a[i2], a[j]);
+    }
+    for(size_t len = 2; len <= a.size(); len <<= 1)
+    {
+      const double ang = -2.0 * M_PI / (double) len;
+      for(size_t i2 = 0; i2 < a.size(); i2 += len)
+        for(size_t k = 0; k < len / 2; k++)
+        {
+          const std::complex<double> w = std::polar(1.0, ang * (double) k), u = a[i2 + k], t = a[i2 + k + len / 2] * w;
+          a[i2 + k] = u + t;
+          a[i2 + k + len / 2] = u - t;
+        }
+    }
+    for(int i2 = 0; i2 < N; i2++) { H[2 * i2] = (float) a[i2].real(); H[2 * i2 + 1] = (float) a[i2].imag(); }
+  }
+  tsdgpu_ola_t o = nullptr;
+  if(ola_create(Ne, M - 1, H.data(), 0, nullptr, nchan, &o)) { delete d; return 1; }
+  d->ola = o;
+  // single-SM overlap-save kernel when the motif is short enough for it
+  const char *v = getenv("TSDGPU_OLA_OLS");
+  if(!(v && v[0] == '0'))
+  {
+    Ols16k *k16 = nullptr;
+    if(ols16k_create_taps(taps.data(), M, &k16)) { tsdgpu_ola_destroy(o); delete d; return 1; }
+    if(k16)
+    {
+      o->ols = k16;
+      o->K = M;
+      o->delay = Ne - M + 1;
+      o->fused = false;
+      // the single-SM kernel looks back delay + overlap + residual samples: grow the history the object was created with
+      const int need = 2 * Ne + k16->O + 2;
+      if(o->carry_len < need)
+      {
+        cudaError_t e2 = cudaSuccess;
+        for(int i = 0; i < 2 && e2 == cudaSuccess; i++)
+        {
+          cudaFree(o->d_carry[i]);
+          o->d_carry[i] = nullptr;
+          e2 = cudaMalloc(&o->d_carry[i], (size_t) nchan * need * sizeof(float2));
+          if(e2 == cudaSuccess) e2 = cudaMemset(o->d_carry[i], 0, (size_t) nchan * need * sizeof(float2));
+        }
+        if(e2 != cudaSuccess)
+        {
+          tsdgpu_ola_destroy(o);
+          delete d;
+          return fail(std::string("tsdgpu_detect_create: ") + cudaGetErrorString(e2));
+        }
+        o->carry_len = need;
+      }
+    }
+  }
+  *out = d;
+  return 0;
+}
+
+int tsdgpu_detect_dims(tsdgpu_detect_t d, int *Ne, int *N, int *M, int *delais_corr, float *norme_motif)
+{
+  if(!d) return fail("tsdgpu_detect_dims: null handle");
+  if(Ne) *Ne = d->Ne;
+  if(N) *N = d->N;
+  if(M) *M = d->M;
+  if(delais_corr) *delais_corr = d->Ne;                    // detection.cc:170
+  if(norme_motif) *norme_motif = d->norme_motif;
+  return 0;
+}
+
+static int detect_run_device(tsdgpu_detect_s *d, const float2 *x, long long xs, int n, float *score, long long ss, float2 *corr,
+                             long long cs)
+{
+  Runtime &r = rt();
+  tsdgpu_ola_s *o = d->ola;
+  // running sums over [carry tail, x] BEFORE the block filter advances its history
+  const size_t needP = (size_t) d->nchan * ((size_t) d->Ne + n + 2);
+  if(needP > d->P_cap)
+  {
+    if(d->P) { TSD_CUDA(cudaStreamSynchronize(r.stream)); cudaFree(d->P); d->P = nullptr; d->P_cap = 0; }
+    TSD_CUDA(cudaMalloc(&d->P, needP * sizeof(double)));
+    d->P_cap = needP;
+  }
+  detect_energy_scan_kernel<<<d->nchan, 1024, 0, r.stream>>>(x, xs, o->d_carry[o->cur], o->carry_len, d->Ne, n, d->P);
+  TSD_LAUNCH_CHECK();
+  long long n_out = 0;
+  if(ola_run_device(o, x, xs, n, corr, cs, &n_out)) return 1;
+  if(n_out != n) return fail("tsdgpu_detect_step: internal: correlator emitted a different count");
+  dim3 grid((unsigned) std::min(1024, (n + 255) / 256), d->nchan);
+  detect_score_kernel<<<grid, 256, 0, r.stream>>>(corr, cs, d->P, score, ss, d->Ne, d->M, n, d->ratio, d->K_inv);
+  TSD_LAUNCH_CHECK();
+  return 0;
+}
+
+int tsdgpu_detect_step(tsdgpu_detect_t d, const void *x, long long xs, int n, float *score, long long ss, void *corr, long long cs,
+                       int mem)
+{
+  TSD_ENTER(d ? d->device : -1);
+  if(!d || !x || !score || !corr) return fail("tsdgpu_detect_step: null argument");
+  if(n <= 0 || n % d->Ne) return fail("tsdgpu_detect_step: n must be a positive multiple of Ne (the reference asserts corr.rows() == n, detection.cc:227)");
+  if(xs < n || ss < n || cs < n) return fail("tsdgpu_detect_step: stride smaller than n");
+  if(mem == TSDGPU_DEVICE) return detect_run_device(d, (const float2 *) x, xs, n, score, ss, (float2 *) corr, cs);
+  Runtime &r = rt();
+  if((size_t) n > d->stage_cap)
+  {
+    TSD_CUDA(cudaStreamSynchronize(r.stream));
+    if(d->d_x) cudaFree(d->d_x);
+    if(d->d_corr) cudaFree(d->d_corr);
+    if(d->d_score) cudaFree(d->d_score);
+    d->d_x = d->d_corr = nullptr;
+    d->d_score = nullptr;
+    d->stage_cap = 0;
+    TSD_CUDA(cudaMalloc(&d->d_x, (size_t) d->nchan * n * sizeof(float2)));
+    TSD_CUDA(cudaMalloc(&d->d_corr, (size_t) d->nchan * n * sizeof(float2)));
+    TSD_CUDA(cudaMalloc(&d->d_score, (size_t) d->nchan * n * sizeof(float)));
+    d->stage_cap = (size_t) n;
+  }
+  TSD_CUDA(cudaMemcpy2DAsync(d->d_x, (size_t) n * 8, x, (size_t) xs * 8, (size_t) n * 8, d->nchan, cudaMemcpyHostToDevice, r.stream));
+  if(detect_run_device(d, d->d_x, n, n, d->d_score, n, d->d_corr, n)) return 1;
+  TSD_CUDA(cudaMemcpy2DAsync(score, (size_t) ss * 4, d->d_score, (size_t) n * 4, (size_t) n * 4, d->nchan, cudaMemcpyDeviceToHost, r.stream));
+  TSD_CUDA(cudaMemcpy2DAsync(corr, (size_t) cs * 8, d->d_corr, (size_t) n * 8, (size_t) n * 8, d->nchan, cudaMemcpyDeviceToHost, r.stream));
+  TSD_CUDA(cudaStreamSynchronize(r.stream));
+  return 0;
+}
+
+int tsdgpu_detect_destroy(tsdgpu_detect_t d)
+{
+  if(!d) return 0;
+  TSD_ENTER(d->device);
+  cudaStreamSynchronize(rt().stream);
+  tsdgpu_ola_destroy(d->ola);
+  if(d->P) cudaFree(d->P);
+  if(d->d_x) cudaFree(d->d_x);
+  if(d->d_corr) cudaFree(d->d_corr);
+  if(d->d_score) cudaFree(d->d_score);
+  delete d;
   return 0;
 }
 

@@ -648,9 +648,18 @@ int ols16k_create(const float *H, int N, int K, Ols16k **out)
   }
   // the caller's promise (fir_len) is checked: energy outside the K-tap support must be rounding noise
   if(!(e_out <= 1e-9 * e_in)) return 0;
+  std::vector<std::complex<double>> taps((size_t) K);
+  for(int m = 0; m < K; m++) taps[m] = a[(size_t) (N - K + m)];
+  return ols16k_create_taps(taps.data(), K, out);
+}
+
+int ols16k_create_taps(const std::complex<double> *taps, int K, Ols16k **out)
+{
+  *out = nullptr;
+  if(K < 1 || K - 1 > 8192) return 0;
   const int O = (K - 1 <= 4096) ? 4096 : 8192;
   std::vector<std::complex<double>> hm((size_t) OLS_M);
-  for(int m = 0; m < K; m++) hm[m] = a[(size_t) (N - K + m)];
+  for(int m = 0; m < K; m++) hm[m] = taps[m];
   fft_double(hm, false);
   // thread-major constants: thread t = 32 w + l owns gains k = (2w + (l>>4)) + 32 (l&15) + 512 k3 and the twiddles
   // W_M^(l * ((2w + c) + 32 k2)) at [c*16 + k2]

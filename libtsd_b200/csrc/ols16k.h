@@ -1,6 +1,7 @@
 // Internal interface of the single-SM overlap-save kernel (ols16k.cu), used by ola.cu.
 #pragma once
 #include <cuda_runtime.h>
+#include <complex>
 
 namespace tsdgpu {
 
@@ -13,6 +14,8 @@ struct Ols16k
 // Builds the device constants from the reference-layout gains H[N] = DFT([0^(N-K), h]) (fourier.cc:962-965).
 // *out stays null (status 0) when this path does not serve the case (K-1 > 8192, or H is not the transform of K taps).
 int ols16k_create(const float *H, int N, int K, Ols16k **out);
+// Same from the K taps themselves (complex, double): y_fir[u] = sum_m taps[m] stream[u - m].
+int ols16k_create_taps(const std::complex<double> *taps, int K, Ols16k **out);
 void ols16k_destroy(Ols16k *o);
 int ols16k_smem_bytes(int O);
 // y[c][i] = sum_m h[m] stream[t0 + i - delay - m] for i in [0, out_count); x[0] of this call is stream sample

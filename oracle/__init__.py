@@ -282,6 +282,31 @@ class _RefFilter:
             self.L.tsdref_filter_free(self.h)
 
 
+class _RefDetect:
+    FIELDS = ("position", "position_prec", "score", "gain", "theta", "SNR_dB", "sigma_noise")
+
+    def __init__(self, L, motif, Ne, seuil, mode, err):
+        m = _c64(motif)
+        self.L, self._err = L, err
+        self.h = _vp(L.tsdref_detect_new(_ptr(m), _i(len(m)), _i(Ne), _f(seuil), _i(1 if mode == "rif" else 0)))
+        if not self.h:
+            raise RuntimeError("reference: " + err())
+
+    def step(self, x):
+        """-> (score[n] float32, [dict per detection])"""
+        x = _c64(x)
+        score = np.empty(len(x), np.float32)
+        dets = np.empty((4096, 7), np.float32)
+        nd = _i()
+        if self.L.tsdref_detect_step(self.h, _ptr(x), _i(len(x)), _ptr(score), _ptr(dets), _i(4096), C.byref(nd)):
+            raise RuntimeError("reference: " + self._err())
+        return score, [dict(zip(self.FIELDS, map(float, dets[i]))) for i in range(nd.value)]
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.tsdref_detect_free(self.h)
+
+
 class _RefPlan:
     def __init__(self, L, n, err):
         self.L, self._err = L, err
@@ -309,7 +334,7 @@ class _Ref:
         L.tsdref_last_error.restype = C.c_char_p
         for name in ("tsdref_fir_new", "tsdref_rif_fft_new", "tsdref_ola_new", "tsdref_ola_new2", "tsdref_itrp_new",
                      "tsdref_reechan_new", "tsdref_fftplan_new", "tsdref_polyphase_new", "tsdref_itrp_new2",
-                     "tsdref_reechan_new_f32"):
+                     "tsdref_reechan_new_f32", "tsdref_detect_new"):
             getattr(L, name).restype = _vp
         self.L = L
 
@@ -411,6 +436,10 @@ class _Ref:
         k = {"sinc": 0, "cspline": 1, "lineaire": 2, "lagrange": 3}[kind]
         return _RefFilter(self.L, self.L.tsdref_itrp_new2(_f(ratio), _i(k), _i(1 if cplx else 0), _i(K), _i(nphases), _f(fcut),
                                                           _i(degree)), self._err)
+
+    def detecteur(self, motif, Ne=0, seuil=0.5, mode="ola"):
+        """détecteur_création({Ne, motif, seuil, mode}) (detection.cc:511-514)."""
+        return _RefDetect(self.L, motif, Ne, seuil, mode, self._err)
 
     def cspline_lut(self, n=256, c=0.0):
         lut = np.empty((n + 1, 4), np.float32)

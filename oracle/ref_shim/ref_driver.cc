@@ -259,6 +259,51 @@ int tsdref_cspline_lut(int n, float c, float *lut)
   });
 }
 
+// détecteur_création(config) (detection.cc:68-516): normalised-correlation detector, OLA (mode 0) or FIR (mode 1)
+// correlator.  step() returns the score signal and the detections the reference hands to gere_detection, as rows of
+// {position, position_prec, score, gain, theta, SNR_dB, sigma_noise}.
+struct RefDetect
+{
+  sptr<Detecteur> d;
+  std::vector<Detection> dets;
+};
+void *tsdref_detect_new(const float *motif, int M, int Ne, float seuil, int mode)
+{
+  RefDetect *r = new RefDetect;
+  int rc = guarded([&] {
+    DetecteurConfig c;
+    c.Ne = Ne;
+    c.motif = Veccf::map((const cfloat *) motif, M).clone();
+    c.seuil = seuil;
+    c.mode = mode ? DetecteurConfig::MODE_RIF : DetecteurConfig::MODE_OLA;
+    c.gere_detection = [r](const Detection &det) { r->dets.push_back(det); };
+    r->d = détecteur_création(c);
+  });
+  if(rc) { delete r; return nullptr; }
+  return r;
+}
+int tsdref_detect_step(void *h, const float *x, int n, float *score, float *dets, int cap, int *ndet)
+{
+  RefDetect *r = (RefDetect *) h;
+  return guarded([&] {
+    r->dets.clear();
+    const Veccf xv = Veccf::map((const cfloat *) x, n);
+    Vecf y;
+    r->d->step(xv, y);
+    if(y.rows() != n) échec("tsdref_detect_step: {} scores for {} samples", y.rows(), n);
+    memcpy(score, y.data(), sizeof(float) * n);
+    *ndet = (int) r->dets.size();
+    if(*ndet > cap) échec("tsdref_detect_step: {} detections > capacity {}", *ndet, cap);
+    for(int i = 0; i < *ndet; i++)
+    {
+      const Detection &d = r->dets[i];
+      float *o = dets + 7 * i;
+      o[0] = (float) d.position; o[1] = d.position_prec; o[2] = d.score; o[3] = d.gain; o[4] = d.θ; o[5] = d.SNR_dB; o[6] = d.σ_noise;
+    }
+  });
+}
+void tsdref_detect_free(void *h) { delete(RefDetect *) h; }
+
 // filtre_reechan<cfloat>(ratio) (ra.cc:180-183) = what resample()/rééchan() builds (tsd.hpp:700-705)
 void *tsdref_reechan_new(float ratio)
 {

@@ -432,6 +432,26 @@ Tab cos_i(const Tab &x) { return unary(x, [](auto v) { return f_cos(v); }); }
 Tab exp_i(const Tab &x) { return unary(x, [](auto v) { return f_exp(v); }); }
 Tab log10_i(const Tab &x) { return unary(x, [](auto v) { return f_log10(v); }); }
 Tab square_i(const Tab &x) { return unary(x, [](auto v) { return (decltype(v)) (v * v); }); }
+template<typename T> static T f_sqrt(T v)
+{
+  if constexpr(std::is_integral<T>::value) return (T) std::sqrt((double) v); else return std::sqrt(v);
+}
+Tab sqrt_i(const Tab &x) { return unary(x, [](auto v) { return f_sqrt(v); }); }   // tableau.cc:1704
+// tableau.cc:1172-1183: element > (T) x, result = boolean table (B, 8 bits)
+Tab Tab::operator>(double x) const
+{
+  Tab y(B, 8, rows(), cols());
+  with_type(*this, [&]<typename T>(T *) {
+    if constexpr(is_cplx<T>::value) échec("tab_shim: operator>(double) on a complex table");
+    else
+    {
+      const T *p = (const T *) rawptr();
+      char *r = (char *) y.rawptr();
+      for(entier i = 0; i < nelems(); i++) r[i] = p[i] > (T) x;
+    }
+  });
+  return y;
+}
 template<typename Op> static Tab c2r(const Tab &x, Op op)
 {
   Tab y;
