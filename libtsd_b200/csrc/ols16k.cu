@@ -58,6 +58,7 @@ struct OlsParams
   const float4 *tmem_init;    // [512 threads][32 float4]: 16 float4 of gains, 16 of twiddles
   long long x_stride, y_stride, out_count, total;
   int carry_len, n, base, jblocks, aligned;
+  int offset_roles;
   unsigned *prof;             // optional per-phase clock trace of CTA 0 (TSDGPU_OLS_PROF), else null
 };
 
@@ -266,6 +267,19 @@ template<int END> struct OlsX<END, END>
   static __device__ __forceinline__ void ld_cols_even(uint32_t, float2 (&)[32]) {}
   static __device__ __forceinline__ void ld_cols_odd(uint32_t, float2 (&)[32]) {}
 };
+// mbarrier wait that lets the hardware suspend the warp until the phase completes (or the hint expires) instead of
+// re-issuing try_wait every few cycles: the spinning producer lane and the warps parked on row / column barriers were
+// taking ~12 % of the issue slots of the kernel (ncu: 146 M TRYWAIT executions per 4 ms launch)
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, unsigned parity)
+{
+  asm volatile(
+    "{\n\t.reg .pred p;\n\t"
+    "WAIT_%=:\n\t"
+    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+    "@p bra DONE_%=;\n\t"
+    "bra WAIT_%=;\n\t"
+    "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_cta(uint64_t *bar)
 {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -306,11 +320,11 @@ template<int OQ>   // overlap in quarters of M: O = 4096 * OQ
 __global__ void __launch_bounds__(OLS_THREADS, 1) ols16k_kernel(OlsParams p)
 {
   constexpr int O = 4096 * OQ, L = OLS_M - O, NX = 8 * OQ;   // window samples n1 < NX live in X
-  constexpr uint32_t S_BYTES = L * 8 + 16, X_BYTES = O * 8 + 16;
+  constexpr uint32_t S_BYTES = L * 8 + 16;
   extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t sE = smem_u32(smem), sS = sE + OLS_E_BYTES;
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + OLS_E_BYTES + S_BYTES);
-  uint64_t *s_full = bars, *x_full = bars + 1, *w_free = bars + 2, *e_free = bars + 3;
+  uint64_t *s_full = bars, *w_free = bars + 2, *e_free = bars + 1;   // e_free[r] at bars + 1 + 2 r (r = 0, 1): columns 8r..8r+7 of E read
   uint64_t *row_full = bars + 4;   // [16]: rows 2w', 2w'+1 of E written by every warp -> their owner may start P2
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4 + OLS_MATH_WARPS);
   const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
@@ -318,9 +332,9 @@ __global__ void __launch_bounds__(OLS_THREADS, 1) ols16k_kernel(OlsParams p)
   if(tid == 0)
   {
     mbar_init(s_full, 1);
-    mbar_init(x_full, 1);
     mbar_init(w_free, OLS_MATH_WARPS);
-    mbar_init(e_free, OLS_MATH_WARPS);
+    mbar_init(e_free, OLS_MATH_WARPS / 2);
+    mbar_init(e_free + 2, OLS_MATH_WARPS / 2);
     for(int i = 0; i < OLS_MATH_WARPS; i++) mbar_init(row_full + i, OLS_MATH_WARPS);
     mbar_fence_init();
   }
@@ -353,7 +367,7 @@ __global__ void __launch_bounds__(OLS_THREADS, 1) ols16k_kernel(OlsParams p)
         const long long a0 = pos0 & ~1LL;                          // 16-byte aligned start
         const bool fast = p.aligned && a0 >= 0 && a0 + OLS_M + 2 <= p.n;
         const float2 *src = p.x + (long long) chan * p.x_stride + a0;
-        if(it > 0) mbar_wait(w_free, (it - 1) & 1);                // S consumed by every math warp
+        if(it > 0) mbar_wait_sleep(w_free, (it - 1) & 1);                // S consumed by the input warps (both rounds)
         if(fast)
         {
           mbar_expect_tx(s_full, S_BYTES);
@@ -366,19 +380,6 @@ __global__ void __launch_bounds__(OLS_THREADS, 1) ols16k_kernel(OlsParams p)
           }
         }
         else mbar_arrive_cta(s_full);
-        if(it > 0) mbar_wait(e_free, (it - 1) & 1);                // previous block has left E
-        if(fast)
-        {
-          mbar_expect_tx(x_full, X_BYTES);
-#pragma unroll 1
-          for(uint32_t off = 0; off < X_BYTES; off += OLS_PIECE)
-          {
-            const uint32_t nb = (X_BYTES - off < OLS_PIECE + 4096) ? X_BYTES - off : OLS_PIECE;
-            bulk_g2s(smem + off, reinterpret_cast<const unsigned char *>(src) + off, nb, x_full);
-            if(nb != OLS_PIECE) break;
-          }
-        }
-        else mbar_arrive_cta(x_full);
       }
     }
   }
@@ -414,64 +415,68 @@ __global__ void __launch_bounds__(OLS_THREADS, 1) ols16k_kernel(OlsParams p)
     // registers) right before each use: 1 STS + 16 broadcast LDS.128 instead of 30 constant-bank loads
     const float2 tw1c = c_ols_tw1[(2 * w) * 16 + l];
 
-    int chan = (int) (first / p.jblocks), j = (int) (first - (long long) chan * p.jblocks) - 1;
-    for(long long b = first; b < last; b++)
-    {
-      const unsigned it = (unsigned) (b - first);
-      if(++j == p.jblocks) { j = 0; chan++; }
-      const long long pos0 = (long long) j * L + p.base;
+    // The sixteen math warps share P2 (a warp owns two rows of E), but the two phases that touch all of E are split between
+    // two ROLES so that they run at the same time instead of one after the other: the output warps (0-3, 8-11: two per
+    // scheduler) read block b out of E, finish its inverse transform and store it (P3), while the input warps (4-7, 12-15)
+    // already load the window of block b+1 and run its first pass (P1); each role takes the sixteen n2 columns in two
+    // rounds.  The shared-memory / store traffic of one role overlaps the butterflies of the other.
+    const bool out_role = ((w >> 2) & 1) == 0;
+    const int ri = (w & 3) | ((w >> 3) << 2);          // 0..7 within the role: columns n2 = ri, ri + 8
+
+    // P1 of block (chan1, j1), iteration number it1: window -> radix-32 over n1 -> rows of E
+    auto phase1 = [&](int chan1, int j1, unsigned it1) {
+      const long long pos0 = (long long) j1 * L + p.base;
       const long long a0 = pos0 & ~1LL;
       const bool fast = p.aligned && a0 >= 0 && a0 + OLS_M + 2 <= p.n;
-      float2 v[32];
-      ols_stamp(p, it, w, l, 0);
-
-      // Every phase is written as a software pipeline inside the thread: loads of the second half are in flight while the
-      // first half is transformed, and every result leaves for shared / global memory as soon as its butterfly is done.
-      // The sixteen warps run the same code almost in lock-step, so this is what lets the shared-memory pipe and the
-      // FMA pipe work at the same time.
-
-      // ---- P1: window -> radix-32 over n1 -> E ----
-      mbar_wait(s_full, it & 1);
-      if(fast)
+      const float2 *xc = p.x + (long long) chan1 * p.x_stride;
+      const float2 *cr = p.carry + (long long) chan1 * p.carry_len + p.carry_len;
+      mbar_wait_sleep(s_full, it1 & 1);
+      // EXPERIMENT (TSDGPU_OLS_OFFSET=1, off by default: measured -2 %): start one step behind the output warps
+      if(it1 > 0 && p.offset_roles) mbar_wait_sleep(e_free, (it1 - 1) & 1);
+#pragma unroll 1
+      for(int r = 0; r < 2; r++)
       {
-        const uint32_t sh = (uint32_t) (pos0 & 1) * 8u + (uint32_t) (32 * w) * 8u + lx;
-#pragma unroll
-        for(int h = 0; h < 2; h++)      // even n1 first: the first radix-16 starts while the odd half is still arriving
-#pragma unroll
-          for(int n1 = NX + h; n1 < 32; n1 += 2) v[n1] = lds64(sS + sh + (uint32_t) (512 * (n1 - NX)) * 8u);
-        mbar_wait(x_full, it & 1);
-#pragma unroll
-        for(int h = 0; h < 2; h++)
-#pragma unroll
-          for(int n1 = h; n1 < NX; n1 += 2) v[n1] = lds64(sE + sh + (uint32_t) (512 * n1) * 8u);
-      }
-      else
-      {
-        mbar_wait(x_full, it & 1);
-        // edge block (start / end of the call, or unaligned rows): bounds-checked loads straight into registers
-        const float2 *xc = p.x + (long long) chan * p.x_stride;
-        const float2 *cr = p.carry + (long long) chan * p.carry_len + p.carry_len;
-#pragma unroll
-        for(int n1 = 0; n1 < 32; n1++)
+        const int n2 = ri + 8 * r;
+        float2 v[32];
+        if(fast)
         {
-          const long long pos = pos0 + 512 * n1 + 32 * w + l;
-          float2 val = make_float2(0.f, 0.f);
-          if(pos >= 0) { if(pos < p.n) val = ldg_stream(xc + pos); }
-          else if(pos >= -(long long) p.carry_len) val = __ldg(cr + pos);
-          v[n1] = val;
+          // the O overlap samples were loaded (as new samples) one block ago: straight from L2 into registers, issued
+          // first so that they travel while the shared-memory loads run; the L new samples come from the staging
+          const float2 *xo = xc + pos0 + 32 * n2 + l;
+#pragma unroll
+          for(int h = 0; h < 2; h++)
+#pragma unroll
+            for(int n1 = h; n1 < NX; n1 += 2) v[n1] = __ldg(xo + 512 * n1);
+          const uint32_t sh = (uint32_t) (pos0 & 1) * 8u + (uint32_t) (32 * n2) * 8u + lx;
+#pragma unroll
+          for(int h = 0; h < 2; h++)      // even n1 first: the first radix-16 starts while the odd half is still arriving
+#pragma unroll
+            for(int n1 = NX + h; n1 < 32; n1 += 2) v[n1] = lds64(sS + sh + (uint32_t) (512 * (n1 - NX)) * 8u);
         }
-      }
-      __syncwarp();
-      if(l == 0) mbar_arrive_cta(w_free);
-      ols_stamp(p, it, w, l, 1);
-      fft16s<false, 2>(&v[0]);
-      fft16s<false, 2>(&v[1]);
-      ols_stamp(p, it, w, l, 2);
-      mbar_wait(w_free, it & 1);   // every warp has read its part of X (inside E) before anyone overwrites it
-      {
-        // last radix-2 stage: rows k1 = K and K + 16 are stored as soon as they exist.  One arrival per row pair: the
-        // owner of rows (2w', 2w'+1) starts P2 when all sixteen warps have written them.
-        const uint32_t a = sE + (uint32_t) (32 * w) * 8u + lx;
+        else
+        {
+          // edge block (start / end of the call, or unaligned rows): bounds-checked loads straight into registers
+#pragma unroll
+          for(int n1 = 0; n1 < 32; n1++)
+          {
+            const long long pos = pos0 + 512 * n1 + 32 * n2 + l;
+            float2 val = make_float2(0.f, 0.f);
+            if(pos >= 0) { if(pos < p.n) val = ldg_stream(xc + pos); }
+            else if(pos >= -(long long) p.carry_len) val = __ldg(cr + pos);
+            v[n1] = val;
+          }
+        }
+        __syncwarp();
+        if(l == 0) mbar_arrive_cta(w_free);            // staging consumed (16 arrivals: 8 warps x 2 rounds)
+        if(r == 0 && it1 > 0) ols_stamp(p, it1 - 1, w, l, 1);
+        fft16s<false, 2>(&v[0]);
+        fft16s<false, 2>(&v[1]);
+        if(r == 0 && it1 > 0) ols_stamp(p, it1 - 1, w, l, 2);
+        if(it1 > 0) mbar_wait_sleep(e_free + 2 * r, (it1 - 1) & 1);  // the output warps have read these eight columns of the previous block
+        if(r == 0 && it1 > 0) ols_stamp(p, it1 - 1, w, l, 3);
+        // last radix-2 stage: rows k1 = K and K + 16 are stored as soon as they exist.  One arrival per row pair and
+        // round: the owner of rows (2w', 2w'+1) starts P2 when all sixteen columns have been written.
+        const uint32_t a = sE + (uint32_t) (32 * n2) * 8u + lx;
 #define OLS_P1(K)                                                                              \
         {                                                                                          \
           float2 lo, hi;                                                                           \
@@ -491,9 +496,54 @@ __global__ void __launch_bounds__(OLS_THREADS, 1) ols16k_kernel(OlsParams p)
         OLS_P1(0) OLS_P1(1) OLS_P1(2) OLS_P1(3) OLS_P1(4) OLS_P1(5) OLS_P1(6) OLS_P1(7)
         OLS_P1(8) OLS_P1(9) OLS_P1(10) OLS_P1(11) OLS_P1(12) OLS_P1(13) OLS_P1(14) OLS_P1(15)
 #undef OLS_P1
+        if(r == 0 && it1 > 0) ols_stamp(p, it1 - 1, w, l, 11);
       }
-      ols_stamp(p, it, w, l, 3);
-      mbar_wait(row_full + w, it & 1);
+    };
+
+    // P3 of block (chan3, j3): rows of E -> inverse radix-32 over k1 -> the L valid outputs
+    auto phase3 = [&](int chan3, int j3, unsigned it3) {
+#pragma unroll 1
+      for(int r = 0; r < 2; r++)
+      {
+        const int n2 = ri + 8 * r;
+        float2 v[32];
+        const uint32_t a = sE + (uint32_t) (32 * n2) * 8u + lx;
+#pragma unroll
+        for(int h = 0; h < 2; h++)
+#pragma unroll
+          for(int k1 = h; k1 < 32; k1 += 2) v[k1] = lds64(a + (uint32_t) (k1 * 512) * 8u);
+        __syncwarp();
+        if(l == 0) mbar_arrive_cta(e_free + 2 * r);    // 8 arrivals per round: columns 8r..8r+7 may be overwritten
+        if(r == 0) ols_stamp(p, it3, w, l, 1);
+        const long long i0 = (long long) j3 * L + 32 * n2 + l;   // output index of window sample n = O + 32 n2 + l
+        float2 *yc = p.y + (long long) chan3 * p.y_stride + i0;
+        const int rem = (int) min(p.out_count - i0, (long long) L);   // outputs of this lane's column still inside the call
+        // inverse radix-32 whose last stage hands every output pair (n1 = K, K + 16) to the store as soon as it exists
+        fft16s<true, 2>(&v[0]);
+        fft16s<true, 2>(&v[1]);
+        if(r == 0) ols_stamp(p, it3, w, l, 2);
+#define OLS_OUT(K)                                                                                   \
+        {                                                                                                \
+          float2 lo, hi;                                                                                 \
+          comb32<true, K>(v[2 * K], v[2 * K + 1], lo, hi);                                               \
+          if(K >= NX && 512 * (K - NX) < rem) ols_stg(yc + 512 * (K - NX), lo);                          \
+          if(K + 16 >= NX && 512 * (K + 16 - NX) < rem) ols_stg(yc + 512 * (K + 16 - NX), hi);           \
+        }
+        OLS_OUT(0) OLS_OUT(1) OLS_OUT(2) OLS_OUT(3) OLS_OUT(4) OLS_OUT(5) OLS_OUT(6) OLS_OUT(7)
+        OLS_OUT(8) OLS_OUT(9) OLS_OUT(10) OLS_OUT(11) OLS_OUT(12) OLS_OUT(13) OLS_OUT(14) OLS_OUT(15)
+#undef OLS_OUT
+        if(r == 0) ols_stamp(p, it3, w, l, 11);
+      }
+    };
+
+    int chan = (int) (first / p.jblocks), j = (int) (first - (long long) chan * p.jblocks);
+    if(!out_role && first < last) phase1(chan, j, 0u);
+    for(long long b = first; b < last; b++)
+    {
+      const unsigned it = (unsigned) (b - first);
+      float2 v[32];
+      ols_stamp(p, it, w, l, 0);
+      mbar_wait_sleep(row_full + w, it & 1);
       ols_stamp(p, it, w, l, 4);
 
       // ---- P2: everything between the two exchanges, inside the warp's own 8 KiB ----
@@ -564,38 +614,18 @@ __global__ void __launch_bounds__(OLS_THREADS, 1) ols16k_kernel(OlsParams p)
         for(int r = 16 * c; r < 16 * c + 16; r++) sts64(sEw + (uint32_t) (r * 32) * 8u + lx, v[r]);
       }
       ols_stamp(p, it, w, l, 9);
-      tc::named_bar(2, OLS_MATH_THREADS);
+      // the output warps need every row of the block; the input warps only announce theirs and move on to the next window
+      if(out_role) tc::named_bar(2, OLS_MATH_THREADS);
+      else asm volatile("bar.arrive 2, %0;" ::"n"(OLS_MATH_THREADS) : "memory");
       ols_stamp(p, it, w, l, 10);
 
-      // ---- P3: E -> inverse radix-32 over k1 -> outputs ----
-      {
-        const uint32_t a = sE + (uint32_t) (32 * w) * 8u + lx;
-#pragma unroll
-        for(int h = 0; h < 2; h++)
-#pragma unroll
-          for(int k1 = h; k1 < 32; k1 += 2) v[k1] = lds64(a + (uint32_t) (k1 * 512) * 8u);
-      }
-      __syncwarp();
-      if(l == 0) mbar_arrive_cta(e_free);
-      ols_stamp(p, it, w, l, 11);
-      {
-        const long long i0 = (long long) j * L + 32 * w + l;   // output index of window sample n = O + 32 w + l
-        float2 *yc = p.y + (long long) chan * p.y_stride + i0;
-        const int rem = (int) min(p.out_count - i0, (long long) L);   // outputs of this lane's column still inside the call
-        // inverse radix-32 whose last stage hands every output pair (n1 = K, K + 16) to the store as soon as it exists
-        fft16s<true, 2>(&v[0]);
-        fft16s<true, 2>(&v[1]);
-#define OLS_OUT(K)                                                                                   \
-        {                                                                                                \
-          float2 lo, hi;                                                                                 \
-          comb32<true, K>(v[2 * K], v[2 * K + 1], lo, hi);                                               \
-          if(K >= NX && 512 * (K - NX) < rem) ols_stg(yc + 512 * (K - NX), lo);                       \
-          if(K + 16 >= NX && 512 * (K + 16 - NX) < rem) ols_stg(yc + 512 * (K + 16 - NX), hi);        \
-        }
-        OLS_OUT(0) OLS_OUT(1) OLS_OUT(2) OLS_OUT(3) OLS_OUT(4) OLS_OUT(5) OLS_OUT(6) OLS_OUT(7)
-        OLS_OUT(8) OLS_OUT(9) OLS_OUT(10) OLS_OUT(11) OLS_OUT(12) OLS_OUT(13) OLS_OUT(14) OLS_OUT(15)
-#undef OLS_OUT
-      }
+      // ---- P3 of this block (output warps) alongside P1 of the next one (input warps) ----
+      int chan_n = chan, j_n = j + 1;
+      if(j_n == p.jblocks) { j_n = 0; chan_n++; }
+      if(out_role) phase3(chan, j, it);
+      else if(b + 1 < last) phase1(chan_n, j_n, it + 1);
+      chan = chan_n;
+      j = j_n;
       ols_stamp(p, it, w, l, 12);
     }
   }
@@ -745,6 +775,7 @@ int ols16k_run(Ols16k *o, const float2 *x, long long xs, int n, const float2 *ca
   const int grid = (int) std::min<long long>(r.num_sms, p.total);
   const int smem = ols16k_smem_bytes(o->O);
   p.prof = nullptr;
+  p.offset_roles = getenv("TSDGPU_OLS_OFFSET") ? atoi(getenv("TSDGPU_OLS_OFFSET")) : 0;
   const char *prof_path = getenv("TSDGPU_OLS_PROF");   // profiling aid: clock trace of CTA 0 written to this file
   const size_t prof_words = (size_t) OLS_PROF_NIT * OLS_MATH_WARPS * OLS_PROF_PTS;
   if(prof_path)
