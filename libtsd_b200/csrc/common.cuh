@@ -146,12 +146,12 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes)
 {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-// The suspend-time hint lets the hardware park the warp until the phase completes instead of re-issuing try_wait every
-// few cycles: spinning waiters were taking a measurable share of the issue slots of the warp-specialised kernels
-// (ols16k: 146 M TRYWAIT per 4 ms launch, +3 % throughput with the hint).  TSD_MBAR_SPIN restores the plain form.
+// TSD_MBAR_SLEEP adds a suspend-time hint (the hardware parks the warp instead of re-issuing try_wait every few cycles).
+// Measured: +3 % for ols16k, whose waits are long (its own mbar_wait_sleep), -2..4 % for the tensor-core kernels, whose
+// waits are short and frequent (the wake-up costs more than the spinning): off by default here.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
 {
-#ifndef TSD_MBAR_SPIN
+#ifdef TSD_MBAR_SLEEP
   asm volatile(
     "{\n\t.reg .pred p;\n\t"
     "WAIT_%=:\n\t"
