@@ -462,14 +462,16 @@ int fft_plan_create(int n, int batch, tsdgpu_fft_s **out)
     p->ring = 64;
     p->lag = 32;
     p->staged = 1;
-    if(const char *v = getenv("TSDGPU_FFT_MODE")) p->staged = v[0] == 'p' ? 0 : 1;
+    if(const char *v = getenv("TSDGPU_FFT_MODE")) { p->staged = v[0] == 'p' ? 0 : 1; p->pipe = v[0] == 't' ? 1 : 0; }   // staged (default) | persistent | tma
+    if(const char *v = getenv("TSDGPU_FFT_PRING")) p->pipe_ring = std::max(2, atoi(v));
     if(const char *v = getenv("TSDGPU_FFT_CHUNK")) p->chunk = std::max(1, atoi(v));
     if(const char *v = getenv("TSDGPU_FFT_STREAMS")) p->nstreams = std::min((int) Runtime::MAX_AUX, std::max(1, atoi(v)));
     if(aux_init()) { fft_plan_destroy(p); return 1; }   // twiddle tables (and the auxiliary streams of the staged form)
     if(const char *v = getenv("TSDGPU_FFT_LAG")) p->lag = std::max(1, atoi(v));
     if(const char *v = getenv("TSDGPU_FFT_RING")) p->ring = atoi(v);
     if(p->ring <= p->lag) p->ring = p->lag + 16;
-    const size_t slots = p->staged ? (size_t) p->chunk * p->nstreams : (size_t) p->ring;
+    size_t slots = p->staged ? (size_t) p->chunk * p->nstreams : (size_t) p->ring;
+    if(p->pipe) slots = std::max(slots, (size_t) p->pipe_ring * (size_t) std::max(1, rt().num_sms / 16));
     if(cudaMalloc(&p->scratch, slots * 65536 * sizeof(float2)) != cudaSuccess ||
        cudaMalloc(&p->flags, ((size_t) 2 * batch + 1) * sizeof(unsigned)) != cudaSuccess)
     {
@@ -567,6 +569,7 @@ int fft_exec_device(tsdgpu_fft_s *p, const float2 *x, long long xs, float2 *y, l
       // stage B of transform t overwrites y[t] while stage A items of the same transform have
       // long finished, but A reads x[t] == y[t] only before B(t) starts: in place is safe.
     }
+    if(p->pipe && fft64k_pipe_usable(x, xs, y, ys)) return fft64k_pipe_run(p, x, xs, y, ys, batch, forward);
     if(p->staged)
     {
       KernelTimer timer;

@@ -11,6 +11,9 @@ struct tsdgpu_fft_s
   unsigned *flags = nullptr;   // done_a[batch], done_b[batch], ticket
   int ring = 0, lag = 0, ctas = 0;
   int staged = 1, chunk = 32, nstreams = 4;   // staged form: transforms per stage kernel, auxiliary streams
+  // TMA-fed persistent form (fft64k_pipe.cu): TSDGPU_FFT_MODE=tma (measured on a par with the staged default)
+  int pipe = 0, pipe_ring = 8;   // scratch slots per set of 16 CTAs
+  bool pipe_ready = false;
   bool smem_optin = false;     // shared-memory kernel: > 48 KiB of dynamic shared memory enabled
   // generic radix-2 path
   float2 *work[2] = {nullptr, nullptr};
@@ -31,4 +34,7 @@ int fft_plan_create(int n, int batch, tsdgpu_fft_s **out);
 void fft_plan_destroy(tsdgpu_fft_s *p);
 // device pointers, enqueued on the library stream
 int fft_exec_device(tsdgpu_fft_s *p, const float2 *x, long long xs, float2 *y, long long ys, bool forward);
+// fft64k_pipe.cu
+bool fft64k_pipe_usable(const float2 *x, long long xs, const float2 *y, long long ys);
+int fft64k_pipe_run(tsdgpu_fft_s *p, const float2 *x, long long xs, float2 *y, long long ys, int batch, bool forward);
 }

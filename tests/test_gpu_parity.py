@@ -211,6 +211,33 @@ def test_fft_device_inplace_and_many(tsd):
     assert np.max(np.abs(X1[-1].cpu().numpy() - Xref)) / rms(Xref) <= 2e-6
 
 
+@pytest.mark.parametrize("mode", ["tma", "persistent"])
+def test_fft64k_other_schedules(tsd, cpu_oracle, mode, monkeypatch):
+    """The 65536-point plan has three schedules of the same tile arithmetic (staged = default, persistent with tickets,
+    TMA-fed persistent pipeline: fft64k_pipe.cu).  The opt-in ones must agree with the reference plan too, for batches
+    below / above the scratch ring, in place, and bit-for-bit with the default schedule."""
+    import torch
+    from libtsd_b200 import fourier as Fo
+    rng = np.random.default_rng(11)
+    ref = cpu_oracle.fft(65536)
+    monkeypatch.delenv("TSDGPU_FFT_MODE", raising=False)
+    for batch in (1, 3, 300):
+        x = cn(rng, batch, 65536)
+        xt = torch.from_numpy(x).cuda()
+        base = Fo.tfrplan_creation(65536, batch=batch).step(xt, True).cpu().numpy()
+        monkeypatch.setenv("TSDGPU_FFT_MODE", mode)
+        plan = Fo.tfrplan_creation(65536, batch=batch)
+        monkeypatch.delenv("TSDGPU_FFT_MODE")
+        X = plan.step(xt, True)
+        Xh = X.cpu().numpy()
+        for b in sorted({0, batch // 2, batch - 1}):
+            assert rel_err(Xh[b], ref.step(x[b], True), rms(x)) <= TOL
+        assert np.array_equal(Xh, base)            # same arithmetic, same order of operations
+        back = plan.step(X, False, out=X)          # in place
+        tsd.synchronize()
+        assert rms(back.cpu().numpy() - x) / rms(x) <= 5e-6
+
+
 def test_fft_replan_and_errors(tsd):
     from libtsd_b200 import fourier as Fo
     rng = np.random.default_rng(6)
