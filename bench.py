@@ -42,6 +42,8 @@ WORKLOADS = {
     "resample": ("polyphase/LUT resampler 147/160 on 512 ch x 8Mi cf32, sinc LUT 64 taps x 257 phases", 8.0 + 8.0 * 147 / 160),
     # secondary line of SURVEY 8(d) config 5: the stock resample() chain (15-tap interpolator only at this ratio)
     "reechan": ("stock resample() / filtre_reechan 147/160 on 512 ch x 8Mi cf32 (15-tap sinc interpolator x 257 phases)", 8.0 + 8.0 * 147 / 160),
+    # the reference's DEFAULT block-filter shape: filtre_rif_fft(h) = Ne 512, N 1024 (fourier.cc:946-990)
+    "rif_fft": ("filtre_rif_fft default shape: 1024 ch x 1Mi cf32, 255-tap low-pass, Ne=512, N=1024", 16.0),
 }
 
 
@@ -162,6 +164,21 @@ def cpu_workload_setup(workload):
                 f = O.itrp(147.0 / 160.0, lut, 256)
                 return lambda: f.step(x)
         return make_job, n, kind, f"1 channel x {n} cf32 samples per host thread, filtre_itrp 147/160, sinc 64x257"
+    if workload == "rif_fft":
+        h = O.design_rif_fen(255, "lp", 0.1)
+        n = 1 << 20
+        x = cn(n)
+        if have_ref:
+            def make_job():
+                f = O.rif_fft(1, h)
+                return lambda: f.step(x)
+        else:
+            H = O.ola_make_H(h, 1024)
+
+            def make_job():
+                f = O.ola(512, 255, H)
+                return lambda: f.step(x)
+        return make_job, n, kind, f"1 channel x {n} cf32 samples per host thread, filtre_rif_fft 255 taps (Ne=512, N=1024)"
     if workload == "reechan":
         n = 1 << 20
         x = cn(n)
@@ -238,7 +255,7 @@ class GpuWorkload:
         self.torch = torch
         O = _Setup
         g = torch.Generator(device="cuda")
-        g.manual_seed({"ola": 0x7D5D0004, "fft": 0x7D5D0002, "fir": 0x7D5D0003, "resample": 0x7D5D0005, "reechan": 0x7D5D0005}[name])
+        g.manual_seed({"ola": 0x7D5D0004, "fft": 0x7D5D0002, "fir": 0x7D5D0003, "resample": 0x7D5D0005, "reechan": 0x7D5D0005, "rif_fft": 0x7D5D0006}[name])
 
         pad = int(os.environ.get("TSDGPU_BENCH_PAD", "0"))   # experiment: channel stride n + pad instead of n
 
@@ -292,6 +309,15 @@ class GpuWorkload:
             self.x = randc(self.nchan, self.n)
             self.samples_per_step = self.nchan * self.n
             self.step = lambda: self.flt.step(self.x)
+        elif name == "rif_fft":
+            self.nchan, self.n = max(1, int(1024 * scale)), 1 << 20
+            h = O.design_rif_fen(255, "lp", 0.1)
+            self.flt = Fo.filtre_rif_fft(h, nchan=self.nchan).ola
+            assert self.flt.N == 1024 and self.flt.Ne == 512
+            self.x = randc(self.nchan, self.n)
+            self.y = emptyc(self.nchan, self.n)
+            self.samples_per_step = self.nchan * self.n
+            self.step = lambda: self.flt.step(self.x, out=self.y)
         elif name == "reechan":
             self.nchan, self.n = max(1, int(512 * scale)), 1 << 23
             self.flt = F.filtre_reechan(147.0 / 160.0, self.nchan)
@@ -308,6 +334,7 @@ KERNELS = {
     "fir": "fir_tc_kernel (tcgen05 3xTF32 Toeplitz GEMM)",
     "resample": "resamp_tc_kernel (tcgen05 3xTF32 banded filter-bank GEMM, CTA pairs)",
     "reechan": "resamp_tc_kernel (tcgen05 3xTF32 banded filter-bank GEMM, CTA pairs)",
+    "rif_fft": "ols16k_kernel<1> (same single-SM overlap-save kernel: the device's transform size is independent of Ne / N)",
 }
 
 
@@ -467,6 +494,13 @@ def e2e_measure(name, steps, warmup, barrier=None, world=1, pageable=False):
     elif name == "fir":
         nchan, n = 64, 1 << 20
         flt = F.filtre_rif(O.design_rif_fen(127, "lp", 0.1), np.complex64, nchan)
+        tx, x = hostbuf(nchan, n)
+        ty, y = hostbuf(nchan, n)
+        step = lambda: flt.step(x, out=y)   # noqa: E731
+        out_per_step = n
+    elif name == "rif_fft":
+        nchan, n = 256, 1 << 20
+        flt = Fo.filtre_rif_fft(O.design_rif_fen(255, "lp", 0.1), nchan=nchan).ola
         tx, x = hostbuf(nchan, n)
         ty, y = hostbuf(nchan, n)
         step = lambda: flt.step(x, out=y)   # noqa: E731
@@ -645,7 +679,7 @@ def main():
     # the other BASELINE configs, same measurement, in the same run (fewer steps: they only need a stable mean)
     extra = {}
     if not args.no_extra:
-        for name in ("fft", "fir", "resample", "reechan", "ola"):
+        for name in ("fft", "fir", "resample", "reechan", "rif_fft", "ola"):
             if name == args.workload:
                 continue
             r, _ = measure_workload(name, min(args.steps, 6), 3, args.scale, stream, barrier, world,

@@ -47,7 +47,14 @@ constexpr int OLS_MATH_REGS = 112, OLS_PROD_REGS = 24;  // 512 * 112 + 128 * 24 
 constexpr int OLS_E_BYTES = OLS_M * 8;                 // exchange buffer
 constexpr int OLS_PIECE = 16384;                       // bytes per bulk copy
 
-// W512^(n2*k1) at [k1*16 + n2], k1 < 32, n2 < 16 (host-built in double)
+// OLS_TW1_OUTER = 1 (experiment, measured -1 %: 164.8 vs 166.4 Gsamples/s): the W512^(n2*k1) products sit in P1 / P3, where
+// n2 is the same for the whole warp and the twiddle a constant-bank operand, instead of P2 (the FMA-bound phase).  P2 gets
+// ~1 200 cycles shorter, but the hand-over phase is bound by the serial chain of each role warp (load -> butterflies ->
+// wait -> store), and the extra products sit on that chain.  Default 0: products in P2.
+#ifndef OLS_TW1_OUTER
+#define OLS_TW1_OUTER 0
+#endif
+// W512^(n2*k1), k1 < 32, n2 < 16 (host-built in double): at [n2*32 + k1] (OLS_TW1_OUTER) or [k1*16 + n2]
 __constant__ float2 c_ols_tw1[512];
 
 struct OlsParams
@@ -413,7 +420,9 @@ __global__ void __launch_bounds__(OLS_THREADS, 1) ols16k_kernel(OlsParams p)
     // W512^(n2 * k1), k1 = 2w + c, is the same for every lane: lane r = c*16 + n2 keeps entry r in two registers and the
     // warp spreads the 32 entries through the first 256 bytes of its own rows of E (free while the data sits in
     // registers) right before each use: 1 STS + 16 broadcast LDS.128 instead of 30 constant-bank loads
+#if !OLS_TW1_OUTER
     const float2 tw1c = c_ols_tw1[(2 * w) * 16 + l];
+#endif
 
     // The sixteen math warps share P2 (a warp owns two rows of E), but the two phases that touch all of E are split between
     // two ROLES so that they run at the same time instead of one after the other: the output warps (0-3, 8-11: two per
@@ -477,10 +486,17 @@ __global__ void __launch_bounds__(OLS_THREADS, 1) ols16k_kernel(OlsParams p)
         // last radix-2 stage: rows k1 = K and K + 16 are stored as soon as they exist.  One arrival per row pair and
         // round: the owner of rows (2w', 2w'+1) starts P2 when all sixteen columns have been written.
         const uint32_t a = sE + (uint32_t) (32 * n2) * 8u + lx;
+        const float2 *tw1 = c_ols_tw1 + 32 * n2;   // W512^(n2*k1), the same for every lane
 #define OLS_P1(K)                                                                              \
         {                                                                                          \
           float2 lo, hi;                                                                           \
           comb32<false, K>(v[2 * K], v[2 * K + 1], lo, hi);                                        \
+          if(OLS_TW1_OUTER)                                                                        \
+          {                                                                                        \
+            const float2 ta = tw1[K], tb = tw1[K + 16];                                            \
+            if(K) lo = cmul_s(lo, ta.x, ta.y);                                                     \
+            hi = cmul_s(hi, tb.x, tb.y);                                                           \
+          }                                                                                        \
           sts64(a + (uint32_t) (K * 512) * 8u, lo);                                                \
           sts64(a + (uint32_t) ((K + 16) * 512) * 8u, hi);                                         \
           if(K & 1)                                                                                \
@@ -514,6 +530,18 @@ __global__ void __launch_bounds__(OLS_THREADS, 1) ols16k_kernel(OlsParams p)
           for(int k1 = h; k1 < 32; k1 += 2) v[k1] = lds64(a + (uint32_t) (k1 * 512) * 8u);
         __syncwarp();
         if(l == 0) mbar_arrive_cta(e_free + 2 * r);    // 8 arrivals per round: columns 8r..8r+7 may be overwritten
+        if(OLS_TW1_OUTER)
+        {
+          const float2 *tw1 = c_ols_tw1 + 32 * n2;     // conj W512^(n2*k1)
+#pragma unroll
+          for(int h = 0; h < 2; h++)
+#pragma unroll
+            for(int k1 = h ? 1 : 2; k1 < 32; k1 += 2)
+            {
+              const float2 t = tw1[k1];
+              v[k1] = cmulc_s(v[k1], t.x, t.y);
+            }
+        }
         if(r == 0) ols_stamp(p, it3, w, l, 1);
         const long long i0 = (long long) j3 * L + 32 * n2 + l;   // output index of window sample n = O + 32 n2 + l
         float2 *yc = p.y + (long long) chan3 * p.y_stride + i0;
@@ -549,15 +577,18 @@ __global__ void __launch_bounds__(OLS_THREADS, 1) ols16k_kernel(OlsParams p)
       // ---- P2: everything between the two exchanges, inside the warp's own 8 KiB ----
       // W512 twiddle table of the warp: row 31 of its region, each lane overwrites the element it has just read; the
       // row is rewritten last (by the final store of row 31), after the last table read
-      const uint32_t tab = sEw + 31u * 256u;
 #pragma unroll
       for(int r = 0; r < 32; r++) v[r] = lds64(sEw + (uint32_t) (r * 32) * 8u + lx);
+#if !OLS_TW1_OUTER
+      const uint32_t tab = sEw + 31u * 256u;
       sts64(tab + lx, tw1c);
       __syncwarp();
+#endif
 #pragma unroll
       for(int c = 0; c < 2; c++)
       {
-        // k1 = 2w + c: W512 twiddle, radix-16 over n2, W_M twiddle, rows c*16 + k2 into the transpose
+        // k1 = 2w + c: (W512 twiddle,) radix-16 over n2, W_M twiddle, rows c*16 + k2 into the transpose
+#if !OLS_TW1_OUTER
 #pragma unroll
         for(int i = 8 * c; i < 8 * c + 8; i++)
         {
@@ -565,6 +596,7 @@ __global__ void __launch_bounds__(OLS_THREADS, 1) ols16k_kernel(OlsParams p)
           if(i != 8 * c) v[2 * i] = cmul_s(v[2 * i], t.x, t.y);
           v[2 * i + 1] = cmul_s(v[2 * i + 1], t.z, t.w);
         }
+#endif
         fft16s<false, 1>(&v[16 * c]);
         mul_tmem16<false>(&v[16 * c], tm + 64 + 32 * c);
         if(c == 0) OlsX<0, 16>::st_rows(sEw + lx, v);   // row r, column n3 = lane, at r*32 + (lane ^ r)
@@ -595,14 +627,17 @@ __global__ void __launch_bounds__(OLS_THREADS, 1) ols16k_kernel(OlsParams p)
       }
       __syncwarp();
       OlsX<0, 32>::ld_rows(sEw + lx, v);
+#if !OLS_TW1_OUTER
       sts64(tab + lx, tw1c);
       __syncwarp();
+#endif
       ols_stamp(p, it, w, l, 8);
 #pragma unroll
       for(int c = 0; c < 2; c++)
       {
         mul_tmem16<true>(&v[16 * c], tm + 64 + 32 * c);
         fft16s<true, 1>(&v[16 * c]);
+#if !OLS_TW1_OUTER
 #pragma unroll
         for(int i = 8 * c; i < 8 * c + 8; i++)
         {
@@ -610,6 +645,7 @@ __global__ void __launch_bounds__(OLS_THREADS, 1) ols16k_kernel(OlsParams p)
           if(i != 8 * c) v[2 * i] = cmulc_s(v[2 * i], t.x, t.y);
           v[2 * i + 1] = cmulc_s(v[2 * i + 1], t.z, t.w);
         }
+#endif
 #pragma unroll
         for(int r = 16 * c; r < 16 * c + 16; r++) sts64(sEw + (uint32_t) (r * 32) * 8u + lx, v[r]);
       }
@@ -720,7 +756,7 @@ int ols16k_create_taps(const std::complex<double> *taps, int K, Ols16k **out)
       for(int n2 = 0; n2 < 16; n2++)
       {
         const double ang = -2.0 * M_PI * (double) (k1 * n2) / 512.0;
-        t1[k1 * 16 + n2] = make_float2((float) cos(ang), (float) sin(ang));
+        t1[OLS_TW1_OUTER ? n2 * 32 + k1 : k1 * 16 + n2] = make_float2((float) cos(ang), (float) sin(ang));
       }
     TSD_CUDA(cudaMemcpyToSymbol(c_ols_tw1, t1.data(), 512 * sizeof(float2)));
     TSD_CUDA(cudaFuncSetAttribute(ols16k_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ols16k_smem_bytes(4096)));
