@@ -17,6 +17,12 @@ struct HostStage
   void *in[2] = {nullptr, nullptr}, *out[2] = {nullptr, nullptr};
   size_t in_bytes = 0, out_bytes = 0;
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+  // pageable caller memory (what a libtsd application's Veccf is): pinned bounce buffers per slot, filled / drained by the
+  // copy-thread pool (runtime.cu) instead of the driver's single-threaded staging
+  void *pin_in[2] = {nullptr, nullptr}, *pin_out[2] = {nullptr, nullptr};
+  size_t pin_in_bytes[2] = {0, 0}, pin_out_bytes[2] = {0, 0};
+  cudaEvent_t ev_pin_in[2] = {nullptr, nullptr}, ev_pin_out[2] = {nullptr, nullptr};
+  struct Pending { bool active = false; void *dst = nullptr; size_t dpitch = 0, width = 0, height = 0; } pend[2];
 };
 // One Runtime per CUDA device (runtime.cu keeps a table).  A host thread works on one device at a time
 // (tsdgpu_init / tsdgpu_set_device; every object remembers the device it was created on and its entry points switch

@@ -714,7 +714,7 @@ int tsdgpu_fft_exec(tsdgpu_fft_t p, const void *x, long long xs, void *y, long l
   const int rc = host_pipeline(
     full_batch, group,
     [&](int slot, long long first, long long count) -> int {
-      TSD_CUDA(cudaMemcpy2DAsync(hs.in[slot], row, xh + first * xs, (size_t) xs * 8, row, (size_t) count, cudaMemcpyHostToDevice, rt().copy_in));
+      if(stage_in(slot, hs.in[slot], row, xh + first * xs, (size_t) xs * 8, row, (size_t) count)) return 1;
       return 0;
     },
     [&](long long count) { return count; },
@@ -726,7 +726,7 @@ int tsdgpu_fft_exec(tsdgpu_fft_t p, const void *x, long long xs, void *y, long l
       return r2;
     },
     [&](int slot, long long out_first, long long count) -> int {
-      TSD_CUDA(cudaMemcpy2DAsync(yh + out_first * ys, (size_t) ys * 8, hs.out[slot], row, row, (size_t) count, cudaMemcpyDeviceToHost, rt().copy_out));
+      if(stage_out(slot, yh + out_first * ys, (size_t) ys * 8, hs.out[slot], row, row, (size_t) count)) return 1;
       return 0;
     },
     &done);

@@ -342,8 +342,8 @@ int tsdgpu_fir_step(tsdgpu_fir_t f, const void *x, long long xs, int n, void *y,
   return host_pipeline(
     n, chunk,
     [&](int slot, long long first, long long count) -> int {
-      TSD_CUDA(cudaMemcpy2DAsync(hs.in[slot], (size_t) chunk * ssz, xh + (size_t) first * ssz, (size_t) xs * ssz,
-                                 (size_t) count * ssz, f->nchan, cudaMemcpyHostToDevice, rt().copy_in));
+      if(stage_in(slot, hs.in[slot], (size_t) chunk * ssz, xh + (size_t) first * ssz, (size_t) xs * ssz,
+                                 (size_t) count * ssz, f->nchan)) return 1;
       return 0;
     },
     [&](long long count) { return count; },
@@ -352,8 +352,8 @@ int tsdgpu_fir_step(tsdgpu_fir_t f, const void *x, long long xs, int n, void *y,
       return fir_run_device(f, hs.in[slot], chunk, (int) count, hs.out[slot], chunk);
     },
     [&](int slot, long long out_first, long long count) -> int {
-      TSD_CUDA(cudaMemcpy2DAsync(yh + (size_t) out_first * ssz, (size_t) ys * ssz, hs.out[slot], (size_t) chunk * ssz,
-                                 (size_t) count * ssz, f->nchan, cudaMemcpyDeviceToHost, rt().copy_out));
+      if(stage_out(slot, yh + (size_t) out_first * ssz, (size_t) ys * ssz, hs.out[slot], (size_t) chunk * ssz,
+                                 (size_t) count * ssz, f->nchan)) return 1;
       return 0;
     },
     nullptr);

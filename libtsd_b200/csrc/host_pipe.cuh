@@ -12,6 +12,12 @@ namespace tsdgpu {
 
 HostStage &host_stage();
 int host_stage_reserve(size_t in_bytes, size_t out_bytes);
+// 2-D copies between caller memory and a device slot (runtime.cu).  Pinned / registered caller memory: one
+// cudaMemcpy2DAsync on the copy stream.  Pageable memory: through the slot's pinned bounce buffer, filled (stage_in) or
+// drained (stage_out: deferred until the slot is used again, or stage_flush) by the copy-thread pool.
+int stage_in(int slot, void *dst_dev, size_t dpitch, const void *src_host, size_t spitch, size_t width, size_t height);
+int stage_out(int slot, void *dst_host, size_t dpitch, const void *src_dev, size_t spitch, size_t width, size_t height);
+int stage_flush();
 
 // unit = one chunkable item (a sample position for the streaming filters, a transform for the FFT).
 // copy_in(slot, first, count) / copy_out(slot, out_first, out_count) issue the 2-D copies,
@@ -23,6 +29,7 @@ int host_pipeline(long long total, long long chunk, CopyIn copy_in, OutCount out
 {
   Runtime &r = rt();
   HostStage &hs = host_stage();
+  hs.pend[0].active = hs.pend[1].active = false;   // nothing survives a call (an earlier call may have stopped on an error)
   long long produced = 0;
   int k = 0;
   for(long long first = 0; first < total; first += chunk, k++)
@@ -50,6 +57,7 @@ int host_pipeline(long long total, long long chunk, CopyIn copy_in, OutCount out
   }
   TSD_CUDA(cudaStreamSynchronize(r.copy_out));
   TSD_CUDA(cudaStreamSynchronize(r.stream));
+  if(stage_flush()) return 1;
   if(out_total) *out_total = produced;
   return 0;
 }

@@ -1032,8 +1032,7 @@ int tsdgpu_ola_step(tsdgpu_ola_t f, const void *x, long long xs, int n, void *y,
   return host_pipeline(
     n, chunk,
     [&](int slot, long long first, long long count) -> int {
-      TSD_CUDA(cudaMemcpy2DAsync(hs.in[slot], (size_t) chunk * 8, xh + first, (size_t) xs * 8, (size_t) count * 8, f->nchan,
-                                 cudaMemcpyHostToDevice, rt().copy_in));
+      if(stage_in(slot, hs.in[slot], (size_t) chunk * 8, xh + first, (size_t) xs * 8, (size_t) count * 8, f->nchan)) return 1;
       return 0;
     },
     [&](long long count) { return tsdgpu_ola_out_count(f, (int) count); },
@@ -1041,8 +1040,7 @@ int tsdgpu_ola_step(tsdgpu_ola_t f, const void *x, long long xs, int n, void *y,
       return ola_run_device(f, (const float2 *) hs.in[slot], chunk, (int) count, (float2 *) hs.out[slot], out_cap, got);
     },
     [&](int slot, long long out_first, long long count) -> int {
-      TSD_CUDA(cudaMemcpy2DAsync(yh + out_first, (size_t) ys * 8, hs.out[slot], (size_t) out_cap * 8, (size_t) count * 8, f->nchan,
-                                 cudaMemcpyDeviceToHost, rt().copy_out));
+      if(stage_out(slot, yh + out_first, (size_t) ys * 8, hs.out[slot], (size_t) out_cap * 8, (size_t) count * 8, f->nchan)) return 1;
       return 0;
     },
     n_out);

@@ -264,8 +264,8 @@ int tsdgpu_poly_step(tsdgpu_poly_t f, const void *x, long long xs, int n, void *
   return host_pipeline(
     n, chunk,
     [&](int slot, long long first, long long count) -> int {
-      TSD_CUDA(cudaMemcpy2DAsync(hs.in[slot], (size_t) chunk * ssz, xh + (size_t) first * ssz, (size_t) xs * ssz,
-                                 (size_t) count * ssz, f->nchan, cudaMemcpyHostToDevice, rt().copy_in));
+      if(stage_in(slot, hs.in[slot], (size_t) chunk * ssz, xh + (size_t) first * ssz, (size_t) xs * ssz,
+                                 (size_t) count * ssz, f->nchan)) return 1;
       return 0;
     },
     [&](long long count) { return poly_out_count(f, count); },
@@ -273,8 +273,8 @@ int tsdgpu_poly_step(tsdgpu_poly_t f, const void *x, long long xs, int n, void *
       return poly_run_device(f, hs.in[slot], chunk, (int) count, hs.out[slot], out_cap, got);
     },
     [&](int slot, long long out_first, long long count) -> int {
-      TSD_CUDA(cudaMemcpy2DAsync(yh + (size_t) out_first * ssz, (size_t) ys * ssz, hs.out[slot], (size_t) out_cap * ssz,
-                                 (size_t) count * ssz, f->nchan, cudaMemcpyDeviceToHost, rt().copy_out));
+      if(stage_out(slot, yh + (size_t) out_first * ssz, (size_t) ys * ssz, hs.out[slot], (size_t) out_cap * ssz,
+                                 (size_t) count * ssz, f->nchan)) return 1;
       return 0;
     },
     n_out);

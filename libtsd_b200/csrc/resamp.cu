@@ -694,8 +694,7 @@ int tsdgpu_resamp_step(tsdgpu_resamp_t f, const void *x, long long xs, int n, vo
   return host_pipeline(
     n, chunk,
     [&](int slot, long long first, long long count) -> int {
-      TSD_CUDA(cudaMemcpy2DAsync(hs.in[slot], (size_t) chunk * es, xh + first * es, (size_t) xs * es, (size_t) count * es, f->nchan,
-                                 cudaMemcpyHostToDevice, rt().copy_in));
+      if(stage_in(slot, hs.in[slot], (size_t) chunk * es, xh + first * es, (size_t) xs * es, (size_t) count * es, f->nchan)) return 1;
       return 0;
     },
     [&](long long count) { return tsdgpu_resamp_out_count(f, (int) count); },
@@ -703,8 +702,7 @@ int tsdgpu_resamp_step(tsdgpu_resamp_t f, const void *x, long long xs, int n, vo
       return resamp_run_device(f, (const float2 *) hs.in[slot], chunk, (int) count, (float2 *) hs.out[slot], out_cap, out_cap, got);
     },
     [&](int slot, long long out_first, long long count) -> int {
-      TSD_CUDA(cudaMemcpy2DAsync(yh + out_first * es, (size_t) ys * es, hs.out[slot], (size_t) out_cap * es, (size_t) count * es, f->nchan,
-                                 cudaMemcpyDeviceToHost, rt().copy_out));
+      if(stage_out(slot, yh + out_first * es, (size_t) ys * es, hs.out[slot], (size_t) out_cap * es, (size_t) count * es, f->nchan)) return 1;
       return 0;
     },
     n_out);

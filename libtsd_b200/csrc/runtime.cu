@@ -1,5 +1,10 @@
 // Runtime of libtsdgpu: device selection, the library stream, error reporting, launch counter.
 #include "common.cuh"
+#include <atomic>
+#include <condition_variable>
+#include <cstring>
+#include <functional>
+#include <thread>
 #include "host_pipe.cuh"
 #include "tsdgpu.h"
 
@@ -96,6 +101,14 @@ static void shutdown_device(Runtime &r)
     if(hs.ev_out[i]) cudaEventDestroy(hs.ev_out[i]);
     hs.in[i] = hs.out[i] = nullptr;
     hs.ev_in[i] = hs.ev_done[i] = hs.ev_out[i] = nullptr;
+    if(hs.pin_in[i]) cudaFreeHost(hs.pin_in[i]);
+    if(hs.pin_out[i]) cudaFreeHost(hs.pin_out[i]);
+    if(hs.ev_pin_in[i]) cudaEventDestroy(hs.ev_pin_in[i]);
+    if(hs.ev_pin_out[i]) cudaEventDestroy(hs.ev_pin_out[i]);
+    hs.pin_in[i] = hs.pin_out[i] = nullptr;
+    hs.pin_in_bytes[i] = hs.pin_out_bytes[i] = 0;
+    hs.ev_pin_in[i] = hs.ev_pin_out[i] = nullptr;
+    hs.pend[i].active = false;
   }
   hs.in_bytes = hs.out_bytes = 0;
   for(auto &pr : r.timed)
@@ -179,6 +192,186 @@ int aux_join(int n)
 }
 
 HostStage &host_stage() { return rt().hs; }
+
+// ---- copy-thread pool: parallel memcpy between pageable caller memory and the pinned bounce buffers ------------------
+namespace {
+struct CopyPool
+{
+  std::vector<std::thread> th;
+  std::mutex m, user;               // m: pool state; user: one parallel copy at a time
+  std::condition_variable cv, cv_done;
+  const std::function<void(int)> *job = nullptr;
+  int ntasks = 0, done = 0, active = 0;   // active: workers inside pull() — run() does not return before it is 0 again
+  std::atomic<int> next{0};
+  unsigned long gen = 0;
+  bool stop = false;
+  int nthreads = 0;
+
+  void start()
+  {
+    if(nthreads) return;
+    const char *v = getenv("TSDGPU_COPY_THREADS");
+    const unsigned hw = std::thread::hardware_concurrency();
+    nthreads = v ? std::max(1, atoi(v)) : (int) std::max(1u, std::min(8u, hw ? hw / 2 : 4u));
+    for(int i = 1; i < nthreads; i++) th.emplace_back([this] { worker(); });
+  }
+  void pull()
+  {
+    for(;;)
+    {
+      const int i = next.fetch_add(1);
+      if(i >= ntasks) break;
+      (*job)(i);
+      std::lock_guard<std::mutex> g(m);
+      if(++done == ntasks) cv_done.notify_all();
+    }
+  }
+  void worker()
+  {
+    unsigned long seen = 0;
+    for(;;)
+    {
+      {
+        std::unique_lock<std::mutex> g(m);
+        cv.wait(g, [&] { return stop || gen != seen; });
+        if(stop) return;
+        seen = gen;
+        active++;
+      }
+      pull();
+      std::lock_guard<std::mutex> g(m);
+      if(--active == 0) cv_done.notify_all();
+    }
+  }
+  void run(int n, const std::function<void(int)> &f)
+  {
+    std::lock_guard<std::mutex> u(user);
+    start();
+    {
+      std::lock_guard<std::mutex> g(m);
+      job = &f;
+      ntasks = n;
+      done = 0;
+      next.store(0);
+      gen++;
+    }
+    cv.notify_all();
+    pull();
+    std::unique_lock<std::mutex> g(m);
+    cv_done.wait(g, [&] { return done >= ntasks && active == 0; });
+    ntasks = 0;   // workers that wake up late for this generation find nothing
+  }
+  ~CopyPool()
+  {
+    {
+      std::lock_guard<std::mutex> g(m);
+      stop = true;
+    }
+    cv.notify_all();
+    for(auto &t : th) t.join();
+  }
+};
+CopyPool &copy_pool()
+{
+  static CopyPool p;
+  return p;
+}
+// rows of `width` bytes, `height` of them; cut into pieces of >= 1 MiB, one task each
+void parallel_copy2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t height)
+{
+  const size_t total = width * height;
+  if(total == 0) return;
+  const size_t piece = std::max<size_t>(1u << 20, (total + 63) / 64);
+  const int ntasks = (int) ((total + piece - 1) / piece);
+  const std::function<void(int)> f = [&](int i) {
+    size_t off = (size_t) i * piece;
+    const size_t end = std::min(total, off + piece);
+    while(off < end)
+    {
+      const size_t row = off / width, col = off % width, len = std::min(width - col, end - off);
+      memcpy((char *) dst + row * dpitch + col, (const char *) src + row * spitch + col, len);
+      off += len;
+    }
+  };
+  if(ntasks == 1) f(0);
+  else copy_pool().run(ntasks, f);
+}
+bool host_ptr_is_pinned(const void *p)
+{
+  cudaPointerAttributes a;
+  if(cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+int pin_reserve(void **buf, size_t *have, size_t need, cudaEvent_t *ev, cudaStream_t s)
+{
+  if(!*ev) TSD_CUDA(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
+  if(need <= *have) return 0;
+  TSD_CUDA(cudaStreamSynchronize(s));
+  if(*buf) cudaFreeHost(*buf);
+  *buf = nullptr;
+  *have = 0;
+  TSD_CUDA(cudaHostAlloc(buf, need, cudaHostAllocDefault));
+  *have = need;
+  return 0;
+}
+int stage_drain(HostStage &hs, int slot)
+{
+  HostStage::Pending &pd = hs.pend[slot];
+  if(!pd.active) return 0;
+  TSD_CUDA(cudaEventSynchronize(hs.ev_pin_out[slot]));
+  parallel_copy2d(pd.dst, pd.dpitch, hs.pin_out[slot], pd.width, pd.width, pd.height);
+  pd.active = false;
+  return 0;
+}
+} // namespace
+
+int stage_in(int slot, void *dst_dev, size_t dpitch, const void *src_host, size_t spitch, size_t width, size_t height)
+{
+  Runtime &r = rt();
+  HostStage &hs = r.hs;
+  static const bool off = getenv("TSDGPU_NO_BOUNCE") != nullptr;   // A/B: let the driver stage pageable memory itself
+  if(off || width * height < (1u << 20) || host_ptr_is_pinned(src_host))
+  {
+    TSD_CUDA(cudaMemcpy2DAsync(dst_dev, dpitch, src_host, spitch, width, height, cudaMemcpyHostToDevice, r.copy_in));
+    return 0;
+  }
+  if(pin_reserve(&hs.pin_in[slot], &hs.pin_in_bytes[slot], width * height, &hs.ev_pin_in[slot], r.copy_in)) return 1;
+  TSD_CUDA(cudaEventSynchronize(hs.ev_pin_in[slot]));   // the previous upload out of this bounce buffer has left it
+  parallel_copy2d(hs.pin_in[slot], width, src_host, spitch, width, height);
+  TSD_CUDA(cudaMemcpy2DAsync(dst_dev, dpitch, hs.pin_in[slot], width, width, height, cudaMemcpyHostToDevice, r.copy_in));
+  TSD_CUDA(cudaEventRecord(hs.ev_pin_in[slot], r.copy_in));
+  return 0;
+}
+
+int stage_out(int slot, void *dst_host, size_t dpitch, const void *src_dev, size_t spitch, size_t width, size_t height)
+{
+  Runtime &r = rt();
+  HostStage &hs = r.hs;
+  static const bool off = getenv("TSDGPU_NO_BOUNCE") != nullptr;
+  if(off || width * height < (1u << 20) || host_ptr_is_pinned(dst_host))
+  {
+    TSD_CUDA(cudaMemcpy2DAsync(dst_host, dpitch, src_dev, spitch, width, height, cudaMemcpyDeviceToHost, r.copy_out));
+    return 0;
+  }
+  if(stage_drain(hs, slot)) return 1;   // the chunk that used this bounce buffer two steps ago
+  if(pin_reserve(&hs.pin_out[slot], &hs.pin_out_bytes[slot], width * height, &hs.ev_pin_out[slot], r.copy_out)) return 1;
+  TSD_CUDA(cudaMemcpy2DAsync(hs.pin_out[slot], width, src_dev, spitch, width, height, cudaMemcpyDeviceToHost, r.copy_out));
+  TSD_CUDA(cudaEventRecord(hs.ev_pin_out[slot], r.copy_out));
+  hs.pend[slot].active = true;
+  hs.pend[slot].dst = dst_host;
+  hs.pend[slot].dpitch = dpitch;
+  hs.pend[slot].width = width;
+  hs.pend[slot].height = height;
+  return 0;
+}
+
+int stage_flush()
+{
+  HostStage &hs = rt().hs;
+  for(int s = 0; s < 2; s++)
+    if(stage_drain(hs, s)) return 1;
+  return 0;
+}
 int host_stage_reserve(size_t in_bytes, size_t out_bytes)
 {
   HostStage &hs = host_stage();

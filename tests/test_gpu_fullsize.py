@@ -114,3 +114,41 @@ def test_resampler_config5_channels(env, port, cpu_oracle):
     m = 1 << 20
     yr = port.itrp(147.0 / 160.0, lut, 256).step(x[63, :m].cpu().numpy())
     assert np.max(np.abs(y[63, : len(yr)].cpu().numpy() - yr)) / rms(x) <= TOL
+
+
+def test_pageable_host_buffers_match_device_path(env):
+    """Host entry points with ordinary (pageable) numpy buffers go through the pinned bounce buffers and the copy-thread
+    pool (runtime.cu: stage_in / stage_out) over several pipeline chunks; pinned buffers take the direct copies.  Both must
+    give what the device-resident call gives: bit for bit where the arithmetic does not depend on how the call is cut into
+    chunks (direct FIR, FFT plan), to rounding (<= 1e-5 of RMS, lengths exact) where the kernel's internal block grid moves
+    with the chunk boundaries (block filter, tensor-core resampler)."""
+    torch, tsd = env
+    from libtsd_b200 import filtrage as F, fourier as Fo
+    rng = np.random.default_rng(5)
+    nchan, n = 4, 1 << 22          # 128 MiB of input: three pipeline chunks of 48 MiB
+    x = (rng.standard_normal((nchan, n), dtype=np.float32) + 1j * rng.standard_normal((nchan, n), dtype=np.float32)).astype(np.complex64)
+    xd = torch.from_numpy(x).cuda()
+    xp = torch.from_numpy(x).pin_memory()
+    h = F.design_rif_fen(127, "lp", 0.1)
+    # direct FIR: pageable, pinned, device; and in place on pageable memory
+    yd = F.filtre_rif(h, np.complex64, nchan).step(xd).cpu().numpy()
+    assert np.array_equal(F.filtre_rif(h, np.complex64, nchan).step(x), yd)
+    yp = torch.empty((nchan, n), dtype=torch.complex64).pin_memory()
+    F.filtre_rif(h, np.complex64, nchan).step(xp.numpy(), out=yp.numpy())
+    assert np.array_equal(yp.numpy(), yd)
+    xi = x.copy()
+    F.filtre_rif(h, np.complex64, nchan).step(xi, out=xi)
+    assert np.array_equal(xi, yd)
+    # block filter (ragged output length per chunk) and resampler (fewer outputs than inputs)
+    h2 = F.design_rif_fen(1023, "lp", 0.2)
+    cfg = Fo.FiltreFFTConfig(15361, 1023, H=Fo.ola_make_H(h2, 16384), fir_len=1023)
+    od = Fo.filtre_fft(cfg, nchan)[0].step(xd).cpu().numpy()
+    oh = Fo.filtre_fft(cfg, nchan)[0].step(x)
+    assert oh.shape == od.shape and np.max(np.abs(oh - od)) <= TOL * np.sqrt(np.mean(np.abs(od) ** 2))
+    rd = F.filtre_reechan(147.0 / 160.0, nchan).step(xd).cpu().numpy()
+    rh = F.filtre_reechan(147.0 / 160.0, nchan).step(x)
+    assert rh.shape == rd.shape and np.max(np.abs(rh - rd)) <= TOL * np.sqrt(np.mean(np.abs(rd) ** 2))
+    # FFT plan, groups of transforms
+    xf = x.reshape(nchan * 64, 65536)
+    Xd = Fo.tfrplan_creation(65536, batch=nchan * 64).step(torch.from_numpy(xf).cuda(), True).cpu().numpy()
+    assert np.array_equal(Fo.tfrplan_creation(65536, batch=nchan * 64).step(xf, True), Xd)
