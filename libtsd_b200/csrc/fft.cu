@@ -462,7 +462,7 @@ int fft_plan_create(int n, int batch, tsdgpu_fft_s **out)
     p->ring = 64;
     p->lag = 32;
     p->staged = 1;
-    if(const char *v = getenv("TSDGPU_FFT_MODE")) { p->staged = v[0] == 'p' ? 0 : 1; p->pipe = v[0] == 't' ? 1 : 0; }   // staged (default) | persistent | tma
+    if(const char *v = getenv("TSDGPU_FFT_MODE")) { p->staged = v[0] == 'p' ? 0 : 1; p->pipe = v[0] == 't' ? 1 : 0; }   // tma (default) | staged | persistent
     if(const char *v = getenv("TSDGPU_FFT_PRING")) p->pipe_ring = std::max(2, atoi(v));
     if(const char *v = getenv("TSDGPU_FFT_CHUNK")) p->chunk = std::max(1, atoi(v));
     if(const char *v = getenv("TSDGPU_FFT_STREAMS")) p->nstreams = std::min((int) Runtime::MAX_AUX, std::max(1, atoi(v)));

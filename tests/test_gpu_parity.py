@@ -211,11 +211,11 @@ def test_fft_device_inplace_and_many(tsd):
     assert np.max(np.abs(X1[-1].cpu().numpy() - Xref)) / rms(Xref) <= 2e-6
 
 
-@pytest.mark.parametrize("mode", ["tma", "persistent"])
+@pytest.mark.parametrize("mode", ["staged", "persistent"])
 def test_fft64k_other_schedules(tsd, cpu_oracle, mode, monkeypatch):
-    """The 65536-point plan has three schedules of the same tile arithmetic (staged = default, persistent with tickets,
-    TMA-fed persistent pipeline: fft64k_pipe.cu).  The opt-in ones must agree with the reference plan too, for batches
-    below / above the scratch ring and in place; the TMA pipeline bit-for-bit with the default schedule."""
+    """The 65536-point plan has three schedules of the same tile arithmetic (TMA-fed persistent pipeline, fft64k_pipe.cu =
+    default; staged kernels; persistent kernel with tickets).  The opt-in ones must agree with the reference plan too, for
+    batches below / above the scratch ring and in place; the staged kernels bit-for-bit with the default schedule."""
     import torch
     from libtsd_b200 import fourier as Fo
     rng = np.random.default_rng(11)
@@ -232,8 +232,8 @@ def test_fft64k_other_schedules(tsd, cpu_oracle, mode, monkeypatch):
         Xh = X.cpu().numpy()
         for b in sorted({0, batch // 2, batch - 1}):
             assert rel_err(Xh[b], ref.step(x[b], True), rms(x)) <= TOL
-        if mode == "tma":
-            assert np.array_equal(Xh, base)        # same tile arithmetic and tables as the staged kernels: bit-identical
+        if mode == "staged":
+            assert np.array_equal(Xh, base)        # same tile arithmetic and tables as the TMA-fed pipeline: bit-identical
         else:
             assert rel_err(Xh, base, rms(x)) <= TOL
         back = plan.step(X, False, out=X)          # in place
