@@ -32,7 +32,9 @@
 // interleaved row pieces, not by the tensor cores; the FP32 FMA formulation (fir.cu) is capped at 146 Gsamples/s.
 #include "tc_common.cuh"
 #include "fir_tc.h"
+#include "tma_host.h"
 
+#include <algorithm>
 #include <cstdlib>
 
 namespace tsdgpu {
@@ -401,6 +403,387 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc_kernel(FirTcParams p)
   }
 }
 
+
+// =====================================================================================================================
+// Round-2 form of the same GEMM (default): PERSISTENT CTAs, the TMA unit on both sides of the SM.
+//   * grid = one CTA per SM; the (channel group, tile) space is cut into gridDim.x contiguous shares, a share that
+//     crosses a channel-group boundary is walked as two items.  Barriers, tensor memory and the generator matrix are set
+//     up once per CTA and launch; ring slots, A stages and accumulator regions are indexed by counters that run across
+//     items, so the pipeline never drains between them.
+//   * loads (TMAL): a chunk [64 channels][32 samples] = two 2-D tensor-map boxes {32 floats, 64 rows} with the 128-byte
+//     swizzle (cp.async.bulk.tensor.2d, SASS UTMALDG), issued by ONE lane, completion by expect_tx on the slot's
+//     mbarrier.  History chunks (positions < 0) come through a second map over the device history; the end of the call,
+//     a short history and a ragged channel group are the tensor map's out-of-bounds zero fill: no special-case path.
+//     The converters read 16-byte pieces at (piece ^ (row & 7)): conflict-free.
+//   * stores: the epilogue warps write their (re, im) pairs into a warp-private staging [8 channel rows][128 outputs]
+//     and hand it to the TMA unit (cp.async.bulk.tensor.2d.global.shared, SASS UTMASTG): 1 KiB contiguous per channel
+//     row instead of 64-byte pieces per store instruction, no STG issue in the epilogue warps; the four tcgen05.ld of a
+//     channel half are issued back to back and waited for once.  Rows / columns beyond nchan / n are clipped by the map.
+constexpr int RAW2_BYTES = 16384;                 // TMAL: two swizzled boxes [64 rows][128 B]
+constexpr int OUT2_BYTES = 8192;                  // per epilogue warp: [8 channel rows][128 outputs] cf32
+constexpr int LOAD_WARP2 = MMA_WARP + 1;
+template<bool TMAL> struct Cfg2
+{
+  static constexpr int NRAW = 6;
+  static constexpr int NLD = TMAL ? 1 : NLOAD;    // loader warps
+  static constexpr int SLOT = TMAL ? RAW2_BYTES : RAW_BYTES;
+  static constexpr int NTHREADS = 32 * (LOAD_WARP2 + NLD);
+  static constexpr int SMEM = 2 * G_BYTES + NRAW * SLOT + 4 * OUT2_BYTES + 1024 /* alignment slack */ + 512 /* barriers */;
+};
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap *map, int c0, int c1, uint64_t *bar)
+{
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst_smem),
+               "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, int c0, int c1, uint32_t src_smem)
+{
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(c0), "r"(c1), "r"(src_smem)
+               : "memory");
+}
+
+template<bool TMAL>
+__global__ void __launch_bounds__(Cfg2<TMAL>::NTHREADS, 1)
+fir_tc2_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap hmap, const __grid_constant__ CUtensorMap ymap, FirTcParams p)
+{
+  using C = Cfg2<TMAL>;
+  constexpr int NR = C::NRAW;
+  extern __shared__ unsigned char raw[];
+  const uint32_t base = (smem_u32(raw) + 1023u) & ~1023u;
+  unsigned char *sm = raw + (base - smem_u32(raw));
+  float *Ghi = reinterpret_cast<float *>(sm), *Glo = reinterpret_cast<float *>(sm + G_BYTES);
+  unsigned char *stages = sm + 2 * G_BYTES;
+  unsigned char *outs = stages + NR * C::SLOT;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(outs + 4 * OUT2_BYTES);
+  uint64_t *full = bars, *empty = bars + NSTAGE, *tfull = bars + 2 * NSTAGE, *tempty = bars + 2 * NSTAGE + 3;
+  uint64_t *rfull = bars + 2 * NSTAGE + 6, *rempty = rfull + NR;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(rempty + NR);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // this CTA's contiguous share of the (channel group, tile) units
+  const int groups = (p.nchan + CH - 1) / CH;
+  const long long units = (long long) groups * p.ntiles;
+  const long long u0 = units * blockIdx.x / gridDim.x, u1 = units * (blockIdx.x + 1) / gridDim.x;
+#define FIR2_ITEMS_BEGIN                                                                                   \
+  for(long long u = u0; u < u1;)                                                                           \
+  {                                                                                                        \
+    const int g = (int) (u / p.ntiles), ts = (int) (u - (long long) g * p.ntiles);                         \
+    const int ntl = (int) min((long long) (p.ntiles - ts), u1 - u), nchunks = 4 * ntl + 4, c0 = g * CH;    \
+    (void) c0; (void) nchunks;
+#define FIR2_ITEMS_END(cnt_chunks, cnt_tiles)                                                              \
+    u += ntl;                                                                                              \
+    cnt_chunks += (unsigned) nchunks;                                                                      \
+    cnt_tiles += (unsigned) ntl;                                                                           \
+  }
+
+  if(tid == 0)
+  {
+    for(int i = 0; i < NSTAGE; i++) { mbar_init(full + i, 4); mbar_init(empty + i, 1); }
+    for(int i = 0; i < 3; i++) { mbar_init(tfull + i, 1); mbar_init(tempty + i, 4); }
+    for(int i = 0; i < NR; i++) { mbar_init(rfull + i, TMAL ? 1 : 32 * C::NLD); mbar_init(rempty + i, 4); }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  constexpr int NPRO = 32 * LOAD_WARP2;   // everyone but the loaders builds the generator matrix
+  if(warp < LOAD_WARP2)
+  {
+    if(warp == MMA_WARP)
+    {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for(int idx = tid; idx < GROWS * 32; idx += NPRO)
+    {
+      const int row = idx >> 5, kk = idx & 31, tap = (row - 96) - kk;
+      const float v = (tap >= 0 && tap < p.K) ? __ldg(p.taps_rev + (p.K - 1 - tap)) : 0.f;
+      const float hi = to_tf32(v), lo = to_tf32(v - hi);
+      const uint32_t off = swz((uint32_t) (row * 128 + kk * 4));
+      *reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(Ghi) + off) = hi;
+      *reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(Glo) + off) = lo;
+    }
+    fence_proxy_async();
+    fence_before();
+    named_bar(1, NPRO);
+    fence_after();
+  }
+  const uint32_t tmem = warp < LOAD_WARP2 ? *tmem_slot : 0u;
+
+  if(warp >= LOAD_WARP2)
+  {
+    if(TMAL)
+    {
+      // ===== loader (one lane): two chunks of a channel row back to back = four boxes, 512 contiguous bytes per row
+      if(lane == 0)
+      {
+        unsigned gi = 0, gt = 0;
+        FIR2_ITEMS_BEGIN
+        for(int it = 0; it < nchunks; it += LGRP)
+        {
+#pragma unroll
+          for(int k = 0; k < LGRP; k++) mbar_wait(rempty + (gi + it + k) % NR, (unsigned) ((((gi + it + k) / NR) & 1) ^ 1));
+#pragma unroll
+          for(int k = 0; k < LGRP; k++)
+          {
+            const unsigned slot = (gi + it + k) % NR;
+            const int pos = (4 * ts - 4 + it + k) * CHUNK;
+            const uint32_t dst = smem_u32(stages + slot * RAW2_BYTES);
+            mbar_expect_tx(rfull + slot, RAW2_BYTES);
+            if(pos >= 0)
+            {
+              tma_load_2d(dst, &xmap, 2 * pos, c0, rfull + slot);
+              tma_load_2d(dst + 8192, &xmap, 2 * pos + 32, c0, rfull + slot);
+            }
+            else
+            {
+              tma_load_2d(dst, &hmap, 2 * (p.halo + pos), c0, rfull + slot);
+              tma_load_2d(dst + 8192, &hmap, 2 * (p.halo + pos) + 32, c0, rfull + slot);
+            }
+          }
+        }
+        FIR2_ITEMS_END(gi, gt)
+      }
+    }
+    else
+    {
+      // ===== loaders, LDGSTS form (see fir_tc_kernel): 16-byte copies into the pitch-272 staging, zero-filling at the edges
+      const int j_lo = (warp - LOAD_WARP2) * (32 / C::NLD), j_hi = j_lo + 32 / C::NLD;
+      const int sp = lane & 15, clb = lane >> 4;
+      unsigned gi = 0, gt = 0;
+      FIR2_ITEMS_BEGIN
+      for(int it = 0; it < nchunks;)
+      {
+        const long long pos0 = (long long) (4 * ts - 4 + it) * CHUNK;
+        const bool group = it + LGRP <= nchunks && pos0 >= 0 && pos0 + LGRP * CHUNK <= p.n && c0 + CH <= p.nchan;
+        mbar_wait(rempty + (gi + it) % NR, (unsigned) ((((gi + it) / NR) & 1) ^ 1));
+        if(!group)
+        {
+          const unsigned slot = (gi + it) % NR;
+          const uint32_t dst0 = smem_u32(stages + slot * RAW_BYTES + clb * RAW_PITCH + sp * 16);
+          const long long pos = pos0 + 2 * sp;
+          for(int j = j_lo; j < j_hi; j++)
+          {
+            const int chan = c0 + clb + 2 * j;
+            const float2 *src = p.x;
+            unsigned bytes = 0;
+            if(chan < p.nchan)
+            {
+              if(pos >= 0)
+              {
+                if(pos < p.n) { src = p.x + (long long) chan * p.x_stride + pos; bytes = pos + 1 < p.n ? 16u : 8u; }
+              }
+              else if(pos >= -(long long) p.halo) { src = p.hist + (long long) chan * p.halo + p.halo + pos; bytes = 16u; }
+            }
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + j * 2 * RAW_PITCH), "l"(src), "r"(bytes) : "memory");
+          }
+          asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(rfull + slot)) : "memory");
+          it += 1;
+          continue;
+        }
+#pragma unroll
+        for(int k = 1; k < LGRP; k++) mbar_wait(rempty + (gi + it + k) % NR, (unsigned) ((((gi + it + k) / NR) & 1) ^ 1));
+        uint32_t dst[LGRP];
+#pragma unroll
+        for(int k = 0; k < LGRP; k++) dst[k] = smem_u32(stages + ((gi + it + k) % NR) * RAW_BYTES + clb * RAW_PITCH + sp * 16);
+        const float2 *src = p.x + (long long) (c0 + clb) * p.x_stride + pos0 + 2 * sp;
+#pragma unroll 4
+        for(int j = j_lo; j < j_hi; j++)
+        {
+          const float2 *sj = src + (long long) j * 2 * p.x_stride;
+#pragma unroll
+          for(int k = 0; k < LGRP; k++)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst[k] + j * 2 * RAW_PITCH), "l"(sj + k * CHUNK) : "memory");
+        }
+#pragma unroll
+        for(int k = 0; k < LGRP; k++)
+          asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(rfull + (gi + it + k) % NR)) : "memory");
+        it += LGRP;
+      }
+      FIR2_ITEMS_END(gi, gt)
+    }
+  }
+  else if(warp >= 4 && warp < 4 + 4 * NGROUP)
+  {
+    // ===== converters (see fir_tc_kernel); group = parity of the running chunk number
+    const int pw = (warp - 4) & 3, grp = (warp - 4) >> 2;
+    const int my_cl = 8 * (2 * pw + (lane >> 4)) + (lane & 7), my_ri = (lane >> 3) & 1;
+    const uint32_t my_a = tmem + ((uint32_t) (pw * 32) << 16) + (uint32_t) (ACOL + 64 * grp);
+    const uint32_t sx = (uint32_t) (my_cl & 7);
+    unsigned gi = 0, gt = 0;
+    FIR2_ITEMS_BEGIN
+    for(int it = (int) ((grp - gi) & 1u); it < nchunks; it += NGROUP)
+    {
+      const unsigned gc = gi + it, slot = gc % NR;
+      mbar_wait(rfull + slot, (gc / NR) & 1);
+      mbar_wait(empty + grp, ((gc / NSTAGE) & 1) ^ 1);
+      fence_after();
+      const unsigned char *row = TMAL ? stages + slot * RAW2_BYTES + my_cl * 128 : stages + slot * RAW_BYTES + my_cl * RAW_PITCH;
+#pragma unroll
+      for(int hq = 0; hq < 2; hq++)
+      {
+        float hi[16], lo[16];
+#pragma unroll
+        for(int m = 0; m < 8; m++)
+        {
+          const float4 x = TMAL ? *reinterpret_cast<const float4 *>(row + hq * 8192 + (((uint32_t) m ^ sx) << 4))
+                                : *reinterpret_cast<const float4 *>(row + (hq * 8 + m) * 16);
+          const float a0 = my_ri ? x.y : x.x, a1 = my_ri ? x.w : x.z;
+          hi[2 * m] = to_tf32(a0);
+          hi[2 * m + 1] = to_tf32(a1);
+          lo[2 * m] = to_tf32(a0 - hi[2 * m]);
+          lo[2 * m + 1] = to_tf32(a1 - hi[2 * m + 1]);
+        }
+        tmem_st16(my_a + hq * 16, hi);
+        tmem_st16(my_a + 32 + hq * 16, lo);
+      }
+      __syncwarp();
+      if(lane == 0) mbar_arrive(rempty + slot);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      fence_before();
+      __syncwarp();
+      if(lane == 0) mbar_arrive(full + grp);
+    }
+    FIR2_ITEMS_END(gi, gt)
+  }
+  else if(warp == MMA_WARP)
+  {
+    // ===== MMA issuer (see fir_tc_kernel)
+    const uint32_t ghi = base, glo = base + G_BYTES;
+    const uint64_t dbase = smem_desc(0);
+    unsigned gi = 0, gt = 0;
+    FIR2_ITEMS_BEGIN
+    for(int it = 0; it < nchunks; it++)
+    {
+      const unsigned gc = gi + it, stage = gc % NSTAGE;
+      mbar_wait(full + stage, (gc / NSTAGE) & 1);
+      const int q4 = it >> 2, r4 = it & 3;
+      const int tl0 = q4 - 1, tl1 = q4;
+      const bool on0 = tl0 >= 0, on1 = tl1 < ntl;
+      const unsigned T0 = gt + (unsigned) tl0, T1 = gt + (unsigned) tl1;   // running tile numbers (T0 only used when on0)
+      if(on1 && r4 == 0) mbar_wait(tempty + T1 % 3, (T1 / 3) & 1);
+      fence_after();
+      const uint32_t xh0 = tmem + (uint32_t) (ACOL + 64 * stage), xl0 = xh0 + 32;
+      int j0a, na, j0b, nb;
+      band_cols(-r4, p.K, j0a, na);
+      band_cols(4 - r4, p.K, j0b, nb);
+      const uint32_t rowa = (uint32_t) ((96 - 32 * r4 + j0a) * 128), rowb = (uint32_t) ((224 - 32 * r4 + j0b) * 128);
+      const uint64_t gha = dbase + ((ghi + rowa) >> 4), gla = dbase + ((glo + rowa) >> 4);
+      const uint64_t ghb = dbase + ((ghi + rowb) >> 4), glb = dbase + ((glo + rowb) >> 4);
+      const uint32_t da = tmem + (uint32_t) ((on0 ? T0 % 3 : 0u) * NCOL + j0a), db = tmem + (uint32_t) (T1 % 3 * NCOL + j0b);
+      const uint32_t ida = IDESC | ((uint32_t) (na >> 3) << 17), idb = IDESC | ((uint32_t) (nb >> 3) << 17);
+      if(elect_one())
+      {
+        if(on0 && na > 0)
+        {
+#pragma unroll
+          for(int ks = 0; ks < 4; ks++)
+          {
+            mma_tf32(da, xh0 + 8 * ks, gla + 2 * ks, ida);
+            mma_tf32(da, xl0 + 8 * ks, gha + 2 * ks, ida);
+            mma_tf32(da, xh0 + 8 * ks, gha + 2 * ks, ida);
+          }
+        }
+        if(on0 && r4 == 3) mma_commit(tfull + T0 % 3);
+        if(on1 && nb > 0)
+        {
+#pragma unroll
+          for(int ks = 0; ks < 4; ks++)
+          {
+            mma_tf32(db, xh0 + 8 * ks, glb + 2 * ks, idb);
+            mma_tf32(db, xl0 + 8 * ks, ghb + 2 * ks, idb);
+            mma_tf32(db, xh0 + 8 * ks, ghb + 2 * ks, idb);
+          }
+        }
+        mma_commit(empty + stage);
+      }
+      __syncwarp();
+    }
+    FIR2_ITEMS_END(gi, gt)
+  }
+  else
+  {
+    // ===== epilogue: warp w owns TMEM lanes 32 w ... 32 w + 31 = channels 16 w ... 16 w + 15; per channel half (8 channels)
+    // four tcgen05.ld.16x256b.x4 (thread t: (re, im) of outputs 32 cb + 8 i + 2 (t % 4) + {0, 1} of channel t / 4) -> one
+    // wait -> 16 STS.128 into the warp's staging [8 rows][128 outputs] -> one TMA store of the box {256 floats, 8 rows}
+    auto zero_region = [&](unsigned region) {
+#pragma unroll
+      for(int q = 0; q < 4; q++)
+      {
+        const uint32_t taddr = tmem + ((uint32_t) (warp * 32) << 16) + (uint32_t) (region * NCOL + q * 32);
+        asm volatile(
+          "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, "
+          "%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(0u) : "memory");
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    };
+    for(unsigned region = 0; region < 3; region++)
+    {
+      zero_region(region);
+      fence_before();
+      __syncwarp();
+      if(lane == 0) mbar_arrive(tempty + region);
+    }
+    unsigned char *my_out = outs + warp * OUT2_BYTES;
+    const uint32_t my_out_s = smem_u32(my_out);
+    unsigned char *my_piece = my_out + (lane >> 2) * 1024 + (lane & 3) * 16;
+    unsigned gi = 0, gt = 0;
+    FIR2_ITEMS_BEGIN
+    for(int tl = 0; tl < ntl; tl++)
+    {
+      const unsigned T = gt + (unsigned) tl, region = T % 3;
+      mbar_wait(tfull + region, (T / 3) & 1);
+      fence_after();
+#pragma unroll
+      for(int half = 0; half < 2; half++)
+      {
+        uint32_t r[4][16];
+#pragma unroll
+        for(int cb = 0; cb < 4; cb++)
+        {
+          const uint32_t taddr = tmem + ((uint32_t) (warp * 32 + half * 16) << 16) + (uint32_t) (region * NCOL + cb * 32);
+          asm volatile(
+            "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(r[cb][0]), "=r"(r[cb][1]), "=r"(r[cb][2]), "=r"(r[cb][3]), "=r"(r[cb][4]), "=r"(r[cb][5]), "=r"(r[cb][6]), "=r"(r[cb][7]),
+              "=r"(r[cb][8]), "=r"(r[cb][9]), "=r"(r[cb][10]), "=r"(r[cb][11]), "=r"(r[cb][12]), "=r"(r[cb][13]), "=r"(r[cb][14]), "=r"(r[cb][15])
+            : "r"(taddr)
+            : "memory");
+        }
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if(lane == 0) bulk_wait_read0();      // the previous store of this warp has read the staging
+        __syncwarp();
+#pragma unroll
+        for(int cb = 0; cb < 4; cb++)
+#pragma unroll
+          for(int i = 0; i < 4; i++)
+            *reinterpret_cast<uint4 *>(my_piece + (cb * 32 + 8 * i) * 8) = make_uint4(r[cb][4 * i], r[cb][4 * i + 2], r[cb][4 * i + 1], r[cb][4 * i + 3]);
+        fence_proxy_async();
+        __syncwarp();
+        if(lane == 0)
+        {
+          tma_store_2d(&ymap, 2 * TILE * (ts + tl), c0 + 16 * warp + 8 * half, my_out_s);
+          bulk_commit();
+        }
+      }
+      zero_region(region);
+      fence_before();
+      __syncwarp();
+      if(lane == 0) mbar_arrive(tempty + region);
+    }
+    FIR2_ITEMS_END(gi, gt)
+    if(lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+  // ---- teardown
+  fence_before();
+  __syncthreads();
+  if(warp == MMA_WARP)
+  {
+    fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS) : "memory");
+  }
+#undef FIR2_ITEMS_BEGIN
+#undef FIR2_ITEMS_END
+}
+
 } // namespace tc
 
 bool fir_tc_eligible(int kind_cf32_f32, int K, const void *x, long long x_stride, const void *y, long long y_stride, const void *hist, int halo)
@@ -423,9 +806,17 @@ extern "C" int tsdgpu_debug_tcprof_dump(const char *path)
 }
 #endif
 
-int fir_tc_launch(const FirTcParams &p0)
+// TSDGPU_FIR_TC_VARIANT: 1 = round-1 kernel (one CTA per span, LDGSTS loads, STG stores), 2 = persistent + TMA stores with
+// the LDGSTS loader, 3 / unset = persistent + TMA loads + TMA stores (default).  Read at every call (tests switch it).
+static int fir_tc_variant()
 {
-  FirTcParams p = p0;
+  const char *e = getenv("TSDGPU_FIR_TC_VARIANT");
+  const int x = e ? atoi(e) : 3;
+  return (x >= 1 && x <= 3) ? x : 3;
+}
+
+static int fir_tc_launch_v1(FirTcParams p)
+{
   Runtime &r = rt();
   static bool attr_set = false;
   if(!attr_set)
@@ -433,7 +824,6 @@ int fir_tc_launch(const FirTcParams &p0)
     TSD_CUDA(cudaFuncSetAttribute(tc::fir_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
     attr_set = true;
   }
-  p.ntiles = (p.n + tc::TILE - 1) / tc::TILE;
   const int groups = (p.nchan + tc::CH - 1) / tc::CH;
   // tiles per CTA: long spans amortise the 4 halo chunks and the set-up, short spans balance the 148 SMs
   // every CTA pays one extra tile's worth of halo chunks; pick the span in [4, 32] that minimises waves x (span + 1)
@@ -449,6 +839,36 @@ int fir_tc_launch(const FirTcParams &p0)
   p.span = span;
   dim3 grid((p.ntiles + span - 1) / span, groups);
   tc::fir_tc_kernel<<<grid, tc::NTHREADS, tc::SMEM_BYTES, r.stream>>>(p);
+  TSD_LAUNCH_CHECK();
+  return 0;
+}
+
+int fir_tc_launch(const FirTcParams &p0)
+{
+  FirTcParams p = p0;
+  Runtime &r = rt();
+  p.ntiles = (p.n + tc::TILE - 1) / tc::TILE;
+  p.span = 0;
+  const int variant = fir_tc_variant();
+  // tensor maps over float32 views of the rows: x [nchan][2 n], history [nchan][2 halo], y [nchan][2 n]
+  CUtensorMap xmap, hmap, ymap;
+  const bool maps = variant >= 2 && (unsigned long long) p.x_stride * 8 < (1ull << 40) && (unsigned long long) p.y_stride * 8 < (1ull << 40) &&
+                    tma_map_rows(&ymap, p.y, 2ull * p.n, p.nchan, (unsigned long long) p.y_stride * 8, 256, 8, false) &&
+                    tma_map_rows(&xmap, p.x, 2ull * p.n, p.nchan, (unsigned long long) p.x_stride * 8, 32, tc::CH, true) &&
+                    tma_map_rows(&hmap, p.hist, 2ull * p.halo, p.nchan, (unsigned long long) p.halo * 8, 32, tc::CH, true);
+  if(!maps) return fir_tc_launch_v1(p);
+  static bool attr_set = false;
+  if(!attr_set)
+  {
+    TSD_CUDA(cudaFuncSetAttribute(tc::fir_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg2<true>::SMEM));
+    TSD_CUDA(cudaFuncSetAttribute(tc::fir_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg2<false>::SMEM));
+    attr_set = true;
+  }
+  const long long units = (long long) ((p.nchan + tc::CH - 1) / tc::CH) * p.ntiles;
+  // one CTA per SM; small calls: at least 4 tiles per CTA (every item pays one tile's worth of halo chunks)
+  const int grid = (int) std::max<long long>(1, std::min<long long>(r.num_sms, (units + 3) / 4));
+  if(variant == 2) tc::fir_tc2_kernel<false><<<grid, tc::Cfg2<false>::NTHREADS, tc::Cfg2<false>::SMEM, r.stream>>>(xmap, hmap, ymap, p);
+  else tc::fir_tc2_kernel<true><<<grid, tc::Cfg2<true>::NTHREADS, tc::Cfg2<true>::SMEM, r.stream>>>(xmap, hmap, ymap, p);
   TSD_LAUNCH_CHECK();
   return 0;
 }

@@ -127,14 +127,19 @@ def test_fir_config3_shape_subset(tsd, cpu_oracle):
     assert rel_err(y, yref, rms(x)) <= TOL
 
 
-@pytest.mark.parametrize("K,nchan,n", [(127, 70, 4100), (127, 3, 1000), (100, 64, 65536), (31, 2, 500), (1, 1, 300), (97, 65, 129), (127, 130, 20001)])
-def test_fir_tensor_core_path(tsd, cpu_oracle, monkeypatch, K, nchan, n):
-    """cf32 data, <= 127 real taps: the tcgen05 3xTF32 Toeplitz-GEMM kernel (fir_tc.cu) against the oracle, streamed in
-    ragged blocks (state carried), ragged channel groups and tiles; and against the FP32 FMA kernel on the same input."""
+@pytest.mark.parametrize("variant", ["3", "2", "1"])
+@pytest.mark.parametrize("K,nchan,n", [(127, 70, 4100), (127, 3, 1000), (100, 64, 65536), (31, 2, 500), (1, 1, 300), (97, 65, 129), (127, 130, 20001),
+                                       (127, 200, 70000)])
+def test_fir_tensor_core_path(tsd, cpu_oracle, monkeypatch, K, nchan, n, variant):
+    """cf32 data, <= 127 real taps: the tcgen05 3xTF32 Toeplitz-GEMM kernels (fir_tc.cu) against the oracle, streamed in
+    ragged blocks (state carried), ragged channel groups and tiles; and against the FP32 FMA kernel on the same input.
+    Variants: 3 = persistent CTAs with tensor-map loads and stores (default), 2 = persistent, LDGSTS loads + tensor-map
+    stores, 1 = the round-1 kernel (one CTA per span)."""
     from libtsd_b200 import filtrage as F
     rng = np.random.default_rng(K * 1000 + nchan)
     h = (rng.standard_normal(K) / np.sqrt(K)).astype(np.float32)
     monkeypatch.setenv("TSDGPU_FIR_TC", "1")
+    monkeypatch.setenv("TSDGPU_FIR_TC_VARIANT", variant)
     f_tc = F.filtre_rif(h, np.complex64, nchan)
     refs = [cpu_oracle.fir(1, h) for _ in range(min(nchan, 3))]
     outs_tc, xs = [], []
