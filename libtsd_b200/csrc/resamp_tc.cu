@@ -18,11 +18,13 @@
 // fp32 accuracy: x = x_hi + x_lo, T = T_hi + T_lo (tf32 parts), three MMAs per K-step, fp32 accumulation.
 #include "tc_common.cuh"
 #include "resamp_tc.h"
+#include "tma_host.h"
 
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 namespace tsdgpu {
 namespace rtc {
@@ -35,10 +37,18 @@ constexpr int NT = 2;                            // coefficient-block ring (pair
 constexpr int NT_MAX = 4;
 constexpr int RAW_PITCH = 272, RAW_BYTES = CH * RAW_PITCH;
 constexpr int TB_PART = TILE * 128, TB_BYTES = 2 * TB_PART;     // 128 rows x 32 tf32, hi + lo
-constexpr int MAXSPAN = 16;                      // tiles per CTA: its slice of the schedule (16 KiB) sits in shared memory
-constexpr int LUT_SMEM_MAX = 66 * 1024;          // the LUT too when it fits (64 taps x 257 phases = 64.25 KiB)
-constexpr int NB_MAX = 512;                       // (chunk, tile) blocks per CTA: their bands are tabulated in the prologue
-constexpr int SMEM_BYTES = NT * TB_BYTES + NRAW * RAW_BYTES + MAXSPAN * TILE * 8 + LUT_SMEM_MAX + 1024 + 512 + 2 * MAXSPAN * 4 + 64 + NB_MAX * 8 + NB_MAX * 2;
+constexpr int MAXSPAN = 12;                      // tiles per CTA: its slice of the schedule (12 KiB) sits in shared memory
+constexpr int LUT_SMEM_MAX = 64 * 1024 + 512;    // the LUT too when it fits (64 taps x 257 phases = 64.25 KiB)
+constexpr int NB_MAX = 384;                       // (chunk, tile) blocks per CTA: their bands are tabulated in the prologue
+// TMA form (round 2): raw slots are two swizzled tensor-map boxes [64 rows][128 B]; the epilogue warps own 4 KiB each of
+// store staging (two buffers of [8 channel rows][32 outputs]) that they hand to the TMA unit
+constexpr int RAW2_BYTES = 16384, OUT2_BYTES = 4096;
+constexpr int smem_bytes(bool tma)
+{
+  return NT * TB_BYTES + NRAW * (tma ? RAW2_BYTES : RAW_BYTES) + (tma ? 4 * OUT2_BYTES : 0) + MAXSPAN * TILE * 8 + LUT_SMEM_MAX + 1024 + 512 +
+         2 * MAXSPAN * 4 + 64 + NB_MAX * 8 + NB_MAX * 2;
+}
+static_assert(smem_bytes(true) <= 232448 - 1024, "shared memory of the TMA form");
 constexpr int ACOL = 3 * NCOL;
 constexpr int CONV_WARP0 = 4, GEN_WARP0 = 8, NGEN = 16, MMA_WARP = GEN_WARP0 + NGEN, LOAD_WARP = MMA_WARP + 1;
 constexpr int NTHREADS = 32 * (LOAD_WARP + 1);
@@ -119,8 +129,26 @@ template<bool PAIR> __device__ __forceinline__ void wait_in_mma(uint64_t *bar, u
   else mbar_wait(bar, parity);
 }   // arithmetic shift: floor for negatives too
 
-template<bool LUTS, bool PAIR> __global__ void __launch_bounds__(NTHREADS, 1) resamp_tc_kernel(ResampTcParams p)
+__device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap *map, int c0, int c1, uint64_t *bar)
 {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst_smem),
+               "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, int c0, int c1, uint32_t src_smem)
+{
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(c0), "r"(c1), "r"(src_smem)
+               : "memory");
+}
+
+// TMA = true (default when the output rows are 16-byte aligned): interior input chunks arrive as two 2-D tensor-map boxes
+// {32 floats, 64 rows} with the 128-byte swizzle (UTMALDG; the end of the call and ragged channel groups are the map's zero
+// fill; only the history chunks, whose rows have odd length, keep the LDGSTS path), and the epilogue warps store through
+// the TMA unit (UTMASTG): 256 contiguous bytes per channel row and store instead of 64-byte pieces, no STG issue.
+template<bool LUTS, bool PAIR, bool TMA> __global__ void __launch_bounds__(NTHREADS, 1)
+resamp_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap ymap, ResampTcParams p)
+{
+  constexpr int RAWB = TMA ? RAW2_BYTES : RAW_BYTES;
   const uint32_t rank = PAIR ? cluster_rank() : 0u;
 #ifdef TSD_TC_PROF
   const long long t_entry = clock64();
@@ -134,7 +162,8 @@ template<bool LUTS, bool PAIR> __global__ void __launch_bounds__(NTHREADS, 1) re
   unsigned char *sm = raw + (base - smem_u32(raw));
   unsigned char *tring = sm;                                  // [NT][hi 16 KiB | lo 16 KiB]
   unsigned char *stages = sm + NT * TB_BYTES;                 // [NRAW][64 rows x 272 B]
-  int2 *sched_s = reinterpret_cast<int2 *>(stages + NRAW * RAW_BYTES);           // [T][128] schedule of this CTA's tiles
+  unsigned char *outs = stages + NRAW * RAWB;                 // TMA: [4 epilogue warps][2 buffers][8 rows x 256 B]
+  int2 *sched_s = reinterpret_cast<int2 *>(outs + (TMA ? 4 * OUT2_BYTES : 0));   // [T][128] schedule of this CTA's tiles
   float *lut_s = reinterpret_cast<float *>(sched_s + MAXSPAN * TILE);
   uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(lut_s) + LUT_SMEM_MAX);
   uint64_t *full = bars, *empty = full + NSTAGE, *tfull = empty + NSTAGE, *tempty = tfull + 3;
@@ -186,7 +215,28 @@ template<bool LUTS, bool PAIR> __global__ void __launch_bounds__(NTHREADS, 1) re
       const bool interior = pos0 >= 0 && c0 + CH <= p.nchan;
       const bool pair = interior && it + 1 < nchunks && pos0 + 2 * CHUNK <= p.n;
       mbar_wait(rempty + it % NRAW, (unsigned) (((it / NRAW) & 1) ^ 1));
-      if(pair)
+      if(TMA && pos0 >= 0)
+      {
+        // one or two chunks through the TMA unit: lane 0 posts the byte count and issues the boxes, the others just arrive
+        const int nk = it + 1 < nchunks ? 2 : 1;
+        if(nk == 2) mbar_wait(rempty + (it + 1) % NRAW, (unsigned) ((((it + 1) / NRAW) & 1) ^ 1));
+        for(int k = 0; k < nk; k++)
+        {
+          uint64_t *bar = rfull + (it + k) % NRAW;
+          if(lane == 0)
+          {
+            const uint32_t dst = smem_u32(stages + ((it + k) % NRAW) * RAW2_BYTES);
+            const int cx = 2 * ((int) pos0 + k * CHUNK);
+            mbar_expect_tx(bar, RAW2_BYTES);
+            tma_load_2d(dst, &xmap, cx, c0, bar);
+            tma_load_2d(dst + 8192, &xmap, cx + 32, c0, bar);
+          }
+          else mbar_arrive(bar);
+        }
+        it += nk;
+        continue;
+      }
+      if(!TMA && pair)
       {
         mbar_wait(rempty + (it + 1) % NRAW, (unsigned) ((((it + 1) / NRAW) & 1) ^ 1));
         const uint32_t da = smem_u32(stages + (it % NRAW) * RAW_BYTES + clb * RAW_PITCH + sp * 16);
@@ -205,10 +255,13 @@ template<bool LUTS, bool PAIR> __global__ void __launch_bounds__(NTHREADS, 1) re
         continue;
       }
       // history / end of the call / ragged channel group: per-sample zero-filling copies (the history rows have odd length)
-      const uint32_t dst0 = smem_u32(stages + (it % NRAW) * RAW_BYTES + clb * RAW_PITCH + sp * 16);
+      const uint32_t dst0 = TMA ? smem_u32(stages + (it % NRAW) * RAW2_BYTES + (sp >> 3) * 8192)
+                                : smem_u32(stages + (it % NRAW) * RAW_BYTES + clb * RAW_PITCH + sp * 16);
       for(int j = 0; j < 32; j++)
       {
         const int chan = c0 + clb + 2 * j;
+        // TMA layout: row r of the half-chunk box at 128 r, 16-byte piece q at (q ^ (r & 7))
+        const uint32_t dstj = TMA ? dst0 + (uint32_t) (clb + 2 * j) * 128u + ((uint32_t) ((sp & 7) ^ ((clb + 2 * j) & 7)) << 4) : dst0 + j * 2 * RAW_PITCH;
 #pragma unroll
         for(int e = 0; e < 2; e++)
         {
@@ -220,7 +273,7 @@ template<bool LUTS, bool PAIR> __global__ void __launch_bounds__(NTHREADS, 1) re
             if(pos >= 0) { if(pos < p.n) { src = p.x + (long long) chan * p.x_stride + pos; bytes = 8u; } }
             else if(pos >= -(long long) p.hist_len) { src = p.hist + (long long) chan * p.hist_len + p.hist_len + pos; bytes = 8u; }
           }
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst0 + j * 2 * RAW_PITCH + e * 8), "l"(src), "r"(bytes) : "memory");
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dstj + e * 8), "l"(src), "r"(bytes) : "memory");
         }
       }
       asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(rfull + it % NRAW)) : "memory");
@@ -335,7 +388,8 @@ template<bool LUTS, bool PAIR> __global__ void __launch_bounds__(NTHREADS, 1) re
       PROF_BEGIN(t_c)
       fence_after();
       const uint32_t my_a = tmem + ((uint32_t) (pw * 32) << 16) + (uint32_t) (ACOL + 64 * stage);
-      const unsigned char *row = stages + slot * RAW_BYTES + my_cl * RAW_PITCH;
+      const unsigned char *row = TMA ? stages + slot * RAW2_BYTES + my_cl * 128 : stages + slot * RAW_BYTES + my_cl * RAW_PITCH;
+      const uint32_t sx = (uint32_t) (my_cl & 7);
 #pragma unroll
       for(int hq = 0; hq < 2; hq++)
       {
@@ -343,7 +397,8 @@ template<bool LUTS, bool PAIR> __global__ void __launch_bounds__(NTHREADS, 1) re
 #pragma unroll
         for(int m = 0; m < 8; m++)
         {
-          const float4 x = *reinterpret_cast<const float4 *>(row + (hq * 8 + m) * 16);
+          const float4 x = TMA ? *reinterpret_cast<const float4 *>(row + hq * 8192 + (((uint32_t) m ^ sx) << 4))
+                               : *reinterpret_cast<const float4 *>(row + (hq * 8 + m) * 16);
           const float a0 = my_ri ? x.y : x.x, a1 = my_ri ? x.w : x.z;
           hi[2 * m] = to_tf32(a0);
           hi[2 * m + 1] = to_tf32(a1);
@@ -528,12 +583,58 @@ template<bool LUTS, bool PAIR> __global__ void __launch_bounds__(NTHREADS, 1) re
       __syncwarp();
       if(lane == 0) arrive_to_mma<PAIR>(tempty + region);
     }
+    unsigned char *my_out = outs + warp * OUT2_BYTES;
+    unsigned char *my_piece = my_out + (lane >> 2) * 256 + (lane & 3) * 16;
+    unsigned nst = 0;   // stores issued by this warp: buffer = parity
     for(int tl = 0; tl < T; tl++)
     {
       const int region = tl % 3;
       mbar_wait(tfull + region, (unsigned) ((tl / 3) & 1));
       fence_after();
       const long long j0 = (long long) (ts + tl) * TILE + 2 * (lane & 3);
+      if(TMA)
+      {
+        // two tcgen05.ld per wait; per 32 outputs x 8 channels: 4 STS.128 per thread into one of the warp's two staging
+        // buffers, then one tensor-map store of the box {64 floats, 8 rows} (clipped at n_out / nchan by the map)
+#pragma unroll
+        for(int half = 0; half < 2; half++)
+#pragma unroll
+          for(int cp = 0; cp < 2; cp++)
+          {
+            uint32_t r[2][16];
+#pragma unroll
+            for(int q = 0; q < 2; q++)
+            {
+              const uint32_t taddr = tmem + ((uint32_t) (warp * 32 + half * 16) << 16) + (uint32_t) (region * NCOL + (2 * cp + q) * 32);
+              asm volatile(
+                "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                : "=r"(r[q][0]), "=r"(r[q][1]), "=r"(r[q][2]), "=r"(r[q][3]), "=r"(r[q][4]), "=r"(r[q][5]), "=r"(r[q][6]), "=r"(r[q][7]),
+                  "=r"(r[q][8]), "=r"(r[q][9]), "=r"(r[q][10]), "=r"(r[q][11]), "=r"(r[q][12]), "=r"(r[q][13]), "=r"(r[q][14]), "=r"(r[q][15])
+                : "r"(taddr)
+                : "memory");
+            }
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for(int q = 0; q < 2; q++)
+            {
+              const uint32_t boff = (nst & 1u) * 2048u;
+              if(lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store before last has read this buffer
+              __syncwarp();
+#pragma unroll
+              for(int i = 0; i < 4; i++)
+                *reinterpret_cast<uint4 *>(my_piece + boff + 64 * i) = make_uint4(r[q][4 * i], r[q][4 * i + 2], r[q][4 * i + 1], r[q][4 * i + 3]);
+              fence_proxy_async();
+              __syncwarp();
+              if(lane == 0)
+              {
+                tma_store_2d(&ymap, 2 * ((ts + tl) * TILE + (2 * cp + q) * 32), c0 + 16 * warp + 8 * half, smem_u32(my_out + boff));
+                bulk_commit();
+              }
+              nst++;
+            }
+          }
+      }
+      else
 #pragma unroll
       for(int half = 0; half < 2; half++)
       {
@@ -574,6 +675,7 @@ template<bool LUTS, bool PAIR> __global__ void __launch_bounds__(NTHREADS, 1) re
       __syncwarp();
       if(lane == 0) arrive_to_mma<PAIR>(tempty + region);
     }
+    if(TMA && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 done:
 #ifdef TSD_TC_PROF
@@ -664,10 +766,10 @@ int resamp_tc_launch(const ResampTcParams &p0)
   static bool attr_set = false;
   if(!attr_set)
   {
-    TSD_CUDA(cudaFuncSetAttribute(rtc::resamp_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, rtc::SMEM_BYTES));
-    TSD_CUDA(cudaFuncSetAttribute(rtc::resamp_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, rtc::SMEM_BYTES));
-    TSD_CUDA(cudaFuncSetAttribute(rtc::resamp_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rtc::SMEM_BYTES));
-    TSD_CUDA(cudaFuncSetAttribute(rtc::resamp_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rtc::SMEM_BYTES));
+#define RTC_ATTR(L, P, T) TSD_CUDA(cudaFuncSetAttribute(rtc::resamp_tc_kernel<L, P, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, rtc::smem_bytes(T)));
+    RTC_ATTR(true, false, false) RTC_ATTR(false, false, false) RTC_ATTR(true, true, false) RTC_ATTR(false, true, false)
+    RTC_ATTR(true, false, true) RTC_ATTR(false, false, true) RTC_ATTR(true, true, true) RTC_ATTR(false, true, true)
+#undef RTC_ATTR
     attr_set = true;
   }
   p.ntiles = (int) ((p.n_out + rtc::TILE - 1) / rtc::TILE);
@@ -694,25 +796,43 @@ int resamp_tc_launch(const ResampTcParams &p0)
   const bool luts = p.lut_elems * 4 <= rtc::LUT_SMEM_MAX;
   // CTA pairs (cta_group::2, clusters of 2 along the channel groups) whenever the groups pair up
   const bool pair = (groups % 2 == 0) && !(getenv("TSDGPU_RESAMP_TC_PAIR") && atoi(getenv("TSDGPU_RESAMP_TC_PAIR")) == 0);
+  // tensor maps (TSDGPU_RESAMP_TC_TMA=0 keeps the LDGSTS / STG form): x as float32 rows [nchan][2 n]; y from this chunk's
+  // first output on, [nchan][2 n_out]
+  CUtensorMap xmap, ymap;
+  memset(&xmap, 0, sizeof(xmap));
+  memset(&ymap, 0, sizeof(ymap));
+  const bool tma = p.vec_store && !(getenv("TSDGPU_RESAMP_TC_TMA") && atoi(getenv("TSDGPU_RESAMP_TC_TMA")) == 0) &&
+                   (unsigned long long) p.x_stride * 8 < (1ull << 40) && (unsigned long long) p.y_stride * 8 < (1ull << 40) &&
+                   tma_map_rows(&xmap, p.x, 2ull * p.n, p.nchan, (unsigned long long) p.x_stride * 8, 32, rtc::CH, true) &&
+                   tma_map_rows(&ymap, p.y + p.out0, 2ull * p.n_out, p.nchan, (unsigned long long) p.y_stride * 8, 64, 8, false);
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(rtc::NTHREADS);
+  cfg.dynamicSmemBytes = rtc::smem_bytes(tma);
+  cfg.stream = r.stream;
+  cudaLaunchAttribute at[1];
   if(pair)
   {
-    cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid.x * grid.y);
-    cfg.blockDim = dim3(rtc::NTHREADS);
-    cfg.dynamicSmemBytes = rtc::SMEM_BYTES;
-    cfg.stream = r.stream;
-    cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2;
     at[0].val.clusterDim.y = 1;
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    if(luts) TSD_CUDA(cudaLaunchKernelEx(&cfg, rtc::resamp_tc_kernel<true, true>, p));
-    else TSD_CUDA(cudaLaunchKernelEx(&cfg, rtc::resamp_tc_kernel<false, true>, p));
   }
-  else if(luts) rtc::resamp_tc_kernel<true, false><<<grid, rtc::NTHREADS, rtc::SMEM_BYTES, r.stream>>>(p);
-  else rtc::resamp_tc_kernel<false, false><<<grid, rtc::NTHREADS, rtc::SMEM_BYTES, r.stream>>>(p);
+  else cfg.gridDim = grid;
+#define RTC_GO(L, P, T) TSD_CUDA(cudaLaunchKernelEx(&cfg, rtc::resamp_tc_kernel<L, P, T>, xmap, ymap, p))
+  if(tma)
+  {
+    if(pair) { if(luts) RTC_GO(true, true, true); else RTC_GO(false, true, true); }
+    else { if(luts) RTC_GO(true, false, true); else RTC_GO(false, false, true); }
+  }
+  else
+  {
+    if(pair) { if(luts) RTC_GO(true, true, false); else RTC_GO(false, true, false); }
+    else { if(luts) RTC_GO(true, false, false); else RTC_GO(false, false, false); }
+  }
+#undef RTC_GO
   TSD_LAUNCH_CHECK();
   return 0;
 }

@@ -639,7 +639,7 @@ def test_reechan_float(tsd, ref, ratio):
             assert rel_err(y, np.stack(yref), 1.0) <= TOL
 
 
-@pytest.mark.parametrize("tc", ["0", "1"])
+@pytest.mark.parametrize("tc", ["0", "1", "1-ldgsts"])
 @pytest.mark.parametrize("ratio,K,nchan,n", [(147 / 160, 64, 70, 20000), (1.3, 15, 3, 5000), (0.6, 31, 64, 70001), (147 / 160, 64, 130, 4097),
                                              (1.9, 64, 128, 9000), (0.5001, 64, 256, 30000), (1.0, 16, 128, 5000),
                                              (147 / 160, 128, 128, 12000), (147 / 160, 64, 192, 6000)])
@@ -649,7 +649,9 @@ def test_itrp_tensor_core_and_fma_paths(tsd, port, cpu_oracle, monkeypatch, tc, 
     (resamp.cu) on the same ragged input: per-call output counts and final phase bit-exact, samples within tolerance,
     state carried over ragged calls.  Checked channels include both CTAs of a pair and the last (ragged) group."""
     from libtsd_b200 import filtrage as F
-    monkeypatch.setenv("TSDGPU_RESAMP_TC", tc)
+    monkeypatch.setenv("TSDGPU_RESAMP_TC", tc[0])
+    # "1" = tensor-map loads and stores (UTMALDG / UTMASTG, default), "1-ldgsts" = round-1 form (LDGSTS loads, STG stores)
+    monkeypatch.setenv("TSDGPU_RESAMP_TC_TMA", "0" if tc.endswith("ldgsts") else "1")
     rng = np.random.default_rng(int(ratio * 100) + K + nchan)
     lut = cpu_oracle.itrp_sinc_lut(K, 256, 0.4)
     g = F.filtre_itrp(ratio, F.InterpolateurLUT(lut), nchan)
