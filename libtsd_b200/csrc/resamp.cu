@@ -539,7 +539,7 @@ static int resamp_run_device(tsdgpu_resamp_s *f, const float2 *x, long long xs, 
     const char *tc_env = getenv("TSDGPU_RESAMP_TC");
     const bool tc_on = !(tc_env && atoi(tc_env) == 0);
     int max_tile_chunks = 0;
-    if(tc_on && resamp_tc_eligible(f->h_sched[b], (long long) cnt, f->K, x, xs, &max_tile_chunks))
+    if(tc_on && resamp_tc_eligible(f->h_sched[b], (long long) cnt, f->K, f->nphases, x, xs, &max_tile_chunks))
     {
       ResampTcParams t;
       t.max_tile_chunks = max_tile_chunks;

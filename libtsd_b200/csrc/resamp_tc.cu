@@ -37,7 +37,10 @@ constexpr int NT = 2;                            // coefficient-block ring (pair
 constexpr int NT_MAX = 4;
 constexpr int RAW_PITCH = 272, RAW_BYTES = CH * RAW_PITCH;
 constexpr int TB_PART = TILE * 128, TB_BYTES = 2 * TB_PART;     // 128 rows x 32 tf32, hi + lo
-constexpr int MAXSPAN = 12;                      // tiles per CTA: its slice of the schedule (12 KiB) sits in shared memory
+#ifndef RTC_MAXSPAN
+#define RTC_MAXSPAN 24                           // A/B builds: 12 = the span limit before the schedule slice was packed
+#endif
+constexpr int MAXSPAN = RTC_MAXSPAN;                    // tiles per CTA: its slice of the schedule (one packed word per output, 12 KiB) sits in shared memory
 constexpr int LUT_SMEM_MAX = 64 * 1024 + 512;    // the LUT too when it fits (64 taps x 257 phases = 64.25 KiB)
 constexpr int NB_MAX = 384;                       // (chunk, tile) blocks per CTA: their bands are tabulated in the prologue
 // TMA form (round 2): raw slots are two swizzled tensor-map boxes [64 rows][128 B]; the epilogue warps own 4 KiB each of
@@ -45,7 +48,7 @@ constexpr int NB_MAX = 384;                       // (chunk, tile) blocks per CT
 constexpr int RAW2_BYTES = 16384, OUT2_BYTES = 4096;
 constexpr int smem_bytes(bool tma)
 {
-  return NT * TB_BYTES + NRAW * (tma ? RAW2_BYTES : RAW_BYTES) + (tma ? 4 * OUT2_BYTES : 0) + MAXSPAN * TILE * 8 + LUT_SMEM_MAX + 1024 + 512 +
+  return NT * TB_BYTES + NRAW * (tma ? RAW2_BYTES : RAW_BYTES) + (tma ? 4 * OUT2_BYTES : 0) + MAXSPAN * TILE * 4 + LUT_SMEM_MAX + 1024 + 512 +
          2 * MAXSPAN * 4 + 64 + NB_MAX * 8 + NB_MAX * 2;
 }
 static_assert(smem_bytes(true) <= 232448 - 1024, "shared memory of the TMA form");
@@ -64,6 +67,14 @@ __device__ long long g_rtcprof[1024][32][4];
 #include "tc_prof.cuh"
 
 __device__ __forceinline__ int floor_div32(int v) { return v >> 5; }
+// Schedule slice of a CTA in shared memory: one word per output, (in_j - in_0) << 10 | p_j (in_0 = newest input of the
+// CTA's first output; resamp_tc_eligible checks the ranges), all ones for rows past the end.  Unpacked to what the
+// generators need per row: {K-1 - in_j, p_j * K}, second word < 0 for rows past the end.
+constexpr uint32_t SCHED_NONE = 0xFFFFFFFFu;
+__device__ __forceinline__ int2 sched_unpack(uint32_t w, int base /* K-1 - in_0 */, int K)
+{
+  return w == SCHED_NONE ? make_int2(0, -1) : make_int2(base - (int) (w >> 10), (int) (w & 1023u) * K);
+}
 
 // ---- CTA pair (cta_group::2): two CTAs of a cluster = two groups of 64 channels over the same tiles.  The leader
 // (cluster rank 0) issues M = 256 MMAs that read each CTA's own A rows from its tensor memory and half of the
@@ -163,7 +174,7 @@ resamp_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
   unsigned char *tring = sm;                                  // [NT][hi 16 KiB | lo 16 KiB]
   unsigned char *stages = sm + NT * TB_BYTES;                 // [NRAW][64 rows x 272 B]
   unsigned char *outs = stages + NRAW * RAWB;                 // TMA: [4 epilogue warps][2 buffers][8 rows x 256 B]
-  int2 *sched_s = reinterpret_cast<int2 *>(outs + (TMA ? 4 * OUT2_BYTES : 0));   // [T][128] schedule of this CTA's tiles
+  uint32_t *sched_s = reinterpret_cast<uint32_t *>(outs + (TMA ? 4 * OUT2_BYTES : 0));   // [T][128] packed schedule of this CTA's tiles
   float *lut_s = reinterpret_cast<float *>(sched_s + MAXSPAN * TILE);
   uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(lut_s) + LUT_SMEM_MAX);
   uint64_t *full = bars, *empty = full + NSTAGE, *tfull = empty + NSTAGE, *tempty = tfull + 3;
@@ -192,7 +203,7 @@ resamp_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
   }
   __syncthreads();   // barriers initialised (everybody is still at the top of the kernel)
   uint32_t tmem = 0;
-  int c_begin = 0, nchunks = 0;
+  int c_begin = 0, nchunks = 0, in0 = 0, sbase = 0;
 #ifdef TSD_TC_PROF
   long long t_pro = 0;
 #endif
@@ -302,12 +313,13 @@ resamp_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
     cA[lane] = floor_div32(p.sched[jf].x - (K - 1));
     cB[lane] = floor_div32(p.sched[jl].x);
   }
+  in0 = __ldg(&p.sched[(long long) ts * TILE].x);
+  sbase = K - 1 - in0;
   for(int i = tid; i < T * TILE; i += NPRO)
   {
     const long long j = (long long) ts * TILE + i;
-    // per output: {K-1 - in_j, p_j * K} (second word < 0 marks rows past the end): all the generators need per row
-    int2 e = make_int2(0, -1);
-    if(j < p.n_out) { const int2 q = __ldg(p.sched + j); e = make_int2(K - 1 - q.x, q.y * K); }
+    uint32_t e = SCHED_NONE;
+    if(j < p.n_out) { const int2 q = __ldg(p.sched + j); e = ((uint32_t) (q.x - in0) << 10) | (uint32_t) q.y; }
     sched_s[i] = e;
   }
   if(LUTS)
@@ -339,14 +351,14 @@ resamp_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
     // after the chunk" and "valid and not entirely before it" are prefix properties -> two binary searches.
     // Position in the walk (chunks ascending, then tiles): blocks of earlier chunks + the other tile of this chunk.
     const int tl = warp;
-    const int2 *srow = sched_s + tl * TILE;
+    const uint32_t *srow = sched_s + tl * TILE;
     for(int c = cA[tl] + lane; c <= cB[tl]; c += 32)
     {
       int lo = 0, hi = TILE;
-      while(lo < hi) { const int m = (lo + hi) >> 1; const int2 e = srow[m]; if(e.y >= 0 && c * CHUNK + e.x > K - 1) lo = m + 1; else hi = m; }
+      while(lo < hi) { const int m = (lo + hi) >> 1; const int2 e = sched_unpack(srow[m], sbase, K); if(e.y >= 0 && c * CHUNK + e.x > K - 1) lo = m + 1; else hi = m; }
       const int jlo = lo;
       hi = TILE;
-      while(lo < hi) { const int m = (lo + hi) >> 1; const int2 e = srow[m]; if(e.y >= 0 && c * CHUNK + 31 + e.x >= 0) lo = m + 1; else hi = m; }
+      while(lo < hi) { const int m = (lo + hi) >> 1; const int2 e = sched_unpack(srow[m], sbase, K); if(e.y >= 0 && c * CHUNK + 31 + e.x >= 0) lo = m + 1; else hi = m; }
       const int jend = lo;
       // band [j0, j0 + nn): multiple of 16 columns (32 for a pair: each CTA supplies nn / 2 rows of the block)
       constexpr int GRAN = PAIR ? 32 : 16;
@@ -437,7 +449,7 @@ resamp_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
       for(int b0 = 0; b0 < nb; b0 += NBK)
       {
         unsigned char *thi[NBK];
-        const int2 *srow[NBK];
+        const uint32_t *srow[NBK];
         int nh[NBK], jb[NBK];
 #pragma unroll
         for(int k = 0; k < NBK; k++)
@@ -464,7 +476,7 @@ resamp_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
 #pragma unroll
           for(int r = 0; r < GR; r++)
           {
-            const int2 e = srow[k][min(jb[k] + gw + NGEN * r, TILE - 1)];      // broadcast read
+            const int2 e = sched_unpack(srow[k][min(jb[k] + gw + NGEN * r, TILE - 1)], sbase, K);      // broadcast read
             const int tap = tcol + e.x;
             const bool ok = (e.y >= 0) & ((unsigned) tap < (unsigned) K);
             const int idx = ok ? e.y + tap : 0;
@@ -735,9 +747,10 @@ extern "C" int tsdgpu_debug_rtcprof_dump(const char *path)
 }
 #endif
 
-bool resamp_tc_eligible(const int2 *sched_host, long long n_out, int K, const void *x, long long x_stride, int *max_tile_chunks)
+bool resamp_tc_eligible(const int2 *sched_host, long long n_out, int K, int nphases, const void *x, long long x_stride, int *max_tile_chunks)
 {
   if(K < 1 || K > 4096 || n_out < 1) return false;
+  if(nphases + 1 > 1024) return false;   // packed schedule word: 10 bits of LUT row
   if(((uintptr_t) x & 15) != 0 || (x_stride % 2) != 0) return false;
   const long long ntiles = (n_out + rtc::TILE - 1) / rtc::TILE;
   // chunks per tile: the CTA tabulates the bands of its (chunk, tile) blocks, at most NB_MAX of them
@@ -747,6 +760,8 @@ bool resamp_tc_eligible(const int2 *sched_host, long long n_out, int K, const vo
     const int endc = sched_host[std::min<long long>(t * rtc::TILE + rtc::TILE, n_out) - 1].x >> 5;
     const int begc = (sched_host[t * rtc::TILE].x - (K - 1)) >> 5;
     mc = std::max(mc, endc - begc + 1);
+    // packed schedule word: 22 bits of input offset within a CTA's span of <= MAXSPAN tiles
+    if((long long) sched_host[std::min<long long>(t * rtc::TILE + rtc::TILE, n_out) - 1].x - sched_host[t * rtc::TILE].x >= (1 << 21) / rtc::MAXSPAN) return false;
   }
   if(mc > rtc::NB_MAX) return false;
   *max_tile_chunks = mc;

@@ -21,7 +21,7 @@ struct ResampTcParams
   int ntiles, span, vec_store, band, groups;   // filled by resamp_tc_launch
 };
 
-bool resamp_tc_eligible(const int2 *sched_host, long long n_out, int K, const void *x, long long x_stride, int *max_tile_chunks);
+bool resamp_tc_eligible(const int2 *sched_host, long long n_out, int K, int nphases, const void *x, long long x_stride, int *max_tile_chunks);
 int resamp_tc_launch(const ResampTcParams &p);
 
 }
