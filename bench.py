@@ -331,9 +331,9 @@ class GpuWorkload:
 KERNELS = {
     "ola": "ols16k_kernel<1> (single-SM overlap-save, 16384-point transforms, TMEM constants, TMA bulk prefetch)",
     "fft": "fft64k_pipe_kernel (TMA-fed persistent four-step pipeline: 3-D tensor-map column tiles, 6-slot shared-memory ring)",
-    "fir": "fir_tc_kernel (tcgen05 3xTF32 Toeplitz GEMM)",
-    "resample": "resamp_tc_kernel (tcgen05 3xTF32 banded filter-bank GEMM, CTA pairs)",
-    "reechan": "resamp_tc_kernel (tcgen05 3xTF32 banded filter-bank GEMM, CTA pairs)",
+    "fir": "fir_tc2_kernel (tcgen05 3xTF32 Toeplitz GEMM; persistent CTAs, tensor-map loads and stores)",
+    "resample": "resamp_tc_kernel (tcgen05 3xTF32 banded filter-bank GEMM, CTA pairs, tensor-map loads and stores)",
+    "reechan": "resamp_tc_kernel (tcgen05 3xTF32 banded filter-bank GEMM, CTA pairs, tensor-map loads and stores)",
     "rif_fft": "ols16k_kernel<1> (same single-SM overlap-save kernel: the device's transform size is independent of Ne / N)",
 }
 

@@ -175,6 +175,26 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
     "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 #endif
 }
+// Wait of a role that is idle for a long time by design (an epilogue warp waiting a whole tile time for its accumulator,
+// a loader waiting for a free staging slot): try_wait with a suspend-time hint, so that the warp is parked instead of
+// re-issuing SYNCS / BRA every few cycles next to the warps that have work.  TSD_LONGWAIT=0 builds spin like mbar_wait.
+#ifndef TSD_LONGWAIT
+#define TSD_LONGWAIT 1
+#endif
+__device__ __forceinline__ void mbar_wait_long(uint64_t *bar, unsigned parity)
+{
+#if TSD_LONGWAIT
+  asm volatile(
+    "{\n\t.reg .pred p;\n\t"
+    "WAIT_%=:\n\t"
+    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+    "@p bra DONE_%=;\n\t"
+    "bra WAIT_%=;\n\t"
+    "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");
+#else
+  mbar_wait(bar, parity);
+#endif
+}
 // global -> shared, completion counted on the mbarrier (bytes multiple of 16, both 16-B aligned)
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, uint64_t *bar)
 {

@@ -521,7 +521,7 @@ fir_tc2_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
         for(int it = 0; it < nchunks; it += LGRP)
         {
 #pragma unroll
-          for(int k = 0; k < LGRP; k++) mbar_wait(rempty + (gi + it + k) % NR, (unsigned) ((((gi + it + k) / NR) & 1) ^ 1));
+          for(int k = 0; k < LGRP; k++) mbar_wait_long(rempty + (gi + it + k) % NR, (unsigned) ((((gi + it + k) / NR) & 1) ^ 1));
 #pragma unroll
           for(int k = 0; k < LGRP; k++)
           {
@@ -731,7 +731,7 @@ fir_tc2_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
     for(int tl = 0; tl < ntl; tl++)
     {
       const unsigned T = gt + (unsigned) tl, region = T % 3;
-      mbar_wait(tfull + region, (T / 3) & 1);
+      mbar_wait_long(tfull + region, (T / 3) & 1);
       fence_after();
 #pragma unroll
       for(int half = 0; half < 2; half++)

@@ -53,7 +53,11 @@ constexpr int smem_bytes(bool tma)
 }
 static_assert(smem_bytes(true) <= 232448 - 1024, "shared memory of the TMA form");
 constexpr int ACOL = 3 * NCOL;
-constexpr int CONV_WARP0 = 4, GEN_WARP0 = 8, NGEN = 16, MMA_WARP = GEN_WARP0 + NGEN, LOAD_WARP = MMA_WARP + 1;
+#ifndef RTC_NCG
+#define RTC_NCG 1                                 // converter groups of 4 warps; 2 (alternating chunks like fir_tc.cu, 30 warps at 64 registers) measured: no gain
+#endif
+constexpr int NCG = RTC_NCG;
+constexpr int CONV_WARP0 = 4, GEN_WARP0 = CONV_WARP0 + 4 * NCG, NGEN = 16, MMA_WARP = GEN_WARP0 + NGEN, LOAD_WARP = MMA_WARP + 1;
 constexpr int NTHREADS = 32 * (LOAD_WARP + 1);
 constexpr int NPRO = NTHREADS - 32;             // threads of the prologue: the loader (last warp) starts copying at once
 constexpr int GROWS = (TILE + NGEN - 1) / NGEN;   // rows per generator warp and block: j = gw + NGEN * r
@@ -197,7 +201,7 @@ resamp_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
     constexpr int NC = PAIR ? 2 : 1;
     for(int i = 0; i < NSTAGE; i++) { mbar_init(full + i, 4 * NC); mbar_init(empty + i, 1); }
     for(int i = 0; i < 3; i++) { mbar_init(tfull + i, 1); mbar_init(tempty + i, 4 * NC); }
-    for(int i = 0; i < NRAW; i++) { mbar_init(rfull + i, 32); mbar_init(rempty + i, 4); }
+    for(int i = 0; i < NRAW; i++) { mbar_init(rfull + i, 32); mbar_init(rempty + i, 4); }   // a chunk is read by ONE converter group
     for(int i = 0; i < NTR; i++) { mbar_init(bfull + i, NGEN * NC); mbar_init(bempty + i, 1); }
     mbar_fence_init();
   }
@@ -225,7 +229,7 @@ resamp_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
       const long long pos0 = (long long) (c_begin + it) * CHUNK;
       const bool interior = pos0 >= 0 && c0 + CH <= p.nchan;
       const bool pair = interior && it + 1 < nchunks && pos0 + 2 * CHUNK <= p.n;
-      mbar_wait(rempty + it % NRAW, (unsigned) (((it / NRAW) & 1) ^ 1));
+      mbar_wait_long(rempty + it % NRAW, (unsigned) (((it / NRAW) & 1) ^ 1));
       if(TMA && pos0 >= 0)
       {
         // one or two chunks through the TMA unit: lane 0 posts the byte count and issues the boxes, the others just arrive
@@ -382,13 +386,14 @@ resamp_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
   t_pro = clock64();
 #endif
 
-  if(warp >= CONV_WARP0 && warp < CONV_WARP0 + 4)
+  if(warp >= CONV_WARP0 && warp < CONV_WARP0 + 4 * NCG)
   {
-    // ===== converters (one warp per TMEM lane quadrant): raw row (channel, re|im) -> tf32 hi / lo -> tensor memory
-    const int pw = warp - CONV_WARP0;
+    // ===== converters (one warp per TMEM lane quadrant, NCG groups alternating chunks): raw row (channel, re|im) -> tf32
+    // hi / lo -> tensor memory
+    const int pw = (warp - CONV_WARP0) & 3, cgrp = (warp - CONV_WARP0) >> 2;
     const int my_cl = 8 * (2 * pw + (lane >> 4)) + (lane & 7), my_ri = (lane >> 3) & 1;
     PROF_DECL
-    for(int it = 0; it < nchunks; it++)
+    for(int it = cgrp; it < nchunks; it += NCG)
     {
       const int slot = it % NRAW, stage = it & 1;
       PROF_BEGIN(t_w)
@@ -601,7 +606,7 @@ resamp_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
     for(int tl = 0; tl < T; tl++)
     {
       const int region = tl % 3;
-      mbar_wait(tfull + region, (unsigned) ((tl / 3) & 1));
+      mbar_wait_long(tfull + region, (unsigned) ((tl / 3) & 1));
       fence_after();
       const long long j0 = (long long) (ts + tl) * TILE + 2 * (lane & 3);
       if(TMA)

@@ -15,7 +15,7 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_registers",
         "launch__occupancy_limit_shared_mem", "smsp__inst_executed.sum", "sm__cycles_elapsed.max", "sm__cycles_active.avg"]
 STALLS = "smsp__average_warps_issue_stalled_"
-SCALE = {"ola": 0.125, "fft": 0.0625, "fir": 0.0625, "resample": 0.125}
+SCALE = {"ola": 0.125, "fft": 0.0625, "fir": 0.25, "resample": 0.125}
 for w in sys.argv[1:] or ("ola", "fft", "fir", "resample"):
     lc = os.path.join(OUT, f"r02_launches_{w}.csv")
     if os.path.exists(lc):

@@ -6,7 +6,7 @@
 set -x
 mkdir -p gpurun_out
 declare -A KERN=( [ola]=ols16k [fft]=fft64k [fir]=fir_tc [resample]=resamp_tc )
-declare -A SCALE=( [ola]=0.125 [fft]=0.0625 [fir]=0.0625 [resample]=0.125 )
+declare -A SCALE=( [ola]=0.125 [fft]=0.0625 [fir]=0.25 [resample]=0.125 )
 declare -A SKIP=( [ola]=3 [fft]=6 [fir]=3 [resample]=3 )
 for w in ${1:-ola fft fir resample}; do
   CMD="python bench.py --workload $w --scale ${SCALE[$w]} --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-extra"
