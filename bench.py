@@ -591,6 +591,67 @@ def strong_and_gathered(steps, warmup, stream, barrier, world, rank):
         return float(t.item()) / steps
 
     ms_strong = timed(lambda: [compute(gi) for gi in range(G)])
+    samples = float(total_ch) * n
+    recv = (world - 1) / world * total_ch * n_out * 8.0          # bytes every GPU receives per step
+    del y
+    torch.cuda.empty_cache()
+
+    # (a) gather by the COPY ENGINES over peer-mapped (symmetric) memory: every rank's kernel stores its shard straight into
+    # its slot of the local gathered buffer, and a side stream pushes the slot into the same place of every peer's buffer
+    # (cudaMemcpyAsync peer-to-peer: DMA over NVLink, no SM taken from the persistent filter kernel) while the next channel
+    # group is being filtered.  Measured on 2 GPUs (profiles/multi/p2p_gather_test.py): copy engines 771 GB/s per direction;
+    # the filter kernel storing directly into peer memory only 498 GB/s (62 Gsamples/s: remote stores stall the math warps),
+    # NCCL's all-gather kernel next to the persistent kernel 390 GB/s.
+    gath_ce = None
+    try:
+        import torch.distributed._symmetric_memory as symm_mem
+        full = symm_mem.empty((G, world, cg, n_out), dtype=torch.complex64, device=f"cuda:{torch.cuda.current_device()}")
+        hdl = symm_mem.rendezvous(full, dist.group.WORLD)
+        peers = [hdl.get_buffer(r, full.shape, full.dtype) for r in range(world)]
+        side = torch.cuda.Stream()
+        pushed = [torch.cuda.Event() for _ in range(G)]
+        first = [True]
+
+        def gathered_ce():
+            cur = torch.cuda.current_stream()
+            for gi in range(G):
+                if not first[0]:
+                    cur.wait_event(pushed[gi])                 # last step's push of this slot has read it
+                flts[gi].step(x[gi * cg:(gi + 1) * cg], out=full[gi, rank])
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                side.wait_event(ev)
+                with torch.cuda.stream(side):
+                    for d in range(1, world):
+                        r = (rank + d) % world                 # every rank starts with another peer: no hot spot
+                        peers[r][gi, rank].copy_(full[gi, rank], non_blocking=True)
+                    pushed[gi].record(side)
+            first[0] = False
+            cur.wait_stream(side)                              # the step ends when my pushes have landed
+
+        hdl.barrier()
+        ms_ce = timed(gathered_ce)
+        hdl.barrier()
+        # every slot of my buffer must hold the shard its owner computed: compare checksums of slot [0][r] with the owner's
+        cs = torch.stack([torch.view_as_real(full[0, r, 0, :Ne * (n // Ne)]).double().sum() for r in range(world)])
+        allcs = [torch.zeros_like(cs) for _ in range(world)]
+        dist.all_gather(allcs, cs)
+        same = all(bool(torch.equal(allcs[0], c)) for c in allcs)
+        gath_ce = {"value": samples / (ms_ce * 1e-3) / 1e9, "unit": "Gsamples/s", "ms_per_step": ms_ce, "channels_per_gpu": cpr,
+                   "collective": f"none: the kernel stores its shard into the local gathered buffer, copy engines push it to the {world - 1} peer(s) "
+                                 f"over NVLink per group of {cg} channels (symmetric memory), overlapped with the next group's filtering",
+                   "link_gbs_per_gpu_received": recv / (ms_ce * 1e-3) / 1e9, "link_peak_gbs": 770.0,
+                   "link_peak_source": "peer-copy figure of /opt/skills/guides/B200_PROFILING.md",
+                   "link_frac": recv / (ms_ce * 1e-3) / 1e9 / 770.0, "layout": "[group][rank][channel][sample]",
+                   "all_ranks_hold_identical_data": same}
+        del peers, hdl, full
+    except Exception as e:   # symmetric memory unavailable (no peer access): the NCCL figure below stands alone
+        gath_ce = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+    gc.collect()
+    torch.cuda.empty_cache()
+
+    # (b) the same with NCCL's all-gather (its kernel has to share the SMs with the persistent filter kernel)
+    y = torch.empty((G, cg, n_out), dtype=torch.complex64, device="cuda")
     full = torch.empty((G, world, cg, n_out), dtype=torch.complex64, device="cuda")   # gathered layout [group][rank][channel][sample]
 
     def gathered():
@@ -601,19 +662,23 @@ def strong_and_gathered(steps, warmup, stream, barrier, world, rank):
         for w in works:
             w.wait()
     ms_gath = timed(gathered)
-    samples = float(total_ch) * n
-    recv = (world - 1) / world * total_ch * n_out * 8.0          # bytes every GPU receives per step
     del x, y, full, flts
     gc.collect()
     torch.cuda.empty_cache()
+    nccl = {"value": samples / (ms_gath * 1e-3) / 1e9, "unit": "Gsamples/s", "ms_per_step": ms_gath, "channels_per_gpu": cpr,
+            "collective": f"ncclAllGather per group of {cg} channels, overlapped with the next group's filtering",
+            "link_gbs_per_gpu_received": recv / (ms_gath * 1e-3) / 1e9, "link_peak_gbs": 770.0,
+            "link_peak_source": "peer-copy figure of /opt/skills/guides/B200_PROFILING.md",
+            "link_frac": recv / (ms_gath * 1e-3) / 1e9 / 770.0,
+            "layout": "[group][rank][channel][sample]"}
+    if gath_ce and "value" in gath_ce:
+        gath = dict(gath_ce)
+        gath["nccl_all_gather"] = nccl
+    else:
+        gath = dict(nccl)
+        gath["copy_engine_gather"] = gath_ce
     return ({"value": samples / (ms_strong * 1e-3) / 1e9, "unit": "Gsamples/s", "ms_per_step": ms_strong, "channels_per_gpu": cpr,
-             "scaling": "strong", "collective": "none"},
-            {"value": samples / (ms_gath * 1e-3) / 1e9, "unit": "Gsamples/s", "ms_per_step": ms_gath, "channels_per_gpu": cpr,
-             "collective": f"ncclAllGather per group of {cg} channels, overlapped with the next group's filtering",
-             "link_gbs_per_gpu_received": recv / (ms_gath * 1e-3) / 1e9, "link_peak_gbs": 770.0,
-             "link_peak_source": "peer-copy figure of /opt/skills/guides/B200_PROFILING.md",
-             "link_frac": recv / (ms_gath * 1e-3) / 1e9 / 770.0,
-             "layout": "[group][rank][channel][sample]"})
+             "scaling": "strong", "collective": "none"}, gath)
 
 
 def main():
