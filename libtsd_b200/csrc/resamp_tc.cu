@@ -33,8 +33,10 @@ using namespace tc;
 constexpr int TILE = 128, CH = 64, NCOL = 128, CHUNK = 32;
 constexpr int NRAW = 4;                          // raw staging ring
 constexpr int NSTAGE = 2;                        // A-operand stages in tensor memory
-constexpr int NT = 2;                            // coefficient-block ring (pair: 4 slots of half the rows, same 64 KiB)
-constexpr int NT_MAX = 4;
+// coefficient-block ring: 2 blocks of 32 KiB (pair: 4 slots of half the rows) next to a LUT resident in shared memory;
+// 4 blocks (pair: 8 half slots) when the LUT is read through L2 instead (LUTS = false: the ring takes the LUT's place)
+constexpr int nt_of(bool luts) { return luts ? 2 : 4; }
+constexpr int NT_MAX = 8;
 constexpr int RAW_PITCH = 272, RAW_BYTES = CH * RAW_PITCH;
 constexpr int TB_PART = TILE * 128, TB_BYTES = 2 * TB_PART;     // 128 rows x 32 tf32, hi + lo
 #ifndef RTC_MAXSPAN
@@ -46,12 +48,12 @@ constexpr int NB_MAX = 384;                       // (chunk, tile) blocks per CT
 // TMA form (round 2): raw slots are two swizzled tensor-map boxes [64 rows][128 B]; the epilogue warps own 4 KiB each of
 // store staging (two buffers of [8 channel rows][32 outputs]) that they hand to the TMA unit
 constexpr int RAW2_BYTES = 16384, OUT2_BYTES = 4096;
-constexpr int smem_bytes(bool tma)
+constexpr int smem_bytes(bool tma, bool luts)
 {
-  return NT * TB_BYTES + NRAW * (tma ? RAW2_BYTES : RAW_BYTES) + (tma ? 4 * OUT2_BYTES : 0) + MAXSPAN * TILE * 4 + LUT_SMEM_MAX + 1024 + 512 +
+  return nt_of(luts) * TB_BYTES + NRAW * (tma ? RAW2_BYTES : RAW_BYTES) + (tma ? 4 * OUT2_BYTES : 0) + MAXSPAN * TILE * 4 + (luts ? LUT_SMEM_MAX : 0) + 1024 + 512 +
          2 * MAXSPAN * 4 + 64 + NB_MAX * 8 + NB_MAX * 2;
 }
-static_assert(smem_bytes(true) <= 232448 - 1024, "shared memory of the TMA form");
+static_assert(smem_bytes(true, true) <= 232448 - 1024 && smem_bytes(true, false) <= 232448 - 1024 && smem_bytes(false, false) <= 232448 - 1024, "shared memory");
 constexpr int ACOL = 3 * NCOL;
 #ifndef RTC_NCG
 #define RTC_NCG 1                                 // converter groups of 4 warps; 2 (alternating chunks like fir_tc.cu, 30 warps at 64 registers) measured: no gain
@@ -170,6 +172,7 @@ resamp_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
   unsigned long long gt_entry;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_entry));
 #endif
+  constexpr int NT = LUTS ? 2 : 4;   // = nt_of(LUTS)
   constexpr int NTR = PAIR ? 2 * NT : NT;                       // ring slots
   constexpr int TBP = PAIR ? TB_PART / 2 : TB_PART, TBB = 2 * TBP;   // bytes of the hi (= lo) part of a slot, of a slot
   extern __shared__ unsigned char raw[];
@@ -180,7 +183,7 @@ resamp_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
   unsigned char *outs = stages + NRAW * RAWB;                 // TMA: [4 epilogue warps][2 buffers][8 rows x 256 B]
   uint32_t *sched_s = reinterpret_cast<uint32_t *>(outs + (TMA ? 4 * OUT2_BYTES : 0));   // [T][128] packed schedule of this CTA's tiles
   float *lut_s = reinterpret_cast<float *>(sched_s + MAXSPAN * TILE);
-  uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(lut_s) + LUT_SMEM_MAX);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(lut_s) + (LUTS ? LUT_SMEM_MAX : 0));
   uint64_t *full = bars, *empty = full + NSTAGE, *tfull = empty + NSTAGE, *tempty = tfull + 3;
   uint64_t *rfull = tempty + 3, *rempty = rfull + NRAW, *bfull = rempty + NRAW, *bempty = bfull + NT_MAX;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bempty + NT_MAX);
@@ -786,7 +789,7 @@ int resamp_tc_launch(const ResampTcParams &p0)
   static bool attr_set = false;
   if(!attr_set)
   {
-#define RTC_ATTR(L, P, T) TSD_CUDA(cudaFuncSetAttribute(rtc::resamp_tc_kernel<L, P, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, rtc::smem_bytes(T)));
+#define RTC_ATTR(L, P, T) TSD_CUDA(cudaFuncSetAttribute(rtc::resamp_tc_kernel<L, P, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, rtc::smem_bytes(T, L)));
     RTC_ATTR(true, false, false) RTC_ATTR(false, false, false) RTC_ATTR(true, true, false) RTC_ATTR(false, true, false)
     RTC_ATTR(true, false, true) RTC_ATTR(false, false, true) RTC_ATTR(true, true, true) RTC_ATTR(false, true, true)
 #undef RTC_ATTR
@@ -813,7 +816,8 @@ int resamp_tc_launch(const ResampTcParams &p0)
   p.groups = groups;
   p.vec_store = ((((uintptr_t) (p.y + p.out0)) & 15) == 0 && (p.y_stride % 2) == 0) ? 1 : 0;
   dim3 grid((p.ntiles + span - 1) / span, groups);
-  const bool luts = p.lut_elems * 4 <= rtc::LUT_SMEM_MAX;
+  // TSDGPU_RESAMP_TC_LUTS=0: LUT through L2 + the deeper coefficient ring even when the LUT would fit shared memory (A/B)
+  const bool luts = p.lut_elems * 4 <= rtc::LUT_SMEM_MAX && !(getenv("TSDGPU_RESAMP_TC_LUTS") && atoi(getenv("TSDGPU_RESAMP_TC_LUTS")) == 0);
   // CTA pairs (cta_group::2, clusters of 2 along the channel groups) whenever the groups pair up
   const bool pair = (groups % 2 == 0) && !(getenv("TSDGPU_RESAMP_TC_PAIR") && atoi(getenv("TSDGPU_RESAMP_TC_PAIR")) == 0);
   // tensor maps (TSDGPU_RESAMP_TC_TMA=0 keeps the LDGSTS / STG form): x as float32 rows [nchan][2 n]; y from this chunk's
@@ -827,7 +831,7 @@ int resamp_tc_launch(const ResampTcParams &p0)
                    tma_map_rows(&ymap, p.y + p.out0, 2ull * p.n_out, p.nchan, (unsigned long long) p.y_stride * 8, 64, 8, false);
   cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3(rtc::NTHREADS);
-  cfg.dynamicSmemBytes = rtc::smem_bytes(tma);
+  cfg.dynamicSmemBytes = rtc::smem_bytes(tma, luts);
   cfg.stream = r.stream;
   cudaLaunchAttribute at[1];
   if(pair)
