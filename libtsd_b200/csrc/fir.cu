@@ -261,9 +261,11 @@ static int fir_run_device(tsdgpu_fir_s *f, const void *x, long long xs, int n, v
   // cf32 data, <= 127 real taps: banded Toeplitz GEMM on the tensor cores (3xTF32, fir_tc.cu); TSDGPU_FIR_TC=0 keeps FP32 FMA
   const char *tc_env = getenv("TSDGPU_FIR_TC");
   const bool tc_on = !(tc_env && atoi(tc_env) == 0);
-  if(tc_on && fir_tc_eligible(f->kind == TSDGPU_FIR_CF32_F32, f->K, src, src_stride, y, ys, hist_old, f->halo))
+  const bool tc_real = tc_on && f->kind == TSDGPU_FIR_F32_F32 && fir_tc_real_eligible(f->K, src, src_stride, y, ys, hist_old, f->halo);
+  if(tc_real || (tc_on && fir_tc_eligible(f->kind == TSDGPU_FIR_CF32_F32, f->K, src, src_stride, y, ys, hist_old, f->halo)))
   {
     FirTcParams t;
+    t.real = tc_real ? 1 : 0;
     t.x = (const float2 *) src;
     t.y = (float2 *) y;
     t.hist = (const float2 *) hist_old;

@@ -443,7 +443,10 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, int c0, int
                : "memory");
 }
 
-template<bool TMAL>
+// REAL = true (FiltreRIF<float,float>, e.g. the README example / BASELINE config 1): the 128 GEMM rows are 128 real-valued
+// channels instead of {re, im} x 64; a chunk is ONE box {32 floats, 128 rows}, the converters read four samples per 16-byte
+// piece, the epilogue writes real outputs.  Generator matrix, MMA issue and accumulator handling are the same.
+template<bool TMAL, bool REAL>
 __global__ void __launch_bounds__(Cfg2<TMAL>::NTHREADS, 1)
 fir_tc2_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap hmap, const __grid_constant__ CUtensorMap ymap, FirTcParams p)
 {
@@ -462,14 +465,16 @@ fir_tc2_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // this CTA's contiguous share of the (channel group, tile) units
-  const int groups = (p.nchan + CH - 1) / CH;
+  static_assert(TMAL || !REAL, "real-valued data: tensor-map form only");
+  constexpr int CHG = REAL ? 2 * CH : CH;   // channels per group
+  const int groups = (p.nchan + CHG - 1) / CHG;
   const long long units = (long long) groups * p.ntiles;
   const long long u0 = units * blockIdx.x / gridDim.x, u1 = units * (blockIdx.x + 1) / gridDim.x;
 #define FIR2_ITEMS_BEGIN                                                                                   \
   for(long long u = u0; u < u1;)                                                                           \
   {                                                                                                        \
     const int g = (int) (u / p.ntiles), ts = (int) (u - (long long) g * p.ntiles);                         \
-    const int ntl = (int) min((long long) (p.ntiles - ts), u1 - u), nchunks = 4 * ntl + 4, c0 = g * CH;    \
+    const int ntl = (int) min((long long) (p.ntiles - ts), u1 - u), nchunks = 4 * ntl + 4, c0 = g * CHG;   \
     (void) c0; (void) nchunks;
 #define FIR2_ITEMS_END(cnt_chunks, cnt_tiles)                                                              \
     u += ntl;                                                                                              \
@@ -529,7 +534,12 @@ fir_tc2_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
             const int pos = (4 * ts - 4 + it + k) * CHUNK;
             const uint32_t dst = smem_u32(stages + slot * RAW2_BYTES);
             mbar_expect_tx(rfull + slot, RAW2_BYTES);
-            if(pos >= 0)
+            if(REAL)
+            {
+              if(pos >= 0) tma_load_2d(dst, &xmap, pos, c0, rfull + slot);
+              else tma_load_2d(dst, &hmap, p.halo + pos, c0, rfull + slot);
+            }
+            else if(pos >= 0)
             {
               tma_load_2d(dst, &xmap, 2 * pos, c0, rfull + slot);
               tma_load_2d(dst + 8192, &xmap, 2 * pos + 32, c0, rfull + slot);
@@ -606,7 +616,7 @@ fir_tc2_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
   {
     // ===== converters (see fir_tc_kernel); group = parity of the running chunk number
     const int pw = (warp - 4) & 3, grp = (warp - 4) >> 2;
-    const int my_cl = 8 * (2 * pw + (lane >> 4)) + (lane & 7), my_ri = (lane >> 3) & 1;
+    const int my_cl = REAL ? 32 * pw + lane : 8 * (2 * pw + (lane >> 4)) + (lane & 7), my_ri = (lane >> 3) & 1;
     const uint32_t my_a = tmem + ((uint32_t) (pw * 32) << 16) + (uint32_t) (ACOL + 64 * grp);
     const uint32_t sx = (uint32_t) (my_cl & 7);
     unsigned gi = 0, gt = 0;
@@ -622,6 +632,23 @@ fir_tc2_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
       for(int hq = 0; hq < 2; hq++)
       {
         float hi[16], lo[16];
+        if(REAL)
+        {
+          // row = channel: 32 real samples = eight 16-byte pieces of ONE 128-byte swizzled row
+#pragma unroll
+          for(int m = 0; m < 4; m++)
+          {
+            const float4 x = *reinterpret_cast<const float4 *>(row + (((uint32_t) (hq * 4 + m) ^ sx) << 4));
+            const float a[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+            for(int e = 0; e < 4; e++)
+            {
+              hi[4 * m + e] = to_tf32(a[e]);
+              lo[4 * m + e] = to_tf32(a[e] - hi[4 * m + e]);
+            }
+          }
+        }
+        else
 #pragma unroll
         for(int m = 0; m < 8; m++)
         {
@@ -725,7 +752,9 @@ fir_tc2_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
     }
     unsigned char *my_out = outs + warp * OUT2_BYTES;
     const uint32_t my_out_s = smem_u32(my_out);
-    unsigned char *my_piece = my_out + (lane >> 2) * 1024 + (lane & 3) * 16;
+    // cf32: staging [8 channel rows][128 outputs x 8 B]; real: [16 channel rows][128 outputs x 4 B] (TMEM lanes t/4 and t/4 + 8
+    // are two different channels there)
+    unsigned char *my_piece = REAL ? my_out + (lane >> 2) * 512 + (lane & 3) * 8 : my_out + (lane >> 2) * 1024 + (lane & 3) * 16;
     unsigned gi = 0, gt = 0;
     FIR2_ITEMS_BEGIN
     for(int tl = 0; tl < ntl; tl++)
@@ -755,12 +784,21 @@ fir_tc2_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
         for(int cb = 0; cb < 4; cb++)
 #pragma unroll
           for(int i = 0; i < 4; i++)
-            *reinterpret_cast<uint4 *>(my_piece + (cb * 32 + 8 * i) * 8) = make_uint4(r[cb][4 * i], r[cb][4 * i + 2], r[cb][4 * i + 1], r[cb][4 * i + 3]);
+          {
+            if(REAL)
+            {
+              *reinterpret_cast<uint2 *>(my_piece + (cb * 32 + 8 * i) * 4) = make_uint2(r[cb][4 * i], r[cb][4 * i + 1]);
+              *reinterpret_cast<uint2 *>(my_piece + 8 * 512 + (cb * 32 + 8 * i) * 4) = make_uint2(r[cb][4 * i + 2], r[cb][4 * i + 3]);
+            }
+            else
+              *reinterpret_cast<uint4 *>(my_piece + (cb * 32 + 8 * i) * 8) = make_uint4(r[cb][4 * i], r[cb][4 * i + 2], r[cb][4 * i + 1], r[cb][4 * i + 3]);
+          }
         fence_proxy_async();
         __syncwarp();
         if(lane == 0)
         {
-          tma_store_2d(&ymap, 2 * TILE * (ts + tl), c0 + 16 * warp + 8 * half, my_out_s);
+          if(REAL) tma_store_2d(&ymap, TILE * (ts + tl), c0 + 32 * warp + 16 * half, my_out_s);
+          else tma_store_2d(&ymap, 2 * TILE * (ts + tl), c0 + 16 * warp + 8 * half, my_out_s);
           bulk_commit();
         }
       }
@@ -785,6 +823,15 @@ fir_tc2_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
 }
 
 } // namespace tc
+
+// real-valued data (f32 x f32): tensor-map form only -> 16-byte aligned rows and pitches
+bool fir_tc_real_eligible(int K, const void *x, long long x_stride, const void *y, long long y_stride, const void *hist, int halo)
+{
+  const char *e = getenv("TSDGPU_FIR_TC_VARIANT");
+  if(e && atoi(e) >= 1 && atoi(e) <= 2) return false;
+  return tma_encode_fn() && K >= 1 && K <= 127 && (((uintptr_t) x & 15) == 0) && (x_stride % 4 == 0) && (((uintptr_t) y & 15) == 0) &&
+         (y_stride % 4 == 0) && (((uintptr_t) hist & 15) == 0) && (halo % 4 == 0);
+}
 
 bool fir_tc_eligible(int kind_cf32_f32, int K, const void *x, long long x_stride, const void *y, long long y_stride, const void *hist, int halo)
 {
@@ -849,10 +896,18 @@ int fir_tc_launch(const FirTcParams &p0)
   Runtime &r = rt();
   p.ntiles = (p.n + tc::TILE - 1) / tc::TILE;
   p.span = 0;
-  const int variant = fir_tc_variant();
+  const int variant = p.real ? 3 : fir_tc_variant();
   // tensor maps over float32 views of the rows: x [nchan][2 n], history [nchan][2 halo], y [nchan][2 n]
   CUtensorMap xmap, hmap, ymap;
-  const bool maps = variant >= 2 && (unsigned long long) p.x_stride * 8 < (1ull << 40) && (unsigned long long) p.y_stride * 8 < (1ull << 40) &&
+  if(p.real)
+  {
+    // real-valued data: rows of n floats, 128 channel rows per box (x_stride / y_stride / halo count floats here)
+    if(!(tma_map_rows(&ymap, p.y, (unsigned long long) p.n, p.nchan, (unsigned long long) p.y_stride * 4, 128, 16, false) &&
+         tma_map_rows(&xmap, p.x, (unsigned long long) p.n, p.nchan, (unsigned long long) p.x_stride * 4, 32, 2 * tc::CH, true) &&
+         tma_map_rows(&hmap, p.hist, (unsigned long long) p.halo, p.nchan, (unsigned long long) p.halo * 4, 32, 2 * tc::CH, true)))
+      return fail("fir_tc_launch: cuTensorMapEncodeTiled refused the real-valued rows");
+  }
+  const bool maps = p.real || variant >= 2 && (unsigned long long) p.x_stride * 8 < (1ull << 40) && (unsigned long long) p.y_stride * 8 < (1ull << 40) &&
                     tma_map_rows(&ymap, p.y, 2ull * p.n, p.nchan, (unsigned long long) p.y_stride * 8, 256, 8, false) &&
                     tma_map_rows(&xmap, p.x, 2ull * p.n, p.nchan, (unsigned long long) p.x_stride * 8, 32, tc::CH, true) &&
                     tma_map_rows(&hmap, p.hist, 2ull * p.halo, p.nchan, (unsigned long long) p.halo * 8, 32, tc::CH, true);
@@ -860,15 +915,18 @@ int fir_tc_launch(const FirTcParams &p0)
   static bool attr_set = false;
   if(!attr_set)
   {
-    TSD_CUDA(cudaFuncSetAttribute(tc::fir_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg2<true>::SMEM));
-    TSD_CUDA(cudaFuncSetAttribute(tc::fir_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg2<false>::SMEM));
+    TSD_CUDA(cudaFuncSetAttribute(tc::fir_tc2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg2<true>::SMEM));
+    TSD_CUDA(cudaFuncSetAttribute(tc::fir_tc2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg2<false>::SMEM));
+    TSD_CUDA(cudaFuncSetAttribute(tc::fir_tc2_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg2<true>::SMEM));
     attr_set = true;
   }
-  const long long units = (long long) ((p.nchan + tc::CH - 1) / tc::CH) * p.ntiles;
+  const int chg = p.real ? 2 * tc::CH : tc::CH;
+  const long long units = (long long) ((p.nchan + chg - 1) / chg) * p.ntiles;
   // one CTA per SM; small calls: at least 4 tiles per CTA (every item pays one tile's worth of halo chunks)
   const int grid = (int) std::max<long long>(1, std::min<long long>(r.num_sms, (units + 3) / 4));
-  if(variant == 2) tc::fir_tc2_kernel<false><<<grid, tc::Cfg2<false>::NTHREADS, tc::Cfg2<false>::SMEM, r.stream>>>(xmap, hmap, ymap, p);
-  else tc::fir_tc2_kernel<true><<<grid, tc::Cfg2<true>::NTHREADS, tc::Cfg2<true>::SMEM, r.stream>>>(xmap, hmap, ymap, p);
+  if(p.real) tc::fir_tc2_kernel<true, true><<<grid, tc::Cfg2<true>::NTHREADS, tc::Cfg2<true>::SMEM, r.stream>>>(xmap, hmap, ymap, p);
+  else if(variant == 2) tc::fir_tc2_kernel<false, false><<<grid, tc::Cfg2<false>::NTHREADS, tc::Cfg2<false>::SMEM, r.stream>>>(xmap, hmap, ymap, p);
+  else tc::fir_tc2_kernel<true, false><<<grid, tc::Cfg2<true>::NTHREADS, tc::Cfg2<true>::SMEM, r.stream>>>(xmap, hmap, ymap, p);
   TSD_LAUNCH_CHECK();
   return 0;
 }

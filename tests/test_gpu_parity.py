@@ -157,6 +157,33 @@ def test_fir_tensor_core_path(tsd, cpu_oracle, monkeypatch, K, nchan, n, variant
     assert f_tc.index == f_fma.index
 
 
+@pytest.mark.parametrize("K,nchan,n", [(31, 1, 500), (127, 130, 4100), (100, 128, 65536), (1, 3, 300), (97, 257, 1029), (127, 300, 70000)])
+def test_fir_tensor_core_path_real_data(tsd, cpu_oracle, monkeypatch, K, nchan, n):
+    """FiltreRIF<float,float> (the README example's types): the tensor-core kernel with 128 real-valued channels per group
+    (fir_tc2_kernel<true, true>) against the oracle, streamed in ragged blocks, and against the FP32 FMA kernel."""
+    from libtsd_b200 import filtrage as F
+    rng = np.random.default_rng(K * 1000 + nchan + 7)
+    h = (rng.standard_normal(K) / np.sqrt(K)).astype(np.float32)
+    monkeypatch.setenv("TSDGPU_FIR_TC", "1")
+    monkeypatch.delenv("TSDGPU_FIR_TC_VARIANT", raising=False)
+    f_tc = F.filtre_rif(h, np.float32, nchan)
+    refs = [cpu_oracle.fir(0, h) for _ in range(min(nchan, 3))]
+    outs_tc, xs = [], []
+    for blk in (n, 130, 7, 1, 4096):
+        x = rng.standard_normal((nchan, blk)).astype(np.float32)
+        xs.append(x)
+        y = f_tc.step(x)
+        assert y.dtype == np.float32 and y.shape == x.shape
+        outs_tc.append(y)
+        for c, r in enumerate(refs):
+            assert rel_err(y[c], r.step(x[c]), rms(x)) <= TOL
+    monkeypatch.setenv("TSDGPU_FIR_TC", "0")
+    f_fma = F.filtre_rif(h, np.float32, nchan)
+    for x, y in zip(xs, outs_tc):
+        assert rel_err(f_fma.step(x), y, rms(x)) <= TOL
+    assert f_tc.index == f_fma.index
+
+
 def test_fir_errors(tsd):
     from libtsd_b200 import filtrage as F
     with pytest.raises(tsd.TsdGpuError):
