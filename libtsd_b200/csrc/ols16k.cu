@@ -97,28 +97,58 @@ __host__ __device__ constexpr float ols_cos32(int k)
        : k == 14 ? -0.92387953251128675613f : k == 15 ? -0.98078528040323044913f : -1.f;
 }
 __host__ __device__ constexpr float ols_sin32(int k) { return ols_cos32(k - 8); }
+// OLS_CONST_TW = 1 (default): the radix-32 / 16 butterfly twiddles (w, i w) = (wr, wi, -wi, wr) come from a __constant__
+// table: the packed FFMA2 / FMUL2 take them as ONE uniform-register operand pair fetched by LDCU.128, where the
+// compile-time literals of OLS_CONST_TW = 0 are materialised with up to four UMOV / HFMA2 / MOV per twiddle (HFMA2 sits on
+// the FMA pipe; ~13 % of the executed instructions of the kernel were such moves).
+#ifndef OLS_CONST_TW
+#define OLS_CONST_TW 1
+#endif
+// Where the table form is used: P3 only (butterflies fft16s and the last radix-2 stage comb32).  Measured at the BASELINE
+// size on one box: literals everywhere 167.3 Gsamples/s, table in P3 168.9, table in P1 + P3 161.2 (ptxas then hoists the 32
+// swizzled transpose addresses of P2 out of the block loop and spills them: 152 B of stack), table everywhere 169.0 (128 B
+// of stack), table in the fft16s of P1 + P3 only 166.0.
+#ifndef OLS_CT_P1F
+#define OLS_CT_P1F 0
+#endif
+#ifndef OLS_CT_P1C
+#define OLS_CT_P1C 0
+#endif
+#ifndef OLS_CT_P3F
+#define OLS_CT_P3F 1
+#endif
+#ifndef OLS_CT_P3C
+#define OLS_CT_P3C 1
+#endif
+__constant__ float4 c_ols_w32[2][32];   // [inverse][k] = (cos, -+sin, +-sin, cos) of 2 pi k / 32
 // v * W32^K (forward, W = exp(-2 pi i / 32)) or its conjugate (inverse): the twiddle and its rotation are constants
-template<bool INV, int K> __device__ __forceinline__ float2 mul_w32(float2 v)
+// CT: table form (used in the hand-over phases P1 / P3; in P2, where every register is taken, the table operands cost spills)
+template<bool INV, int K, bool CT> __device__ __forceinline__ float2 mul_w32(float2 v)
 {
   if(K == 0) return v;
   if(K == 8) return mul2(make_float2(v.y, v.x), INV ? make_float2(-1.f, 1.f) : make_float2(1.f, -1.f));   // -+ i
+  if(CT && OLS_CONST_TW)
+  {
+    const float4 t = c_ols_w32[INV ? 1 : 0][K & 31];
+    return cmul_rot(v, make_float2(t.x, t.y), make_float2(t.z, t.w));
+  }
   constexpr float wr = ols_cos32(K), wi = INV ? ols_sin32(K) : -ols_sin32(K);
   return cmul_rot(v, make_float2(wr, wi), make_float2(-wi, wr));
 }
 // 16-point DFT of v[0], v[S], ..., v[15 S]; natural order in and out
-template<bool INV, int S> __device__ __forceinline__ void fft16s(float2 *v)
+template<bool INV, int S, bool CT = false> __device__ __forceinline__ void fft16s(float2 *v)
 {
 #pragma unroll
   for(int b = 0; b < 4; b++) bf4<INV>(v[b * S], v[(4 + b) * S], v[(8 + b) * S], v[(12 + b) * S]);
-  v[5 * S] = mul_w32<INV, 2>(v[5 * S]);
-  v[6 * S] = mul_w32<INV, 4>(v[6 * S]);
-  v[7 * S] = mul_w32<INV, 6>(v[7 * S]);
-  v[9 * S] = mul_w32<INV, 4>(v[9 * S]);
-  v[10 * S] = mul_w32<INV, 8>(v[10 * S]);
-  v[11 * S] = mul_w32<INV, 12>(v[11 * S]);
-  v[13 * S] = mul_w32<INV, 6>(v[13 * S]);
-  v[14 * S] = mul_w32<INV, 12>(v[14 * S]);
-  v[15 * S] = mul_w32<INV, 18>(v[15 * S]);
+  v[5 * S] = mul_w32<INV, 2, CT>(v[5 * S]);
+  v[6 * S] = mul_w32<INV, 4, CT>(v[6 * S]);
+  v[7 * S] = mul_w32<INV, 6, CT>(v[7 * S]);
+  v[9 * S] = mul_w32<INV, 4, CT>(v[9 * S]);
+  v[10 * S] = mul_w32<INV, 8, CT>(v[10 * S]);
+  v[11 * S] = mul_w32<INV, 12, CT>(v[11 * S]);
+  v[13 * S] = mul_w32<INV, 6, CT>(v[13 * S]);
+  v[14 * S] = mul_w32<INV, 12, CT>(v[14 * S]);
+  v[15 * S] = mul_w32<INV, 18, CT>(v[15 * S]);
 #pragma unroll
   for(int k0 = 0; k0 < 4; k0++) bf4<INV>(v[(4 * k0) * S], v[(4 * k0 + 1) * S], v[(4 * k0 + 2) * S], v[(4 * k0 + 3) * S]);
   float2 t;
@@ -127,7 +157,7 @@ template<bool INV, int S> __device__ __forceinline__ void fft16s(float2 *v)
 #undef OLS_SWAP
 }
 // X[k] = E[k] + W32^k O[k], X[k+16] = E[k] - W32^k O[k] as four packed FMAs
-template<bool INV, int K> __device__ __forceinline__ void comb32(float2 e, float2 o, float2 &lo, float2 &hi)
+template<bool INV, int K, bool CT = false> __device__ __forceinline__ void comb32(float2 e, float2 o, float2 &lo, float2 &hi)
 {
   if(K == 0)
   {
@@ -142,8 +172,16 @@ template<bool INV, int K> __device__ __forceinline__ void comb32(float2 e, float
     hi = fma2(os, INV ? make_float2(1.f, -1.f) : make_float2(-1.f, 1.f), e);
     return;
   }
-  constexpr float wr = ols_cos32(K), wi = INV ? ols_sin32(K) : -ols_sin32(K);
   const float2 ox = bcast2(o.x), oy = bcast2(o.y);
+  if(CT && OLS_CONST_TW)
+  {
+    const float4 t = c_ols_w32[INV ? 1 : 0][K];
+    const float2 w = make_float2(t.x, t.y), rw = make_float2(t.z, t.w);
+    lo = fma2(oy, rw, fma2(ox, w, e));
+    hi = fma2(oy, make_float2(-rw.x, -rw.y), fma2(ox, make_float2(-w.x, -w.y), e));
+    return;
+  }
+  constexpr float wr = ols_cos32(K), wi = INV ? ols_sin32(K) : -ols_sin32(K);
   lo = fma2(oy, make_float2(-wi, wr), fma2(ox, make_float2(wr, wi), e));
   hi = fma2(oy, make_float2(wi, -wr), fma2(ox, make_float2(-wr, -wi), e));
 }
@@ -478,8 +516,8 @@ __global__ void __launch_bounds__(OLS_THREADS, 1) ols16k_kernel(OlsParams p)
         __syncwarp();
         if(l == 0) mbar_arrive_cta(w_free);            // staging consumed (16 arrivals: 8 warps x 2 rounds)
         if(r == 0 && it1 > 0) ols_stamp(p, it1 - 1, w, l, 1);
-        fft16s<false, 2>(&v[0]);
-        fft16s<false, 2>(&v[1]);
+        fft16s<false, 2, OLS_CT_P1F>(&v[0]);
+        fft16s<false, 2, OLS_CT_P1F>(&v[1]);
         if(r == 0 && it1 > 0) ols_stamp(p, it1 - 1, w, l, 2);
         if(it1 > 0) mbar_wait_sleep(e_free + 2 * r, (it1 - 1) & 1);  // the output warps have read these eight columns of the previous block
         if(r == 0 && it1 > 0) ols_stamp(p, it1 - 1, w, l, 3);
@@ -490,7 +528,7 @@ __global__ void __launch_bounds__(OLS_THREADS, 1) ols16k_kernel(OlsParams p)
 #define OLS_P1(K)                                                                              \
         {                                                                                          \
           float2 lo, hi;                                                                           \
-          comb32<false, K>(v[2 * K], v[2 * K + 1], lo, hi);                                        \
+          comb32<false, K, OLS_CT_P1C>(v[2 * K], v[2 * K + 1], lo, hi);                            \
           if(OLS_TW1_OUTER)                                                                        \
           {                                                                                        \
             const float2 ta = tw1[K], tb = tw1[K + 16];                                            \
@@ -547,13 +585,13 @@ __global__ void __launch_bounds__(OLS_THREADS, 1) ols16k_kernel(OlsParams p)
         float2 *yc = p.y + (long long) chan3 * p.y_stride + i0;
         const int rem = (int) min(p.out_count - i0, (long long) L);   // outputs of this lane's column still inside the call
         // inverse radix-32 whose last stage hands every output pair (n1 = K, K + 16) to the store as soon as it exists
-        fft16s<true, 2>(&v[0]);
-        fft16s<true, 2>(&v[1]);
+        fft16s<true, 2, OLS_CT_P3F>(&v[0]);
+        fft16s<true, 2, OLS_CT_P3F>(&v[1]);
         if(r == 0) ols_stamp(p, it3, w, l, 2);
 #define OLS_OUT(K)                                                                                   \
         {                                                                                                \
           float2 lo, hi;                                                                                 \
-          comb32<true, K>(v[2 * K], v[2 * K + 1], lo, hi);                                               \
+          comb32<true, K, OLS_CT_P3C>(v[2 * K], v[2 * K + 1], lo, hi);                                   \
           if(K >= NX && 512 * (K - NX) < rem) ols_stg(yc + 512 * (K - NX), lo);                          \
           if(K + 16 >= NX && 512 * (K + 16 - NX) < rem) ols_stg(yc + 512 * (K + 16 - NX), hi);           \
         }
@@ -759,6 +797,14 @@ int ols16k_create_taps(const std::complex<double> *taps, int K, Ols16k **out)
         t1[OLS_TW1_OUTER ? n2 * 32 + k1 : k1 * 16 + n2] = make_float2((float) cos(ang), (float) sin(ang));
       }
     TSD_CUDA(cudaMemcpyToSymbol(c_ols_tw1, t1.data(), 512 * sizeof(float2)));
+    std::vector<float4> w32(64);
+    for(int k = 0; k < 32; k++)
+    {
+      const float wr = ols_cos32(k), ws = ols_sin32(k);
+      w32[k] = make_float4(wr, -ws, ws, wr);        // forward: w = (cos, -sin), i w = (sin, cos)
+      w32[32 + k] = make_float4(wr, ws, -ws, wr);   // inverse: conj
+    }
+    TSD_CUDA(cudaMemcpyToSymbol(c_ols_w32, w32.data(), 64 * sizeof(float4)));
     TSD_CUDA(cudaFuncSetAttribute(ols16k_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ols16k_smem_bytes(4096)));
     TSD_CUDA(cudaFuncSetAttribute(ols16k_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ols16k_smem_bytes(8192)));
     rt().ols_ready = true;
