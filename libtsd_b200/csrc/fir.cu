@@ -14,9 +14,11 @@
 // global stores are fully coalesced.
 #include "common.cuh"
 #include "fir_tc.h"
+#include "ols16k.h"
 #include "host_pipe.cuh"
 #include "tsdgpu.h"
 
+#include <complex>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -192,6 +194,7 @@ struct tsdgpu_fir_s
   int cur = 0;
   void *d_stage = nullptr;    // device staging for TSDGPU_HOST calls
   size_t stage_bytes = 0;
+  Ols16k *ols = nullptr;      // cf32 data, K >= 128: the same filter on the single-SM overlap-save kernel (delay 0)
 };
 
 template<int DC, int TC, int R>
@@ -258,6 +261,21 @@ static int fir_run_device(tsdgpu_fir_s *f, const void *x, long long xs, int n, v
   const int unit = (int) (16 / ssz);
   p.use_tma = (((uintptr_t) src & 15) == 0) && (src_stride % unit == 0) && (n % unit == 0) && (f->halo % unit == 0);
   int rc;
+  // cf32 data, 128 ... 8192 taps (real or complex), calls of >= 2048 samples: y[n] = sum_k h[k] x[n-k] is what the single-SM
+  // overlap-save kernel computes with delay 0 and the FIR history as its carry (ols16k.cu: 16 B per sample whatever K,
+  // ~0.5e-6 of the RMS against the direct sum) -- the FP32 FMA kernel needs 4 K (8 K) flop per sample: 36 Gsamples/s at
+  // K = 512.  TSDGPU_FIR_OLS=0 keeps the direct form.
+  if(f->ols && n >= 2048 && !(getenv("TSDGPU_FIR_OLS") && atoi(getenv("TSDGPU_FIR_OLS")) == 0))
+  {
+    {
+      KernelTimer timer;
+      rc = ols16k_run(f->ols, (const float2 *) src, src_stride, n, (const float2 *) hist_old, f->halo, (float2 *) y, ys, n, 0, 0, f->nchan);
+    }
+    if(rc) return rc;
+    f->cur ^= 1;
+    f->total += n;
+    return 0;
+  }
   // cf32 data, <= 127 real taps: banded Toeplitz GEMM on the tensor cores (3xTF32, fir_tc.cu); TSDGPU_FIR_TC=0 keeps FP32 FMA
   const char *tc_env = getenv("TSDGPU_FIR_TC");
   const bool tc_on = !(tc_env && atoi(tc_env) == 0);
@@ -322,6 +340,13 @@ int tsdgpu_fir_create(int kind, const float *taps, int K, int nchan, tsdgpu_fir_
     TSD_CUDA(cudaMemsetAsync(f->d_hist[i], 0, (size_t) nchan * f->halo * ssz, rt().stream));
   }
   TSD_CUDA(cudaStreamSynchronize(rt().stream));
+  if(f->DC == 2 && K >= 128)
+  {
+    std::vector<std::complex<double>> ht((size_t) K);
+    for(int m = 0; m < K; m++)
+      ht[m] = f->TC == 2 ? std::complex<double>(taps[2 * m], taps[2 * m + 1]) : std::complex<double>(taps[m], 0.0);
+    if(ols16k_create_taps(ht.data(), K, &f->ols)) { tsdgpu_fir_destroy(f); return 1; }
+  }
   *out = f;
   return 0;
 }
@@ -436,6 +461,7 @@ int tsdgpu_fir_destroy(tsdgpu_fir_t f)
   cudaFree(f->d_hist[0]);
   cudaFree(f->d_hist[1]);
   if(f->d_stage) cudaFree(f->d_stage);
+  ols16k_destroy(f->ols);
   delete f;
   return 0;
 }

@@ -184,6 +184,45 @@ def test_fir_tensor_core_path_real_data(tsd, cpu_oracle, monkeypatch, K, nchan, 
     assert f_tc.index == f_fma.index
 
 
+@pytest.mark.parametrize("kind,K", [(1, 128), (1, 500), (1, 1000), (1, 4095), (2, 300), (1, 8192)])
+def test_fir_long_filters_on_the_overlap_save_kernel(tsd, cpu_oracle, monkeypatch, kind, K):
+    """filtre_rif with 128 ... 8192 taps on cf32 data: calls of >= 2048 samples run on the single-SM overlap-save kernel
+    (delay 0, FIR history as carry), shorter ones on the FP32 FMA kernel; the state carries across both, results match the
+    reference's direct sum, and the two paths agree with each other."""
+    from libtsd_b200 import filtrage as F
+    rng = np.random.default_rng(4000 + K + kind)
+    taps = (cn(rng, K) if kind == 2 else rng.standard_normal(K).astype(np.float32)) / np.float32(np.sqrt(K))
+    nchan = 3
+    g = F.filtre_rif(taps, np.complex64, nchan)
+    refs = [cpu_oracle.fir(kind, taps) for _ in range(nchan)]
+    xs, ys, yrefs = [], [], []
+    for n in (5000, 100, 2048, 12289, 1, 30001):
+        x = cn(rng, nchan, n)
+        y = g.step(x)
+        xs.append(x)
+        ys.append(y)
+        yref = np.stack([r.step(x[c]) for c, r in enumerate(refs)])
+        yrefs.append(yref)
+        assert y.shape == (nchan, n)
+        # K <= 4095: the north-star bar against the reference.  K = 8192: the reference's own sequential float32 sum is
+        # 1e-5 of the RMS away from the exact result there (checked below), the bar is applied to the float64 truth
+        if K <= 4095:
+            assert rel_err(y, yref, rms(x)) <= TOL
+    assert g.index == sum(x.shape[1] for x in xs) % K
+    from scipy.signal import fftconvolve
+    xa, ya, ra = np.concatenate(xs, axis=1), np.concatenate(ys, axis=1), np.concatenate(yrefs, axis=1)
+    truth = np.stack([fftconvolve(xa[c].astype(np.complex128), taps.astype(np.complex128 if kind == 2 else np.float64))[:xa.shape[1]]
+                      for c in range(nchan)])
+    e_gpu, e_ref = rel_err(ya, truth, rms(xa)), rel_err(ra, truth, rms(xa))
+    assert e_gpu <= TOL and e_gpu <= max(e_ref, 2e-6), (e_gpu, e_ref)
+    assert rel_err(ya, ra, rms(xa)) <= TOL + e_ref
+    monkeypatch.setenv("TSDGPU_FIR_OLS", "0")
+    g2 = F.filtre_rif(taps, np.complex64, nchan)
+    for x, y in zip(xs, ys):
+        # 8192 float32 products summed one after the other: the FMA kernel (like the reference) is itself ~1e-5 off there
+        assert rel_err(g2.step(x), y, rms(x)) <= (TOL if K <= 4095 else 3 * TOL)
+
+
 def test_fir_errors(tsd):
     from libtsd_b200 import filtrage as F
     with pytest.raises(tsd.TsdGpuError):
