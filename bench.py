@@ -44,6 +44,8 @@ WORKLOADS = {
     "reechan": ("stock resample() / filtre_reechan 147/160 on 512 ch x 8Mi cf32 (15-tap sinc interpolator x 257 phases)", 8.0 + 8.0 * 147 / 160),
     # the reference's DEFAULT block-filter shape: filtre_rif_fft(h) = Ne 512, N 1024 (fourier.cc:946-990)
     "rif_fft": ("filtre_rif_fft default shape: 1024 ch x 1Mi cf32, 255-tap low-pass, Ne=512, N=1024", 16.0),
+    # a long direct-form filter through the reference's filtre_rif interface (filtre-rt.cc:53-109): 511 taps
+    "fir_long": ("direct FIR, long filter: 256 ch x 1Mi cf32, 511-tap low-pass, filtre_rif one step() per channel", 16.0),
 }
 
 
@@ -164,6 +166,14 @@ def cpu_workload_setup(workload):
                 f = O.itrp(147.0 / 160.0, lut, 256)
                 return lambda: f.step(x)
         return make_job, n, kind, f"1 channel x {n} cf32 samples per host thread, filtre_itrp 147/160, sinc 64x257"
+    if workload == "fir_long":
+        h = O.design_rif_fen(511, "lp", 0.1)
+        x = cn(1 << 18)
+
+        def make_job():
+            f = O.fir(1, h)
+            return lambda: f.step(x)
+        return make_job, 1 << 18, kind, "1 channel x 262144 cf32 per host thread, 511 taps"
     if workload == "rif_fft":
         h = O.design_rif_fen(255, "lp", 0.1)
         n = 1 << 20
@@ -255,7 +265,7 @@ class GpuWorkload:
         self.torch = torch
         O = _Setup
         g = torch.Generator(device="cuda")
-        g.manual_seed({"ola": 0x7D5D0004, "fft": 0x7D5D0002, "fir": 0x7D5D0003, "resample": 0x7D5D0005, "reechan": 0x7D5D0005, "rif_fft": 0x7D5D0006}[name])
+        g.manual_seed({"ola": 0x7D5D0004, "fft": 0x7D5D0002, "fir": 0x7D5D0003, "resample": 0x7D5D0005, "reechan": 0x7D5D0005, "rif_fft": 0x7D5D0006, "fir_long": 0x7D5D0007}[name])
 
         pad = int(os.environ.get("TSDGPU_BENCH_PAD", "0"))   # experiment: channel stride n + pad instead of n
 
@@ -318,6 +328,14 @@ class GpuWorkload:
             self.y = emptyc(self.nchan, self.n)
             self.samples_per_step = self.nchan * self.n
             self.step = lambda: self.flt.step(self.x, out=self.y)
+        elif name == "fir_long":
+            self.nchan, self.n = max(1, int(256 * scale)), 1 << 20
+            h = O.design_rif_fen(511, "lp", 0.1)
+            self.flt = F.filtre_rif(h, np.complex64, self.nchan)
+            self.x = randc(self.nchan, self.n)
+            self.y = emptyc(self.nchan, self.n)
+            self.samples_per_step = self.nchan * self.n
+            self.step = lambda: self.flt.step(self.x, out=self.y)
         elif name == "reechan":
             self.nchan, self.n = max(1, int(512 * scale)), 1 << 23
             self.flt = F.filtre_reechan(147.0 / 160.0, self.nchan)
@@ -335,6 +353,7 @@ KERNELS = {
     "resample": "resamp_tc_kernel (tcgen05 3xTF32 banded filter-bank GEMM, CTA pairs, tensor-map loads and stores)",
     "reechan": "resamp_tc_kernel (tcgen05 3xTF32 banded filter-bank GEMM, CTA pairs, tensor-map loads and stores)",
     "rif_fft": "ols16k_kernel<1> (same single-SM overlap-save kernel: the device's transform size is independent of Ne / N)",
+    "fir_long": "ols16k_kernel<1> (delay 0, FIR history as carry: filtre_rif with >= 128 taps on cf32 data)",
 }
 
 
@@ -494,6 +513,13 @@ def e2e_measure(name, steps, warmup, barrier=None, world=1, pageable=False):
     elif name == "fir":
         nchan, n = 64, 1 << 20
         flt = F.filtre_rif(O.design_rif_fen(127, "lp", 0.1), np.complex64, nchan)
+        tx, x = hostbuf(nchan, n)
+        ty, y = hostbuf(nchan, n)
+        step = lambda: flt.step(x, out=y)   # noqa: E731
+        out_per_step = n
+    elif name == "fir_long":
+        nchan, n = 64, 1 << 20
+        flt = F.filtre_rif(O.design_rif_fen(511, "lp", 0.1), np.complex64, nchan)
         tx, x = hostbuf(nchan, n)
         ty, y = hostbuf(nchan, n)
         step = lambda: flt.step(x, out=y)   # noqa: E731
@@ -745,7 +771,7 @@ def main():
     # the other BASELINE configs, same measurement, in the same run (fewer steps: they only need a stable mean)
     extra = {}
     if not args.no_extra and not args.gather_only:
-        for name in ("fft", "fir", "resample", "reechan", "rif_fft", "ola"):
+        for name in ("fft", "fir", "resample", "reechan", "rif_fft", "fir_long", "ola"):
             if name == args.workload:
                 continue
             r, _ = measure_workload(name, min(args.steps, 6), 3, args.scale, stream, barrier, world,
