@@ -865,11 +865,10 @@ static int fir_tc_variant()
 static int fir_tc_launch_v1(FirTcParams p)
 {
   Runtime &r = rt();
-  static bool attr_set = false;
-  if(!attr_set)
+  if(!r.fir_tc1_ready)
   {
     TSD_CUDA(cudaFuncSetAttribute(tc::fir_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
-    attr_set = true;
+    r.fir_tc1_ready = true;
   }
   const int groups = (p.nchan + tc::CH - 1) / tc::CH;
   // tiles per CTA: long spans amortise the 4 halo chunks and the set-up, short spans balance the 148 SMs
@@ -912,13 +911,12 @@ int fir_tc_launch(const FirTcParams &p0)
                     tma_map_rows(&xmap, p.x, 2ull * p.n, p.nchan, (unsigned long long) p.x_stride * 8, 32, tc::CH, true) &&
                     tma_map_rows(&hmap, p.hist, 2ull * p.halo, p.nchan, (unsigned long long) p.halo * 8, 32, tc::CH, true);
   if(!maps) return fir_tc_launch_v1(p);
-  static bool attr_set = false;
-  if(!attr_set)
+  if(!r.fir_tc2_ready)
   {
     TSD_CUDA(cudaFuncSetAttribute(tc::fir_tc2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg2<true>::SMEM));
     TSD_CUDA(cudaFuncSetAttribute(tc::fir_tc2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg2<false>::SMEM));
     TSD_CUDA(cudaFuncSetAttribute(tc::fir_tc2_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg2<true>::SMEM));
-    attr_set = true;
+    r.fir_tc2_ready = true;
   }
   const int chg = p.real ? 2 * tc::CH : tc::CH;
   const long long units = (long long) ((p.nchan + chg - 1) / chg) * p.ntiles;

@@ -567,7 +567,7 @@ static int resamp_run_device(tsdgpu_resamp_s *f, const float2 *x, long long xs, 
       q.nchan = f->nchan;
       q.s_cta_max = s_cta_max;
       q.s_w_max = s_w_max;
-      static size_t smem_set = 0;   // the attribute is per function, not per filter object
+      size_t &smem_set = r.resamp2_smem_set;   // the attribute is per function and device, not per filter object
       if(smem2 > smem_set)
       {
         TSD_CUDA(cudaFuncSetAttribute(resamp_banded_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(smem2, 64 * 1024)));

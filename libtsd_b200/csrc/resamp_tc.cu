@@ -786,14 +786,13 @@ int resamp_tc_launch(const ResampTcParams &p0)
 {
   ResampTcParams p = p0;
   Runtime &r = rt();
-  static bool attr_set = false;
-  if(!attr_set)
+  if(!r.resamp_tc_ready)
   {
 #define RTC_ATTR(L, P, T) TSD_CUDA(cudaFuncSetAttribute(rtc::resamp_tc_kernel<L, P, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, rtc::smem_bytes(T, L)));
     RTC_ATTR(true, false, false) RTC_ATTR(false, false, false) RTC_ATTR(true, true, false) RTC_ATTR(false, true, false)
     RTC_ATTR(true, false, true) RTC_ATTR(false, false, true) RTC_ATTR(true, true, true) RTC_ATTR(false, true, true)
 #undef RTC_ATTR
-    attr_set = true;
+    r.resamp_tc_ready = true;
   }
   p.ntiles = (int) ((p.n_out + rtc::TILE - 1) / rtc::TILE);
   p.band = !(getenv("TSDGPU_RESAMP_TC_BAND") && atoi(getenv("TSDGPU_RESAMP_TC_BAND")) == 0);
