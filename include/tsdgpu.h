@@ -171,6 +171,21 @@ int tsdgpu_ola_destroy(tsdgpu_ola_t f);
 int tsdgpu_periodogramme_tfd(const void *x, long long x_stride, int n, int nchan, int N, const float *fenetre,
                              float *out, long long out_stride, int *n_frames, int *n_bins, int mem);
 
+/* ---- rt_spectrum(SpectrumConfig): averaged power spectrum in dB ------------------------------------------------------ */
+/* (fourier.hpp:909-952; Spectrum, src/fourier/fourier.cc:1162-1343).  A block of BS samples per channel is cut into nsubs
+ * sub-blocks of Nf = BS / nsubs samples; each is multiplied by `fenetre` (Nf floats, ALREADY normalised to energy Nf as
+ * fourier.cc:1203 does: sqrt(Nf / sum f^2) f), transformed by the unitary plan, |X|^2 is fft-shifted and accumulated — in
+ * place, or at offset i * sweep_step and times the edge (masque_hf) / centre (masque_bf) mask when sweep_active.  The block
+ * that completes nmeans blocks returns Ns values per channel, 10 log10(sum / (nmeans nsubs Nf) [/ coverage] + FLT_MIN), and
+ * clears the sums (*n_out = Ns); the other blocks return nothing (*n_out = 0; the reference resizes y to 0).
+ * Ns = Nf, or Nf + (nsubs - 1) sweep_step in sweep mode.  step() refuses n != BS like the reference's assertion. */
+typedef struct tsdgpu_spectrum_s *tsdgpu_spectrum_t;
+int tsdgpu_spectrum_create(int BS, int nmeans, int nsubs, int sweep_active, int sweep_step, int masque_bf, int masque_hf,
+                           const float *fenetre, int nchan, tsdgpu_spectrum_t *out);
+int tsdgpu_spectrum_dims(tsdgpu_spectrum_t s, int *Nf, int *Ns);
+int tsdgpu_spectrum_step(tsdgpu_spectrum_t s, const void *x, long long x_stride, int n, float *y, long long y_stride, int *n_out, int mem);
+int tsdgpu_spectrum_destroy(tsdgpu_spectrum_t s);
+
 /* ---- normalised-correlation detector: the hot part of détecteur_création(config) / Detecteur::step -------------------- */
 /* (fourier.hpp:577-679; src/fourier/detection.cc:120-260, MODE_OLA).  The reference correlates the stream with a fixed
  * motif through its block filter (traitement_freq = "X *= conj(fft(motif))", nb_zeros_min = M - 1, :146-170), tracks the

@@ -116,6 +116,32 @@ int main()
       printf("periodogramme_tfd %d x %d : ecart max %.2e dB\n", Mg.rows(), Mg.cols(), e);
       bad += e > 1e-3;
     }
+    {
+      // rt_spectrum: sub-blocks + sweep + masks, two averages; empty results in between like the reference
+      SpectrumConfig sc;
+      sc.BS = 4096;
+      sc.nmeans = 2;
+      sc.nsubs = 4;
+      sc.sweep.active = oui;
+      sc.sweep.step = 512;
+      sc.sweep.masque_bf = 8;
+      sc.sweep.masque_hf = 16;
+      soit sc_c = rt_spectrum(sc), sc_g = tsd::gpu::rt_spectrum_gpu(sc);
+      double e = 0;
+      int vides = 0;
+      pour(auto b = 0; b < 4; b++)
+      {
+        soit xs = bruit(4096, 20 + b);
+        Vecf yc, yg;
+        sc_c->step(xs, yc);
+        sc_g->step(xs, yg);
+        si(yc.rows() != yg.rows()) e = 1e9;
+        sinon si(yc.rows() == 0) vides++;
+        sinon e = std::max(e, ecart_reel(yc, yg));
+      }
+      printf("rt_spectrum  BS 4096, 4 sous-blocs, balayage : %d resultats vides, ecart max %.2e dB\n", vides, e);
+      bad += (e > 1e-3) + (vides != 2);
+    }
     // filtre_itrp 147/160, sinc 64 x 257
     soit it = itrp_sinc<cfloat>({64, 256, 0.4f, "hn"});
     soit rc = filtre_itrp<cfloat>(147.0f / 160.0f, it);

@@ -55,6 +55,17 @@ int main()
     c.traitement_freq = [](Veccf &X) { pour(auto i = X.rows() / 4; i < X.rows() / 2; i++) X(i) = 0; };   // test-filtres.cc:428-432 style
     soit [ola, N] = filtre_fft(c);
     imprime("filtre_fft_rappel", ola->step(x));
+    SpectrumConfig sc;                                                            // fourier.hpp:909-952 -> rt_spectrum
+    sc.BS = 4096;
+    sc.nmeans = 2;
+    sc.nsubs = 2;
+    soit sp = rt_spectrum(sc);
+    Vecf s1, s2;
+    sp->step(x.head(4096), s1);
+    sp->step(x.segment(4096, 4096), s2);
+    Veccf sdb(s2.rows());
+    pour(auto i = 0; i < s2.rows(); i++) sdb(i) = cfloat(s2(i), (float) s1.rows());
+    imprime("rt_spectrum_dB", sdb);
     printf("noyaux_gpu %lld\n", tsdgpu_launch_count ? tsdgpu_launch_count(0) : 0LL);
   }
   catch(const std::exception &e) { printf("exception: %s\n", e.what()); retourne 2; }

@@ -346,4 +346,38 @@ inline Tabf periodogramme_tfd_gpu(const Veccf &x, entier N)
   retourne M;
 }
 
+// rt_spectrum(config) (fourier.hpp:952; Spectrum, fourier.cc:1162-1343): same Filtre<cfloat,float,SpectrumConfig> interface,
+// the windowing / transforms / fft-shifted accumulation / dB conversion on the device (tsdgpu_spectrum_*).  config.plan (an
+// optional user FFT plan) has no role here.
+struct SpectrumGpu : Filtre<cfloat, float, tsd::fourier::SpectrumConfig>
+{
+  tsdgpu_spectrum_t h = nullptr;
+  int Ns = 0;
+  ~SpectrumGpu() { si(h) tsdgpu_spectrum_destroy(h); }
+  void configure_impl(const tsd::fourier::SpectrumConfig &c)
+  {
+    si(h) { tsdgpu_spectrum_destroy(h); h = nullptr; }
+    soit Nf = c.Nf();
+    Vecf f = tsd::filtrage::fenêtre(c.fenetre, Nf, non);
+    f = sqrt(Nf / abs2(f).somme()) * f;                                  // fourier.cc:1203
+    verifie(tsdgpu_spectrum_create(c.BS, c.nmeans, c.nsubs, c.sweep.active ? 1 : 0, c.sweep.step, c.sweep.masque_bf, c.sweep.masque_hf,
+                                   f.data(), 1, &h),
+            "rt_spectrum (gpu)");
+    Ns = c.Ns();
+  }
+  void step(const Vecteur<cfloat> &x, Vecf &y)
+  {
+    y.resize(Ns);
+    int n_out = 0;
+    verifie(tsdgpu_spectrum_step(h, x.data(), x.rows(), x.rows(), y.data(), Ns, &n_out, TSDGPU_HOST), "Spectrum::step (gpu)");
+    si(n_out != Ns) y.resize(n_out);
+  }
+};
+inline sptr<Filtre<cfloat, float, tsd::fourier::SpectrumConfig>> rt_spectrum_gpu(const tsd::fourier::SpectrumConfig &config)
+{
+  soit res = std::make_shared<SpectrumGpu>();
+  res->configure(config);
+  retourne res;
+}
+
 } // namespace tsd::gpu

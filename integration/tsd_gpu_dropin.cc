@@ -10,7 +10,7 @@
 //                                                         (dsp/filter.hpp:1333-1381,1662-1666,1897-1913, dsp/dsp.hpp:499-503)
 //   tsd::rééchan                                          (tsd.hpp:700-705 -> filtre_reechan<T>)
 // fft() / ifft() / rfft() / Spectrum go through the fftplan_defaut hook, installed by the static initialiser below.
-// filtre_fft(config) (fourier.cc:935-940) is a plain function, hence a strong symbol in libtsd itself: routing it needs the
+// filtre_fft(config) (fourier.cc:935-940) and rt_spectrum(config) (:1339) are plain functions, hence strong symbols in libtsd itself: routing them needs the
 // one-line `__attribute__((weak))` on the reference definition (or `objcopy --weaken-symbol`, which is what the check
 // build in oracle/Makefile does on its private copy of fourier.o); -DTSD_GPU_DROPIN_FILTRE_FFT then defines it here.
 #include "tsd_gpu_adapters.hpp"
@@ -45,6 +45,8 @@ std::tuple<sptr<Filtre<cfloat, cfloat, FiltreFFTConfig>>, entier> filtre_fft(con
 {
   retourne tsd::gpu::filtre_fft_gpu(config);
 }
+// rt_spectrum(config) (fourier.cc:1339-1344): a plain function as well, same treatment
+sptr<Filtre<cfloat, float, SpectrumConfig>> rt_spectrum(const SpectrumConfig &config) { retourne tsd::gpu::rt_spectrum_gpu(config); }
 }
 #endif
 

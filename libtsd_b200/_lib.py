@@ -57,6 +57,10 @@ _SIGS = {
     "tsdgpu_ola_create_fen": (_i, [_i, _i, _vp, _vp, _i, C.POINTER(_vp)]),
     "tsdgpu_ola_create_cb": (_i, [_i, _i, _vp, _vp, _vp, _i, C.POINTER(_vp)]),
     "tsdgpu_periodogramme_tfd": (_i, [_vp, C.c_longlong, _i, _i, _i, _vp, _vp, C.c_longlong, C.POINTER(_i), C.POINTER(_i), _i]),
+    "tsdgpu_spectrum_create": (_i, [_i, _i, _i, _i, _i, _i, _i, _vp, _i, C.POINTER(_vp)]),
+    "tsdgpu_spectrum_dims": (_i, [_vp, C.POINTER(_i), C.POINTER(_i)]),
+    "tsdgpu_spectrum_step": (_i, [_vp, _vp, C.c_longlong, _i, _vp, C.c_longlong, C.POINTER(_i), _i]),
+    "tsdgpu_spectrum_destroy": (_i, [_vp]),
     "tsdgpu_ola_dims": (_i, [_vp, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "tsdgpu_ola_out_count": (_ll, [_vp, _i]),
     "tsdgpu_ola_step": (_i, [_vp, _vp, _ll, _i, _vp, _ll, C.POINTER(_ll), _i]),

@@ -176,6 +176,81 @@ def periodogramme_tfd(x, N: int, fenetre=None):
     return out[0] if b.ndim == 1 else out
 
 
+@dataclass
+class SpectrumConfig:
+    """tsd::fourier::SpectrumConfig (fourier.hpp:909-947)."""
+    BS: int = 1024                # dimension des blocs d'entrée
+    nmeans: int = 10              # nombre de spectres moyennés
+    nsubs: int = 1                # sous-blocs par bloc (balayage fréquentiel / multi-threading)
+    sweep_active: bool = False
+    sweep_step: int = 1024
+    sweep_masque_bf: int = 0
+    sweep_masque_hf: int = 0
+    fenetre: str = "hn"           # Fenetre::HANN by default; "re" / "hm"
+
+    def Nf(self) -> int:
+        return self.BS // self.nsubs
+
+    def Ns(self) -> int:
+        return self.Nf() + (self.nsubs - 1) * self.sweep_step if self.sweep_active else self.Nf()
+
+
+class Spectrum:
+    """rt_spectrum(config) (fourier.hpp:952; Spectrum, fourier.cc:1162-1343): averaged power spectrum in dB.  step(x) takes
+    exactly BS samples per channel and returns Ns values per channel when the block completes `nmeans` blocks, else an
+    empty array (the reference resizes y to 0).  ``nchan`` independent channels share the configuration."""
+
+    def __init__(self, config: SpectrumConfig, nchan: int = 1, fenetre=None):
+        from .filtrage import fenetre as _fen
+        self.config, self.nchan = config, int(nchan)
+        Nf = config.Nf()
+        if fenetre is None:
+            f = _fen(config.fenetre, Nf, False).astype(np.float32)
+            # f = sqrt(Nf / abs2(f).somme()) * f  (fourier.cc:1203): float32 throughout
+            f = (np.float32(np.sqrt(np.float32(Nf) / np.sum(f * f, dtype=np.float32))) * f).astype(np.float32)
+        else:
+            f = np.ascontiguousarray(fenetre, np.float32)
+        if f.shape != (Nf,):
+            raise TsdGpuError(f"rt_spectrum: la fenêtre doit comporter Nf = {Nf} points")
+        self.fenetre = f
+        self._h = _vp()
+        check(lib().tsdgpu_spectrum_create(int(config.BS), int(config.nmeans), int(config.nsubs), 1 if config.sweep_active else 0,
+                                           int(config.sweep_step), int(config.sweep_masque_bf), int(config.sweep_masque_hf),
+                                           f.ctypes.data_as(_vp), self.nchan, C.byref(self._h)))
+        nf, ns = C.c_int(), C.c_int()
+        check(lib().tsdgpu_spectrum_dims(self._h, C.byref(nf), C.byref(ns)))
+        self.Nf, self.Ns = nf.value, ns.value
+        self._cnt = 0
+
+    def step(self, x):
+        b = Batch(x, np.complex64, self.nchan)
+        last = self._cnt + 1 == self.config.nmeans
+        if b.torch:
+            import torch
+            out = torch.empty((self.nchan, self.Ns if last else 0), dtype=torch.float32, device=b.arr.device)
+            optr = out.data_ptr() if last else None
+        else:
+            out = np.empty((self.nchan, self.Ns if last else 0), np.float32)
+            optr = out.ctypes.data if last else None
+        no = C.c_int()
+        check(lib().tsdgpu_spectrum_step(self._h, b.ptr, b.stride, b.n, _vp(optr), max(self.Ns, 1), C.byref(no), b.mem))
+        self._cnt = 0 if last else self._cnt + 1
+        assert no.value == (self.Ns if last else 0)
+        return out[0] if b.ndim == 1 else out
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                lib().tsdgpu_spectrum_destroy(h)
+            except Exception:
+                pass
+
+
+def rt_spectrum(config: SpectrumConfig, nchan: int = 1, fenetre=None) -> Spectrum:
+    return Spectrum(config, nchan, fenetre)
+
+
 def reechan_freq(x, lom: float):
     """rééchan_freq<T>(x, lom) (fourier.hpp:143, fourier.cc:1391-1419): delay-free resampling of a whole signal by
     zero-padding (lom > 1) or truncating (lom < 1) its spectrum.  n2 = round(n * lom); the two transforms run on GPU

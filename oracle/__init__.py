@@ -282,6 +282,31 @@ class _RefFilter:
             self.L.tsdref_filter_free(self.h)
 
 
+class _RefSpectrum:
+    """rt_spectrum(SpectrumConfig) (fourier.hpp:909-952, fourier.cc:1162-1343); fenetre: 0 = none, 1 = Hann, 3 = Hamming."""
+
+    def __init__(self, L, err, BS, nmeans, nsubs, sweep_active, sweep_step, masque_bf, masque_hf, fenetre):
+        self.L, self._err = L, err
+        nf, ns = _i(), _i()
+        self.h = _vp(L.tsdref_spectrum_new(_i(BS), _i(nmeans), _i(nsubs), _i(1 if sweep_active else 0), _i(sweep_step), _i(masque_bf),
+                                           _i(masque_hf), _i(fenetre), C.byref(nf), C.byref(ns)))
+        if not self.h:
+            raise RuntimeError("reference: " + err())
+        self.BS, self.Nf, self.Ns = BS, nf.value, ns.value
+
+    def step(self, x):
+        x = _c64(x)
+        y = np.empty(self.Ns + 8, np.float32)
+        no = _i()
+        if self.L.tsdref_spectrum_step(self.h, _ptr(x), _i(len(x)), _ptr(y), _i(len(y)), C.byref(no)):
+            raise RuntimeError("reference: " + self._err())
+        return y[: no.value].copy()
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.tsdref_spectrum_free(self.h)
+
+
 class _RefDetect:
     FIELDS = ("position", "position_prec", "score", "gain", "theta", "SNR_dB", "sigma_noise")
 
@@ -334,7 +359,7 @@ class _Ref:
         L.tsdref_last_error.restype = C.c_char_p
         for name in ("tsdref_fir_new", "tsdref_rif_fft_new", "tsdref_ola_new", "tsdref_ola_new2", "tsdref_itrp_new",
                      "tsdref_reechan_new", "tsdref_fftplan_new", "tsdref_polyphase_new", "tsdref_itrp_new2",
-                     "tsdref_reechan_new_f32", "tsdref_detect_new"):
+                     "tsdref_reechan_new_f32", "tsdref_detect_new", "tsdref_spectrum_new"):
             getattr(L, name).restype = _vp
         self.L = L
 
@@ -394,6 +419,9 @@ class _Ref:
         f = _RefFilter(self.L, h, self._err)
         f.N = no.value
         return f
+
+    def spectrum(self, BS=1024, nmeans=10, nsubs=1, sweep_active=False, sweep_step=1024, masque_bf=0, masque_hf=0, fenetre=1):
+        return _RefSpectrum(self.L, self._err, BS, nmeans, nsubs, sweep_active, sweep_step, masque_bf, masque_hf, fenetre)
 
     def periodogramme_tfd(self, x, N):
         """periodogramme_tfd(x, N) (fourier.cc:1451-1481) -> [frames, N2/2] float32 (dB)."""

@@ -174,6 +174,41 @@ int tsdref_periodogramme_tfd(const float *x, int n, int N, float *out, int cap, 
   });
 }
 
+// rt_spectrum(SpectrumConfig) (fourier.hpp:909-952, fourier.cc:1162-1343): averaged power spectrum in dB
+void *tsdref_spectrum_new(int BS, int nmeans, int nsubs, int sweep_active, int sweep_step, int masque_bf, int masque_hf, int fenetre,
+                          int *Nf, int *Ns)
+{
+  void *res = nullptr;
+  guarded([&] {
+    tsd::fourier::SpectrumConfig c;
+    c.BS = BS;
+    c.nmeans = nmeans;
+    c.nsubs = nsubs;
+    c.sweep.active = sweep_active != 0;
+    c.sweep.step = sweep_step;
+    c.sweep.masque_bf = masque_bf;
+    c.sweep.masque_hf = masque_hf;
+    c.fenetre = (tsd::filtrage::Fenetre) fenetre;
+    *Nf = c.Nf();
+    *Ns = c.Ns();
+    res = new sptr<Filtre<cfloat, float, tsd::fourier::SpectrumConfig>>(tsd::fourier::rt_spectrum(c));
+  });
+  return res;
+}
+// one block of BS samples; *n_out = length of the spectrum this call returned (0 while the average is incomplete)
+int tsdref_spectrum_step(void *h, const float *x, int n, float *y, int cap, int *n_out)
+{
+  return guarded([&] {
+    auto &f = *(sptr<Filtre<cfloat, float, tsd::fourier::SpectrumConfig>> *) h;
+    Vecf r;
+    f->step(Veccf::map((const cfloat *) x, n).clone(), r);
+    *n_out = r.rows();
+    if(r.rows() > cap) échec("tsdref_spectrum_step: capacity");
+    if(r.rows() > 0) memcpy(y, r.data(), sizeof(float) * r.rows());
+  });
+}
+void tsdref_spectrum_free(void *h) { delete (sptr<Filtre<cfloat, float, tsd::fourier::SpectrumConfig>> *) h; }
+
 // rééchan_freq<T>(x, lom) (fourier.cc:1391-1419); kind 0 = float, 1 = cfloat.  y needs round(n * lom) elements.
 int tsdref_reechan_freq(int kind, const void *x, int n, float lom, void *y, int cap, int *n_out)
 {

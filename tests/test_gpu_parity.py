@@ -615,6 +615,39 @@ def test_ola_fenetre_odd_Ne_is_refused(tsd):
         Fo.filtre_fft(Fo.FiltreFFTConfig(511, 1, avec_fenetrage=True))
 
 
+@pytest.mark.parametrize("BS,nmeans,nsubs,sweep,step,mbf,mhf,fen", [
+    (1024, 3, 1, False, 0, 0, 0, "hn"), (4096, 2, 4, False, 0, 0, 0, "hn"), (4096, 2, 4, True, 512, 8, 16, "hn"),
+    (1000, 1, 1, False, 0, 0, 0, "re"), (3072, 2, 3, True, 1024, 0, 5, "hm"), (65536, 2, 1, False, 0, 0, 0, "hn"), (2002, 2, 2, True, 700, 3, 0, "hn")])
+def test_rt_spectrum_vs_reference(tsd, ref, BS, nmeans, nsubs, sweep, step, mbf, mhf, fen):
+    """rt_spectrum / Spectrum (fourier.cc:1162-1343): averaged, fft-shifted power spectrum in dB — plain averaging, sub-blocks,
+    frequency sweep with edge / centre masks, windows, a non power-of-two and an odd Nf — against the reference object block
+    by block: empty results until the nmeans-th block, then Ns values within 1e-3 dB (masked-out bins at the 10 log10(FLT_MIN) floor on both sides)."""
+    import torch
+    from libtsd_b200 import fourier as Fo
+    rng = np.random.default_rng(BS + nsubs)
+    cfg = Fo.SpectrumConfig(BS=BS, nmeans=nmeans, nsubs=nsubs, sweep_active=sweep, sweep_step=step, sweep_masque_bf=mbf,
+                            sweep_masque_hf=mhf, fenetre=fen)
+    nchan = 3
+    g = Fo.rt_spectrum(cfg, nchan)
+    gd = Fo.rt_spectrum(cfg, nchan)
+    refs = [ref.spectrum(BS, nmeans, nsubs, sweep, step, mbf, mhf, {"re": 0, "hn": 1, "hm": 3}[fen]) for _ in range(nchan)]
+    assert (g.Nf, g.Ns) == (refs[0].Nf, refs[0].Ns) == (cfg.Nf(), cfg.Ns())
+    tone = np.exp(2j * np.pi * 0.123 * np.arange(BS)).astype(np.complex64)
+    for blk in range(2 * nmeans + 1):
+        x = (cn(rng, nchan, BS) + 3 * tone[None]).astype(np.complex64)
+        y = g.step(x)
+        yd = gd.step(torch.from_numpy(x).cuda()).cpu().numpy()
+        for c, r in enumerate(refs):
+            yr = r.step(x[c])
+            assert y[c].shape == yr.shape == yd[c].shape
+            if yr.size:
+                assert np.max(np.abs(y[c] - yr)) <= 1e-3 and np.array_equal(y[c], yd[c])
+                floor = yr < -300          # masked-out bins: 10 log10(FLT_MIN) on both sides (device log10f: last-digit differences)
+                assert np.all(y[c][floor] < -300) and np.all(y[c][~floor] > -300)
+    with pytest.raises(tsd.TsdGpuError):
+        g.step(cn(rng, nchan, BS - 1))
+
+
 def test_ola_errors(tsd):
     from libtsd_b200 import fourier as Fo
     with pytest.raises(tsd.TsdGpuError):
