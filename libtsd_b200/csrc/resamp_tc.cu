@@ -59,7 +59,10 @@ constexpr int ACOL = 3 * NCOL;
 #define RTC_NCG 1                                 // converter groups of 4 warps; 2 (alternating chunks like fir_tc.cu, 30 warps at 64 registers) measured: no gain
 #endif
 constexpr int NCG = RTC_NCG;
-constexpr int CONV_WARP0 = 4, GEN_WARP0 = CONV_WARP0 + 4 * NCG, NGEN = 16, MMA_WARP = GEN_WARP0 + NGEN, LOAD_WARP = MMA_WARP + 1;
+#ifndef RTC_NGEN
+#define RTC_NGEN 16                               // generator warps (20, at 64 registers: 177 vs 190 Gsamples/s; fewer than 24 prologue warps cannot tabulate 24-tile spans)
+#endif
+constexpr int CONV_WARP0 = 4, GEN_WARP0 = CONV_WARP0 + 4 * NCG, NGEN = RTC_NGEN, MMA_WARP = GEN_WARP0 + NGEN, LOAD_WARP = MMA_WARP + 1;
 constexpr int NTHREADS = 32 * (LOAD_WARP + 1);
 constexpr int NPRO = NTHREADS - 32;             // threads of the prologue: the loader (last warp) starts copying at once
 constexpr int GROWS = (TILE + NGEN - 1) / NGEN;   // rows per generator warp and block: j = gw + NGEN * r
