@@ -96,6 +96,17 @@ def main():
     out["pg_M64"] = R.periodogramme_tfd(xp, 64)
     out["pg_M100"] = R.periodogramme_tfd(xp, 100)
 
+    # rt_spectrum / Spectrum (fourier.cc:1162-1343): plain averaging, and sub-blocks + sweep + masks on a non power-of-two Nf
+    rng = np.random.default_rng(81)
+    for key, (BS, nmeans, nsubs, sweep, step, mbf, mhf, fen) in {"a": (512, 3, 1, False, 0, 0, 0, 1), "b": (1200, 2, 3, True, 250, 4, 7, 1)}.items():
+        sp = R.spectrum(BS, nmeans, nsubs, sweep, step, mbf, mhf, fen)
+        xs = cn(rng, 2 * nmeans * BS)
+        ys = [sp.step(xs[i * BS:(i + 1) * BS]) for i in range(2 * nmeans)]
+        out["sp_cfg_" + key] = np.array([BS, nmeans, nsubs, int(sweep), step, mbf, mhf, fen], np.int32)
+        out["sp_x_" + key] = xs
+        out["sp_lens_" + key] = np.array([len(y) for y in ys], np.int32)
+        out["sp_y_" + key] = np.concatenate(ys)
+
     # rééchan_freq (fourier.cc:1391-1419): real and complex input, up and down
     rng = np.random.default_rng(79)
     xr = rng.standard_normal(1000).astype(np.float32)

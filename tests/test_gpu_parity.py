@@ -648,6 +648,28 @@ def test_rt_spectrum_vs_reference(tsd, ref, BS, nmeans, nsubs, sweep, step, mbf,
         g.step(cn(rng, nchan, BS - 1))
 
 
+def test_rt_spectrum_golden(tsd):
+    """rt_spectrum against the committed golden vectors of the reference build (tests/golden/make_golden.py): which blocks
+    return a spectrum, its length, values within 1e-3 dB."""
+    import os
+    from libtsd_b200 import fourier as Fo
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_vectors.npz"))
+    for key in ("a", "b"):
+        BS, nmeans, nsubs, sweep, step, mbf, mhf, fen = (int(v) for v in G["sp_cfg_" + key])
+        g = Fo.rt_spectrum(Fo.SpectrumConfig(BS=BS, nmeans=nmeans, nsubs=nsubs, sweep_active=bool(sweep), sweep_step=step,
+                                             sweep_masque_bf=mbf, sweep_masque_hf=mhf, fenetre={0: "re", 1: "hn", 3: "hm"}[fen]))
+        x, lens, yref = G["sp_x_" + key], G["sp_lens_" + key], G["sp_y_" + key]
+        pos = 0
+        for i, ln in enumerate(lens):
+            y = g.step(x[i * BS:(i + 1) * BS])
+            assert len(y) == ln
+            if ln:
+                r = yref[pos:pos + ln]
+                ok = r > -300
+                assert np.max(np.abs(y[ok] - r[ok])) <= 1e-3 and np.all(y[~ok] < -300)
+                pos += ln
+
+
 def test_ola_errors(tsd):
     from libtsd_b200 import fourier as Fo
     with pytest.raises(tsd.TsdGpuError):
