@@ -223,6 +223,30 @@ def test_fir_long_filters_on_the_overlap_save_kernel(tsd, cpu_oracle, monkeypatc
         assert rel_err(g2.step(x), y, rms(x)) <= (TOL if K <= 4095 else 3 * TOL)
 
 
+def test_fir_long_and_tensor_paths_unaligned_views_and_in_place(tsd, cpu_oracle):
+    """Device tensors that start at an odd sample offset (rows not 16-byte aligned: the tensor-map / bulk-copy forms must fall
+    back) and in-place calls (x is y), for a 127-tap filter (tensor-core kernel) and a 300-tap one (overlap-save kernel)."""
+    import torch
+    from libtsd_b200 import filtrage as F
+    rng = np.random.default_rng(77)
+    nchan, n = 5, 9001
+    xh = cn(rng, nchan, n + 3)
+    for K in (127, 300):
+        h = (rng.standard_normal(K) / np.sqrt(K)).astype(np.float32)
+        refs = [cpu_oracle.fir(1, h) for _ in range(nchan)]
+        yref = np.stack([r.step(xh[c, 1:1 + n]) for c, r in enumerate(refs)])
+        xd = torch.from_numpy(xh).cuda()
+        f = F.filtre_rif(h, np.complex64, nchan)
+        y = f.step(xd[:, 1:1 + n])                       # odd offset: 8-byte aligned rows only
+        assert rel_err(y.cpu().numpy(), yref, rms(xh)) <= TOL
+        g = F.filtre_rif(h, np.complex64, nchan)
+        buf = xd[:, 1:1 + n].contiguous()
+        out = g.step(buf, out=buf)                       # in place
+        tsd.synchronize()
+        assert out.data_ptr() == buf.data_ptr()
+        assert rel_err(buf.cpu().numpy(), yref, rms(xh)) <= TOL
+
+
 def test_fir_errors(tsd):
     from libtsd_b200 import filtrage as F
     with pytest.raises(tsd.TsdGpuError):
