@@ -330,6 +330,14 @@ __device__ __forceinline__ void mbar_arrive_cta(uint64_t *bar)
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// OLS_L1PF = 1 (experiment): the O overlap samples of a window are L2 hits whose latency (~700 cycles) sits at the head of each
+// P1 round; prefetch.global.L1 brings the NEXT round's lines into the small L1 that is left beside the shared memory while
+// the current round computes
+#ifndef OLS_L1PF
+#define OLS_L1PF 0
+#endif
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 // profiling aid: lane 0 of every math warp of CTA 0 records the SM clock at phase boundaries of a few blocks
 constexpr int OLS_PROF_IT0 = 8, OLS_PROF_NIT = 6, OLS_PROF_PTS = 14;
 __device__ __forceinline__ void ols_stamp(const OlsParams &p, unsigned it, int w, int l, int pt)
@@ -494,6 +502,12 @@ __global__ void __launch_bounds__(OLS_THREADS, 1) ols16k_kernel(OlsParams p)
           for(int h = 0; h < 2; h++)
 #pragma unroll
             for(int n1 = h; n1 < NX; n1 += 2) v[n1] = __ldg(xo + 512 * n1);
+          if(OLS_L1PF && r == 0 && (l & 15) == 0)
+          {
+            // round 1 of this warp: column n2 + 8, one prefetch per 128-byte line (lanes 0 and 16)
+#pragma unroll
+            for(int n1 = 0; n1 < NX; n1++) prefetch_l1(xo + 256 + 512 * n1);
+          }
           const uint32_t sh = (uint32_t) (pos0 & 1) * 8u + (uint32_t) (32 * n2) * 8u + lx;
 #pragma unroll
           for(int h = 0; h < 2; h++)      // even n1 first: the first radix-16 starts while the odd half is still arriving
