@@ -337,7 +337,8 @@ int tsdgpu_fir_create(int kind, const float *taps, int K, int nchan, tsdgpu_fir_
     TSD_CUDA(cudaMemsetAsync(f->d_hist[i], 0, (size_t) nchan * f->halo * ssz, rt().stream));
   }
   TSD_CUDA(cudaStreamSynchronize(rt().stream));
-  if(f->DC == 2 && K >= 128)
+  // complex taps cost the direct form 8 K flop per sample and have no tensor-core kernel: the overlap-save kernel wins from ~32 taps on
+  if(f->DC == 2 && (K >= 128 || (f->TC == 2 && K >= 32)))
   {
     std::vector<std::complex<double>> ht((size_t) K);
     for(int m = 0; m < K; m++)

@@ -21,3 +21,18 @@ for K in (128, 512, 2048):
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 3
         print(f"K={len(h)} TSDGPU_FIR_OLS={ols}: {ms:.2f} ms, {nchan * n / ms / 1e6:.1f} Gsamples/s", flush=True)
+# complex taps (cf32 x cf32): no tensor-core kernel, 8 K flop per sample in the direct form
+for K in (33, 63, 127):
+    rng = np.random.default_rng(K)
+    hc = ((rng.standard_normal(K) + 1j * rng.standard_normal(K)) / np.sqrt(K)).astype(np.complex64)
+    for ols in ("1", "0"):
+        os.environ["TSDGPU_FIR_OLS"] = ols
+        f = F.filtre_rif(hc, np.complex64, nchan)
+        for _ in range(2): f.step(x, out=y)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3): f.step(x, out=y)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        print(f"complex taps K={K} TSDGPU_FIR_OLS={ols}: {ms:.2f} ms, {nchan * n / ms / 1e6:.1f} Gsamples/s", flush=True)
