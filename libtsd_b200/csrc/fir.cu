@@ -195,6 +195,9 @@ struct tsdgpu_fir_s
   void *d_stage = nullptr;    // device staging for TSDGPU_HOST calls
   size_t stage_bytes = 0;
   Ols16k *ols = nullptr;      // cf32 data, K >= 128: the same filter on the single-SM overlap-save kernel (delay 0)
+  // real-valued data, K >= 128: two channels ride the overlap-save kernel as the real and imaginary part of one complex channel
+  float2 *d_pair[3] = {nullptr, nullptr, nullptr};   // packed input [pairs][n], packed output [pairs][n], packed history [pairs][halo]
+  size_t pair_cap = 0;        // samples per pair row the buffers hold
 };
 
 template<int DC, int TC, int R>
@@ -215,6 +218,23 @@ static int fir_launch(tsdgpu_fir_s *f, const FirParams &p)
   return 0;
 }
 
+// real rows 2p, 2p+1 -> one complex row p (a missing odd partner reads as zero); and back
+__global__ void fir_pair_pack_kernel(const float *x, long long xs, int n, int nchan, float2 *xp, long long xps)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, p = blockIdx.y;
+  if(i >= n) return;
+  const float a = x[(long long) (2 * p) * xs + i], b = (2 * p + 1 < nchan) ? x[(long long) (2 * p + 1) * xs + i] : 0.f;
+  xp[(long long) p * xps + i] = make_float2(a, b);
+}
+__global__ void fir_pair_unpack_kernel(const float2 *yp, long long yps, int n, int nchan, float *y, long long ys)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, p = blockIdx.y;
+  if(i >= n) return;
+  const float2 v = yp[(long long) p * yps + i];
+  y[(long long) (2 * p) * ys + i] = v.x;
+  if(2 * p + 1 < nchan) y[(long long) (2 * p + 1) * ys + i] = v.y;
+}
+
 static int fir_run_device(tsdgpu_fir_s *f, const void *x, long long xs, int n, void *y, long long ys)
 {
   if(n <= 0) return 0;
@@ -226,6 +246,35 @@ static int fir_run_device(tsdgpu_fir_s *f, const void *x, long long xs, int n, v
     if(f->DC == 1) fir_hist_kernel<1><<<grid, 256, 0, rt().stream>>>(x, xs, n, hist_old, hist_new, f->halo);
     else fir_hist_kernel<2><<<grid, 256, 0, rt().stream>>>(x, xs, n, hist_old, hist_new, f->halo);
     TSD_LAUNCH_CHECK();
+  }
+  // real-valued data, 128 ... 8192 real taps, calls of >= 2048 samples: channels 2p, 2p+1 become the real and imaginary part of
+  // one complex channel (exact for real taps), which the overlap-save kernel filters with delay 0; packing and unpacking are two
+  // small streaming kernels (24 B of HBM traffic per real sample in all, whatever K; the direct form needs 2 K flop per sample)
+  if(f->ols && f->DC == 1 && n >= 2048 && !(getenv("TSDGPU_FIR_OLS") && atoi(getenv("TSDGPU_FIR_OLS")) == 0))
+  {
+    const int pairs = (f->nchan + 1) / 2;
+    if((size_t) n > f->pair_cap)
+    {
+      TSD_CUDA(cudaStreamSynchronize(rt().stream));
+      for(int i = 0; i < 2; i++) { if(f->d_pair[i]) cudaFree(f->d_pair[i]); f->d_pair[i] = nullptr; }
+      f->pair_cap = 0;
+      const size_t cap = ((size_t) n + 1) & ~(size_t) 1;   // even row pitch: 16-byte aligned rows for the bulk copies
+      for(int i = 0; i < 2; i++) TSD_CUDA(cudaMalloc(&f->d_pair[i], (size_t) pairs * cap * sizeof(float2)));
+      if(!f->d_pair[2]) TSD_CUDA(cudaMalloc(&f->d_pair[2], (size_t) pairs * f->halo * sizeof(float2)));
+      f->pair_cap = cap;
+    }
+    const long long ps = (long long) f->pair_cap;
+    fir_pair_pack_kernel<<<dim3((n + 255) / 256, pairs), 256, 0, rt().stream>>>((const float *) x, xs, n, f->nchan, f->d_pair[0], ps);
+    fir_pair_pack_kernel<<<dim3((f->halo + 255) / 256, pairs), 256, 0, rt().stream>>>((const float *) hist_old, f->halo, f->halo, f->nchan, f->d_pair[2],
+                                                                                    f->halo);
+    TSD_LAUNCH_CHECK();
+    const int rc = ols16k_run(f->ols, f->d_pair[0], ps, n, f->d_pair[2], f->halo, f->d_pair[1], ps, n, 0, 0, pairs);
+    if(rc) return rc;
+    fir_pair_unpack_kernel<<<dim3((n + 255) / 256, pairs), 256, 0, rt().stream>>>(f->d_pair[1], ps, n, f->nchan, (float *) y, ys);
+    TSD_LAUNCH_CHECK();
+    f->cur ^= 1;
+    f->total += n;
+    return 0;
   }
   // 2. main kernel.  In-place operation needs a private copy of the input: tiles read the
   //    halo of their left neighbour, which that neighbour overwrites.
@@ -265,7 +314,7 @@ static int fir_run_device(tsdgpu_fir_s *f, const void *x, long long xs, int n, v
   // overlap-save kernel computes with delay 0 and the FIR history as its carry (ols16k.cu: 16 B per sample whatever K,
   // ~0.5e-6 of the RMS against the direct sum) -- the FP32 FMA kernel needs 4 K (8 K) flop per sample: 36 Gsamples/s at
   // K = 512.  TSDGPU_FIR_OLS=0 keeps the direct form.
-  if(f->ols && n >= 2048 && !(getenv("TSDGPU_FIR_OLS") && atoi(getenv("TSDGPU_FIR_OLS")) == 0))
+  if(f->ols && f->DC == 2 && n >= 2048 && !(getenv("TSDGPU_FIR_OLS") && atoi(getenv("TSDGPU_FIR_OLS")) == 0))
   {
     rc = ols16k_run(f->ols, (const float2 *) src, src_stride, n, (const float2 *) hist_old, f->halo, (float2 *) y, ys, n, 0, 0, f->nchan);   // times itself
     if(rc) return rc;
@@ -338,7 +387,7 @@ int tsdgpu_fir_create(int kind, const float *taps, int K, int nchan, tsdgpu_fir_
   }
   TSD_CUDA(cudaStreamSynchronize(rt().stream));
   // complex taps cost the direct form 8 K flop per sample and have no tensor-core kernel: the overlap-save kernel wins from ~32 taps on
-  if(f->DC == 2 && (K >= 128 || (f->TC == 2 && K >= 32)))
+  if((f->DC == 2 && (K >= 128 || (f->TC == 2 && K >= 32))) || (f->DC == 1 && K >= 128))
   {
     std::vector<std::complex<double>> ht((size_t) K);
     for(int m = 0; m < K; m++)
@@ -460,6 +509,8 @@ int tsdgpu_fir_destroy(tsdgpu_fir_t f)
   cudaFree(f->d_hist[1]);
   if(f->d_stage) cudaFree(f->d_stage);
   ols16k_destroy(f->ols);
+  for(int i = 0; i < 3; i++)
+    if(f->d_pair[i]) cudaFree(f->d_pair[i]);
   delete f;
   return 0;
 }

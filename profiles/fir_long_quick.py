@@ -36,3 +36,19 @@ for K in (33, 63, 127):
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 3
         print(f"complex taps K={K} TSDGPU_FIR_OLS={ols}: {ms:.2f} ms, {nchan * n / ms / 1e6:.1f} Gsamples/s", flush=True)
+# real-valued data, long filters: channel pairs on the overlap-save kernel vs the FMA kernel
+xr = torch.randn((2 * nchan, n), dtype=torch.float32, device="cuda")
+yr = torch.empty_like(xr)
+for K in (255, 511):
+    h = F.design_rif_fen(K, "lp", 0.1)
+    for ols in ("1", "0"):
+        os.environ["TSDGPU_FIR_OLS"] = ols
+        f = F.filtre_rif(h, np.float32, 2 * nchan)
+        for _ in range(2): f.step(xr, out=yr)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3): f.step(xr, out=yr)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        print(f"real data K={K} TSDGPU_FIR_OLS={ols}: {ms:.2f} ms, {2 * nchan * n / ms / 1e6:.1f} G real samples/s", flush=True)

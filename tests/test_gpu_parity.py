@@ -223,6 +223,39 @@ def test_fir_long_filters_on_the_overlap_save_kernel(tsd, cpu_oracle, monkeypatc
         assert rel_err(g2.step(x), y, rms(x)) <= (TOL if K <= 4095 else 3 * TOL)
 
 
+@pytest.mark.parametrize("K,nchan", [(300, 5), (128, 2), (2047, 1), (511, 64)])
+def test_fir_long_filters_real_data_in_channel_pairs(tsd, cpu_oracle, monkeypatch, K, nchan):
+    """FiltreRIF<float,float> with >= 128 taps: calls of >= 2048 samples pack channels 2p, 2p+1 into one complex channel for the
+    overlap-save kernel (odd channel counts: the last one rides alone), shorter ones use the FMA kernel; state carried across
+    both, in-place call, agreement with the direct form."""
+    import torch
+    from libtsd_b200 import filtrage as F
+    rng = np.random.default_rng(K + nchan)
+    h = (rng.standard_normal(K) / np.sqrt(K)).astype(np.float32)
+    g = F.filtre_rif(h, np.float32, nchan)
+    refs = [cpu_oracle.fir(0, h) for _ in range(min(nchan, 4))]
+    chans = list(range(min(nchan, 3))) + [nchan - 1]
+    xs, ys = [], []
+    for n in (5000, 100, 2049, 12288, 1, 20001):
+        x = rng.standard_normal((nchan, n)).astype(np.float32)
+        y = g.step(x)
+        assert y.dtype == np.float32 and y.shape == x.shape
+        xs.append(x)
+        ys.append(y)
+        for c, r in zip(chans, refs):
+            assert rel_err(y[c], r.step(x[c]), rms(x)) <= TOL
+    assert g.index == sum(x.shape[1] for x in xs) % K
+    monkeypatch.setenv("TSDGPU_FIR_OLS", "0")
+    g2 = F.filtre_rif(h, np.float32, nchan)
+    for x, y in zip(xs, ys):
+        assert rel_err(g2.step(x), y, rms(x)) <= TOL
+    monkeypatch.delenv("TSDGPU_FIR_OLS")
+    g3 = F.filtre_rif(h, np.float32, nchan)
+    buf = torch.from_numpy(xs[0]).cuda()
+    g3.step(buf, out=buf)                       # in place
+    assert rel_err(buf.cpu().numpy(), ys[0], rms(xs[0])) <= TOL
+
+
 def test_fir_long_and_tensor_paths_unaligned_views_and_in_place(tsd, cpu_oracle):
     """Device tensors that start at an odd sample offset (rows not 16-byte aligned: the tensor-map / bulk-copy forms must fall
     back) and in-place calls (x is y), for a 127-tap filter (tensor-core kernel) and a 300-tap one (overlap-save kernel)."""
