@@ -289,7 +289,32 @@ struct tsdgpu_resamp_s
   size_t sched_cap = 0;
   int next_buf = 0;
   size_t smem_set = 0;
+  // real-valued data with a LUT interpolator (filtre_itrp<float>, filtre_reechan<float>): channels 2p, 2p+1 ride a complex
+  // object as the real and imaginary part of channel p (exact: the LUT is real); this object then only packs / unpacks, the
+  // streaming state (history, phase) lives in `pair`
+  tsdgpu_resamp_s *pair = nullptr;
+  float2 *pair_x = nullptr, *pair_y = nullptr;
+  size_t pair_x_cap = 0, pair_y_cap = 0;   // samples per row
 };
+
+// real rows 2p, 2p+1 -> one complex row p (a missing odd partner reads as zero); and back
+__global__ void resamp_pair_pack_kernel(const float *x, long long xs, long long n, int nchan, float2 *xp, long long xps)
+{
+  const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  const int p = blockIdx.y;
+  if(i >= n) return;
+  const float a = x[(long long) (2 * p) * xs + i], b = (2 * p + 1 < nchan) ? x[(long long) (2 * p + 1) * xs + i] : 0.f;
+  xp[(long long) p * xps + i] = make_float2(a, b);
+}
+__global__ void resamp_pair_unpack_kernel(const float2 *yp, long long yps, long long n, int nchan, float *y, long long ys)
+{
+  const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  const int p = blockIdx.y;
+  if(i >= n) return;
+  const float2 v = yp[(long long) p * yps + i];
+  y[(long long) (2 * p) * ys + i] = v.x;
+  if(2 * p + 1 < nchan) y[(long long) (2 * p + 1) * ys + i] = v.y;
+}
 
 // Integer-exact form of the recurrence for 1 < increment <= 1.125 (ratio in [8/9, 1)), in units of 2^-23 (P = phase *
 // 2^23).  In this range every value of the float32 chain of ra.cc:64-73 is a multiple of 2^-23 below 4, so:
@@ -452,6 +477,50 @@ static int resamp_run_device(tsdgpu_resamp_s *f, const float2 *x, long long xs, 
   *n_out = 0;
   if(n <= 0) return 0;
   Runtime &r = rt();
+  if(f->pair)
+  {
+    // real-valued data: pack channel pairs, run the complex object (tensor-core kernel when eligible), unpack
+    const int pairs = f->pair->nchan;
+    const long long cnt = tsdgpu_resamp_out_count(f, n);
+    if(cnt > ycap) return fail("tsdgpu_resamp_step: output capacity too small");
+    const size_t xcap = ((size_t) n + 1) & ~(size_t) 1, ycap2 = ((size_t) std::max<long long>(cnt, 1) + 1) & ~(size_t) 1;
+    if(xcap > f->pair_x_cap || ycap2 > f->pair_y_cap)
+    {
+      TSD_CUDA(cudaStreamSynchronize(r.stream));
+      if(xcap > f->pair_x_cap)
+      {
+        if(f->pair_x) cudaFree(f->pair_x);
+        f->pair_x = nullptr;
+        f->pair_x_cap = 0;
+        TSD_CUDA(cudaMalloc(&f->pair_x, (size_t) pairs * xcap * sizeof(float2)));
+        f->pair_x_cap = xcap;
+      }
+      if(ycap2 > f->pair_y_cap)
+      {
+        if(f->pair_y) cudaFree(f->pair_y);
+        f->pair_y = nullptr;
+        f->pair_y_cap = 0;
+        TSD_CUDA(cudaMalloc(&f->pair_y, (size_t) pairs * ycap2 * sizeof(float2)));
+        f->pair_y_cap = ycap2;
+      }
+    }
+    resamp_pair_pack_kernel<<<dim3((unsigned) ((n + 255) / 256), pairs), 256, 0, r.stream>>>((const float *) x, xs, n, f->nchan, f->pair_x,
+                                                                                               (long long) f->pair_x_cap);
+    TSD_LAUNCH_CHECK();
+    f->pair->phase = f->phase;
+    long long got = 0;
+    if(resamp_run_device(f->pair, f->pair_x, (long long) f->pair_x_cap, n, f->pair_y, (long long) f->pair_y_cap, (long long) f->pair_y_cap, &got)) return 1;
+    if(got != cnt) return fail("tsdgpu_resamp_step: internal error (paired output count)");
+    if(got > 0)
+    {
+      resamp_pair_unpack_kernel<<<dim3((unsigned) ((got + 255) / 256), pairs), 256, 0, r.stream>>>(f->pair_y, (long long) f->pair_y_cap, got, f->nchan,
+                                                                                                     (float *) y, ys);
+      TSD_LAUNCH_CHECK();
+    }
+    f->phase = f->pair->phase;
+    *n_out = got;
+    return 0;
+  }
   float2 *hist_old = f->d_hist[f->cur], *hist_new = f->d_hist[f->cur ^ 1];
   const bool generic = f->dc == 1 || f->mode != 0;   // real data / exact-delay coefficients: one thread per output
   if(f->hist_len > 0)
@@ -653,6 +722,16 @@ static int resamp_create(float ratio, const float *lut, int K, int nphases, int 
     TSD_CUDA(cudaMemsetAsync(f->d_hist[i], 0, bytes, rt().stream));
   }
   TSD_CUDA(cudaStreamSynchronize(rt().stream));
+  // real-valued data + LUT: a complex object over channel pairs does the work (TSDGPU_RESAMP_PAIR=0: one thread per output,
+  // resamp_gen_kernel<float>, 4 Gsamples/s where the pairs reach > 100)
+  if(f->dc == 1 && mode == 0 && !(getenv("TSDGPU_RESAMP_PAIR") && atoi(getenv("TSDGPU_RESAMP_PAIR")) == 0))
+  {
+    if(resamp_create(ratio, lut, K, nphases, 0, 1, (nchan + 1) / 2, &f->pair))
+    {
+      tsdgpu_resamp_destroy(f);
+      return 1;
+    }
+  }
   *out = f;
   return 0;
 }
@@ -754,6 +833,18 @@ int tsdgpu_resamp_get_state(tsdgpu_resamp_t f, float *phase, void *hist_host)
   TSD_ENTER(f ? f->device : -1);
   if(!f) return fail("tsdgpu_resamp_get_state: null handle");
   if(phase) *phase = f->phase;
+  if(f->pair && hist_host && f->hist_len > 0)
+  {
+    // the history lives in the complex object: [pairs][hist_len] (re = channel 2p, im = channel 2p+1) -> real rows
+    const int pairs = f->pair->nchan, hl = f->hist_len;
+    std::vector<float2> h((size_t) pairs * hl);
+    TSD_CUDA(cudaStreamSynchronize(rt().stream));
+    TSD_CUDA(cudaMemcpy(h.data(), f->pair->d_hist[f->pair->cur], h.size() * sizeof(float2), cudaMemcpyDeviceToHost));
+    float *o = (float *) hist_host;
+    for(int c = 0; c < f->nchan; c++)
+      for(int i = 0; i < hl; i++) o[(size_t) c * hl + i] = (c & 1) ? h[(size_t) (c >> 1) * hl + i].y : h[(size_t) (c >> 1) * hl + i].x;
+    return 0;
+  }
   if(hist_host && f->hist_len > 0)
   {
     TSD_CUDA(cudaStreamSynchronize(rt().stream));
@@ -768,6 +859,21 @@ int tsdgpu_resamp_set_state(tsdgpu_resamp_t f, float phase, const void *hist_hos
   if(!f) return fail("tsdgpu_resamp_set_state: null handle");
   if(!(phase >= 0.0f) || !(phase < 1e9f)) return fail("tsdgpu_resamp_set_state: invalid phase");
   TSD_CUDA(cudaStreamSynchronize(rt().stream));
+  if(f->pair)
+  {
+    const int pairs = f->pair->nchan, hl = f->hist_len;
+    if(hl > 0)
+    {
+      if(!hist_host) return fail("tsdgpu_resamp_set_state: null history");
+      const float *in = (const float *) hist_host;
+      std::vector<float2> h((size_t) pairs * hl, make_float2(0.f, 0.f));
+      for(int c = 0; c < f->nchan; c++)
+        for(int i = 0; i < hl; i++) ((c & 1) ? h[(size_t) (c >> 1) * hl + i].y : h[(size_t) (c >> 1) * hl + i].x) = in[(size_t) c * hl + i];
+      TSD_CUDA(cudaMemcpy(f->pair->d_hist[f->pair->cur], h.data(), h.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    }
+    f->phase = f->pair->phase = phase;
+    return 0;
+  }
   if(f->hist_len > 0)
   {
     if(!hist_host) return fail("tsdgpu_resamp_set_state: null history");
@@ -793,6 +899,9 @@ int tsdgpu_resamp_destroy(tsdgpu_resamp_t f)
     if(f->ev_sched[b]) cudaEventDestroy(f->ev_sched[b]);
   }
   if(f->sched_stream) cudaStreamDestroy(f->sched_stream);
+  if(f->pair) tsdgpu_resamp_destroy(f->pair);
+  if(f->pair_x) cudaFree(f->pair_x);
+  if(f->pair_y) cudaFree(f->pair_y);
   delete f;
   return 0;
 }

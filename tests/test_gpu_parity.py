@@ -846,6 +846,46 @@ def test_itrp_tensor_core_and_fma_paths(tsd, port, cpu_oracle, monkeypatch, tc, 
         assert np.float32(g.phase) == np.float32(refs[0].phase)
 
 
+@pytest.mark.parametrize("nchan", [1, 3, 64])
+def test_itrp_real_data_rides_complex_channel_pairs(tsd, ref, cpu_oracle, monkeypatch, nchan):
+    """filtre_itrp<float> with a LUT interpolator: channels 2p, 2p+1 are filtered as one complex channel (tensor-core kernel
+    when eligible).  Against the reference's own filtre_itrp<float> objects (counts and phase bit-exact), against the
+    one-thread-per-output kernel, and through a state hand-over (get_state / set_state on the REAL rows) in the middle."""
+    from libtsd_b200 import filtrage as F
+    rng = np.random.default_rng(500 + nchan)
+    lut = cpu_oracle.itrp_sinc_lut(64, 256, 0.4)
+    ratio = 147 / 160
+    g = F.filtre_itrp(ratio, F.InterpolateurLUT(lut), nchan, np.float32)
+    refs = [ref.itrp2(ratio, "sinc", cplx=False, K=64, nphases=256, fcut=0.4) for _ in range(min(nchan, 3))]
+    xs, ys = [], []
+    for n in (20000, 131, 1, 4096):
+        x = rng.standard_normal((nchan, n)).astype(np.float32)
+        y = g.step(x)
+        assert y.dtype == np.float32
+        xs.append(x)
+        ys.append(y)
+        for c, r in enumerate(refs):
+            yr = r.step(x[c])
+            assert y[c].shape == yr.shape
+            if yr.size:
+                assert rel_err(y[c], yr, rms(x)) <= TOL
+    # hand-over: a second object takes the state after the first two calls and must continue identically
+    a = F.filtre_itrp(ratio, F.InterpolateurLUT(lut), nchan, np.float32)
+    a.step(xs[0]); a.step(xs[1])
+    ph, hist = a.get_state()
+    assert hist.dtype == np.float32 and hist.shape[0] == nchan
+    b = F.filtre_itrp(ratio, F.InterpolateurLUT(lut), nchan, np.float32)
+    b.set_state(ph, hist)
+    assert np.array_equal(b.step(xs[2]), ys[2]) and np.array_equal(b.step(xs[3]), ys[3])
+    assert np.float32(b.phase) == np.float32(g.phase)
+    # the generic kernel (one thread per output) gives the same samples
+    monkeypatch.setenv("TSDGPU_RESAMP_PAIR", "0")
+    s1 = F.filtre_itrp(ratio, F.InterpolateurLUT(lut), nchan, np.float32)
+    for x, y in zip(xs, ys):
+        y1 = s1.step(x)
+        assert y1.shape == y.shape and rel_err(y1, y, rms(x)) <= TOL
+
+
 def test_tensor_kernels_do_not_depend_on_stale_shared_memory(tsd, cpu_oracle):
     """Bit-identical results when another kernel has scribbled over the SMs' shared memory in between: the tolerance
     tests above can pass on left-overs of the previous launch (a prologue loop that skips a few table entries did,
