@@ -123,15 +123,17 @@ __global__ void fft_czt_post(const float2 *w, const float2 *chirp_tail, float2 *
 // coalesced.  N/16 threads per transform; CTAs of 256 threads pack 4096/N transforms when N < 4096.
 template<bool INV>
 __global__ void __launch_bounds__(1024, 1) fft_smem_kernel(const float2 *x, long long x_stride, float2 *y, long long y_stride, int N, int batch,
-                                                           float scale)
+                                                           float scale, int R = 1)
 {
+  // R > 1 (decimation in time of a larger transform, fft_split_*): transform b = t * R + r reads x[t][r + R m], m < N
   extern __shared__ float2 fft_sm[];
   const int T = N >> 4;
   const int local = threadIdx.x / T, j = threadIdx.x - local * T;
   const long long b = (long long) blockIdx.x * (blockDim.x / T) + local;
   const bool active = b < batch;
   float2 *sm = fft_sm + (size_t) local * N;
-  const float2 *in = x + b * x_stride;
+  const long long es = R;   // element stride of the input
+  const float2 *in = R == 1 ? x + b * x_stride : x + (b / R) * x_stride + (b % R);
   float2 *out = y + b * y_stride;
   float2 v[16];
   int Ns = 1, rem = N;
@@ -144,7 +146,7 @@ __global__ void __launch_bounds__(1024, 1) fft_smem_kernel(const float2 *x, long
     if(active)
     {
 #pragma unroll
-      for(int t = 0; t < 16; t++) v[t] = first ? in[j + t * T] : sm[j + t * T];
+      for(int t = 0; t < 16; t++) v[t] = first ? in[(j + t * T) * es] : sm[j + t * T];
     }
     if(!first) __syncthreads();
     const int k = j & (Ns - 1);
@@ -179,7 +181,7 @@ __global__ void __launch_bounds__(1024, 1) fft_smem_kernel(const float2 *x, long
 #pragma unroll
       for(int m = 0; m < 4; m++)
 #pragma unroll
-        for(int t = 0; t < 4; t++) v[4 * m + t] = first ? in[j + m * T + t * Q] : sm[j + m * T + t * Q];
+        for(int t = 0; t < 4; t++) v[4 * m + t] = first ? in[(j + m * T + t * Q) * es] : sm[j + m * T + t * Q];
     }
     if(!first) __syncthreads();
 #pragma unroll
@@ -218,8 +220,8 @@ __global__ void __launch_bounds__(1024, 1) fft_smem_kernel(const float2 *x, long
 #pragma unroll
       for(int m = 0; m < 8; m++)
       {
-        v[2 * m] = first ? in[j + m * T] : sm[j + m * T];
-        v[2 * m + 1] = first ? in[j + m * T + Hh] : sm[j + m * T + Hh];
+        v[2 * m] = first ? in[(j + m * T) * es] : sm[j + m * T];
+        v[2 * m + 1] = first ? in[(j + m * T + Hh) * es] : sm[j + m * T + Hh];
       }
     }
     // no barrier needed: this pass writes global memory only
@@ -237,6 +239,61 @@ __global__ void __launch_bounds__(1024, 1) fft_smem_kernel(const float2 *x, long
       }
     }
   }
+}
+
+// ------------------------------------------------------------------ 2^k > 16384 (other than 65536): N = R x 16384
+// Decimation in time: F_r = FFT_M(x[r + R m]) (fft_smem_kernel with element stride R -> work[t][r][k], contiguous), then
+//   X[k + M q] = sum_r W_R^(r q) * (W_N^(r k) F_r[k]),  q < R
+// one thread per (t, k): R coalesced loads, twiddles on exact dyadic angles, an R-point DFT in registers, R coalesced
+// stores.  Two passes over the data instead of log2(N) (the reference's own radix-2 structure, fourier.cc:86-117).
+template<bool INV, int R>
+__global__ void fft_split_combine_kernel(const float2 *w, float2 *y, long long y_stride, int M, int batch, float scale)
+{
+  const long long idx = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  if(idx >= (long long) M * batch) return;
+  const int t = (int) (idx / M), k = (int) (idx - (long long) t * M);
+  const float2 *src = w + (long long) t * R * M + k;
+  float2 v[R];
+#pragma unroll
+  for(int r = 0; r < R; r++) v[r] = src[(long long) r * M];
+  const float two_over_n = 2.0f / (float) ((long long) R * M);
+#pragma unroll
+  for(int r = 1; r < R; r++) v[r] = cmul(v[r], twiddle<INV>((unsigned) ((long long) r * k), two_over_n));
+  if(R == 2)
+  {
+    const float2 a = cadd(v[0], v[1]), d = csub(v[0], v[1]);
+    v[0] = a;
+    v[1] = d;
+  }
+  else if(R == 4) fft4<INV>(v[0], v[1], v[2], v[3]);
+  else if(R == 8)
+  {
+    // two 4-point transforms of the even / odd inputs, then X[q] = E[q] + W8^q O[q], X[q + 4] = E[q] - W8^q O[q]
+    float2 e[4] = {v[0], v[2], v[4], v[6]}, o[4] = {v[1], v[3], v[5], v[7]};
+    fft4<INV>(e[0], e[1], e[2], e[3]);
+    fft4<INV>(o[0], o[1], o[2], o[3]);
+    const float h = 0.70710678118654752f, sg = INV ? 1.f : -1.f;
+    const float2 w8[4] = {make_float2(1.f, 0.f), make_float2(h, sg * h), make_float2(0.f, sg), make_float2(-h, sg * h)};
+#pragma unroll
+    for(int q = 0; q < 4; q++)
+    {
+      const float2 ow = q == 0 ? o[0] : cmul(o[q], w8[q]);
+      v[q] = cadd(e[q], ow);
+      v[q + 4] = csub(e[q], ow);
+    }
+  }
+  else
+  {
+    float2 u[16];
+#pragma unroll
+    for(int r = 0; r < 16; r++) u[r] = v[r % R];
+    fft16<INV>(u);
+#pragma unroll
+    for(int r = 0; r < 16; r++) v[r % R] = u[r];
+  }
+  float2 *dst = y + (long long) t * y_stride + k;
+#pragma unroll
+  for(int q = 0; q < R; q++) dst[(long long) q * M] = make_float2(v[q].x * scale, v[q].y * scale);
 }
 
 // ------------------------------------------------------------------ N = 65536 pipeline
@@ -644,6 +701,36 @@ int fft_exec_device(tsdgpu_fft_s *p, const float2 *x, long long xs, float2 *y, l
     KernelTimer timer;
     if(forward) fft_smem_kernel<false><<<grid, threads, smem, r.stream>>>(x, xs, y, ys, N, batch, scale);
     else fft_smem_kernel<true><<<grid, threads, smem, r.stream>>>(x, xs, y, ys, N, batch, scale);
+    TSD_LAUNCH_CHECK();
+    return 0;
+  }
+  // ---- 32768, 131072, 262144 (and 65536 when the pipeline cannot serve the buffers): R strided 16384-point transforms + one
+  // combine pass.  TSDGPU_FFT_SPLIT=0 keeps the radix-2 passes.
+  if(N > 16384 && N <= 16 * 16384 && !(getenv("TSDGPU_FFT_SPLIT") && atoi(getenv("TSDGPU_FFT_SPLIT")) == 0))
+  {
+    const int M = 16384, R = N / M;
+    if(ensure_work(p, 0)) return 1;
+    if(!p->smem_optin)
+    {
+      TSD_CUDA(cudaFuncSetAttribute(fft_smem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+      TSD_CUDA(cudaFuncSetAttribute(fft_smem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+      p->smem_optin = true;
+    }
+    const long long subs = (long long) batch * R;
+    const float s1 = 1.0f / sqrtf((float) M), s2 = 1.0f / sqrtf((float) R);
+    KernelTimer timer;
+    if(forward) fft_smem_kernel<false><<<(unsigned) subs, M / 16, (size_t) M * sizeof(float2), r.stream>>>(x, xs, p->work[0], M, M, (int) subs, s1, R);
+    else fft_smem_kernel<true><<<(unsigned) subs, M / 16, (size_t) M * sizeof(float2), r.stream>>>(x, xs, p->work[0], M, M, (int) subs, s1, R);
+    TSD_LAUNCH_CHECK();
+    const int grid = grid_for((long long) M * batch, 256);
+#define SPLIT_GO(RR)                                                                                                        \
+    if(forward) fft_split_combine_kernel<false, RR><<<grid, 256, 0, r.stream>>>(p->work[0], y, ys, M, batch, s2);             \
+    else fft_split_combine_kernel<true, RR><<<grid, 256, 0, r.stream>>>(p->work[0], y, ys, M, batch, s2);
+    if(R == 2) { SPLIT_GO(2) }
+    else if(R == 4) { SPLIT_GO(4) }
+    else if(R == 8) { SPLIT_GO(8) }
+    else { SPLIT_GO(16) }
+#undef SPLIT_GO
     TSD_LAUNCH_CHECK();
     return 0;
   }

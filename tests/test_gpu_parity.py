@@ -291,7 +291,7 @@ def test_fir_errors(tsd):
 
 
 # ------------------------------------------------------------------------------------- FFT
-@pytest.mark.parametrize("n", [1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 65536, 131072])
+@pytest.mark.parametrize("n", [1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 65536, 131072, 262144, 524288])
 def test_fft_vs_oracle(tsd, cpu_oracle, n):
     """fft/ifft against the reference plan (sizes of test_fft_valide, test-fourier.cc:263, pow2 subset + 65536)."""
     from libtsd_b200 import fourier as Fo
