@@ -34,6 +34,7 @@ struct Runtime
   bool ols_ready = false;            // ols16k.cu: constant table + shared-memory opt-in done on this device
   // shared-memory opt-ins (cudaFuncSetAttribute is per device) of the tensor-core kernels and the banded resampler kernel
   bool fir_tc1_ready = false, fir_tc2_ready = false, resamp_tc_ready = false;
+  bool ola_sandwich_ready = false;
   size_t resamp2_smem_set = 0;
   int device = -1;
   int num_sms = 0;

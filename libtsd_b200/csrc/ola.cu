@@ -378,6 +378,154 @@ __global__ void ola_gather_kernel(const float2 *x, long long x_stride, const flo
     work[(long long) q * N + n] = v;
   }
 }
+// ---- fused frame kernel of the batch pipeline (16 <= N <= 16384): gather (+ window) -> forward transform -> x H -> inverse
+// transform, the frame resident in shared memory in between (one read of the Ne samples, one write of the N-point result,
+// one launch instead of four).  Same Stockham passes and unitary scalings as fft_smem_kernel (fft.cu), parametrised by where
+// a pass loads from / stores to.  SYNC_FIRST: the first pass reads shared memory as well (inverse leg) -> barrier before
+// anything is stored; STORE_SM: the last pass stores into shared memory (forward leg) -> barrier in the radix-2 tail too.
+template<bool INV, bool SYNC_FIRST, bool STORE_SM, class LoadF, class StoreF>
+__device__ __forceinline__ void ola_smem_fft(LoadF load, StoreF store, float2 *sm, int N, int j, bool active)
+{
+  const int T = N >> 4;
+  float2 v[16];
+  int Ns = 1, rem = N;
+  bool first = true;
+  while(rem >= 16)
+  {
+    rem >>= 4;
+    const bool last = rem == 1;
+    if(active)
+    {
+#pragma unroll
+      for(int t = 0; t < 16; t++) v[t] = first ? load(j + t * T) : sm[j + t * T];
+    }
+    if(!first || SYNC_FIRST) __syncthreads();
+    const int k = j & (Ns - 1);
+    if(Ns > 1) mul_geometric(v, make_float2(1.f, 0.f), twiddle<INV>((unsigned) k, 2.0f / (float) (Ns * 16)));
+    fft16<INV>(v);
+    const int j0 = (j - k) * 16 + k;
+    if(active)
+    {
+#pragma unroll
+      for(int t = 0; t < 16; t++)
+      {
+        if(last) store(j0 + t * Ns, v[t]);
+        else sm[j0 + t * Ns] = v[t];
+      }
+    }
+    if(!last) __syncthreads();
+    Ns <<= 4;
+    first = false;
+  }
+  if(rem >= 4)
+  {
+    rem >>= 2;
+    const bool last = rem == 1;
+    const int Q = N >> 2;
+    if(active)
+    {
+#pragma unroll
+      for(int m = 0; m < 4; m++)
+#pragma unroll
+        for(int t = 0; t < 4; t++) v[4 * m + t] = first ? load(j + m * T + t * Q) : sm[j + m * T + t * Q];
+    }
+    if(!first || SYNC_FIRST) __syncthreads();
+#pragma unroll
+    for(int m = 0; m < 4; m++)
+    {
+      const int jj = j + m * T, k = jj & (Ns - 1);
+      if(Ns > 1)
+      {
+        const float2 w = twiddle<INV>((unsigned) k, 2.0f / (float) (Ns * 4)), w2 = cmul(w, w);
+        v[4 * m + 1] = cmul(v[4 * m + 1], w);
+        v[4 * m + 2] = cmul(v[4 * m + 2], w2);
+        v[4 * m + 3] = cmul(v[4 * m + 3], cmul(w2, w));
+      }
+      fft4<INV>(v[4 * m], v[4 * m + 1], v[4 * m + 2], v[4 * m + 3]);
+      const int j0 = (jj - k) * 4 + k;
+      if(active)
+      {
+#pragma unroll
+        for(int t = 0; t < 4; t++)
+        {
+          if(last) store(j0 + t * Ns, v[4 * m + t]);
+          else sm[j0 + t * Ns] = v[4 * m + t];
+        }
+      }
+    }
+    if(!last) __syncthreads();
+    Ns <<= 2;
+    first = false;
+  }
+  if(rem == 2)
+  {
+    const int Hh = N >> 1;
+    if(active)
+    {
+#pragma unroll
+      for(int m = 0; m < 8; m++)
+      {
+        v[2 * m] = first ? load(j + m * T) : sm[j + m * T];
+        v[2 * m + 1] = first ? load(j + m * T + Hh) : sm[j + m * T + Hh];
+      }
+    }
+    if(STORE_SM || (first && SYNC_FIRST)) __syncthreads();
+#pragma unroll
+    for(int m = 0; m < 8; m++)
+    {
+      const int jj = j + m * T, k = jj & (Ns - 1);
+      const float2 wb = Ns > 1 ? cmul(v[2 * m + 1], twiddle<INV>((unsigned) k, 2.0f / (float) (Ns * 2))) : v[2 * m + 1];
+      const float2 a = cadd(v[2 * m], wb), d = csub(v[2 * m], wb);
+      const int j0 = (jj - k) * 2 + k;
+      if(active)
+      {
+        store(j0, a);
+        store(j0 + Ns, d);
+      }
+    }
+  }
+}
+
+// frame q of the chunk: plain mode q = chan * nb + blk; windowed mode q = (chan * nb + blk) * 2 + ph (the two frames of a block)
+template<bool FEN>
+__global__ void __launch_bounds__(1024, 1) ola_sandwich_kernel(const float2 *x, long long x_stride, const float2 *carry, int carry_len, float2 *work,
+                                                               const float2 *H, const float *fen, int N, int Ne, int Nz, int nb, int b0, int residual,
+                                                               int batch, float scale)
+{
+  extern __shared__ float2 ola_sm[];
+  const int T = N >> 4, local = threadIdx.x / T, j = threadIdx.x - local * T;
+  const long long q = (long long) blockIdx.x * (blockDim.x / T) + local;
+  const bool active = q < batch;
+  float2 *sm = ola_sm + (size_t) local * N;
+  const int per = FEN ? 2 * nb : nb;
+  const int chan = active ? (int) (q / per) : 0, r = (int) (q - (long long) chan * per), blk = FEN ? r >> 1 : r, ph = FEN ? r & 1 : 1;
+  const float2 *xc = x + (long long) chan * x_stride;
+  const float2 *cr = carry + (long long) chan * carry_len + carry_len;
+  const long long first_pos = (long long) (b0 + blk) * Ne - residual - ((FEN && ph == 0) ? Ne / 2 : 0);
+  auto gather = [&](int n) -> float2 {
+    float2 v = make_float2(0.f, 0.f);
+    if(n >= Nz)
+    {
+      const long long pos = first_pos + n - Nz;
+      v = (pos >= 0) ? xc[pos] : cr[pos];
+      if(FEN)
+      {
+        const float w = fen[n - Nz];
+        v.x *= w;
+        v.y *= w;
+      }
+    }
+    return v;
+  };
+  auto to_sm = [&](int idx, float2 v) { sm[idx] = make_float2(v.x * scale, v.y * scale); };
+  ola_smem_fft<false, false, true>(gather, to_sm, sm, N, j, active);
+  __syncthreads();
+  auto from_sm = [&](int idx) -> float2 { const float2 v = sm[idx]; return H ? cmul(v, __ldg(H + idx)) : v; };
+  float2 *dst = work + q * N;
+  auto to_work = [&](int idx, float2 v) { dst[idx] = make_float2(v.x * scale, v.y * scale); };
+  ola_smem_fft<true, true, false>(from_sm, to_work, sm, N, j, active);
+}
+
 __global__ void ola_mulH_kernel(float2 *work, const float2 *H, int N, long long total)
 {
   for(long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long) gridDim.x * blockDim.x)
@@ -767,6 +915,41 @@ static int ola_spectral_step(tsdgpu_ola_s *f, int batch, int per_chan)
   return 0;
 }
 
+// bytes of frames in flight per chunk of the batch pipeline (TSDGPU_OLA_WORK_MB, default 256).  Measured: smaller chunks that
+// would stay in the 126 MB L2 are SLOWER (windowed mode 25.7 / 23.1 / 18.1 Gsamples/s at 256 / 64 / 16 MiB): the per-chunk
+// launch sequence, not the HBM round trip of the frames, bounds this path.
+static long long ola_work_budget()
+{
+  static const long long mb = [] { const char *e = getenv("TSDGPU_OLA_WORK_MB"); const int v = e ? atoi(e) : 256; return (long long) (v >= 1 && v <= 4096 ? v : 256); }();
+  return mb << 20;
+}
+// gather -> FFT -> x H -> IFFT of a chunk in ONE launch when the frame fits shared memory (power of two, 16 ... 16384) and the
+// spectral step is a multiplication (no host callback); TSDGPU_OLA_SANDWICH=0 keeps the four launches
+static bool ola_sandwich_ok(const tsdgpu_ola_s *f)
+{
+  const int N = f->N;
+  return !f->cb && N >= 16 && N <= 16384 && (N & (N - 1)) == 0 && !(getenv("TSDGPU_OLA_SANDWICH") && atoi(getenv("TSDGPU_OLA_SANDWICH")) == 0);
+}
+template<bool FEN>
+static int ola_sandwich(tsdgpu_ola_s *f, const float2 *x, long long xs, int batch, int nb, int b0)
+{
+  Runtime &r = rt();
+  const int N = f->N, T = N / 16, threads = std::max(256, T), per_cta = threads / T;
+  const size_t smem = (size_t) per_cta * N * sizeof(float2);
+  if(!r.ola_sandwich_ready)
+  {
+    TSD_CUDA(cudaFuncSetAttribute(ola_sandwich_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+    TSD_CUDA(cudaFuncSetAttribute(ola_sandwich_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+    r.ola_sandwich_ready = true;
+  }
+  const unsigned grid = (unsigned) ((batch + per_cta - 1) / per_cta);
+  KernelTimer timer;
+  ola_sandwich_kernel<FEN><<<grid, threads, smem, r.stream>>>(x, xs, f->d_carry[f->cur], f->carry_len, f->work, f->d_H, f->d_fen, N, f->Ne, f->Nz, nb,
+                                                              b0, f->residual, batch, 1.0f / sqrtf((float) N));
+  TSD_LAUNCH_CHECK();
+  return 0;
+}
+
 static int ola_run_unfused(tsdgpu_ola_s *f, const float2 *x, long long xs, float2 *y, long long ys, int B)
 {
   Runtime &r = rt();
@@ -775,19 +958,26 @@ static int ola_run_unfused(tsdgpu_ola_s *f, const float2 *x, long long xs, float
   // blocks per chunk: bounded work buffer (<= 256 MiB) and grid (<= 65535 rows per launch)
   if(f->nchan > 65535) return fail("tsdgpu_ola_step: more than 65535 channels on the unfused path");
   long long per_block = (long long) f->nchan * N * (long long) sizeof(float2);
-  const int nb_max = (int) std::max(1LL, std::min((256LL << 20) / per_block, 65535LL / f->nchan));
+  const int nb_max = (int) std::max(1LL, std::min(ola_work_budget() / per_block, 65535LL / f->nchan));
   for(int b0 = 0; b0 < B; b0 += nb_max)
   {
     const int nb = std::min(nb_max, B - b0);
     const int batch = f->nchan * nb;
     if(ola_reserve_plan(f, batch)) return 1;
-    dim3 gg((N + 255) / 256, batch);
-    ola_gather_kernel<<<gg, 256, 0, r.stream>>>(x, xs, f->d_carry[f->cur], f->carry_len, f->work, N, Ne, Nz, nb, b0,
-                                               f->residual);
-    TSD_LAUNCH_CHECK();
-    if(fft_exec_device(f->plan, f->work, N, f->work, N, true)) return 1;
-    if(ola_spectral_step(f, batch, nb)) return 1;
-    if(fft_exec_device(f->plan, f->work, N, f->work, N, false)) return 1;
+    if(ola_sandwich_ok(f))
+    {
+      if(ola_sandwich<false>(f, x, xs, batch, nb, b0)) return 1;
+    }
+    else
+    {
+      dim3 gg((N + 255) / 256, batch);
+      ola_gather_kernel<<<gg, 256, 0, r.stream>>>(x, xs, f->d_carry[f->cur], f->carry_len, f->work, N, Ne, Nz, nb, b0,
+                                                 f->residual);
+      TSD_LAUNCH_CHECK();
+      if(fft_exec_device(f->plan, f->work, N, f->work, N, true)) return 1;
+      if(ola_spectral_step(f, batch, nb)) return 1;
+      if(fft_exec_device(f->plan, f->work, N, f->work, N, false)) return 1;
+    }
     dim3 gs((Ne + 255) / 256, batch);
     ola_scatter_kernel<<<gs, 256, 0, r.stream>>>(f->work, f->d_svg, y, ys, N, Ne, Nz, nb, b0);
     TSD_LAUNCH_CHECK();
@@ -804,20 +994,27 @@ static int ola_run_fen(tsdgpu_ola_s *f, const float2 *x, long long xs, float2 *y
   const int N = f->N, Ne = f->Ne, Nz = f->Nz;
   if(2LL * f->nchan > 65535) return fail("tsdgpu_ola_step: more than 32767 channels in the windowed mode");
   const long long per_block = 2LL * f->nchan * N * (long long) sizeof(float2);
-  const int nb_max = (int) std::max(1LL, std::min((256LL << 20) / per_block, 65535LL / (2LL * f->nchan)));
+  const int nb_max = (int) std::max(1LL, std::min(ola_work_budget() / per_block, 65535LL / (2LL * f->nchan)));
   const long long g0 = f->blocks_done, e_first = std::max(g0, 1LL);
   for(int b0 = 0; b0 < B; b0 += nb_max)
   {
     const int nb = std::min(nb_max, B - b0);
     const int batch = f->nchan * nb * 2;
     if(ola_reserve_plan(f, batch)) return 1;
-    dim3 gg((N + 255) / 256, batch);
-    ola_gather_fen_kernel<<<gg, 256, 0, r.stream>>>(x, xs, f->d_carry[f->cur], f->carry_len, f->work, f->d_fen, N, Ne, Nz, nb,
-                                                   b0, f->residual);
-    TSD_LAUNCH_CHECK();
-    if(fft_exec_device(f->plan, f->work, N, f->work, N, true)) return 1;
-    if(ola_spectral_step(f, batch, 2 * nb)) return 1;
-    if(fft_exec_device(f->plan, f->work, N, f->work, N, false)) return 1;
+    if(ola_sandwich_ok(f))
+    {
+      if(ola_sandwich<true>(f, x, xs, batch, nb, b0)) return 1;
+    }
+    else
+    {
+      dim3 gg((N + 255) / 256, batch);
+      ola_gather_fen_kernel<<<gg, 256, 0, r.stream>>>(x, xs, f->d_carry[f->cur], f->carry_len, f->work, f->d_fen, N, Ne, Nz, nb,
+                                                     b0, f->residual);
+      TSD_LAUNCH_CHECK();
+      if(fft_exec_device(f->plan, f->work, N, f->work, N, true)) return 1;
+      if(ola_spectral_step(f, batch, 2 * nb)) return 1;
+      if(fft_exec_device(f->plan, f->work, N, f->work, N, false)) return 1;
+    }
     dim3 gs((Ne + 255) / 256, f->nchan * nb);
     ola_scatter_fen_kernel<<<gs, 256, 0, r.stream>>>(f->work, f->d_last, y, ys, N, Ne, Nz, nb, g0 + b0, g0 + b0 - e_first);
     TSD_LAUNCH_CHECK();
