@@ -12,6 +12,9 @@
 // fp32 accuracy from tf32 inputs: x = x_hi + x_lo, h = h_hi + h_lo (each part rounded to tf32), three MMAs
 // x_hi*h_lo + x_lo*h_hi + x_hi*h_hi accumulated in fp32 by the tensor core (measured error 3.7e-6 of the signal RMS).
 //
+// Two kernels share this formulation: fir_tc_kernel (round 1, described first: one CTA per span of tiles, LDGSTS loads, STG
+// stores) and fir_tc2_kernel (round 2, the default, further down: persistent CTAs, tensor-map loads and stores, also for
+// real-valued data).
 // One CTA (448 threads, 1 per SM, all 512 TMEM columns) = 64 channels x `span` tiles, input-stationary: every input
 // chunk crosses shared memory once as raw cf32 rows and tensor memory once as the split A operand, and feeds the two
 // output tiles it overlaps, whose accumulators are live in TMEM together (3 regions of 128 columns: two accumulating,
