@@ -246,16 +246,20 @@ __global__ void __launch_bounds__(1024, 1) fft_smem_kernel(const float2 *x, long
 //   X[k + M q] = sum_r W_R^(r q) * (W_N^(r k) F_r[k]),  q < R
 // one thread per (t, k): R coalesced loads, twiddles on exact dyadic angles, an R-point DFT in registers, R coalesced
 // stores.  Two passes over the data instead of log2(N) (the reference's own radix-2 structure, fourier.cc:86-117).
+// G > 1 (two-level plans, N >= 2^19): the R inputs of item (t, g) are interleaved with those of the other G - 1 items of
+// transform t, i.e. sub-transform r of item g sits at row g + G r of work[t][G R][M]
 template<bool INV, int R>
-__global__ void fft_split_combine_kernel(const float2 *w, float2 *y, long long y_stride, int M, int batch, float scale)
+__global__ void fft_split_combine_kernel(const float2 *w, float2 *y, long long y_stride, int M, int batch, float scale, int G = 1)
 {
-  const long long idx = (long long) blockIdx.x * blockDim.x + threadIdx.x;
-  if(idx >= (long long) M * batch) return;
+  // grid-stride loop (the launches size their grids with grid_for, which caps the number of blocks)
+  for(long long idx = (long long) blockIdx.x * blockDim.x + threadIdx.x; idx < (long long) M * batch; idx += (long long) gridDim.x * blockDim.x)
+  {
   const int t = (int) (idx / M), k = (int) (idx - (long long) t * M);
-  const float2 *src = w + (long long) t * R * M + k;
+  const float2 *src = w + ((long long) (t / G) * G * R + (t % G)) * M + k;
+  const long long rs = (long long) G * M;
   float2 v[R];
 #pragma unroll
-  for(int r = 0; r < R; r++) v[r] = src[(long long) r * M];
+  for(int r = 0; r < R; r++) v[r] = src[r * rs];
   const float two_over_n = 2.0f / (float) ((long long) R * M);
 #pragma unroll
   for(int r = 1; r < R; r++) v[r] = cmul(v[r], twiddle<INV>((unsigned) ((long long) r * k), two_over_n));
@@ -294,6 +298,7 @@ __global__ void fft_split_combine_kernel(const float2 *w, float2 *y, long long y
   float2 *dst = y + (long long) t * y_stride + k;
 #pragma unroll
   for(int q = 0; q < R; q++) dst[(long long) q * M] = make_float2(v[q].x * scale, v[q].y * scale);
+  }
 }
 
 // ------------------------------------------------------------------ N = 65536 pipeline
@@ -731,6 +736,40 @@ int fft_exec_device(tsdgpu_fft_s *p, const float2 *x, long long xs, float2 *y, l
     else if(R == 8) { SPLIT_GO(8) }
     else { SPLIT_GO(16) }
 #undef SPLIT_GO
+    TSD_LAUNCH_CHECK();
+    return 0;
+  }
+  // ---- 2^19 ... 2^22: two levels, N = 16 x R2 x 16384: strided 16384-point transforms, R2-point combines into sixteen
+  // transforms of N / 16 points, 16-point combine: three passes over the data
+  if(N > 16 * 16384 && N <= 256 * 16384 && !(getenv("TSDGPU_FFT_SPLIT") && atoi(getenv("TSDGPU_FFT_SPLIT")) == 0))
+  {
+    const int M = 16384, M2 = N / 16, R2 = M2 / M, RT = 16 * R2;
+    if(ensure_work(p, 0) || ensure_work(p, 1)) return 1;
+    if(!p->smem_optin)
+    {
+      TSD_CUDA(cudaFuncSetAttribute(fft_smem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+      TSD_CUDA(cudaFuncSetAttribute(fft_smem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+      p->smem_optin = true;
+    }
+    const long long subs = (long long) batch * RT;
+    const float s1 = 1.0f / sqrtf((float) M), s2 = 1.0f / sqrtf((float) R2), s3 = 0.25f;
+    KernelTimer timer;
+    if(forward) fft_smem_kernel<false><<<(unsigned) subs, M / 16, (size_t) M * sizeof(float2), r.stream>>>(x, xs, p->work[0], M, M, (int) subs, s1, RT);
+    else fft_smem_kernel<true><<<(unsigned) subs, M / 16, (size_t) M * sizeof(float2), r.stream>>>(x, xs, p->work[0], M, M, (int) subs, s1, RT);
+    TSD_LAUNCH_CHECK();
+    const int g2 = grid_for((long long) M * batch * 16, 256);
+#define SPLIT_GO2(RR)                                                                                                               \
+    if(forward) fft_split_combine_kernel<false, RR><<<g2, 256, 0, r.stream>>>(p->work[0], p->work[1], M2, M, batch * 16, s2, 16);       \
+    else fft_split_combine_kernel<true, RR><<<g2, 256, 0, r.stream>>>(p->work[0], p->work[1], M2, M, batch * 16, s2, 16);
+    if(R2 == 2) { SPLIT_GO2(2) }
+    else if(R2 == 4) { SPLIT_GO2(4) }
+    else if(R2 == 8) { SPLIT_GO2(8) }
+    else { SPLIT_GO2(16) }
+#undef SPLIT_GO2
+    TSD_LAUNCH_CHECK();
+    const int g3 = grid_for((long long) M2 * batch, 256);
+    if(forward) fft_split_combine_kernel<false, 16><<<g3, 256, 0, r.stream>>>(p->work[1], y, ys, M2, batch, s3);
+    else fft_split_combine_kernel<true, 16><<<g3, 256, 0, r.stream>>>(p->work[1], y, ys, M2, batch, s3);
     TSD_LAUNCH_CHECK();
     return 0;
   }

@@ -291,7 +291,7 @@ def test_fir_errors(tsd):
 
 
 # ------------------------------------------------------------------------------------- FFT
-@pytest.mark.parametrize("n", [1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 65536, 131072, 262144, 524288])
+@pytest.mark.parametrize("n", [1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 65536, 131072, 262144, 524288, 8388608])
 def test_fft_vs_oracle(tsd, cpu_oracle, n):
     """fft/ifft against the reference plan (sizes of test_fft_valide, test-fourier.cc:263, pow2 subset + 65536)."""
     from libtsd_b200 import fourier as Fo
@@ -309,6 +309,25 @@ def test_fft_vs_oracle(tsd, cpu_oracle, n):
     # unitary + round trip (test-fourier.cc:287-312: RMS error <= 5e-6)
     assert abs(rms(X) / rms(x) - 1) < 1e-5
     assert rms(x2 - x) / rms(x) <= 5e-6
+
+
+@pytest.mark.parametrize("n,batch", [(32768, 300), (131072, 70), (262144, 40), (1048576, 3), (4194304, 2)])
+def test_fft_split_plans_large_batches(tsd, n, batch):
+    """Plans of 2^15 ... 2^22 points (strided 16384-point transforms + combine passes) with batches large enough that the
+    combine kernels run their grid-stride loops, against numpy's float64 transform on every row; round trip."""
+    import torch
+    from libtsd_b200 import fourier as Fo
+    g = torch.Generator(device="cuda")
+    g.manual_seed(n)
+    x = torch.empty((batch, n), dtype=torch.complex64, device="cuda")
+    torch.view_as_real(x).normal_(generator=g)
+    plan = Fo.tfrplan_creation(n, batch=batch)
+    X = plan.step(x, True)
+    Xt = torch.fft.fft(x.to(torch.complex128), dim=1) / np.sqrt(n)
+    scale = float(torch.sqrt(torch.mean(torch.abs(Xt) ** 2)))
+    assert float(torch.max(torch.abs(X.to(torch.complex128) - Xt))) / scale <= 3e-6
+    x2 = plan.step(X, False)
+    assert float(torch.sqrt(torch.mean(torch.abs(x2 - x) ** 2))) / float(torch.sqrt(torch.mean(torch.abs(x) ** 2))) <= 5e-6
 
 
 def test_fft_vs_float64_dft(tsd):
